@@ -1,0 +1,158 @@
+/* psn_b200.h -- C ABI of the B200-native batched Poisson solver (libpsn_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of tahmidawal/Superresolution_for_PDEs: the per-sample
+ * sparse assemble-and-solve that manufactures every training / evaluation sample.  The reference
+ * has no FFI of its own (it is pure Python); each entry point below names the reference
+ * interface it replaces (paths relative to the reference repository root).  The Python shims in
+ * superresolution_for_pdes_b200/ bind these symbols with ctypes and keep the reference's class
+ * and method signatures.
+ *
+ * Conventions
+ *  - all arrays are float64 (int32 where stated), C-contiguous, row index = y, column = x;
+ *  - every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer on the
+ *    library's device; the library detects which (cudaPointerGetAttributes) and stages host
+ *    data through its own device buffers in overlapped chunks;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  When every
+ *    data pointer is a device pointer the call only ENQUEUES work on `stream` and returns
+ *    without synchronising, except for small D2H reads of convergence counters on the
+ *    large-grid path; with host pointers the call returns after the results are in place;
+ *  - return value: 0 on success, negative PSN_ERR_* otherwise (psn_last_error() has the text).
+ *    No exceptions cross the ABI.  There is no CPU fallback: without a CUDA device every
+ *    compute entry point fails with PSN_ERR_CUDA.
+ *
+ * Operator (reference: src/data_generation.py:35-58 `_create_laplacian`, :79-104 `solve_poisson`;
+ * src/enhanced_data_generation.py:47-68 `solve_poisson_superfine`):
+ *     diag(theta) * L * u = f,   L = 5-point Laplacian / h^2,  h = 1/(n-1),
+ *     all n*n nodes unknown, out-of-array neighbours are zero.
+ * Solved matrix-free in fp64 by multigrid-preconditioned CG to a relative residual `rtol`
+ * (true residual recomputed at exit).
+ *
+ * status[] values per sample:
+ *   0 PSN_ST_CONVERGED   true relative residual <= rtol
+ *   1 PSN_ST_FP64_FLOOR  residual stagnated at the fp64 round-off floor above rtol (as accurate as
+ *                        a backward-stable direct solve; happens for very smooth f on large grids)
+ *   2 PSN_ST_MAXITER     max_iter reached without convergence
+ *   3 PSN_ST_BREAKDOWN   non-finite / non-SPD data (e.g. theta == 0, NaN input)
+ */
+#ifndef PSN_B200_H
+#define PSN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSN_OK 0
+#define PSN_ERR_INVALID (-1)     /* bad argument (shape, NULL output, unsupported size) */
+#define PSN_ERR_CUDA (-2)        /* CUDA runtime error, or no CUDA device */
+#define PSN_ERR_NOMEM (-3)       /* device allocation failed */
+#define PSN_ERR_UNSUPPORTED (-4) /* valid request this build does not implement */
+
+#define PSN_OPERATOR_REFERENCE 0 /* diag(theta) L u = f -- what the reference computes (default) */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int psn_version(void);
+
+/* Number of CUDA devices visible to the process (0 if none / no driver). */
+int psn_get_device_count(void);
+
+/* Bind the library to `device` (-1: keep the current device), create its streams and caches.
+ * Replaces nothing in the reference (which has no device); called once per process (one process
+ * per GPU).  Idempotent for the same device. */
+int psn_init(int device);
+
+/* Release every device buffer, stream and cached plan. */
+void psn_shutdown(void);
+
+/* Text of the last error on this thread's most recent failing call ("" if none). */
+const char* psn_last_error(void);
+
+/* Solve `batch` independent n x n problems.
+ *
+ * Replaces: PoissonSolver.solve_poisson (src/data_generation.py:79-104) and
+ * EnhancedPoissonSolver.solve_poisson_superfine (src/enhanced_data_generation.py:47-68), batched;
+ * with sin_x/sin_y it also replaces generate_forcing_term (src/data_generation.py:60-77).
+ *
+ *   theta  [batch, master_n, master_n] or NULL (theta == 1, as in every dataset path)
+ *   forcing: exactly one of
+ *     f      [batch, master_n, master_n]
+ *     sin_x, sin_y  [batch, master_n] each: f[i][j] = sin_y[i] * sin_x[j]  (host-evaluated sines
+ *                   => f is bit-identical to the reference's numpy expression)
+ *     k1, k2 [batch]: f = sin(2 pi k1 x_j) sin(2 pi k2 y_i) evaluated on the device
+ *                   (synthetic-throughput mode; not bit-identical to numpy's sin)
+ *   master_n, step: grid node (i, j) reads master node (i*step, j*step); master_n >= (n-1)*step+1.
+ *                   (master_n = n, step = 1 for plain inputs; step > 1 reproduces the
+ *                   `field[::step, ::step]` gathers of src/resolution_comparison.py:56-58)
+ *   operator_mode  PSN_OPERATOR_REFERENCE
+ *   rtol, max_iter relative residual target (e.g. 1e-12) and iteration cap (e.g. 100)
+ *   u      [batch, n, n] out
+ *   iters  [batch] int32 out (may be NULL), relres [batch] out (may be NULL),
+ *   status [batch] int32 out (may be NULL)
+ */
+int psn_solve_batch(int n, int64_t batch,
+                    const double* theta, const double* f,
+                    const double* sin_x, const double* sin_y,
+                    const double* k1, const double* k2,
+                    int master_n, int step,
+                    int operator_mode, double rtol, int max_iter,
+                    double* u, int32_t* iters, double* relres, int32_t* status,
+                    void* stream);
+
+/* Fused super-fine solve + window extract + stride-2 downsample (theta == 1).
+ *
+ * Replaces the body of EnhancedPoissonSolver.generate_subdomain_dataset's loop
+ * (src/enhanced_data_generation.py:121-163): solve_poisson_superfine (:133), extract_subdomain
+ * (:141-143 -> :83, rows = y, cols = x) and downsample (:146-148 -> :96).
+ *
+ *   sin_x, sin_y [batch, n_super];  start_x, start_y [batch] int32 (window origin, column / row)
+ *   outputs (each may be NULL): u_fine, f_fine, theta_fine [batch, n_fine, n_fine];
+ *                               u_coarse, f_coarse, theta_coarse [batch, ceil(n_fine/2), ceil(n_fine/2)]
+ */
+int psn_subdomain_batch(int n_super, int n_fine, int64_t batch,
+                        const double* sin_x, const double* sin_y,
+                        const int32_t* start_x, const int32_t* start_y,
+                        double rtol, int max_iter,
+                        double* u_fine, double* f_fine, double* theta_fine,
+                        double* u_coarse, double* f_coarse, double* theta_coarse,
+                        int32_t* iters, double* relres, int32_t* status,
+                        void* stream);
+
+/* Multi-resolution reference solutions from one master field per example.
+ *
+ * Replaces the solve loop of solve_multi_resolution (src/resolution_comparison.py:50-73; timed
+ * variant src/resolution_comparison_statistical.py:59-90): for each resolution r the inputs are
+ * the stride gathers master[::n_finest/r, ::n_finest/r].
+ *
+ *   resolutions [n_res] int32 (each must divide n_finest);  theta_finest [batch, n_finest, n_finest]
+ *   or NULL;  sin_x, sin_y [batch, n_finest];  u_out[k] -> [batch, r_k, r_k];
+ *   iters / relres / status: [n_res, batch] (may be NULL)
+ */
+int psn_multires(int n_finest, const int32_t* resolutions, int n_res, int64_t batch,
+                 const double* theta_finest, const double* sin_x, const double* sin_y,
+                 double rtol, int max_iter,
+                 double* const* u_out, int32_t* iters, double* relres, int32_t* status,
+                 void* stream);
+
+/* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg, default 2), "tile" (interior
+ * tile edge of the streamed kernels, default 64), "ws_bytes" (workspace budget per pipeline slot),
+ * "smem_max_n" (largest n solved fully in shared memory; 0 = as large as fits). */
+int psn_set_option(const char* name, int64_t value);
+
+/* Per-kernel device timing (CUDA events around every launch).  Off by default because the event
+ * pairs serialise the stream.  psn_profile_read writes a JSON object
+ * {"kernel": {"launches": L, "ms": total}, ...} into buf and returns its length (or the
+ * required size, negated, if buf is too small). */
+int psn_profile_begin(void);
+int psn_profile_read(char* buf, int64_t buf_bytes);
+int psn_profile_end(void);
+
+/* Which path a grid size takes and what it costs: fills info[0..7] =
+ * {resident(1)/streamed(0), levels, first shared-memory level, threads per CTA,
+ *  dynamic shared memory bytes of the dominant kernel, tile edge, workspace bytes per sample, 0}. */
+int psn_describe(int n, int64_t* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSN_B200_H */

@@ -1,0 +1,17 @@
+"""B200-native drop-in for the batched Poisson sample-generation path of
+tahmidawal/Superresolution_for_PDEs.
+
+Host side (this package): the reference's Python entry points with unchanged signatures, RNG
+order and array layouts -- ``PoissonSolver`` (src/data_generation.py), ``EnhancedPoissonSolver``
+(src/enhanced_data_generation.py), ``solve_multi_resolution`` (src/resolution_comparison.py).
+Device side: ``libpsn_b200.so`` (hand-written sm_100a CUDA behind a C ABI, include/psn_b200.h).
+There is no CPU fallback.
+"""
+from . import _lib
+from ._lib import PsnError
+from .data_generation import PoissonSolver
+from .enhanced_data_generation import EnhancedPoissonSolver
+from .resolution_comparison import solve_multi_resolution, solve_multi_resolution_batch
+
+__all__ = ["PoissonSolver", "EnhancedPoissonSolver", "solve_multi_resolution",
+           "solve_multi_resolution_batch", "PsnError", "_lib"]

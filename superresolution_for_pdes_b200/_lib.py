@@ -1,0 +1,255 @@
+"""ctypes binding of libpsn_b200.so (the C ABI declared in include/psn_b200.h).
+
+There is NO CPU fallback: if the CUDA library has not been built, or no CUDA device is
+present, every compute call raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
+(or ``make -C superresolution_for_pdes_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpsn_b200.so")
+
+PSN_OK = 0
+STATUS_CONVERGED, STATUS_FP64_FLOOR, STATUS_MAXITER, STATUS_BREAKDOWN = 0, 1, 2, 3
+
+EXPORTED_SYMBOLS = (
+    "psn_version", "psn_get_device_count", "psn_init", "psn_shutdown", "psn_last_error",
+    "psn_solve_batch", "psn_subdomain_batch", "psn_multires", "psn_set_option",
+    "psn_profile_begin", "psn_profile_read", "psn_profile_end", "psn_describe",
+)
+
+
+class PsnError(RuntimeError):
+    """A call into libpsn_b200.so failed (the message is psn_last_error())."""
+
+
+_lib: Optional[ctypes.CDLL] = None
+_c_dp = ctypes.c_void_p
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once) and declare the prototypes.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PsnError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built and this package has no "
+            "CPU fallback. Run `python -c \"import __graft_entry__ as g; g.build()\"` at the repo root.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.psn_version.restype = ctypes.c_int
+    lib.psn_get_device_count.restype = ctypes.c_int
+    lib.psn_init.argtypes = [ctypes.c_int]
+    lib.psn_init.restype = ctypes.c_int
+    lib.psn_shutdown.restype = None
+    lib.psn_last_error.restype = ctypes.c_char_p
+    lib.psn_solve_batch.argtypes = [
+        ctypes.c_int, ctypes.c_int64, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, ctypes.c_double, ctypes.c_int, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.c_void_p]
+    lib.psn_solve_batch.restype = ctypes.c_int
+    lib.psn_subdomain_batch.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int64, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.c_double, ctypes.c_int,
+        _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, ctypes.c_void_p]
+    lib.psn_subdomain_batch.restype = ctypes.c_int
+    lib.psn_multires.argtypes = [
+        ctypes.c_int, _c_dp, ctypes.c_int, ctypes.c_int64, _c_dp, _c_dp, _c_dp, ctypes.c_double, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_void_p), _c_dp, _c_dp, _c_dp, ctypes.c_void_p]
+    lib.psn_multires.restype = ctypes.c_int
+    lib.psn_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+    lib.psn_set_option.restype = ctypes.c_int
+    lib.psn_profile_begin.restype = ctypes.c_int
+    lib.psn_profile_read.argtypes = [ctypes.c_char_p, ctypes.c_int64]
+    lib.psn_profile_read.restype = ctypes.c_int
+    lib.psn_profile_end.restype = ctypes.c_int
+    lib.psn_describe.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+    lib.psn_describe.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != PSN_OK:
+        msg = load().psn_last_error().decode("utf-8", "replace")
+        raise PsnError(f"libpsn_b200 error {rc}: {msg}")
+
+
+def _ptr(a) -> Optional[int]:
+    """Raw address of a numpy array (host) or a torch tensor (host or device); None stays NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(f"unsupported buffer type {type(a)!r}")
+
+
+def _f64(a, shape=None, name="array"):
+    """numpy inputs -> float64 C-contiguous (copy only if needed); torch tensors pass through."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr") and not isinstance(a, np.ndarray):
+        if str(a.dtype) != "torch.float64" or not a.is_contiguous():
+            raise ValueError(f"{name}: torch tensors must be contiguous float64")
+        if shape is not None and tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(a.shape)}")
+        return a
+    arr = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        if arr.size != int(np.prod(shape)):
+            raise ValueError(f"{name}: expected {int(np.prod(shape))} elements (shape {tuple(shape)}), got shape {arr.shape}")
+        arr = arr.reshape(shape)
+    return arr
+
+
+def device_count() -> int:
+    return int(load().psn_get_device_count())
+
+
+def init(device: int = -1) -> None:
+    _check(load().psn_init(int(device)))
+
+
+def shutdown() -> None:
+    load().psn_shutdown()
+
+
+def set_option(name: str, value: int) -> None:
+    _check(load().psn_set_option(name.encode(), int(value)))
+
+
+def describe(n: int) -> dict:
+    info = (ctypes.c_int64 * 8)()
+    _check(load().psn_describe(int(n), info))
+    return {"resident": bool(info[0]), "levels": int(info[1]), "first_smem_level": int(info[2]),
+            "threads": int(info[3]), "smem_bytes": int(info[4]), "tile": int(info[5]),
+            "workspace_bytes_per_sample": int(info[6])}
+
+
+def profile_begin() -> None:
+    _check(load().psn_profile_begin())
+
+
+def profile_read() -> dict:
+    lib = load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib.psn_profile_read(buf, len(buf))
+    if n < 0:
+        buf = ctypes.create_string_buffer(-n + 16)
+        n = lib.psn_profile_read(buf, len(buf))
+    return json.loads(buf.value.decode())
+
+
+def profile_end() -> None:
+    _check(load().psn_profile_end())
+
+
+class SolveInfo:
+    """Per-sample convergence record of one batched call."""
+
+    def __init__(self, iters: np.ndarray, relres: np.ndarray, status: np.ndarray):
+        self.iters, self.relres, self.status = iters, relres, status
+
+    def to_host(self) -> "SolveInfo":
+        cv = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else a
+        return SolveInfo(cv(self.iters), cv(self.relres), cv(self.status))
+
+    def raise_if_failed(self, what: str = "solve") -> None:
+        if hasattr(self.status, "cpu"):
+            return self.to_host().raise_if_failed(what)
+        bad = np.flatnonzero(np.asarray(self.status) >= STATUS_MAXITER)
+        if bad.size:
+            i = int(bad[0])
+            raise PsnError(
+                f"{what}: {bad.size} of {self.status.size} samples did not converge "
+                f"(first: sample {i}, status {int(self.status.flat[i])}, relres {float(self.relres.flat[i]):.3e}, "
+                f"iters {int(self.iters.flat[i])}); refusing to return unconverged solutions")
+
+
+def solve_batch(n: int, batch: int, *, theta=None, f=None, sin_x=None, sin_y=None, k1=None, k2=None,
+                master_n: Optional[int] = None, step: int = 1, rtol: float = 1e-12, max_iter: int = 100,
+                out=None, stream: int = 0, info_on_host: bool = True):
+    """Batched solve of diag(theta) L u = f.  Buffers may be numpy arrays (host) or torch CUDA
+    tensors (device, float64, contiguous).  Returns (u, SolveInfo)."""
+    lib = load()
+    mn = int(master_n) if master_n is not None else int(n)
+    theta = _f64(theta, (batch, mn, mn), "theta")
+    f = _f64(f, (batch, mn, mn), "f")
+    sin_x = _f64(sin_x, (batch, mn), "sin_x")
+    sin_y = _f64(sin_y, (batch, mn), "sin_y")
+    k1 = _f64(k1, (batch,), "k1")
+    k2 = _f64(k2, (batch,), "k2")
+    if out is None:
+        out = np.empty((batch, n, n), dtype=np.float64)
+    if hasattr(out, "is_cuda") and out.is_cuda:
+        # device-resident call: keep the per-sample record on the device too, so that the call
+        # only enqueues work on `stream` (no host pointer -> no staging, no synchronisation)
+        import torch
+        iters = torch.zeros(batch, dtype=torch.int32, device=out.device)
+        relres = torch.zeros(batch, dtype=torch.float64, device=out.device)
+        status = torch.zeros(batch, dtype=torch.int32, device=out.device)
+    else:
+        iters = np.zeros(batch, dtype=np.int32)
+        relres = np.zeros(batch, dtype=np.float64)
+        status = np.zeros(batch, dtype=np.int32)
+    rc = lib.psn_solve_batch(int(n), int(batch), _ptr(theta), _ptr(f), _ptr(sin_x), _ptr(sin_y), _ptr(k1), _ptr(k2),
+                             mn, int(step), 0, float(rtol), int(max_iter), _ptr(out), _ptr(iters), _ptr(relres),
+                             _ptr(status), ctypes.c_void_p(stream))
+    _check(rc)
+    return out, SolveInfo(iters, relres, status)
+
+
+def subdomain_batch(n_super: int, n_fine: int, batch: int, sin_x, sin_y, start_x, start_y, *,
+                    rtol: float = 1e-12, max_iter: int = 100, stream: int = 0):
+    """Fused super-fine solve + window + stride-2 downsample.  Returns (dict of arrays, SolveInfo)."""
+    lib = load()
+    nc = (n_fine + 1) // 2
+    sin_x = _f64(sin_x, (batch, n_super), "sin_x")
+    sin_y = _f64(sin_y, (batch, n_super), "sin_y")
+    start_x = np.ascontiguousarray(start_x, dtype=np.int32).reshape(batch)
+    start_y = np.ascontiguousarray(start_y, dtype=np.int32).reshape(batch)
+    if batch and (start_x.min() < 0 or start_y.min() < 0 or start_x.max() + n_fine > n_super or start_y.max() + n_fine > n_super):
+        raise ValueError("sub-domain window leaves the super-fine grid")
+    out = {
+        "u_fine": np.empty((batch, n_fine, n_fine)), "f_fine": np.empty((batch, n_fine, n_fine)),
+        "theta_fine": np.empty((batch, n_fine, n_fine)),
+        "u_coarse": np.empty((batch, nc, nc)), "f_coarse": np.empty((batch, nc, nc)),
+        "theta_coarse": np.empty((batch, nc, nc)),
+    }
+    iters = np.zeros(batch, dtype=np.int32)
+    relres = np.zeros(batch, dtype=np.float64)
+    status = np.zeros(batch, dtype=np.int32)
+    rc = lib.psn_subdomain_batch(int(n_super), int(n_fine), int(batch), _ptr(sin_x), _ptr(sin_y), _ptr(start_x), _ptr(start_y),
+                                 float(rtol), int(max_iter), _ptr(out["u_fine"]), _ptr(out["f_fine"]), _ptr(out["theta_fine"]),
+                                 _ptr(out["u_coarse"]), _ptr(out["f_coarse"]), _ptr(out["theta_coarse"]),
+                                 _ptr(iters), _ptr(relres), _ptr(status), ctypes.c_void_p(stream))
+    _check(rc)
+    return out, SolveInfo(iters, relres, status)
+
+
+def multires(n_finest: int, resolutions: Sequence[int], batch: int, theta_finest, sin_x, sin_y, *,
+             rtol: float = 1e-12, max_iter: int = 100, stream: int = 0):
+    """Solve at every resolution from one master theta / forcing per example (stride gathers).
+    Returns ({res: u[batch, res, res]}, SolveInfo with [n_res, batch] arrays)."""
+    lib = load()
+    res = [int(r) for r in resolutions]
+    theta_finest = _f64(theta_finest, (batch, n_finest, n_finest), "theta_finest")
+    sin_x = _f64(sin_x, (batch, n_finest), "sin_x")
+    sin_y = _f64(sin_y, (batch, n_finest), "sin_y")
+    outs = [np.empty((batch, r, r), dtype=np.float64) for r in res]
+    res_arr = np.asarray(res, dtype=np.int32)
+    ptrs = (ctypes.c_void_p * len(res))(*[o.ctypes.data for o in outs])
+    iters = np.zeros((len(res), batch), dtype=np.int32)
+    relres = np.zeros((len(res), batch), dtype=np.float64)
+    status = np.zeros((len(res), batch), dtype=np.int32)
+    rc = lib.psn_multires(int(n_finest), _ptr(res_arr), len(res), int(batch), _ptr(theta_finest), _ptr(sin_x), _ptr(sin_y),
+                          float(rtol), int(max_iter), ptrs, _ptr(iters), _ptr(relres), _ptr(status), ctypes.c_void_p(stream))
+    _check(rc)
+    return dict(zip(res, outs)), SolveInfo(iters, relres, status)

@@ -1,0 +1,865 @@
+// psn_b200.cu -- CUDA kernels (sm_100a) and the C ABI of libpsn_b200.so.
+//
+// Two regimes:
+//   resident  n*n <= 8192 and the hierarchy fits 227 KB of shared memory (n <= ~86):
+//             ONE kernel, one CTA per sample, the whole MG-PCG solve in shared memory/registers.
+//   streamed  larger grids: batched kernels over [B, n, n] arrays in HBM, temporally blocked
+//             shared-memory tiles for the V-cycle legs, per-sample scalars and convergence state
+//             on the device, no host synchronisation inside an iteration.
+// The numerical bodies live in psn_core.cuh (shared with the CPU-only test harness).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/psn_b200.h"
+#include "psn_stream_driver.h"
+
+#define PSN_VERSION 100
+
+// ----------------------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+static int psn_fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                            \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            cudaGetLastError();                                                                 \
+            return psn_fail(e_ == cudaErrorMemoryAllocation ? PSN_ERR_NOMEM : PSN_ERR_CUDA,     \
+                            "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                       \
+    } while (0)
+
+// ----------------------------------------------------------------------------- kernels
+template <int T, int XPT>
+__global__ void __launch_bounds__(T) psn_smem_solve_kernel(const __grid_constant__ PsnPlan plan,
+                                                           const __grid_constant__ PsnSolveArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, T, red, 0};
+    psn_smem_solve_body<XPT>(ctx, plan, a, (long long)blockIdx.x, smem);
+}
+
+#define PSN_TILE_THREADS 256
+#define PSN_COARSE_THREADS 512
+#define PSN_CG_THREADS 256
+
+__global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_pre_kernel(const __grid_constant__ PsnPlan plan,
+                                                                        const __grid_constant__ PsnTileArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PSN_TILE_THREADS, red, 0};
+    psn_tile_pre_body(ctx, plan, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x, smem);
+}
+
+__global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_post_kernel(const __grid_constant__ PsnPlan plan,
+                                                                         const __grid_constant__ PsnTileArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PSN_TILE_THREADS, red, 0};
+    psn_tile_post_body(ctx, plan, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x, smem);
+}
+
+__global__ void __launch_bounds__(PSN_COARSE_THREADS) psn_coarse_vcycle_kernel(const __grid_constant__ PsnPlan plan, int l0,
+                                                                               const double* bg, double* ug,
+                                                                               const PsnSampleState* state) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PSN_COARSE_THREADS, red, 0};
+    psn_coarse_vcycle_body(ctx, plan, l0, bg, ug, state, (long long)blockIdx.x, smem);
+}
+
+__global__ void __launch_bounds__(PSN_CG_THREADS) psn_prologue_kernel(const __grid_constant__ PsnCgArgs a) {
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PSN_CG_THREADS, red, 0};
+    psn_prologue_body(ctx, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(PSN_CG_THREADS) psn_dir_apply_kernel(const __grid_constant__ PsnCgArgs a) {
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PSN_CG_THREADS, red, 0};
+    psn_dir_apply_body(ctx, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(PSN_CG_THREADS) psn_update_kernel(const __grid_constant__ PsnCgArgs a) {
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PSN_CG_THREADS, red, 0};
+    psn_update_body(ctx, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x);
+}
+__global__ void __launch_bounds__(PSN_CG_THREADS) psn_true_residual_kernel(const __grid_constant__ PsnCgArgs a) {
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PSN_CG_THREADS, red, 0};
+    psn_true_residual_body(ctx, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x);
+}
+__global__ void psn_state_init_kernel(const __grid_constant__ PsnCgArgs a, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) psn_state_init(a, b);
+}
+__global__ void psn_state_after_update_kernel(const __grid_constant__ PsnCgArgs a, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) psn_state_after_update(a, b);
+}
+__global__ void psn_state_after_check_kernel(const __grid_constant__ PsnCgArgs a, long long B, int* counter) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int active = 0;
+    if (b < B) active = psn_state_after_check(a, b);
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, __popc(m));
+}
+__global__ void psn_finalize_kernel(const PsnSampleState* state, long long B, int32_t* iters, double* relres, int32_t* status) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const PsnSampleState st = state[b];
+    if (iters) iters[b] = st.iters;
+    if (relres) relres[b] = st.bb > 0.0 ? sqrt(st.rr / st.bb) : 0.0;
+    if (status) status[b] = st.phase == PSN_PHASE_DONE ? st.status : PSN_ST_MAXITER;
+}
+__global__ void psn_fill_kernel(double* p, long long cnt, double v) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ----------------------------------------------------------------------------- library context
+namespace {
+
+struct PlanEntry {
+    PsnPlan plan;
+    double* d_inv;
+};
+
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    Arena arena;      // staging buffers (per chunk)
+    Arena ws_arena;   // streamed-path workspace
+    int* h_counters = nullptr;  // pinned
+    int h_counters_cap = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct ProfRec {
+    const char* name;
+    cudaEvent_t e0, e1;
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    Slot slots[2];
+    std::map<long long, PlanEntry> plans;  // key = n * 16 + nu
+    int nu = 2;
+    int tile = 64;
+    long long ws_bytes = 16ll << 30;
+    int smem_max_n = 0;
+    bool attrs_set = false;
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+};
+
+Context g;
+
+int arena_reserve(Arena& a, size_t bytes) {
+    if (bytes > a.cap) {
+        if (a.base) CU_TRY(cudaFree(a.base));
+        a.base = nullptr;
+        a.cap = 0;
+        CU_TRY(cudaMalloc(&a.base, bytes));
+        a.cap = bytes;
+    }
+    a.off = 0;
+    return PSN_OK;
+}
+template <class T>
+T* arena_take(Arena& a, size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (a.off + bytes > a.cap) return nullptr;
+    T* p = reinterpret_cast<T*>(a.base + a.off);
+    a.off += bytes;
+    return p;
+}
+inline size_t pad256(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
+enum MemKind { MEM_NULL = 0, MEM_HOST = 1, MEM_DEVICE = 2 };
+MemKind classify(const void* p) {
+    if (!p) return MEM_NULL;
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return MEM_HOST;
+    }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? MEM_DEVICE : MEM_HOST;
+}
+
+int ensure_init() {
+    if (g.ready) return PSN_OK;
+    return psn_init(-1);
+}
+
+int get_plan(int n, PlanEntry** out) {
+    const long long key = (long long)n * 16 + g.nu;
+    auto it = g.plans.find(key);
+    if (it == g.plans.end()) {
+        PlanEntry e;
+        psn_plan_levels(&e.plan, n, g.nu);
+        std::vector<double> inv = psn_coarse_inverse(e.plan);
+        e.d_inv = nullptr;
+        CU_TRY(cudaMalloc(&e.d_inv, inv.size() * sizeof(double)));
+        CU_TRY(cudaMemcpy(e.d_inv, inv.data(), inv.size() * sizeof(double), cudaMemcpyHostToDevice));
+        e.plan.coarse_inv = e.d_inv;
+        it = g.plans.emplace(key, e).first;
+    }
+    *out = &it->second;
+    return PSN_OK;
+}
+
+// resident-kernel configuration for a plan; T == 0 -> does not fit
+struct ResidentCfg {
+    int T, XPT;
+    size_t smem;
+};
+ResidentCfg resident_cfg(const PsnPlan& plan) {
+    ResidentCfg c{0, 0, 0};
+    const int nn = plan.n * plan.n;
+    if (g.smem_max_n > 0 && plan.n > g.smem_max_n) return c;
+    if (g.smem_max_n < 0) return c;
+    c.smem = (size_t)psn_smem_solver_doubles(plan) * sizeof(double);
+    if (c.smem + 1024 > g.smem_optin) return c;
+    if (nn <= 128 * 4) { c.T = 128; c.XPT = 4; }
+    else if (nn <= 256 * 8) { c.T = 256; c.XPT = 8; }
+    else if (nn <= 512 * 8) { c.T = 512; c.XPT = 8; }
+    else if (nn <= 512 * 16) { c.T = 512; c.XPT = 16; }
+    return c;
+}
+
+// first level that the shared-memory coarse kernel can take
+int stream_ls(const PsnPlan& plan) {
+    for (int l = 1; l < plan.nlev; ++l) {
+        size_t bytes = ((size_t)2 * plan.lv[l].size + psn_pool_doubles(plan, l)) * sizeof(double);
+        if (bytes + 1024 <= g.smem_optin) return l;
+    }
+    return -1;
+}
+
+int set_kernel_attrs() {
+    if (g.attrs_set) return PSN_OK;
+    const int mx = (int)g.smem_optin - 1024;  // leave room for the static reduction scratch
+    CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_tile_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_tile_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_coarse_vcycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    g.attrs_set = true;
+    return PSN_OK;
+}
+
+// ---- profiling helpers
+struct ProfScope {
+    cudaStream_t s;
+    ProfRec rec;
+    bool on;
+    ProfScope(const char* name, cudaStream_t stream) : s(stream), on(g.profiling) {
+        if (on) {
+            rec.name = name;
+            cudaEventCreate(&rec.e0);
+            cudaEventCreate(&rec.e1);
+            cudaEventRecord(rec.e0, s);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(rec.e1, s);
+            g.prof.push_back(rec);
+        }
+    }
+};
+
+// ---- CUDA backend of the streamed driver
+struct CudaBackend {
+    cudaStream_t s;
+    Slot* slot;
+    cudaError_t err = cudaSuccess;
+    void chk() {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
+    dim3 cg_grid(const PsnCgArgs& a, long long B) { return dim3(a.ntx, a.nty, (unsigned)B); }
+    void zero_counters(int* c, int cnt) {
+        cudaError_t e = cudaMemsetAsync(c, 0, sizeof(int) * cnt, s);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
+    void prologue(const PsnCgArgs& a, long long B) {
+        ProfScope p("prologue", s);
+        psn_prologue_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        chk();
+    }
+    void state_init(const PsnCgArgs& a, long long B) {
+        ProfScope p("state", s);
+        psn_state_init_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B);
+        chk();
+    }
+    void tile_pre(const PsnPlan& plan, const PsnTileArgs& t, long long B) {
+        ProfScope p(t.level == 0 ? "tile_pre_l0" : "tile_pre_coarse", s);
+        const size_t smem = (size_t)psn_tile_pre_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
+        psn_tile_pre_kernel<<<dim3(t.ntx, t.nty, (unsigned)B), PSN_TILE_THREADS, smem, s>>>(plan, t);
+        chk();
+    }
+    void tile_post(const PsnPlan& plan, const PsnTileArgs& t, long long B) {
+        ProfScope p(t.level == 0 ? "tile_post_l0" : "tile_post_coarse", s);
+        const size_t smem = (size_t)psn_tile_post_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
+        psn_tile_post_kernel<<<dim3(t.ntx, t.nty, (unsigned)B), PSN_TILE_THREADS, smem, s>>>(plan, t);
+        chk();
+    }
+    void coarse_vcycle(const PsnPlan& plan, int l0, const double* bg, double* ug, const PsnSampleState* st, long long B) {
+        ProfScope p("coarse_vcycle", s);
+        const size_t smem = ((size_t)2 * plan.lv[l0].size + psn_pool_doubles(plan, l0)) * sizeof(double);
+        psn_coarse_vcycle_kernel<<<(unsigned)B, PSN_COARSE_THREADS, smem, s>>>(plan, l0, bg, ug, st);
+        chk();
+    }
+    void dir_apply(const PsnCgArgs& a, long long B) {
+        ProfScope p("dir_apply_dot", s);
+        psn_dir_apply_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        chk();
+    }
+    void update(const PsnCgArgs& a, long long B) {
+        ProfScope p("update_norm", s);
+        psn_update_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        chk();
+    }
+    void true_residual(const PsnCgArgs& a, long long B) {
+        ProfScope p("true_residual", s);
+        psn_true_residual_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        chk();
+    }
+    void state_after_update(const PsnCgArgs& a, long long B) {
+        ProfScope p("state", s);
+        psn_state_after_update_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B);
+        chk();
+    }
+    void state_after_check(const PsnCgArgs& a, long long B, int* counter) {
+        ProfScope p("state", s);
+        psn_state_after_check_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B, counter);
+        chk();
+    }
+    void fetch_counter_async(const int* c, int it) {
+        cudaError_t e = cudaMemcpyAsync(slot->h_counters + it, c, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaEventRecord(slot->ev[it & 3], s);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
+    int wait_counter(int it) {
+        cudaError_t e = cudaEventSynchronize(slot->ev[it & 3]);
+        if (e != cudaSuccess) {
+            if (err == cudaSuccess) err = e;
+            return 0;  // stop iterating on error
+        }
+        return slot->h_counters[it];
+    }
+};
+
+// ---- one batched problem as seen by the ABI
+struct Problem {
+    int n;
+    long long B;
+    const double *theta, *f, *sx, *sy, *k1, *k2;
+    int mn, step;
+    double rtol;
+    int max_iter;
+    double* u;
+    int32_t* iters;
+    double* relres;
+    int32_t* status;
+    int sub;
+    const int32_t *start_x, *start_y;
+    double *u_fine, *f_fine, *th_fine, *u_coarse, *f_coarse, *th_coarse;
+    cudaStream_t stream;
+};
+
+// stage one input slice: returns device pointer valid on `s`
+template <class T>
+int stage_in(Arena& ar, cudaStream_t s, const T* src, MemKind kind, long long offset, size_t count, const T** out) {
+    if (kind == MEM_NULL) { *out = nullptr; return PSN_OK; }
+    if (kind == MEM_DEVICE) { *out = src + offset; return PSN_OK; }
+    T* d = arena_take<T>(ar, count);
+    if (!d) return psn_fail(PSN_ERR_NOMEM, "staging arena exhausted");
+    CU_TRY(cudaMemcpyAsync(d, src + offset, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    *out = d;
+    return PSN_OK;
+}
+template <class T>
+int stage_out(Arena& ar, T* dst, MemKind kind, long long offset, size_t count, T** out, bool always) {
+    if (kind == MEM_DEVICE) { *out = dst + offset; return PSN_OK; }
+    if (kind == MEM_NULL && !always) { *out = nullptr; return PSN_OK; }
+    T* d = arena_take<T>(ar, count);
+    if (!d) return psn_fail(PSN_ERR_NOMEM, "staging arena exhausted");
+    *out = d;
+    return PSN_OK;
+}
+template <class T>
+int copy_back(cudaStream_t s, T* host_dst, MemKind kind, long long offset, size_t count, const T* dev) {
+    if (kind != MEM_HOST) return PSN_OK;
+    CU_TRY(cudaMemcpyAsync(host_dst + offset, dev, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    return PSN_OK;
+}
+
+size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) {
+    const size_t nn = (size_t)plan.n * plan.n;
+    size_t b = 5 * nn * sizeof(double);
+    for (int l = 1; l <= cfg.ls; ++l) {
+        const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n * sizeof(double);
+        b += (l < cfg.ls ? 3 : 2) * m;
+    }
+    int tx, ty;
+    psn_tile_counts(plan.n, cfg.TH, cfg.TW, &tx, &ty);
+    const int gx = (plan.n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (plan.n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
+    b += ((size_t)tx * ty + 2 * (size_t)gx * gy) * sizeof(double) + sizeof(PsnSampleState);
+    return b + 4096 / 16;
+}
+
+int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, long long Bc, int max_iter, PsnStreamWs* ws) {
+    const size_t nn = (size_t)plan.n * plan.n;
+    memset(ws, 0, sizeof(*ws));
+    ws->cap = Bc;
+    ws->r = arena_take<double>(ar, Bc * nn);
+    ws->q = arena_take<double>(ar, Bc * nn);
+    ws->z = arena_take<double>(ar, Bc * nn);
+    ws->p[0] = arena_take<double>(ar, Bc * nn);
+    ws->p[1] = arena_take<double>(ar, Bc * nn);
+    bool ok = ws->r && ws->q && ws->z && ws->p[0] && ws->p[1];
+    for (int l = 1; l <= cfg.ls && ok; ++l) {
+        const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n;
+        ws->bl[l] = arena_take<double>(ar, Bc * m);
+        ws->ub[l] = arena_take<double>(ar, Bc * m);
+        ok = ws->bl[l] && ws->ub[l];
+        if (l < cfg.ls) {
+            ws->ua[l] = arena_take<double>(ar, Bc * m);
+            ok = ok && ws->ua[l];
+        }
+    }
+    int tx, ty;
+    psn_tile_counts(plan.n, cfg.TH, cfg.TW, &tx, &ty);
+    const int gx = (plan.n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (plan.n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
+    ws->part_rz = arena_take<double>(ar, (size_t)Bc * tx * ty);
+    ws->part_a = arena_take<double>(ar, (size_t)Bc * gx * gy);
+    ws->part_b = arena_take<double>(ar, (size_t)Bc * gx * gy);
+    ws->state = arena_take<PsnSampleState>(ar, Bc);
+    ws->counters = arena_take<int>(ar, max_iter + 8);
+    ok = ok && ws->part_rz && ws->part_a && ws->part_b && ws->state && ws->counters;
+    return ok ? PSN_OK : psn_fail(PSN_ERR_NOMEM, "workspace arena exhausted");
+}
+
+int solve_internal(const Problem& P) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (P.n < 2) return psn_fail(PSN_ERR_INVALID, "n must be >= 2 (got %d)", P.n);
+    if (P.B < 0) return psn_fail(PSN_ERR_INVALID, "batch must be >= 0");
+    if (P.B == 0) return PSN_OK;
+    if (P.step < 1 || P.mn < (P.n - 1) * P.step + 1)
+        return psn_fail(PSN_ERR_INVALID, "master_n=%d too small for n=%d step=%d", P.mn, P.n, P.step);
+    const int nforce = (P.f ? 1 : 0) + ((P.sx || P.sy) ? 1 : 0) + ((P.k1 || P.k2) ? 1 : 0);
+    if (nforce != 1 || (!P.sx != !P.sy) || (!P.k1 != !P.k2))
+        return psn_fail(PSN_ERR_INVALID, "give exactly one forcing: f, (sin_x and sin_y), or (k1 and k2)");
+    if (!(P.rtol > 0.0) || P.max_iter < 1) return psn_fail(PSN_ERR_INVALID, "rtol must be > 0 and max_iter >= 1");
+    if (!P.u && P.sub == 0) return psn_fail(PSN_ERR_INVALID, "output u is NULL");
+    if (P.sub < 0 || P.sub > P.n || (P.sub > 0 && (!P.start_x || !P.start_y)))
+        return psn_fail(PSN_ERR_INVALID, "bad sub-domain request");
+    rc = set_kernel_attrs();
+    if (rc) return rc;
+
+    PlanEntry* pe = nullptr;
+    rc = get_plan(P.n, &pe);
+    if (rc) return rc;
+    const PsnPlan& plan = pe->plan;
+    const ResidentCfg rcfg = resident_cfg(plan);
+    const bool resident = rcfg.T != 0;
+    PsnStreamCfg scfg{0, g.tile, g.tile};
+    if (!resident) {
+        if (P.sub > 0) return psn_fail(PSN_ERR_UNSUPPORTED, "fused sub-domain epilogue needs the resident path (n=%d too large)", P.n);
+        scfg.ls = stream_ls(plan);
+        if (scfg.ls < 1) return psn_fail(PSN_ERR_UNSUPPORTED, "no shared-memory coarse level for n=%d", P.n);
+    }
+
+    const MemKind k_theta = classify(P.theta), k_f = classify(P.f), k_sx = classify(P.sx), k_sy = classify(P.sy),
+                  k_k1 = classify(P.k1), k_k2 = classify(P.k2), k_u = classify(P.u), k_it = classify(P.iters),
+                  k_rr = classify(P.relres), k_st = classify(P.status), k_x0 = classify(P.start_x), k_y0 = classify(P.start_y),
+                  k_uf = classify(P.u_fine), k_ff = classify(P.f_fine), k_tf = classify(P.th_fine),
+                  k_uc = classify(P.u_coarse), k_fc = classify(P.f_coarse), k_tc = classify(P.th_coarse);
+    const MemKind kinds[] = {k_theta, k_f, k_sx, k_sy, k_k1, k_k2, k_u, k_it, k_rr, k_st, k_x0, k_y0, k_uf, k_ff, k_tf, k_uc, k_fc, k_tc};
+    bool any_host = false;
+    for (MemKind k : kinds) any_host = any_host || (k == MEM_HOST);
+
+    const size_t nn = (size_t)P.n * P.n, mm = (size_t)P.mn * P.mn;
+    const int sc = (P.sub + 1) / 2;
+    const size_t ss = (size_t)P.sub * P.sub, scc = (size_t)sc * sc;
+
+    // bytes of staging per sample
+    size_t stage_ps = 64;
+    if (k_theta == MEM_HOST) stage_ps += mm * 8;
+    if (k_f == MEM_HOST) stage_ps += mm * 8;
+    if (k_sx == MEM_HOST) stage_ps += (size_t)P.mn * 8;
+    if (k_sy == MEM_HOST) stage_ps += (size_t)P.mn * 8;
+    if (k_u == MEM_HOST || (!resident && k_u == MEM_NULL)) stage_ps += nn * 8;
+    if (k_uf == MEM_HOST) stage_ps += ss * 8;
+    if (k_ff == MEM_HOST) stage_ps += ss * 8;
+    if (k_tf == MEM_HOST) stage_ps += ss * 8;
+    if (k_uc == MEM_HOST) stage_ps += scc * 8;
+    if (k_fc == MEM_HOST) stage_ps += scc * 8;
+    if (k_tc == MEM_HOST) stage_ps += scc * 8;
+
+    // chunk size
+    long long Bc = P.B;
+    const size_t ws_ps = resident ? 0 : stream_ws_bytes_per_sample(plan, scfg);
+    {
+        const long long budget = g.ws_bytes;
+        const long long per = (long long)(ws_ps + stage_ps);
+        long long cap = per > 0 ? budget / per : P.B;
+        if (cap < 1) cap = 1;
+        if (cap > 65535 && !resident) cap = 65535;   // gridDim.z
+        if (any_host) {
+            // at least ~8 chunks so that copies overlap the solve, but keep chunks large enough to fill the GPU
+            long long want = (P.B + 7) / 8;
+            const long long floor_ = resident ? 4ll * g.sm_count : 64;
+            if (want < floor_) want = floor_;
+            if (cap > want) cap = want;
+        }
+        if (Bc > cap) Bc = cap;
+    }
+    const int nslots = any_host ? 2 : 1;
+    if (any_host) CU_TRY(cudaStreamSynchronize(P.stream));  // device inputs may still be in flight on the caller's stream
+
+    long long chunk_idx = 0;
+    for (long long b0 = 0; b0 < P.B; b0 += Bc, ++chunk_idx) {
+        const long long bc = (P.B - b0 < Bc) ? (P.B - b0) : Bc;
+        Slot& slot = g.slots[chunk_idx % nslots];
+        cudaStream_t s = any_host ? slot.stream : P.stream;
+        if (chunk_idx < nslots) {
+            rc = arena_reserve(slot.arena, pad256(stage_ps * Bc) + 64 * 256 + (size_t)Bc * 64);
+            if (rc) return rc;
+            if (!resident) {
+                rc = arena_reserve(slot.ws_arena, ws_ps * Bc + 64 * 256 + pad256((size_t)(P.max_iter + 8) * 4));
+                if (rc) return rc;
+                if (slot.h_counters_cap < P.max_iter + 8) {
+                    if (slot.h_counters) cudaFreeHost(slot.h_counters);
+                    CU_TRY(cudaMallocHost(&slot.h_counters, sizeof(int) * (P.max_iter + 8)));
+                    slot.h_counters_cap = P.max_iter + 8;
+                }
+            }
+        } else {
+            slot.arena.off = 0;   // stream order on slot.stream protects reuse
+        }
+        Arena& ar = slot.arena;
+
+        PsnRhs rhs;
+        rhs.mn = P.mn;
+        rhs.step = P.step;
+        if ((rc = stage_in(ar, s, P.theta, k_theta, b0 * (long long)mm, bc * mm, &rhs.theta))) return rc;
+        if ((rc = stage_in(ar, s, P.f, k_f, b0 * (long long)mm, bc * mm, &rhs.f))) return rc;
+        if ((rc = stage_in(ar, s, P.sx, k_sx, b0 * (long long)P.mn, bc * (size_t)P.mn, &rhs.sx))) return rc;
+        if ((rc = stage_in(ar, s, P.sy, k_sy, b0 * (long long)P.mn, bc * (size_t)P.mn, &rhs.sy))) return rc;
+        if ((rc = stage_in(ar, s, P.k1, k_k1, b0, (size_t)bc, &rhs.k1))) return rc;
+        if ((rc = stage_in(ar, s, P.k2, k_k2, b0, (size_t)bc, &rhs.k2))) return rc;
+
+        double* d_u = nullptr;
+        int32_t* d_it = nullptr;
+        double* d_rr = nullptr;
+        int32_t* d_st = nullptr;
+        if ((rc = stage_out(ar, P.u, k_u, b0 * (long long)nn, bc * nn, &d_u, !resident))) return rc;
+        if ((rc = stage_out(ar, P.iters, k_it, b0, (size_t)bc, &d_it, false))) return rc;
+        if ((rc = stage_out(ar, P.relres, k_rr, b0, (size_t)bc, &d_rr, false))) return rc;
+        if ((rc = stage_out(ar, P.status, k_st, b0, (size_t)bc, &d_st, false))) return rc;
+
+        if (resident) {
+            PsnSolveArgs a;
+            memset(&a, 0, sizeof(a));
+            a.rhs = rhs;
+            a.rtol = P.rtol;
+            a.max_iter = P.max_iter;
+            a.u = d_u;
+            a.iters = d_it;
+            a.relres = d_rr;
+            a.status = d_st;
+            a.sub = P.sub;
+            if (P.sub > 0) {
+                if ((rc = stage_in(ar, s, P.start_x, k_x0, b0, (size_t)bc, &a.start_x))) return rc;
+                if ((rc = stage_in(ar, s, P.start_y, k_y0, b0, (size_t)bc, &a.start_y))) return rc;
+                if ((rc = stage_out(ar, P.u_fine, k_uf, b0 * (long long)ss, bc * ss, &a.u_fine, false))) return rc;
+                if ((rc = stage_out(ar, P.f_fine, k_ff, b0 * (long long)ss, bc * ss, &a.f_fine, false))) return rc;
+                if ((rc = stage_out(ar, P.th_fine, k_tf, b0 * (long long)ss, bc * ss, &a.th_fine, false))) return rc;
+                if ((rc = stage_out(ar, P.u_coarse, k_uc, b0 * (long long)scc, bc * scc, &a.u_coarse, false))) return rc;
+                if ((rc = stage_out(ar, P.f_coarse, k_fc, b0 * (long long)scc, bc * scc, &a.f_coarse, false))) return rc;
+                if ((rc = stage_out(ar, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, &a.th_coarse, false))) return rc;
+            }
+            {
+                ProfScope pr("smem_solve", s);
+                const unsigned grid = (unsigned)bc;
+                if (rcfg.T == 128) psn_smem_solve_kernel<128, 4><<<grid, 128, rcfg.smem, s>>>(plan, a);
+                else if (rcfg.T == 256) psn_smem_solve_kernel<256, 8><<<grid, 256, rcfg.smem, s>>>(plan, a);
+                else if (rcfg.XPT == 8) psn_smem_solve_kernel<512, 8><<<grid, 512, rcfg.smem, s>>>(plan, a);
+                else psn_smem_solve_kernel<512, 16><<<grid, 512, rcfg.smem, s>>>(plan, a);
+            }
+            CU_TRY(cudaGetLastError());
+            if (P.sub > 0) {
+                if ((rc = copy_back(s, P.u_fine, k_uf, b0 * (long long)ss, bc * ss, a.u_fine))) return rc;
+                if ((rc = copy_back(s, P.f_fine, k_ff, b0 * (long long)ss, bc * ss, a.f_fine))) return rc;
+                if ((rc = copy_back(s, P.th_fine, k_tf, b0 * (long long)ss, bc * ss, a.th_fine))) return rc;
+                if ((rc = copy_back(s, P.u_coarse, k_uc, b0 * (long long)scc, bc * scc, a.u_coarse))) return rc;
+                if ((rc = copy_back(s, P.f_coarse, k_fc, b0 * (long long)scc, bc * scc, a.f_coarse))) return rc;
+                if ((rc = copy_back(s, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, a.th_coarse))) return rc;
+            }
+        } else {
+            slot.ws_arena.off = 0;
+            PsnStreamWs ws;
+            if ((rc = carve_stream_ws(slot.ws_arena, plan, scfg, bc, P.max_iter, &ws))) return rc;
+            CudaBackend bk{s, &slot};
+            psn_stream_solve(bk, plan, scfg, rhs, bc, P.rtol, P.max_iter, d_u, ws);
+            if (bk.err != cudaSuccess) return psn_fail(PSN_ERR_CUDA, "streamed solve failed: %s", cudaGetErrorString(bk.err));
+            {
+                ProfScope pr("state", s);
+                psn_finalize_kernel<<<(unsigned)((bc + 127) / 128), 128, 0, s>>>(ws.state, bc, d_it, d_rr, d_st);
+            }
+            CU_TRY(cudaGetLastError());
+        }
+        if ((rc = copy_back(s, P.u, k_u, b0 * (long long)nn, bc * nn, d_u))) return rc;
+        if ((rc = copy_back(s, P.iters, k_it, b0, (size_t)bc, d_it))) return rc;
+        if ((rc = copy_back(s, P.relres, k_rr, b0, (size_t)bc, d_rr))) return rc;
+        if ((rc = copy_back(s, P.status, k_st, b0, (size_t)bc, d_st))) return rc;
+    }
+    if (any_host) {
+        for (int i = 0; i < nslots; ++i) CU_TRY(cudaStreamSynchronize(g.slots[i].stream));
+    }
+    return PSN_OK;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int psn_version(void) { return PSN_VERSION; }
+
+int psn_get_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return c;
+}
+
+const char* psn_last_error(void) { return g_err; }
+
+int psn_init(int device) {
+    int count = psn_get_device_count();
+    if (count <= 0) return psn_fail(PSN_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device >= count) return psn_fail(PSN_ERR_INVALID, "device %d out of range (%d devices)", device, count);
+    if (device >= 0) CU_TRY(cudaSetDevice(device));
+    int cur = 0;
+    CU_TRY(cudaGetDevice(&cur));
+    if (g.ready && g.device == cur) return PSN_OK;
+    if (g.ready) psn_shutdown();
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, cur));
+    g.device = cur;
+    g.sm_count = prop.multiProcessorCount;
+    g.smem_optin = prop.sharedMemPerBlockOptin;
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(cudaStreamCreateWithFlags(&g.slots[i].stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 4; ++k) CU_TRY(cudaEventCreateWithFlags(&g.slots[i].ev[k], cudaEventDisableTiming));
+    }
+    const char* env = getenv("PSN_WS_BYTES");
+    if (env) g.ws_bytes = atoll(env);
+    g.attrs_set = false;
+    g.ready = true;
+    return PSN_OK;
+}
+
+void psn_shutdown(void) {
+    if (!g.ready) return;
+    cudaDeviceSynchronize();
+    for (auto& kv : g.plans) cudaFree(kv.second.d_inv);
+    g.plans.clear();
+    for (int i = 0; i < 2; ++i) {
+        Slot& s = g.slots[i];
+        if (s.arena.base) cudaFree(s.arena.base);
+        if (s.ws_arena.base) cudaFree(s.ws_arena.base);
+        if (s.h_counters) cudaFreeHost(s.h_counters);
+        for (int k = 0; k < 4; ++k)
+            if (s.ev[k]) cudaEventDestroy(s.ev[k]);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = Slot();
+    }
+    for (auto& r : g.prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g.prof.clear();
+    g.ready = false;
+    cudaGetLastError();
+}
+
+int psn_solve_batch(int n, int64_t batch, const double* theta, const double* f, const double* sin_x, const double* sin_y,
+                    const double* k1, const double* k2, int master_n, int step, int operator_mode, double rtol, int max_iter,
+                    double* u, int32_t* iters, double* relres, int32_t* status, void* stream) {
+    g_err[0] = 0;
+    if (operator_mode != PSN_OPERATOR_REFERENCE)
+        return psn_fail(PSN_ERR_UNSUPPORTED, "operator_mode %d not implemented (only the reference operator diag(theta) L u = f)", operator_mode);
+    Problem P;
+    memset(&P, 0, sizeof(P));
+    P.n = n; P.B = batch; P.theta = theta; P.f = f; P.sx = sin_x; P.sy = sin_y; P.k1 = k1; P.k2 = k2;
+    P.mn = master_n; P.step = step; P.rtol = rtol; P.max_iter = max_iter;
+    P.u = u; P.iters = iters; P.relres = relres; P.status = status; P.stream = (cudaStream_t)stream;
+    return solve_internal(P);
+}
+
+int psn_subdomain_batch(int n_super, int n_fine, int64_t batch, const double* sin_x, const double* sin_y,
+                        const int32_t* start_x, const int32_t* start_y, double rtol, int max_iter,
+                        double* u_fine, double* f_fine, double* theta_fine, double* u_coarse, double* f_coarse, double* theta_coarse,
+                        int32_t* iters, double* relres, int32_t* status, void* stream) {
+    g_err[0] = 0;
+    if (n_fine < 1 || n_fine > n_super) return psn_fail(PSN_ERR_INVALID, "need 1 <= n_fine <= n_super");
+    if (!sin_x || !sin_y) return psn_fail(PSN_ERR_INVALID, "sin_x / sin_y are required");
+    Problem P;
+    memset(&P, 0, sizeof(P));
+    P.n = n_super; P.B = batch; P.sx = sin_x; P.sy = sin_y; P.mn = n_super; P.step = 1;
+    P.rtol = rtol; P.max_iter = max_iter; P.iters = iters; P.relres = relres; P.status = status;
+    P.sub = n_fine; P.start_x = start_x; P.start_y = start_y;
+    P.u_fine = u_fine; P.f_fine = f_fine; P.th_fine = theta_fine;
+    P.u_coarse = u_coarse; P.f_coarse = f_coarse; P.th_coarse = theta_coarse;
+    P.stream = (cudaStream_t)stream;
+    return solve_internal(P);
+}
+
+int psn_multires(int n_finest, const int32_t* resolutions, int n_res, int64_t batch, const double* theta_finest,
+                 const double* sin_x, const double* sin_y, double rtol, int max_iter, double* const* u_out,
+                 int32_t* iters, double* relres, int32_t* status, void* stream) {
+    g_err[0] = 0;
+    if (!resolutions || n_res < 1 || !u_out || !sin_x || !sin_y) return psn_fail(PSN_ERR_INVALID, "resolutions, u_out, sin_x, sin_y are required");
+    for (int k = 0; k < n_res; ++k) {
+        const int r = resolutions[k];
+        if (r < 2 || r > n_finest || n_finest % r != 0) return psn_fail(PSN_ERR_INVALID, "resolution %d does not divide n_finest=%d", r, n_finest);
+    }
+    for (int k = 0; k < n_res; ++k) {
+        Problem P;
+        memset(&P, 0, sizeof(P));
+        P.n = resolutions[k]; P.B = batch; P.theta = theta_finest; P.sx = sin_x; P.sy = sin_y;
+        P.mn = n_finest; P.step = n_finest / resolutions[k]; P.rtol = rtol; P.max_iter = max_iter;
+        P.u = u_out[k];
+        P.iters = iters ? iters + (size_t)k * batch : nullptr;
+        P.relres = relres ? relres + (size_t)k * batch : nullptr;
+        P.status = status ? status + (size_t)k * batch : nullptr;
+        P.stream = (cudaStream_t)stream;
+        int rc = solve_internal(P);
+        if (rc) return rc;
+    }
+    return PSN_OK;
+}
+
+int psn_set_option(const char* name, int64_t value) {
+    g_err[0] = 0;
+    if (!name) return psn_fail(PSN_ERR_INVALID, "option name is NULL");
+    if (!strcmp(name, "nu")) {
+        if (value < 1 || value > 4) return psn_fail(PSN_ERR_INVALID, "nu must be in 1..4");
+        g.nu = (int)value;
+    } else if (!strcmp(name, "tile")) {
+        if (value < 8 || value > 96 || (value & 1)) return psn_fail(PSN_ERR_INVALID, "tile must be even, in 8..96");
+        g.tile = (int)value;
+    } else if (!strcmp(name, "ws_bytes")) {
+        if (value < (1 << 20)) return psn_fail(PSN_ERR_INVALID, "ws_bytes must be >= 1 MiB");
+        g.ws_bytes = value;
+    } else if (!strcmp(name, "smem_max_n")) {
+        g.smem_max_n = (int)value;
+    } else {
+        return psn_fail(PSN_ERR_INVALID, "unknown option '%s'", name);
+    }
+    return PSN_OK;
+}
+
+int psn_profile_begin(void) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    for (auto& r : g.prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    g.prof.clear();
+    g.profiling = true;
+    return PSN_OK;
+}
+
+int psn_profile_read(char* buf, int64_t buf_bytes) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return psn_fail(PSN_ERR_CUDA, "device synchronize failed");
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& r : g.prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        auto& a = agg[r.name];
+        a.first += 1;
+        a.second += ms;
+    }
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+        first = false;
+    }
+    out += "}";
+    if ((int64_t)out.size() + 1 > buf_bytes || !buf) return -(int)(out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)out.size();
+}
+
+int psn_profile_end(void) {
+    g.profiling = false;
+    return PSN_OK;
+}
+
+int psn_describe(int n, int64_t* info) {
+    g_err[0] = 0;
+    if (!info || n < 2) return psn_fail(PSN_ERR_INVALID, "bad arguments");
+    PsnPlan plan;
+    psn_plan_levels(&plan, n, g.nu);
+    if (!g.ready) g.smem_optin = 232448;  // sm_100 opt-in limit; lets the CPU-only tier query the layout
+    const ResidentCfg rc = resident_cfg(plan);
+    memset(info, 0, 8 * sizeof(int64_t));
+    info[1] = plan.nlev;
+    if (rc.T) {
+        info[0] = 1;
+        info[2] = 0;
+        info[3] = rc.T;
+        info[4] = (int64_t)rc.smem;
+        info[5] = 0;
+        info[6] = 0;
+    } else {
+        PsnStreamCfg sc{stream_ls(plan), g.tile, g.tile};
+        info[0] = 0;
+        info[2] = sc.ls;
+        info[3] = PSN_TILE_THREADS;
+        info[4] = (int64_t)psn_tile_post_doubles(sc.TH, sc.TW, plan.nu) * 8;
+        info[5] = g.tile;
+        info[6] = sc.ls >= 1 ? (int64_t)stream_ws_bytes_per_sample(plan, sc) : 0;
+    }
+    return PSN_OK;
+}
+
+}  // extern "C"

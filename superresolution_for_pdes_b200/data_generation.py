@@ -1,0 +1,143 @@
+"""Drop-in for the reference's ``src/data_generation.py`` (class ``PoissonSolver``).
+
+Same constructor, methods, argument meaning, returned dict keys / dtypes / shapes and the same
+consumption order of the global ``np.random`` stream; the per-sample SciPy/SuperLU factorisation
+(reference ``solve_poisson``, src/data_generation.py:79-104) is replaced by one batched call into
+the CUDA library.  The reference's module-top ``matplotlib`` import and its ``__main__`` plotting
+block are not part of the path and are not reproduced.
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Tuple
+
+import numpy as np
+
+from . import _lib
+
+DEFAULT_RTOL = 1e-12
+DEFAULT_MAX_ITER = 100
+
+
+def sine_factors(k1: np.ndarray, k2: np.ndarray, x: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """sin(2 pi k1 x_j), sin(2 pi k2 y_i) with the reference's operand order
+    (``2 * np.pi * k1 * X``, src/data_generation.py:77), so that sin_y[i] * sin_x[j] is
+    bit-identical to the reference's forcing term."""
+    k1 = np.asarray(k1, dtype=np.float64).reshape(-1, 1)
+    k2 = np.asarray(k2, dtype=np.float64).reshape(-1, 1)
+    sx = np.sin((2 * np.pi * k1) * x[None, :])
+    sy = np.sin((2 * np.pi * k2) * x[None, :])
+    return sx, sy
+
+
+class PoissonSolver:
+    def __init__(self, n_coarse: int = 20, n_fine: int = 40, *, rtol: float = DEFAULT_RTOL,
+                 max_iter: int = DEFAULT_MAX_ITER):
+        """Reference: src/data_generation.py:10-33.  ``rtol`` / ``max_iter`` are new keyword-only
+        knobs whose defaults reproduce the reference's results to <= 1e-10 relative L2."""
+        self.n_coarse = n_coarse
+        self.n_fine = n_fine
+        self.rtol = rtol
+        self.max_iter = max_iter
+
+        self.x_coarse = np.linspace(0, 1, n_coarse)
+        self.y_coarse = np.linspace(0, 1, n_coarse)
+        self.x_fine = np.linspace(0, 1, n_fine)
+        self.y_fine = np.linspace(0, 1, n_fine)
+
+        self.X_coarse, self.Y_coarse = np.meshgrid(self.x_coarse, self.y_coarse)
+        self.X_fine, self.Y_fine = np.meshgrid(self.x_fine, self.y_fine)
+        self._L = {}
+        self.last_info = None  # SolveInfo of the most recent batched call
+
+    # The reference stores the assembled sparse Laplacians as attributes (src/data_generation.py:32-33).
+    # The CUDA path is matrix-free; the matrices are only built if somebody reads the attribute.
+    def _create_laplacian(self, n: int):
+        from scipy.sparse import diags  # host-side convenience only, never used by the solve
+        h = 1.0 / (n - 1)
+        n2 = n * n
+        main_diag = -4 * np.ones(n2)
+        off_diag = np.ones(n2 - 1)
+        off_diag[np.arange(n - 1, n2 - 1, n)] = 0
+        L = diags([main_diag, off_diag, off_diag, np.ones(n * (n - 1)), np.ones(n * (n - 1))],
+                  [0, 1, -1, n, -n], shape=(n2, n2))
+        return L / (h * h)
+
+    def _lazy_L(self, n):
+        if n not in self._L:
+            self._L[n] = self._create_laplacian(n)
+        return self._L[n]
+
+    @property
+    def L_coarse(self):
+        return self._lazy_L(self.n_coarse)
+
+    @property
+    def L_fine(self):
+        return self._lazy_L(self.n_fine)
+
+    def generate_forcing_term(self, k1: float, k2: float, grid: str = 'fine') -> np.ndarray:
+        """f(x,y) = sin(k1 2 pi x) sin(k2 2 pi y)  (src/data_generation.py:60-77)."""
+        if grid == 'fine':
+            X, Y = self.X_fine, self.Y_fine
+        else:
+            X, Y = self.X_coarse, self.Y_coarse
+        return np.sin(2 * np.pi * k1 * X) * np.sin(2 * np.pi * k2 * Y)
+
+    def solve_poisson(self, f: np.ndarray, theta: np.ndarray, grid: str = 'fine') -> np.ndarray:
+        """Solve diag(theta) L u = f on the GPU  (src/data_generation.py:79-104)."""
+        n = self.n_fine if grid == 'fine' else self.n_coarse
+        return self._solve_n(f, theta, n)
+
+    def _solve_n(self, f, theta, n: int) -> np.ndarray:
+        f = np.asarray(f)
+        theta = np.asarray(theta)
+        if f.size != n * n or theta.size != n * n:
+            raise ValueError(f"f and theta must have {n * n} elements for the {n}x{n} grid "
+                             f"(got {f.shape} and {theta.shape})")
+        u, info = _lib.solve_batch(n, 1, theta=theta.reshape(1, n, n), f=f.reshape(1, n, n),
+                                   rtol=self.rtol, max_iter=self.max_iter)
+        self.last_info = info
+        info.raise_if_failed("solve_poisson")
+        return u[0]
+
+    def solve_poisson_batch(self, f: np.ndarray, theta, n: int) -> np.ndarray:
+        """New: batched form of ``solve_poisson`` -- f, theta: [B, n, n] (theta may be None = ones)."""
+        f = np.asarray(f)
+        B = f.shape[0]
+        u, info = _lib.solve_batch(n, B, theta=theta, f=f, rtol=self.rtol, max_iter=self.max_iter)
+        self.last_info = info
+        info.raise_if_failed("solve_poisson_batch")
+        return u
+
+    def generate_dataset(self, n_samples: int, k_range: Tuple[float, float] = (1, 5)) -> dict:
+        """Coarse/fine pairs (src/data_generation.py:106-159): the RNG is consumed exactly as in the
+        reference loop (k1 then k2 per sample), then two batched GPU solves replace 2*N factorisations."""
+        ks = np.random.uniform(*k_range, size=(n_samples, 2))  # same stream order as k1, k2 per sample
+        k1 = ks[:, 0].copy()
+        k2 = ks[:, 1].copy()
+        sxf, syf = sine_factors(k1, k2, self.x_fine)
+        sxc, syc = sine_factors(k1, k2, self.x_coarse)
+        u_fine, info_f = _lib.solve_batch(self.n_fine, n_samples, sin_x=sxf, sin_y=syf, rtol=self.rtol, max_iter=self.max_iter)
+        u_coarse, info_c = _lib.solve_batch(self.n_coarse, n_samples, sin_x=sxc, sin_y=syc, rtol=self.rtol, max_iter=self.max_iter)
+        self.last_info = info_f
+        info_f.raise_if_failed("generate_dataset (fine)")
+        info_c.raise_if_failed("generate_dataset (coarse)")
+        dataset = {
+            'u_coarse': u_coarse,
+            'u_fine': u_fine,
+            'f_coarse': syc[:, :, None] * sxc[:, None, :],
+            'f_fine': syf[:, :, None] * sxf[:, None, :],
+            'theta_coarse': np.ones((n_samples, self.n_coarse, self.n_coarse)),
+            'theta_fine': np.ones((n_samples, self.n_fine, self.n_fine)),
+            'k1': k1,
+            'k2': k2,
+        }
+        return dataset
+
+    def save_dataset(self, dataset: dict, path: str = 'data'):
+        """``<path>/pde_dataset.npz`` via np.savez, uncompressed (src/data_generation.py:161-176)."""
+        save_path = Path(path)
+        if not save_path.exists():
+            save_path.mkdir(parents=True)
+        np.savez(save_path / 'pde_dataset.npz', **dataset)

@@ -1,0 +1,90 @@
+"""Drop-in for the solver part of the reference's ``src/resolution_comparison.py`` /
+``src/resolution_comparison_statistical.py``: ``solve_multi_resolution`` (the 40/80/160/320/640
+reference solutions).  The ML tiling / interpolation / plotting code of those files is out of scope.
+"""
+from __future__ import annotations
+
+import time
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .data_generation import DEFAULT_MAX_ITER, DEFAULT_RTOL
+
+
+def _sines_kfirst(k1: np.ndarray, k2: np.ndarray, x: np.ndarray):
+    """Operand order of the evaluation scripts: ``np.sin(k1 * 2 * np.pi * X)``
+    (src/resolution_comparison.py:36), which rounds differently from ``2 * np.pi * k1 * X``."""
+    k1 = np.asarray(k1, dtype=np.float64).reshape(-1, 1)
+    k2 = np.asarray(k2, dtype=np.float64).reshape(-1, 1)
+    return np.sin((k1 * 2 * np.pi) * x[None, :]), np.sin((k2 * 2 * np.pi) * x[None, :])
+
+
+def solve_multi_resolution(n_coarse: int = 40, resolutions: List[int] = [80, 160, 320, 640], *,
+                           k_range: Tuple[float, float] = (10.0, 11.0), timed: bool = False,
+                           rtol: float = DEFAULT_RTOL, max_iter: int = DEFAULT_MAX_ITER, verbose: bool = False):
+    """src/resolution_comparison.py:13-78.  RNG order: k1, k2, then the theta block.
+    ``timed=True`` adds ``solve_times`` (per-resolution wall seconds) like
+    src/resolution_comparison_statistical.py:75-90, which uses ``k_range=(8.0, 12.0)``."""
+    resolutions = list(resolutions)
+    k1 = np.random.uniform(*k_range)
+    k2 = np.random.uniform(*k_range)
+    n_finest = max(resolutions)
+    x = np.linspace(0, 1, n_finest)
+    sx, sy = _sines_kfirst(np.array([k1]), np.array([k2]), x)
+    f_finest = sy[0][:, None] * sx[0][None, :]
+    theta_finest = np.random.uniform(0.5, 2.0, size=(n_finest, n_finest))
+
+    data = {'k1': k1, 'k2': k2, 'f': {}, 'theta': {}, 'u': {}}
+    if timed:
+        data['solve_times'] = {}
+    all_res = [n_coarse] + resolutions
+    for res in all_res:
+        if n_finest % res != 0:
+            raise ValueError(f"resolution {res} does not divide the finest grid {n_finest}")
+        if res == n_finest:
+            data['f'][res] = f_finest
+            data['theta'][res] = theta_finest
+        else:
+            step = n_finest // res
+            data['f'][res] = f_finest[::step, ::step]
+            data['theta'][res] = theta_finest[::step, ::step]
+    if timed:
+        for res in all_res:
+            t0 = time.time()
+            us, info = _lib.multires(n_finest, [res], 1, theta_finest[None], sx, sy, rtol=rtol, max_iter=max_iter)
+            data['solve_times'][res] = time.time() - t0
+            info.raise_if_failed(f"solve_multi_resolution ({res}x{res})")
+            data['u'][res] = us[res][0]
+    else:
+        us, info = _lib.multires(n_finest, all_res, 1, theta_finest[None], sx, sy, rtol=rtol, max_iter=max_iter)
+        info.raise_if_failed("solve_multi_resolution")
+        for res in all_res:
+            data['u'][res] = us[res][0]
+    if verbose:
+        for res in all_res:
+            print(f"u_{res} - min: {data['u'][res].min():.6f}, max: {data['u'][res].max():.6f}")
+    return data
+
+
+def solve_multi_resolution_batch(n_examples: int, n_coarse: int = 40, resolutions: Sequence[int] = (80, 160, 320, 640), *,
+                                 k_range: Tuple[float, float] = (10.0, 11.0), rtol: float = DEFAULT_RTOL,
+                                 max_iter: int = DEFAULT_MAX_ITER):
+    """New: ``n_examples`` independent multi-resolution chains in one call per resolution.  The RNG is
+    consumed exactly as ``n_examples`` consecutive calls of ``solve_multi_resolution`` would."""
+    resolutions = list(resolutions)
+    n_finest = max(resolutions)
+    k1 = np.empty(n_examples)
+    k2 = np.empty(n_examples)
+    theta = np.empty((n_examples, n_finest, n_finest))
+    for e in range(n_examples):
+        k1[e] = np.random.uniform(*k_range)
+        k2[e] = np.random.uniform(*k_range)
+        theta[e] = np.random.uniform(0.5, 2.0, size=(n_finest, n_finest))
+    x = np.linspace(0, 1, n_finest)
+    sx, sy = _sines_kfirst(k1, k2, x)
+    all_res = [n_coarse] + resolutions
+    us, info = _lib.multires(n_finest, all_res, n_examples, theta, sx, sy, rtol=rtol, max_iter=max_iter)
+    info.raise_if_failed("solve_multi_resolution_batch")
+    return {'k1': k1, 'k2': k2, 'theta_finest': theta, 'sin_x': sx, 'sin_y': sy, 'u': us, 'info': info}

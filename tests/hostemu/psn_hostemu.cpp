@@ -1,0 +1,184 @@
+// psn_hostemu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the kernel bodies of superresolution_for_pdes_b200/csrc/psn_core.cuh and the
+// streamed-path driver (psn_stream_driver.h) as plain host C++ with a single virtual thread per
+// CTA, so that the CPU-only test tier can check indexing, halo widths, the temporal-blocking
+// schedule and the per-sample state machine without a GPU.  The product package never loads
+// this library; the shipped path is the CUDA build (libpsn_b200.so) and has no CPU fallback.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../superresolution_for_pdes_b200/csrc/psn_stream_driver.h"
+
+namespace {
+
+struct HostPlan {
+    PsnPlan plan;
+    std::vector<double> inv;
+    HostPlan(int n, int nu) {
+        psn_plan_levels(&plan, n, nu);
+        inv = psn_coarse_inverse(plan);
+        plan.coarse_inv = inv.data();
+    }
+};
+
+struct HostBackend {
+    std::vector<double> smem;
+    std::vector<int> counters_host;
+    HostBackend() : smem(1 << 20) {}
+    void zero_counters(int* c, int n) { memset(c, 0, sizeof(int) * n); counters_host.assign(n, 0); }
+    void prologue(const PsnCgArgs& a, long long B) {
+        PsnHostCtx ctx;
+        for (long long b = 0; b < B; ++b)
+            for (int ty = 0; ty < a.nty; ++ty)
+                for (int tx = 0; tx < a.ntx; ++tx) psn_prologue_body(ctx, a, b, ty, tx);
+    }
+    void state_init(const PsnCgArgs& a, long long B) { for (long long b = 0; b < B; ++b) psn_state_init(a, b); }
+    void tile_pre(const PsnPlan& plan, const PsnTileArgs& t, long long B) {
+        PsnHostCtx ctx;
+        for (long long b = 0; b < B; ++b)
+            for (int ty = 0; ty < t.nty; ++ty)
+                for (int tx = 0; tx < t.ntx; ++tx) {
+                    // poison the scratch so that reads of never-written halo cells show up as NaN
+                    std::fill(smem.begin(), smem.begin() + psn_tile_pre_doubles(t.TH, t.TW, plan.nu), std::nan(""));
+                    psn_tile_pre_body(ctx, plan, t, b, ty, tx, smem.data());
+                }
+    }
+    void tile_post(const PsnPlan& plan, const PsnTileArgs& t, long long B) {
+        PsnHostCtx ctx;
+        for (long long b = 0; b < B; ++b)
+            for (int ty = 0; ty < t.nty; ++ty)
+                for (int tx = 0; tx < t.ntx; ++tx) {
+                    std::fill(smem.begin(), smem.begin() + psn_tile_post_doubles(t.TH, t.TW, plan.nu), std::nan(""));
+                    psn_tile_post_body(ctx, plan, t, b, ty, tx, smem.data());
+                }
+    }
+    void coarse_vcycle(const PsnPlan& plan, int l0, const double* bg, double* ug, const PsnSampleState* st, long long B) {
+        PsnHostCtx ctx;
+        for (long long b = 0; b < B; ++b) psn_coarse_vcycle_body(ctx, plan, l0, bg, ug, st, b, smem.data());
+    }
+    void dir_apply(const PsnCgArgs& a, long long B) {
+        PsnHostCtx ctx;
+        for (long long b = 0; b < B; ++b)
+            for (int ty = 0; ty < a.nty; ++ty)
+                for (int tx = 0; tx < a.ntx; ++tx) psn_dir_apply_body(ctx, a, b, ty, tx);
+    }
+    void update(const PsnCgArgs& a, long long B) {
+        PsnHostCtx ctx;
+        for (long long b = 0; b < B; ++b)
+            for (int ty = 0; ty < a.nty; ++ty)
+                for (int tx = 0; tx < a.ntx; ++tx) psn_update_body(ctx, a, b, ty, tx);
+    }
+    void true_residual(const PsnCgArgs& a, long long B) {
+        PsnHostCtx ctx;
+        for (long long b = 0; b < B; ++b)
+            for (int ty = 0; ty < a.nty; ++ty)
+                for (int tx = 0; tx < a.ntx; ++tx) psn_true_residual_body(ctx, a, b, ty, tx);
+    }
+    void state_after_update(const PsnCgArgs& a, long long B) { for (long long b = 0; b < B; ++b) psn_state_after_update(a, b); }
+    void state_after_check(const PsnCgArgs& a, long long B, int* counter) {
+        for (long long b = 0; b < B; ++b) *counter += psn_state_after_check(a, b);
+    }
+    void fetch_counter_async(const int* c, int it) { counters_host[it] = *c; }
+    int wait_counter(int it) { return counters_host[it]; }
+};
+
+PsnRhs make_rhs(const double* theta, const double* f, const double* sx, const double* sy, const double* k1,
+                const double* k2, int mn, int step) {
+    PsnRhs r;
+    r.theta = theta; r.f = f; r.sx = sx; r.sy = sy; r.k1 = k1; r.k2 = k2; r.mn = mn; r.step = step;
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+// levels / gammas of the plan, for direct comparison with the numpy prototype
+int hostemu_plan(int n, int nu, int* ns, double* gams, double* inv_out) {
+    HostPlan hp(n, nu);
+    for (int l = 0; l < hp.plan.nlev; ++l) { ns[l] = hp.plan.lv[l].n; gams[l] = hp.plan.lv[l].gam; }
+    if (inv_out) memcpy(inv_out, hp.inv.data(), hp.inv.size() * sizeof(double));
+    return hp.plan.nlev;
+}
+
+// resident (one-CTA-per-sample) solver
+int hostemu_solve_smem(int n, long long B, const double* theta, const double* f, const double* sx, const double* sy,
+                       const double* k1, const double* k2, int mn, int step, double rtol, int max_iter, int nu,
+                       double* u, int32_t* iters, double* relres, int32_t* status,
+                       int sub, const int32_t* start_x, const int32_t* start_y,
+                       double* u_fine, double* f_fine, double* u_coarse, double* f_coarse) {
+    if (n * n > 8192) return -1;
+    HostPlan hp(n, nu);
+    PsnSolveArgs a;
+    a.rhs = make_rhs(theta, f, sx, sy, k1, k2, mn, step);
+    a.rtol = rtol; a.max_iter = max_iter; a.u = u; a.iters = iters; a.relres = relres; a.status = status;
+    a.sub = sub; a.start_x = start_x; a.start_y = start_y;
+    a.u_fine = u_fine; a.f_fine = f_fine; a.u_coarse = u_coarse; a.f_coarse = f_coarse;
+    a.th_fine = nullptr; a.th_coarse = nullptr;
+    std::vector<double> smem(psn_smem_solver_doubles(hp.plan) + 64);
+    PsnHostCtx ctx;
+    for (long long b = 0; b < B; ++b) {
+        std::fill(smem.begin(), smem.end(), std::nan(""));
+        psn_smem_solve_body<8192>(ctx, hp.plan, a, b, smem.data());
+    }
+    return 0;
+}
+
+// streamed solver (tile kernels + global CG kernels + coarse shared-memory V-cycle)
+int hostemu_solve_stream(int n, long long B, const double* theta, const double* f, const double* sx, const double* sy,
+                         const double* k1, const double* k2, int mn, int step, double rtol, int max_iter, int nu,
+                         int TH, int TW, int ls, double* u, int32_t* iters, double* relres, int32_t* status) {
+    HostPlan hp(n, nu);
+    const PsnPlan& plan = hp.plan;
+    if (ls < 1 || ls >= plan.nlev) return -1;
+    PsnStreamCfg cfg{ls, TH, TW};
+    PsnStreamWs ws;
+    memset(&ws, 0, sizeof(ws));
+    std::vector<std::vector<double>> keep;
+    auto alloc = [&](size_t cnt) { keep.emplace_back(cnt, std::nan("")); return keep.back().data(); };
+    const size_t nn = (size_t)n * n;
+    ws.cap = B;
+    ws.r = alloc(B * nn); ws.q = alloc(B * nn); ws.z = alloc(B * nn); ws.p[0] = alloc(B * nn); ws.p[1] = alloc(B * nn);
+    for (int l = 1; l <= ls; ++l) {
+        size_t m = (size_t)plan.lv[l].n * plan.lv[l].n;
+        ws.bl[l] = alloc(B * m); ws.ub[l] = alloc(B * m);
+        if (l < ls) ws.ua[l] = alloc(B * m);
+    }
+    int t0x, t0y;
+    psn_tile_counts(n, TH, TW, &t0x, &t0y);
+    const int gx = (n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
+    ws.part_rz = alloc((size_t)B * t0x * t0y);
+    ws.part_a = alloc((size_t)B * gx * gy);
+    ws.part_b = alloc((size_t)B * gx * gy);
+    std::vector<PsnSampleState> st(B);
+    ws.state = st.data();
+    std::vector<int> counters(max_iter + 8);
+    ws.counters = counters.data();
+    HostBackend bk;
+    PsnRhs rhs = make_rhs(theta, f, sx, sy, k1, k2, mn, step);
+    int outer = psn_stream_solve(bk, plan, cfg, rhs, B, rtol, max_iter, u, ws);
+    for (long long b = 0; b < B; ++b) {
+        iters[b] = st[b].iters;
+        status[b] = st[b].phase == PSN_PHASE_DONE ? st[b].status : -1;
+        relres[b] = st[b].bb > 0 ? sqrt(st[b].rr / st[b].bb) : 0.0;
+    }
+    return outer;
+}
+
+// one V-cycle z = M^{-1} r on the full grid (scaled form), for comparison with the numpy prototype
+int hostemu_vcycle(int n, int nu, const double* rin, double* zout) {
+    HostPlan hp(n, nu);
+    const PsnLevel& l0 = hp.plan.lv[0];
+    std::vector<double> smem(2 * l0.size + psn_pool_doubles(hp.plan, 0), 0.0);
+    double* sb = smem.data();
+    double* su = sb + l0.size;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) sb[(i + 1) * l0.pitch + j + 1] = rin[i * n + j];
+    PsnHostCtx ctx;
+    psn_vcycle_smem(ctx, hp.plan, 0, sb, su, su + l0.size);
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) zout[i * n + j] = su[(i + 1) * l0.pitch + j + 1];
+    return 0;
+}
+}

@@ -1,0 +1,206 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes) and the reference-signature
+shims, against the oracle (live SciPy restatement) and the committed golden fixtures.
+
+Tolerance (BASELINE.json north_star): relative L2 <= 1e-10 in fp64; forcing terms bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, KAT_K, kat_inputs, kat_sub
+from oracle import poisson_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.mark.parametrize("n", [20, 40, 80, 160, 320, 640])
+def test_kat_vs_golden(gpu_lib, golden_kat, n):
+    """Known-answer tests against REFERENCE outputs (fixtures made by the unmodified reference)."""
+    cases = [(k, r) for k in range(3) for r in (0, 1) if f"n{n}_k{k}_r{r}_u" in golden_kat]
+    fs, ths = zip(*[kat_inputs(n, k, r) for k, r in cases])
+    u, info = gpu_lib.solve_batch(n, len(cases), theta=np.stack(ths), f=np.stack(fs))
+    s = kat_sub(n)
+    for b, (k, r) in enumerate(cases):
+        key = f"n{n}_k{k}_r{r}"
+        err = O.rel_l2(u[b][::s, ::s], golden_kat[key + "_u"])
+        nerr = abs(np.linalg.norm(u[b]) - golden_kat[key + "_norm"]) / golden_kat[key + "_norm"]
+        res = O.residual_rel(u[b], fs[b], ths[b])
+        print(key, "iters", info.iters[b], "status", info.status[b], "relres", info.relres[b], "err", err, "resid", res)
+        assert info.status[b] in (0, 1)
+        assert err <= TOL and nerr <= TOL
+        # each solve reaches the reference's own residual level (or the 1e-12 target)
+        assert res <= max(1e-12, 10 * golden_kat[key + "_res"])
+
+
+@pytest.mark.parametrize("n", [5, 7, 13, 33, 64, 75, 86, 87, 100, 131, 200])
+def test_odd_and_boundary_sizes_vs_oracle(gpu_lib, n):
+    """Sizes around the resident/streamed switch, odd sizes, single-level grids."""
+    rs = np.random.RandomState(n)
+    B = 3
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    f = np.stack([O.forcing_term(*KAT_K[b], n) for b in range(B)])
+    u, info = gpu_lib.solve_batch(n, B, theta=theta, f=f)
+    for b in range(B):
+        assert info.status[b] in (0, 1)
+        assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= TOL
+
+
+def test_streamed_path_matches_resident(gpu_lib):
+    """Force the streamed kernels on a grid the resident kernel also handles; both must agree."""
+    n, B = 64, 5
+    rs = np.random.RandomState(5)
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    k = rs.uniform(0.5, 12.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    u_res, _ = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    try:
+        gpu_lib.set_option("smem_max_n", -1)
+        gpu_lib.set_option("tile", 32)
+        u_str, info = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    finally:
+        gpu_lib.set_option("smem_max_n", 0)
+        gpu_lib.set_option("tile", 64)
+    assert (info.status <= 1).all()
+    for b in range(B):
+        assert O.rel_l2(u_str[b], u_res[b]) <= 1e-11
+        assert O.rel_l2(u_res[b], O.solve_poisson(np.outer(sy[b], sx[b]), theta[b], n)) <= TOL
+
+
+def test_generate_dataset_matches_reference_fixture(gpu_lib):
+    from superresolution_for_pdes_b200 import PoissonSolver
+    gold = np.load(os.path.join(GOLDEN, "dataset_standard_seed0.npz"))
+    np.random.seed(0)
+    ds = PoissonSolver().generate_dataset(6, k_range=(0.5, 5.0))
+    assert list(ds.keys()) == ["u_coarse", "u_fine", "f_coarse", "f_fine", "theta_coarse", "theta_fine", "k1", "k2"]
+    for k in ("k1", "k2", "f_coarse", "f_fine", "theta_coarse", "theta_fine"):
+        assert ds[k].dtype == np.float64 and ds[k].flags.c_contiguous
+        assert np.array_equal(ds[k], gold[k]), k          # bit-exact
+    for k in ("u_coarse", "u_fine"):
+        assert ds[k].shape == gold[k].shape
+        for b in range(6):
+            assert O.rel_l2(ds[k][b], gold[k][b]) <= TOL, (k, b)
+
+
+def test_generate_subdomain_dataset_matches_reference_fixture(gpu_lib):
+    from superresolution_for_pdes_b200 import EnhancedPoissonSolver
+    gold = np.load(os.path.join(GOLDEN, "dataset_subdomain_seed1.npz"))
+    np.random.seed(1)
+    es = EnhancedPoissonSolver()
+    ds = es.generate_subdomain_dataset(4, k_range=(0.5, 12.0))
+    for k in ("k1", "k2", "f_coarse", "f_fine", "theta_coarse", "theta_fine", "is_subdomain"):
+        assert np.array_equal(ds[k], gold[k]), k
+    assert ds["is_subdomain"].dtype == np.bool_
+    for k in ("u_coarse", "u_fine"):
+        for b in range(4):
+            assert O.rel_l2(ds[k][b], gold[k][b]) <= TOL, (k, b)
+    assert np.array_equal(ds["u_coarse"], ds["u_fine"][:, ::2, ::2])   # downsample identity
+    # combine_datasets semantics (is_subdomain added to dataset1, concatenation order)
+    meta = np.load(os.path.join(GOLDEN, "dataset_combined_meta.npz"))
+    np.random.seed(0)
+    d1 = es.generate_dataset(6, k_range=(0.5, 5.0))
+    comb = es.combine_datasets(d1, ds)
+    assert "is_subdomain" in d1
+    assert np.array_equal(comb["is_subdomain"], meta["is_subdomain"])
+    assert np.array_equal(comb["k1"], meta["k1"]) and np.array_equal(comb["k2"], meta["k2"])
+    norms = np.linalg.norm(comb["u_fine"].reshape(10, -1), axis=1)
+    assert np.allclose(norms, meta["u_fine_norms"], rtol=1e-10, atol=0)
+
+
+def test_multires_chain_matches_reference_fixture(gpu_lib):
+    from superresolution_for_pdes_b200 import solve_multi_resolution
+    gold = np.load(os.path.join(GOLDEN, "multires_seed2.npz"))
+    np.random.seed(2)
+    data = solve_multi_resolution(40, [80, 160, 320, 640])
+    assert data["k1"] == gold["k1"] and data["k2"] == gold["k2"]
+    for res in (40, 80, 160, 320, 640):
+        s = kat_sub(res)
+        assert data["u"][res].shape == (res, res)
+        assert np.linalg.norm(data["f"][res]) == gold[f"f{res}_norm"]       # bit-exact forcing
+        assert data["theta"][res].sum() == gold[f"theta{res}_sum"]
+        assert O.rel_l2(data["u"][res][::s, ::s], gold[f"u{res}"]) <= TOL
+        assert abs(np.linalg.norm(data["u"][res]) - gold[f"u{res}_norm"]) <= TOL * gold[f"u{res}_norm"]
+    np.random.seed(2)
+    timed = solve_multi_resolution(40, [80, 160], timed=True)
+    assert set(timed["solve_times"]) == {40, 80, 160}
+
+
+def test_structural_identities(gpu_lib):
+    """F1/F2/F3 of SURVEY.md: row scaling, sign, non-zero border; linearity of the solve."""
+    n = 40
+    f, theta = kat_inputs(n, 1, 1)
+    one = np.ones((n, n))
+    u, _ = gpu_lib.solve_batch(n, 3, theta=np.stack([theta, one, one]), f=np.stack([f, f / theta, 2.5 * f]))
+    assert O.rel_l2(u[0], u[1]) <= 1e-11            # solve(f, theta) == solve(f/theta, 1)
+    uo, _ = gpu_lib.solve_batch(n, 1, theta=one[None], f=f[None])
+    assert O.rel_l2(u[2], 2.5 * uo[0]) <= 1e-11     # linearity
+    i, j = np.unravel_index(np.argmax(f), f.shape)
+    assert uo[0][i, j] < 0                          # L is negative definite: u has the opposite sign of f
+    assert np.abs(uo[0][0, :]).max() > 1e-6         # border nodes are unknowns, not Dirichlet rows
+
+
+def test_edge_cases(gpu_lib):
+    n = 20
+    # zero forcing -> exact zero, converged
+    u, info = gpu_lib.solve_batch(n, 2, theta=None, f=np.zeros((2, n, n)))
+    assert (u == 0).all() and (info.status == 0).all()
+    # empty batch
+    u, info = gpu_lib.solve_batch(n, 0, theta=None, f=np.zeros((0, n, n)))
+    assert u.shape == (0, n, n)
+    # singular theta (reference: MatrixRankWarning + non-finite output) -> reported, never silent
+    th = np.ones((1, n, n))
+    th[0, 3, 3] = 0.0
+    f = O.forcing_term(2.0, 3.0, n)[None]
+    u, info = gpu_lib.solve_batch(n, 1, theta=th, f=f)
+    assert info.status[0] >= 2
+    with pytest.raises(ValueError):
+        gpu_lib.solve_batch(n, 1, theta=None, f=np.zeros((1, n + 1, n)))
+    from superresolution_for_pdes_b200 import PoissonSolver
+    with pytest.raises(ValueError):
+        PoissonSolver().solve_poisson(np.zeros((39, 40)), np.ones((40, 40)))
+    with pytest.raises(gpu_lib.PsnError):
+        gpu_lib.solve_batch(n, 1, theta=None, f=None)   # no forcing given
+
+
+def test_device_pointers_and_device_sin(gpu_lib):
+    """Device-resident inputs/outputs (torch CUDA tensors) and the on-device forcing mode."""
+    import torch
+    n, B = 80, 16
+    rs = np.random.RandomState(11)
+    k = rs.uniform(0.5, 12.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    u_host, _ = gpu_lib.solve_batch(n, B, sin_x=sx, sin_y=sy)
+    dev = torch.device("cuda:0")
+    out = torch.empty((B, n, n), dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    gpu_lib.solve_batch(n, B, sin_x=torch.from_numpy(sx).to(dev), sin_y=torch.from_numpy(sy).to(dev), out=out, stream=st)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), u_host)      # same kernel, same data -> bit-identical
+    out2 = torch.empty_like(out)
+    gpu_lib.solve_batch(n, B, k1=torch.from_numpy(k[:, 0].copy()).to(dev), k2=torch.from_numpy(k[:, 1].copy()).to(dev), out=out2, stream=st)
+    torch.cuda.synchronize()
+    assert O.rel_l2(out2.cpu().numpy(), u_host) <= 1e-9   # device sin differs from numpy's by ulps only
+
+
+def test_large_batch_properties_640(gpu_lib):
+    """BASELINE-size grid, properties that need no oracle: residual of every sample, agreement
+    with the closed-form DST-I solution on a subset, batch-order independence."""
+    n, B = 640, 24
+    rs = np.random.RandomState(3)
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    k = rs.uniform(8.0, 12.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    u, info = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    assert (info.status == 0).all(), info.status
+    print("640 iters", info.iters, "relres max", info.relres.max())
+    for b in range(B):
+        f = np.outer(sy[b], sx[b])
+        assert O.residual_rel(u[b], f, theta[b]) <= 1e-11
+    for b in range(0, B, 6):
+        assert O.rel_l2(u[b], O.solve_dst(np.outer(sy[b], sx[b]), theta[b])) <= TOL
+    perm = rs.permutation(B)
+    u2, _ = gpu_lib.solve_batch(n, B, theta=theta[perm], sin_x=sx[perm], sin_y=sy[perm])
+    assert np.array_equal(u2, u[perm])    # deterministic, batch-order independent
