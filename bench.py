@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the batched Poisson solve (BASELINE.json metric: Poisson solves/s, fp64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n 640] [--batch B]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Own arm (default).  One "step" = one pass of the hot path over one batch: `psn_solve_batch` on a
+batch of independent n x n fp64 problems (default: the large-grid configuration of BASELINE.json,
+640x640, 512 samples per GPU = 4,096 over 8 GPUs; theta ~ U(0.5,2) iid per node, k ~ U(8,12)).
+  value  whole-job solves/s with inputs resident in HBM (CUDA events, max over ranks);
+  e2e    the same through the C ABI with pinned HOST buffers (H2D of theta + sines and D2H of u
+         inside the timed region);
+  roofline  the dominant kernel's achieved HBM bandwidth from per-launch CUDA events recorded
+         during the timed region, against MEASURED_PEAKS.json;
+  cpu_baseline  the oracle port of the reference's SciPy/SuperLU solve on the host cores (rank 0,
+         N=1 only, bounded sample);
+  also   the 80x80 resident-kernel workload (second half of the BASELINE metric).
+Reference arm (--impl reference): the reference's own CPU algorithm (oracle port: same SciPy
+`spsolve` on the same matrix -- the reference itself is pure Python and cannot travel to the GPU
+box) on all host cores, same metric / config, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "poisson_solves_per_sec"
+UNIT = "solves/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=640, help="grid size of the headline workload")
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU per step (0 = default for n)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--rtol", type=float, default=2.5e-13)
+    return ap.parse_args()
+
+
+def default_batch(n):
+    if n >= 512:
+        return 512
+    if n >= 256:
+        return 2048
+    if n >= 128:
+        return 8192
+    return 148 * 128
+
+
+def workload_name(n, batch, world):
+    return (f"{batch * world} independent {n}x{n} fp64 solves of diag(theta) L u = f per step "
+            f"({batch}/GPU), theta~U(0.5,2) iid, f=sin(2pi k1 x)sin(2pi k2 y), k~U(8,12)")
+
+
+# --------------------------------------------------------------------------- CPU (reference) arm
+def _worker_init():
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def _worker_solve(args):
+    n, seed = args
+    import numpy as np
+    from oracle import poisson_oracle as O
+    rs = np.random.RandomState(seed)
+    k1, k2 = rs.uniform(8.0, 12.0, size=2)
+    theta = rs.uniform(0.5, 2.0, size=(n, n))
+    f = O.forcing_term(k1, k2, n)
+    t0 = time.perf_counter()
+    u = O.solve_poisson(f, theta, n)
+    return time.perf_counter() - t0, float(u[n // 2, n // 2])
+
+
+def host_workers(n):
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    per = max(1, int(1.0e9 * (n / 640.0) ** 2.2))   # SuperLU fill at 640^2 ~ 0.63 GB + matrices
+    return max(1, min(cores, int(0.6 * avail / per)))
+
+
+def cpu_pool_rate(n, steps, warmup, solves_per_worker=1):
+    """Aggregate solves/s of the oracle port on all usable host cores: each step = every worker
+    solves `solves_per_worker` samples.  Returns (value, cores, ms_per_step, sample text)."""
+    import multiprocessing as mp
+    P = host_workers(n)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(P, initializer=_worker_init) as pool:
+        def one_step(tag):
+            t0 = time.perf_counter()
+            pool.map(_worker_solve, [(n, 1000 * tag + w) for w in range(P * solves_per_worker)], chunksize=solves_per_worker)
+            return time.perf_counter() - t0
+        for w in range(warmup):
+            one_step(w)
+        times = [one_step(100 + s) for s in range(steps)]
+    total = sum(times)
+    value = P * solves_per_worker * steps / total
+    sample = f"{steps} steps x {P * solves_per_worker} solves of {n}x{n} (one per worker process, SciPy spsolve/SuperLU, 1 thread each)"
+    return value, P, 1000.0 * total / steps, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.n
+    # bounded: a 640^2 factorisation takes ~7 s per core, so one solve per worker per step
+    steps = max(1, args.steps)
+    warm = args.warmup
+    if n >= 512:
+        steps, warm = min(steps, 6), min(warm, 1)
+    value, P, ms, sample = cpu_pool_rate(n, steps, warm)
+    batch = args.batch or default_batch(n)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(n, batch, args.gpus), "n": n, "solver": "scipy.sparse.linalg.spsolve (SuperLU), oracle port of the reference"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- own arm
+# compulsory HBM bytes per grid node and participating sample of each streamed kernel (DESIGN.md
+# section "Kernels and their rooflines"); `survey` = the same work in SURVEY.md 8(d)'s unfused model
+KERNEL_BYTES = {
+    "tile_pre_l0": {"own": 18.0, "survey": 66.0},      # read r; write u_pre, coarse rhs (1/4)
+    "tile_post_l0": {"own": 26.0, "survey": 66.0},     # read u_pre, r, coarse corr (1/4); write z
+    "dir_apply_dot": {"own": 32.0, "survey": 40.0},    # read z, p; write p, q
+    "update_norm": {"own": 48.0, "survey": 48.0},      # read p, q, x, r; write x, r
+}
+
+
+def run_own(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from superresolution_for_pdes_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.init(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    n = args.n
+    B = args.batch or default_batch(n)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def make_inputs(n_, B_, seed):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed + rank)
+        theta = torch.rand((B_, n_, n_), dtype=torch.float64, device=dev, generator=g) * 1.5 + 0.5
+        k = torch.rand((B_, 2), dtype=torch.float64, device=dev, generator=g) * 4.0 + 8.0
+        return theta, k[:, 0].contiguous(), k[:, 1].contiguous()
+
+    def timed_device(n_, B_, theta, k1, k2, steps, warmup, profile):
+        u = torch.empty((B_, n_, n_), dtype=torch.float64, device=dev)
+        info = None
+        for _ in range(warmup):
+            _, info = _lib.solve_batch(n_, B_, theta=theta, k1=k1, k2=k2, out=u, stream=stream, rtol=args.rtol)
+        barrier()
+        if profile:
+            _lib.profile_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            _, info = _lib.solve_batch(n_, B_, theta=theta, k1=k1, k2=k2, out=u, stream=stream, rtol=args.rtol)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        prof = None
+        if profile:
+            prof = _lib.profile_read()
+            _lib.profile_end()
+        info = info.to_host()
+        if (info.status > 1).any():
+            raise SystemExit(f"bench.py: {int((info.status > 1).sum())} samples did not converge")
+        return ms, info, prof, u
+
+    def timed_e2e(n_, B_, theta, k1, k2, steps, warmup):
+        # host-resident, pinned: theta + host-evaluated sine factors in, u out, all through the C ABI
+        x = np.linspace(0, 1, n_)
+        th_h = torch.empty((B_, n_, n_), dtype=torch.float64, pin_memory=True)
+        th_h.copy_(theta)
+        k1h, k2h = k1.cpu().numpy(), k2.cpu().numpy()
+        sx_h = torch.from_numpy(np.sin((2 * np.pi * k1h)[:, None] * x[None, :])).pin_memory()
+        sy_h = torch.from_numpy(np.sin((2 * np.pi * k2h)[:, None] * x[None, :])).pin_memory()
+        u_h = torch.empty((B_, n_, n_), dtype=torch.float64, pin_memory=True)
+        info = None
+        for _ in range(max(1, min(warmup, 2))):
+            _, info = _lib.solve_batch(n_, B_, theta=th_h, sin_x=sx_h, sin_y=sy_h, out=u_h, rtol=args.rtol)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, info = _lib.solve_batch(n_, B_, theta=th_h, sin_x=sx_h, sin_y=sy_h, out=u_h, rtol=args.rtol)
+        torch.cuda.synchronize()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        if (info.status > 1).any():
+            raise SystemExit("bench.py: e2e samples did not converge")
+        h2d = th_h.numel() * 8 + sx_h.numel() * 8 + sy_h.numel() * 8
+        d2h = u_h.numel() * 8 + B_ * 16
+        return sec, h2d, d2h, float(u_h[0, n_ // 2, n_ // 2])
+
+    # ---- headline workload
+    theta, k1, k2 = make_inputs(n, B, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, info, prof, _ = timed_device(n, B, theta, k1, k2, args.steps, max(3, args.warmup), profile=True)
+    clocks = sampler.stop()
+    value = B * world * args.steps / (ms / 1000.0)
+
+    launches = int(sum(v["launches"] for v in prof.values())) if prof else 0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    sample_iters = float(info.iters.sum())
+    desc = _lib.describe(n)
+    roof = None
+    kernels = {}
+    if prof:
+        for name, rec in prof.items():
+            kernels[name] = {"launches": rec["launches"], "ms_total": round(rec["ms"], 3),
+                             "share": round(rec["ms"] / max(1e-9, sum(r["ms"] for r in prof.values())), 4)}
+        if desc["resident"]:
+            rec = prof.get("smem_solve")
+            if rec:
+                bytes_per_launch = B * (n * n * 8.0 * 2 + 2 * 8.0 + 16.0)   # read theta, write u (+ scalars)
+                avg_s = rec["ms"] / rec["launches"] / 1000.0
+                ach = bytes_per_launch / avg_s / 1e9
+                roof = {"bound": "hbm", "kernel": "psn_smem_solve_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None, "avg_launch_ms": avg_s * 1e3,
+                        "note": "resident kernel is shared-memory/FP64-latency bound; HBM traffic is only theta in + u out"}
+        else:
+            top = max((k for k in prof if k in KERNEL_BYTES), key=lambda k: prof[k]["ms"])
+            rec = prof[top]
+            # every sample takes part in exactly iters[b] launches of each per-iteration kernel (per step)
+            total_bytes = KERNEL_BYTES[top]["own"] * n * n * sample_iters * args.steps
+            ach = total_bytes / (rec["ms"] / 1000.0) / 1e9
+            roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "avg_launch_ms": rec["ms"] / rec["launches"],
+                    "bytes_per_node": KERNEL_BYTES[top]["own"], "peak_source": peak_src,
+                    "achieved_survey_model": KERNEL_BYTES[top]["survey"] * n * n * sample_iters * args.steps / (rec["ms"] / 1000.0) / 1e9,
+                    "all_kernels_GBps": {k: KERNEL_BYTES[k]["own"] * n * n * sample_iters * args.steps / (prof[k]["ms"] / 1000.0) / 1e9
+                                         for k in KERNEL_BYTES if k in prof}}
+
+    # ---- end to end through the C ABI with host buffers
+    e2e_steps = max(1, min(args.steps, 3))
+    sec, h2d, d2h, _ = timed_e2e(n, B, theta, k1, k2, e2e_steps, args.warmup)
+    e2e = {"value": B * world * e2e_steps / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps, "ms_per_step": 1000.0 * sec / e2e_steps}
+    del theta
+
+    # ---- second half of the BASELINE metric: 80x80 resident kernel
+    also = None
+    if not args.no_also and n != 80:
+        n2, B2 = 80, 148 * 128
+        th2, k12, k22 = make_inputs(n2, B2, 5)
+        ms2, info2, prof2, _ = timed_device(n2, B2, th2, k12, k22, max(3, args.steps), 3, profile=True)
+        st2 = max(3, args.steps)
+        sec2, h2d2, d2h2, _ = timed_e2e(n2, B2, th2, k12, k22, 3, 2)
+        rec2 = prof2["smem_solve"]
+        also = {"workload": f"{B2 * world} independent 80x80 fp64 solves per step, theta~U(0.5,2) (resident kernel, one CTA per sample)",
+                "value": B2 * world * st2 / (ms2 / 1000.0), "unit": UNIT, "ms_per_step": ms2 / st2,
+                "mean_iters": float(info2.iters.mean()),
+                "e2e": {"value": B2 * world * 3 / sec2, "unit": UNIT, "h2d_bytes_per_step": int(h2d2), "d2h_bytes_per_step": int(d2h2)},
+                "hbm_GBps": B2 * (n2 * n2 * 16.0) / (rec2["ms"] / rec2["launches"] / 1000.0) / 1e9}
+        del th2
+
+    # ---- CPU baseline (oracle port of the reference) on this box's host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, P, ms_cpu, sample = cpu_pool_rate(n, 2 if n >= 512 else 4, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": P, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n, B, world), "n": n, "batch_per_gpu": B, "rtol": args.rtol,
+                       "solver": "MG-preconditioned CG, V(2,2) red-black GS, matrix-free 5-point zero-ghost stencil",
+                       "path": "resident" if desc["resident"] else "streamed", "mean_iters": float(info.iters.mean()),
+                       "max_iters": int(info.iters.max()),
+                       "l2": f"inputs larger than L2 (theta = {B * n * n * 8 / 1e6:.0f} MB per GPU, workspace {desc['workspace_bytes_per_sample'] * B / 1e9:.1f} GB)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "kernels": kernels, "also": also,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

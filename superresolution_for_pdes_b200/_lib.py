@@ -174,7 +174,7 @@ class SolveInfo:
 
 
 def solve_batch(n: int, batch: int, *, theta=None, f=None, sin_x=None, sin_y=None, k1=None, k2=None,
-                master_n: Optional[int] = None, step: int = 1, rtol: float = 1e-12, max_iter: int = 100,
+                master_n: Optional[int] = None, step: int = 1, rtol: float = 2.5e-13, max_iter: int = 100,
                 out=None, stream: int = 0, info_on_host: bool = True):
     """Batched solve of diag(theta) L u = f.  Buffers may be numpy arrays (host) or torch CUDA
     tensors (device, float64, contiguous).  Returns (u, SolveInfo)."""
@@ -207,7 +207,7 @@ def solve_batch(n: int, batch: int, *, theta=None, f=None, sin_x=None, sin_y=Non
 
 
 def subdomain_batch(n_super: int, n_fine: int, batch: int, sin_x, sin_y, start_x, start_y, *,
-                    rtol: float = 1e-12, max_iter: int = 100, stream: int = 0):
+                    rtol: float = 2.5e-13, max_iter: int = 100, stream: int = 0):
     """Fused super-fine solve + window + stride-2 downsample.  Returns (dict of arrays, SolveInfo)."""
     lib = load()
     nc = (n_fine + 1) // 2
@@ -235,7 +235,7 @@ def subdomain_batch(n_super: int, n_fine: int, batch: int, sin_x, sin_y, start_x
 
 
 def multires(n_finest: int, resolutions: Sequence[int], batch: int, theta_finest, sin_x, sin_y, *,
-             rtol: float = 1e-12, max_iter: int = 100, stream: int = 0):
+             rtol: float = 2.5e-13, max_iter: int = 100, stream: int = 0):
     """Solve at every resolution from one master theta / forcing per example (stride gathers).
     Returns ({res: u[batch, res, res]}, SolveInfo with [n_res, batch] arrays)."""
     lib = load()

@@ -74,9 +74,13 @@ def test_generate_dataset_matches_reference_fixture(gpu_lib):
     np.random.seed(0)
     ds = PoissonSolver().generate_dataset(6, k_range=(0.5, 5.0))
     assert list(ds.keys()) == ["u_coarse", "u_fine", "f_coarse", "f_fine", "theta_coarse", "theta_fine", "k1", "k2"]
+    np.random.seed(0)
+    live = O.generate_dataset(6, k_range=(0.5, 5.0))
     for k in ("k1", "k2", "f_coarse", "f_fine", "theta_coarse", "theta_fine"):
         assert ds[k].dtype == np.float64 and ds[k].flags.c_contiguous
-        assert np.array_equal(ds[k], gold[k]), k          # bit-exact
+        assert np.array_equal(ds[k], live[k]), k          # bit-exact vs the oracle on THIS machine
+        # fixtures were made on another CPU: numpy's SIMD sin may differ there in the last bit
+        assert np.allclose(ds[k], gold[k], rtol=0, atol=1e-15), k
     for k in ("u_coarse", "u_fine"):
         assert ds[k].shape == gold[k].shape
         for b in range(6):
@@ -89,8 +93,11 @@ def test_generate_subdomain_dataset_matches_reference_fixture(gpu_lib):
     np.random.seed(1)
     es = EnhancedPoissonSolver()
     ds = es.generate_subdomain_dataset(4, k_range=(0.5, 12.0))
+    np.random.seed(1)
+    live = O.generate_subdomain_dataset(4, k_range=(0.5, 12.0))
     for k in ("k1", "k2", "f_coarse", "f_fine", "theta_coarse", "theta_fine", "is_subdomain"):
-        assert np.array_equal(ds[k], gold[k]), k
+        assert np.array_equal(ds[k], live[k]), k           # bit-exact vs the oracle on THIS machine
+        assert np.allclose(ds[k], gold[k], rtol=0, atol=1e-15), k
     assert ds["is_subdomain"].dtype == np.bool_
     for k in ("u_coarse", "u_fine"):
         for b in range(4):
@@ -114,10 +121,12 @@ def test_multires_chain_matches_reference_fixture(gpu_lib):
     np.random.seed(2)
     data = solve_multi_resolution(40, [80, 160, 320, 640])
     assert data["k1"] == gold["k1"] and data["k2"] == gold["k2"]
+    f_live = O.forcing_term_kfirst(data["k1"], data["k2"], 640)
     for res in (40, 80, 160, 320, 640):
         s = kat_sub(res)
         assert data["u"][res].shape == (res, res)
-        assert np.linalg.norm(data["f"][res]) == gold[f"f{res}_norm"]       # bit-exact forcing
+        assert np.array_equal(data["f"][res], f_live[::640 // res, ::640 // res])   # bit-exact forcing (this machine)
+        assert abs(np.linalg.norm(data["f"][res]) - gold[f"f{res}_norm"]) <= 1e-13 * gold[f"f{res}_norm"]
         assert data["theta"][res].sum() == gold[f"theta{res}_sum"]
         assert O.rel_l2(data["u"][res][::s, ::s], gold[f"u{res}"]) <= TOL
         assert abs(np.linalg.norm(data["u"][res]) - gold[f"u{res}_norm"]) <= TOL * gold[f"u{res}_norm"]

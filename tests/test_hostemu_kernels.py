@@ -1,0 +1,157 @@
+"""CPU tier: the CUDA kernel BODIES (psn_core.cuh) and the streamed-path driver compiled as host
+code with one virtual thread per CTA (tests/hostemu -- test infrastructure, never loaded by the
+product) against the oracle.  This checks indexing, halo widths, the temporal-blocking schedule,
+the multigrid hierarchy for odd/even sizes and the per-sample state machine without a GPU;
+data races are the one thing it cannot see (compute-sanitizer on the GPU box covers those)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import KAT_K, ROOT, kat_inputs
+from oracle import poisson_oracle as O
+
+HE_DIR = os.path.join(ROOT, "tests", "hostemu")
+HE_LIB = os.path.join(HE_DIR, "libpsn_hostemu.so")
+DP = ctypes.POINTER(ctypes.c_double)
+IP = ctypes.POINTER(ctypes.c_int32)
+
+
+@pytest.fixture(scope="module")
+def he():
+    srcs = [os.path.join(HE_DIR, "psn_hostemu.cpp")] + [
+        os.path.join(ROOT, "superresolution_for_pdes_b200", "csrc", f)
+        for f in ("psn_core.cuh", "psn_plan.h", "psn_stream_driver.h")]
+    if not os.path.exists(HE_LIB) or any(os.path.getmtime(s) > os.path.getmtime(HE_LIB) for s in srcs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", HE_LIB, srcs[0]], check=True)
+    return ctypes.CDLL(HE_LIB)
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(DP)
+
+
+def PI(a):
+    return None if a is None else a.ctypes.data_as(IP)
+
+
+def run_smem(he, n, theta, f=None, sx=None, sy=None, rtol=1e-12, maxit=100, nu=2, sub=None):
+    B = (f if f is not None else sx).shape[0]
+    u = np.full((B, n, n), np.nan)
+    it, rr, st = np.zeros(B, np.int32), np.zeros(B), np.zeros(B, np.int32)
+    extra = [ctypes.c_int(0), None, None, None, None, None, None]
+    outs = None
+    if sub is not None:
+        s, x0, y0 = sub
+        sc = (s + 1) // 2
+        outs = [np.full((B, s, s), np.nan), np.full((B, s, s), np.nan), np.full((B, sc, sc), np.nan), np.full((B, sc, sc), np.nan)]
+        extra = [ctypes.c_int(s), PI(x0), PI(y0)] + [P(o) for o in outs]
+    rc = he.hostemu_solve_smem(ctypes.c_int(n), ctypes.c_longlong(B), P(theta), P(f), P(sx), P(sy), None, None,
+                               ctypes.c_int(n), ctypes.c_int(1), ctypes.c_double(rtol), ctypes.c_int(maxit), ctypes.c_int(nu),
+                               P(u), PI(it), P(rr), PI(st), *extra)
+    assert rc == 0
+    return u, it, rr, st, outs
+
+
+def run_stream(he, n, theta, f, TH, TW, ls, rtol=1e-12, maxit=100, nu=2, mn=None, step=1):
+    B = f.shape[0]
+    u = np.full((B, n, n), np.nan)
+    it, rr, st = np.zeros(B, np.int32), np.zeros(B), np.zeros(B, np.int32)
+    rc = he.hostemu_solve_stream(ctypes.c_int(n), ctypes.c_longlong(B), P(theta), P(f), None, None, None, None,
+                                 ctypes.c_int(mn or n), ctypes.c_int(step), ctypes.c_double(rtol), ctypes.c_int(maxit), ctypes.c_int(nu),
+                                 ctypes.c_int(TH), ctypes.c_int(TW), ctypes.c_int(ls), P(u), PI(it), P(rr), PI(st))
+    assert rc > 0
+    return u, it, rr, st
+
+
+def batch_inputs(n, rough):
+    fs, ths = zip(*[kat_inputs(n, k, rough) for k in range(3)])
+    return np.stack(fs), np.stack(ths)
+
+
+def test_plan_hierarchy():
+    from superresolution_for_pdes_b200 import _lib
+    he = ctypes.CDLL(HE_LIB) if os.path.exists(HE_LIB) else None
+    if he is None:
+        pytest.skip("host emulation library not built")
+    ns = (ctypes.c_int * 12)()
+    g = (ctypes.c_double * 12)()
+    L = he.hostemu_plan(ctypes.c_int(640), ctypes.c_int(2), ns, g, None)
+    assert list(ns)[:L] == [640, 320, 160, 80, 40, 20, 10, 5]
+    assert list(g)[:L] == [0, 1, 3, 7, 15, 31, 63, 127]          # gam' = 2 gam + 1 on even levels
+    L = he.hostemu_plan(ctypes.c_int(37), ctypes.c_int(2), ns, g, None)
+    assert list(ns)[:L] == [37, 18, 9, 4] and list(g)[:L] == [0, 0, 1, 0.5]
+
+
+@pytest.mark.parametrize("n", [5, 6, 7, 9, 13, 20, 37, 40, 75, 80, 86])
+@pytest.mark.parametrize("rough", [0, 1])
+def test_resident_body_matches_oracle(he, n, rough):
+    f, theta = batch_inputs(n, rough)
+    u, it, rr, st, _ = run_smem(he, n, theta, f=f)
+    assert (st <= 1).all() and it.max() <= 12
+    for b in range(3):
+        assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= 1e-10
+
+
+def test_resident_body_fused_subdomain_epilogue(he):
+    n, s = 80, 40
+    x = np.linspace(0, 1, n)
+    k = np.array([[0.5, 11.0], [7.7, 3.1], [12.0, 12.0]])
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    x0 = np.array([0, 39, 17], dtype=np.int32)
+    y0 = np.array([39, 0, 5], dtype=np.int32)
+    u, it, rr, st, (uf, ff, uc, fc) = run_smem(he, n, None, sx=sx, sy=sy, sub=(s, x0, y0))
+    for b in range(3):
+        f = np.outer(sy[b], sx[b])
+        win = (slice(y0[b], y0[b] + s), slice(x0[b], x0[b] + s))      # rows = y, cols = x
+        assert np.array_equal(uf[b], u[b][win]) and np.array_equal(ff[b], f[win])
+        assert np.array_equal(uc[b], u[b][win][::2, ::2]) and np.array_equal(fc[b], f[win][::2, ::2])
+        assert O.rel_l2(u[b], O.solve_poisson(f, np.ones((n, n)), n)) <= 1e-10
+
+
+@pytest.mark.parametrize("n,TH,TW,ls", [(96, 32, 32, 1), (100, 64, 64, 1), (131, 64, 64, 1), (160, 64, 64, 1),
+                                        (160, 32, 64, 2), (64, 16, 16, 2), (45, 8, 24, 1)])
+def test_streamed_bodies_match_oracle(he, n, TH, TW, ls):
+    f, theta = batch_inputs(n, 1)
+    u, it, rr, st = run_stream(he, n, theta, f, TH, TW, ls)
+    assert (st <= 1).all() and it.max() <= 12
+    for b in range(3):
+        assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= 1e-10
+
+
+def test_streamed_tiling_is_exact(he):
+    """Temporal blocking must reproduce the untiled algorithm: different tile shapes give the same
+    iterates up to summation order of the dot products."""
+    n = 96
+    f, theta = batch_inputs(n, 1)
+    ua, ita, _, _ = run_stream(he, n, theta, f, 96, 96, 1)
+    ub, itb, _, _ = run_stream(he, n, theta, f, 16, 32, 1)
+    assert (ita == itb).all()
+    assert O.rel_l2(ub, ua) <= 1e-13
+
+
+def test_stride_gather_and_state_machine(he):
+    n, mn, step = 100, 199, 2
+    rs = np.random.RandomState(0)
+    thm = rs.uniform(0.5, 2.0, size=(4, mn, mn))
+    fm = np.stack([O.forcing_term(3.3, 4.4, mn), np.zeros((mn, mn)), O.forcing_term(0.5, 0.6, mn), O.forcing_term(9.0, 2.0, mn)])
+    u, it, rr, st = run_stream(he, n, thm, fm, 64, 64, 1, mn=mn, step=step)
+    assert st[1] == 0 and it[1] == 0 and (u[1] == 0).all()          # zero rhs finishes at once, others continue
+    for b in (0, 2, 3):
+        assert st[b] <= 1
+        assert O.rel_l2(u[b], O.solve_poisson(fm[b][::2, ::2], thm[b][::2, ::2], n)) <= 1e-10
+    # max_iter is honoured per sample and reported
+    u, it, rr, st = run_stream(he, n, thm, fm, 64, 64, 1, mn=mn, step=step, maxit=3)
+    assert (it[[0, 2, 3]] == 3).all() and (st[[0, 2, 3]] == 2).all()
+
+
+def test_fp64_floor_status(he):
+    """Very smooth forcing on a larger grid: rtol below the fp64 round-off floor ends with status 1
+    (stagnation detected), with an error as small as the direct solver's."""
+    n = 160
+    f, theta = kat_inputs(n, 0, 0)
+    u, it, rr, st = run_stream(he, n, theta[None], f[None], 64, 64, 1, rtol=1e-14)
+    assert st[0] == 1 and it[0] < 30
+    assert O.rel_l2(u[0], O.solve_poisson(f, theta, n)) <= 1e-10

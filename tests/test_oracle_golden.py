@@ -1,0 +1,73 @@
+"""CPU tier: the oracle (oracle/poisson_oracle.py) against the golden fixtures that
+tests/golden/make_golden.py generated from the LIVE, unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, kat_inputs, kat_sub
+from oracle import poisson_oracle as O
+
+
+@pytest.mark.parametrize("n", [20, 40, 80, 160, 320])
+def test_oracle_reproduces_reference_kats(golden_kat, n):
+    for k in range(3):
+        for r in (0, 1):
+            key = f"n{n}_k{k}_r{r}"
+            f, theta = kat_inputs(n, k, r)
+            u = O.solve_poisson(f, theta, n)
+            s = kat_sub(n)
+            # same SciPy entry point on the same matrix: equal to round-off of the LU (bit-equal in the
+            # container that made the fixtures; a different BLAS/SciPy build may differ in the last bits)
+            assert O.rel_l2(u[::s, ::s], golden_kat[key + "_u"]) <= 1e-12
+            assert O.residual_rel(u, f, theta) <= 10 * golden_kat[key + "_res"] + 1e-15
+
+
+def test_oracle_640_and_dst(golden_kat):
+    n = 640
+    f, theta = kat_inputs(n, 2, 1)
+    ud = O.solve_dst(f, theta)
+    s = kat_sub(n)
+    assert O.rel_l2(ud[::s, ::s], golden_kat["n640_k2_r1_u"]) <= 1e-11     # independent closed form
+    assert abs(np.linalg.norm(ud) - golden_kat["n640_k2_r1_norm"]) <= 1e-11 * golden_kat["n640_k2_r1_norm"]
+
+
+def test_dst_agrees_with_lu_everywhere():
+    for n in (5, 7, 20, 33, 80):
+        f, theta = kat_inputs(n, 1, 1)
+        assert O.rel_l2(O.solve_dst(f, theta), O.solve_poisson(f, theta, n)) <= 1e-12
+
+
+def test_oracle_datasets_bit_exact():
+    gold = np.load(os.path.join(GOLDEN, "dataset_standard_seed0.npz"))
+    np.random.seed(0)
+    ds = O.generate_dataset(6, k_range=(0.5, 5.0))
+    for k in gold.files:
+        if k.startswith("u_"):
+            assert O.rel_l2(ds[k], gold[k]) <= 1e-13
+        else:
+            assert np.array_equal(ds[k], gold[k]), k
+    gold = np.load(os.path.join(GOLDEN, "dataset_subdomain_seed1.npz"))
+    np.random.seed(1)
+    sd = O.generate_subdomain_dataset(4, k_range=(0.5, 12.0))
+    for k in gold.files:
+        if k.startswith("u_"):
+            assert O.rel_l2(sd[k], gold[k]) <= 1e-13
+        else:
+            assert np.array_equal(sd[k], gold[k]), k
+
+
+def test_structural_facts_of_the_reference_operator():
+    """SURVEY.md F1-F3, pinned on the oracle."""
+    n = 40
+    f, theta = kat_inputs(n, 1, 1)
+    one = np.ones((n, n))
+    assert O.rel_l2(O.solve_poisson(f, theta, n), O.solve_poisson(f / theta, one, n)) <= 1e-13   # F1 row scaling
+    u = O.solve_poisson(f, one, n)
+    i, j = np.unravel_index(np.argmax(f), f.shape)
+    assert u[i, j] < 0                                                                           # F2 sign
+    assert np.abs(u[0, :]).max() > 1e-6                                                          # F3 free border
+    # bit-exact forcing from 1-D sine factors
+    x = np.linspace(0, 1, n)
+    k1, k2 = 2.3, 3.7
+    assert np.array_equal(np.outer(np.sin(2 * np.pi * k2 * x), np.sin(2 * np.pi * k1 * x)), O.forcing_term(k1, k2, n))
