@@ -72,6 +72,22 @@ __global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_post_kernel(const _
     psn_tile_post_body(ctx, plan, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x, smem);
 }
 
+// register-resident warp-strip V-cycle legs: one warp per (sample, band, strip) task, no shared memory
+#define PSN_STRIP_WARPS 4
+template <int NU, bool POST>
+__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32) psn_strip_kernel(const __grid_constant__ PsnPlan plan,
+                                                                        const __grid_constant__ PsnStripArgs a, long long ntasks) {
+    const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + (threadIdx.x >> 5);
+    if (task >= ntasks) return;
+    const int per = a.nstrips * a.nbands;
+    const long long b = task / per;
+    const int rem = (int)(task - b * per);
+    const int band = rem / a.nstrips, strip = rem - band * a.nstrips;
+    const PsnWarp w{(int)(threadIdx.x & 31)};
+    if (POST) psn_strip_post_body<NU>(w, plan, a, b, band, strip);
+    else psn_strip_pre_body<NU>(w, plan, a, b, band, strip);
+}
+
 __global__ void __launch_bounds__(PSN_COARSE_THREADS) psn_coarse_vcycle_kernel(const __grid_constant__ PsnPlan plan, int l0,
                                                                                const double* bg, double* ug,
                                                                                const PsnSampleState* state) {
@@ -166,6 +182,7 @@ struct Context {
     int tile = 64;
     long long ws_bytes = 16ll << 30;
     int smem_max_n = 0;
+    int vcycle_mode = 1;   // 0: shared-memory tile kernels, 1: register-resident warp strips
     bool attrs_set = false;
     bool profiling = false;
     std::vector<ProfRec> prof;
@@ -315,16 +332,36 @@ struct CudaBackend {
         psn_state_init_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B);
         chk();
     }
-    void tile_pre(const PsnPlan& plan, const PsnTileArgs& t, long long B) {
-        ProfScope p(t.level == 0 ? "tile_pre_l0" : "tile_pre_coarse", s);
-        const size_t smem = (size_t)psn_tile_pre_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
-        psn_tile_pre_kernel<<<dim3(t.ntx, t.nty, (unsigned)B), PSN_TILE_THREADS, smem, s>>>(plan, t);
+    template <bool POST>
+    void strip_launch(const PsnPlan& plan, const PsnStripArgs& a, long long B) {
+        const long long ntasks = B * a.nstrips * a.nbands;
+        const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
+        if (plan.nu == 1) psn_strip_kernel<1, POST><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(plan, a, ntasks);
+        else if (plan.nu == 2) psn_strip_kernel<2, POST><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(plan, a, ntasks);
+        else psn_strip_kernel<3, POST><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(plan, a, ntasks);
+    }
+    void leg_pre(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
+        if (cfg.mode == 1) {
+            ProfScope p(g.level == 0 ? "strip_pre_l0" : "strip_pre_coarse", s);
+            strip_launch<false>(plan, psn_leg_to_strip(plan, cfg, g, false), B);
+        } else {
+            const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
+            ProfScope p(t.level == 0 ? "tile_pre_l0" : "tile_pre_coarse", s);
+            const size_t smem = (size_t)psn_tile_pre_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
+            psn_tile_pre_kernel<<<dim3(t.ntx, t.nty, (unsigned)B), PSN_TILE_THREADS, smem, s>>>(plan, t);
+        }
         chk();
     }
-    void tile_post(const PsnPlan& plan, const PsnTileArgs& t, long long B) {
-        ProfScope p(t.level == 0 ? "tile_post_l0" : "tile_post_coarse", s);
-        const size_t smem = (size_t)psn_tile_post_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
-        psn_tile_post_kernel<<<dim3(t.ntx, t.nty, (unsigned)B), PSN_TILE_THREADS, smem, s>>>(plan, t);
+    void leg_post(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
+        if (cfg.mode == 1) {
+            ProfScope p(g.level == 0 ? "strip_post_l0" : "strip_post_coarse", s);
+            strip_launch<true>(plan, psn_leg_to_strip(plan, cfg, g, true), B);
+        } else {
+            const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
+            ProfScope p(t.level == 0 ? "tile_post_l0" : "tile_post_coarse", s);
+            const size_t smem = (size_t)psn_tile_post_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
+            psn_tile_post_kernel<<<dim3(t.ntx, t.nty, (unsigned)B), PSN_TILE_THREADS, smem, s>>>(plan, t);
+        }
         chk();
     }
     void coarse_vcycle(const PsnPlan& plan, int l0, const double* bg, double* ug, const PsnSampleState* st, long long B) {
@@ -418,6 +455,30 @@ int copy_back(cudaStream_t s, T* host_dst, MemKind kind, long long offset, size_
     return PSN_OK;
 }
 
+// upper bound of the <r,z> partial count over every band choice (smallest band = 16 rows)
+int psn_rz_max(const PsnPlan& plan, const PsnStreamCfg& cfg) {
+    if (cfg.mode != 1) return psn_rz_count(plan, cfg);
+    return psn_strip_count(plan.n, psn_strip_use_post(plan.nu)) * psn_band_count(plan.n, 16);
+}
+
+// rows per warp task on every streamed level: full columns when the batch alone fills the GPU,
+// shorter bands (more tasks, a little halo re-computation) for small batches
+void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
+    for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg->band[l] = 16;
+    const long long target = (long long)g.sm_count * 32;
+    for (int l = 0; l < cfg->ls; ++l) {
+        const int n = plan.lv[l].n;
+        const long long strips = psn_strip_count(n, psn_strip_use_pre(plan.nu));
+        long long nb = (target + Bc * strips - 1) / (Bc * strips);
+        if (nb < 1) nb = 1;
+        if (nb > n / 16) nb = n / 16 > 0 ? n / 16 : 1;
+        int band = (int)((n + nb - 1) / nb);
+        band = (band + 1) & ~1;
+        if (band < 16) band = 16;
+        cfg->band[l] = band;
+    }
+}
+
 size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     const size_t nn = (size_t)plan.n * plan.n;
     size_t b = 5 * nn * sizeof(double);
@@ -425,10 +486,8 @@ size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) 
         const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n * sizeof(double);
         b += (l < cfg.ls ? 3 : 2) * m;
     }
-    int tx, ty;
-    psn_tile_counts(plan.n, cfg.TH, cfg.TW, &tx, &ty);
     const int gx = (plan.n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (plan.n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
-    b += ((size_t)tx * ty + 2 * (size_t)gx * gy) * sizeof(double) + sizeof(PsnSampleState);
+    b += ((size_t)psn_rz_max(plan, cfg) + 2 * (size_t)gx * gy) * sizeof(double) + sizeof(PsnSampleState);
     return b + 4096 / 16;
 }
 
@@ -452,10 +511,8 @@ int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, lon
             ok = ok && ws->ua[l];
         }
     }
-    int tx, ty;
-    psn_tile_counts(plan.n, cfg.TH, cfg.TW, &tx, &ty);
     const int gx = (plan.n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (plan.n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
-    ws->part_rz = arena_take<double>(ar, (size_t)Bc * tx * ty);
+    ws->part_rz = arena_take<double>(ar, (size_t)Bc * psn_rz_max(plan, cfg));
     ws->part_a = arena_take<double>(ar, (size_t)Bc * gx * gy);
     ws->part_b = arena_take<double>(ar, (size_t)Bc * gx * gy);
     ws->state = arena_take<PsnSampleState>(ar, Bc);
@@ -488,7 +545,10 @@ int solve_internal(const Problem& P) {
     const PsnPlan& plan = pe->plan;
     const ResidentCfg rcfg = resident_cfg(plan);
     const bool resident = rcfg.T != 0;
-    PsnStreamCfg scfg{0, g.tile, g.tile};
+    PsnStreamCfg scfg;
+    memset(&scfg, 0, sizeof(scfg));
+    scfg.TH = scfg.TW = g.tile;
+    scfg.mode = g.vcycle_mode;
     if (!resident) {
         if (P.sub > 0) return psn_fail(PSN_ERR_UNSUPPORTED, "fused sub-domain epilogue needs the resident path (n=%d too large)", P.n);
         scfg.ls = stream_ls(plan);
@@ -626,6 +686,7 @@ int solve_internal(const Problem& P) {
             slot.ws_arena.off = 0;
             PsnStreamWs ws;
             if ((rc = carve_stream_ws(slot.ws_arena, plan, scfg, bc, P.max_iter, &ws))) return rc;
+            choose_bands(plan, &scfg, bc);
             CudaBackend bk{s, &slot};
             psn_stream_solve(bk, plan, scfg, rhs, bc, P.rtol, P.max_iter, d_u, ws);
             if (bk.err != cudaSuccess) return psn_fail(PSN_ERR_CUDA, "streamed solve failed: %s", cudaGetErrorString(bk.err));
@@ -774,7 +835,7 @@ int psn_set_option(const char* name, int64_t value) {
     g_err[0] = 0;
     if (!name) return psn_fail(PSN_ERR_INVALID, "option name is NULL");
     if (!strcmp(name, "nu")) {
-        if (value < 1 || value > 4) return psn_fail(PSN_ERR_INVALID, "nu must be in 1..4");
+        if (value < 1 || value > 3) return psn_fail(PSN_ERR_INVALID, "nu must be in 1..3");
         g.nu = (int)value;
     } else if (!strcmp(name, "tile")) {
         if (value < 8 || value > 96 || (value & 1)) return psn_fail(PSN_ERR_INVALID, "tile must be even, in 8..96");
@@ -784,6 +845,9 @@ int psn_set_option(const char* name, int64_t value) {
         g.ws_bytes = value;
     } else if (!strcmp(name, "smem_max_n")) {
         g.smem_max_n = (int)value;
+    } else if (!strcmp(name, "vcycle_mode")) {
+        if (value != 0 && value != 1) return psn_fail(PSN_ERR_INVALID, "vcycle_mode must be 0 (tiles) or 1 (warp strips)");
+        g.vcycle_mode = (int)value;
     } else {
         return psn_fail(PSN_ERR_INVALID, "unknown option '%s'", name);
     }
@@ -851,7 +915,9 @@ int psn_describe(int n, int64_t* info) {
         info[5] = 0;
         info[6] = 0;
     } else {
-        PsnStreamCfg sc{stream_ls(plan), g.tile, g.tile};
+        PsnStreamCfg sc;
+        memset(&sc, 0, sizeof(sc));
+        sc.ls = stream_ls(plan); sc.TH = sc.TW = g.tile; sc.mode = g.vcycle_mode;
         info[0] = 0;
         info[2] = sc.ls;
         info[3] = PSN_TILE_THREADS;

@@ -7,14 +7,37 @@
 // converged samples are masked out per CTA, and the number of still-active samples is read
 // back with a lag of PSN_COUNTER_LAG iterations.
 #pragma once
-#include "psn_core.cuh"
+#include "psn_warp.cuh"
 
 #define PSN_COUNTER_LAG 2
 
 struct PsnStreamCfg {
     int ls;       // first level handled by the shared-memory coarse kernel (levels 0..ls-1 are streamed)
-    int TH, TW;   // interior tile of the pre / post kernels
+    int TH, TW;   // interior tile of the shared-memory tile kernels (mode 0)
+    int mode;     // V-cycle legs: 0 = shared-memory tiles, 1 = register-resident warp strips
+    int band[PSN_MAX_LEVELS];  // mode 1: output rows per warp task on each streamed level (even)
 };
+
+// one leg (down or up) of the V-cycle on one streamed level
+struct PsnLegArgs {
+    int level;
+    const double* b;    // [B, n_l, n_l] right-hand side
+    const double* uin;  // up-leg: pre-smoothed iterate
+    double* uout;
+    double* bc;         // down-leg: restricted residual out
+    const double* ec;   // up-leg: coarse correction in
+    double* part;       // up-leg on level 0: partial <b,u> per task
+    const PsnSampleState* state;
+};
+
+static inline int psn_strip_count(int n, int use) { return (n + use - 1) / use; }
+static inline int psn_band_count(int n, int band) { return (n + band - 1) / band; }
+// number of <r,z> partials per sample produced by the level-0 up-leg
+static inline int psn_rz_count(const PsnPlan& plan, const PsnStreamCfg& cfg) {
+    const int n = plan.n;
+    if (cfg.mode == 1) return psn_strip_count(n, psn_strip_use_post(plan.nu)) * psn_band_count(n, cfg.band[0]);
+    return ((n + cfg.TW - 1) / cfg.TW) * ((n + cfg.TH - 1) / cfg.TH);
+}
 
 // device arrays for one chunk of Bc samples
 struct PsnStreamWs {
@@ -38,6 +61,26 @@ static inline void psn_tile_counts(int n, int TH, int TW, int* ntx, int* nty) {
     *nty = (n + TH - 1) / TH;
 }
 
+static inline PsnTileArgs psn_leg_to_tile(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g) {
+    PsnTileArgs t;
+    t.level = g.level;
+    t.TH = cfg.TH;
+    t.TW = cfg.TW;
+    psn_tile_counts(plan.lv[g.level].n, cfg.TH, cfg.TW, &t.ntx, &t.nty);
+    t.b = g.b; t.uin = g.uin; t.uout = g.uout; t.bc = g.bc; t.ec = g.ec; t.part = g.part; t.state = g.state;
+    return t;
+}
+static inline PsnStripArgs psn_leg_to_strip(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, bool post) {
+    PsnStripArgs a;
+    const int n = plan.lv[g.level].n;
+    a.level = g.level;
+    a.band = cfg.band[g.level];
+    a.nstrips = psn_strip_count(n, post ? psn_strip_use_post(plan.nu) : psn_strip_use_pre(plan.nu));
+    a.nbands = psn_band_count(n, a.band);
+    a.b = g.b; a.uin = g.uin; a.uout = g.uout; a.bc = g.bc; a.ec = g.ec; a.part = g.part; a.state = g.state;
+    return a;
+}
+
 // x: [B, n, n] device array that receives the solution.  Returns the number of outer iterations run.
 template <class BK>
 int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnRhs& rhs, long long B,
@@ -47,9 +90,7 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.n = n;
     cg.ntx = (n + PSN_GT_COLS - 1) / PSN_GT_COLS;
     cg.nty = (n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
-    int t0x, t0y;
-    psn_tile_counts(n, cfg.TH, cfg.TW, &t0x, &t0y);
-    cg.ntiles_rz = t0x * t0y;
+    cg.ntiles_rz = psn_rz_count(plan, cfg);
     cg.rhs = rhs;
     cg.h2 = plan.h2;
     cg.x = x;
@@ -74,35 +115,29 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     for (; it < max_outer; ++it) {
         // ---- z = M^{-1} r : one V(nu,nu) cycle
         for (int l = 0; l < cfg.ls; ++l) {
-            PsnTileArgs t;
-            t.level = l;
-            t.TH = cfg.TH;
-            t.TW = cfg.TW;
-            psn_tile_counts(plan.lv[l].n, cfg.TH, cfg.TW, &t.ntx, &t.nty);
-            t.b = (l == 0) ? ws.r : ws.bl[l];
-            t.uin = nullptr;
-            t.uout = (l == 0) ? ws.q : ws.ua[l];
-            t.bc = ws.bl[l + 1];
-            t.ec = nullptr;
-            t.part = nullptr;
-            t.state = ws.state;
-            bk.tile_pre(plan, t, B);
+            PsnLegArgs g;
+            g.level = l;
+            g.b = (l == 0) ? ws.r : ws.bl[l];
+            g.uin = nullptr;
+            g.uout = (l == 0) ? ws.q : ws.ua[l];
+            g.bc = ws.bl[l + 1];
+            g.ec = nullptr;
+            g.part = nullptr;
+            g.state = ws.state;
+            bk.leg_pre(plan, cfg, g, B);
         }
         bk.coarse_vcycle(plan, cfg.ls, ws.bl[cfg.ls], ws.ub[cfg.ls], ws.state, B);
         for (int l = cfg.ls - 1; l >= 0; --l) {
-            PsnTileArgs t;
-            t.level = l;
-            t.TH = cfg.TH;
-            t.TW = cfg.TW;
-            psn_tile_counts(plan.lv[l].n, cfg.TH, cfg.TW, &t.ntx, &t.nty);
-            t.b = (l == 0) ? ws.r : ws.bl[l];
-            t.uin = (l == 0) ? ws.q : ws.ua[l];
-            t.uout = (l == 0) ? ws.z : ws.ub[l];
-            t.bc = nullptr;
-            t.ec = ws.ub[l + 1];
-            t.part = (l == 0) ? ws.part_rz : nullptr;
-            t.state = ws.state;
-            bk.tile_post(plan, t, B);
+            PsnLegArgs g;
+            g.level = l;
+            g.b = (l == 0) ? ws.r : ws.bl[l];
+            g.uin = (l == 0) ? ws.q : ws.ua[l];
+            g.uout = (l == 0) ? ws.z : ws.ub[l];
+            g.bc = nullptr;
+            g.ec = ws.ub[l + 1];
+            g.part = (l == 0) ? ws.part_rz : nullptr;
+            g.state = ws.state;
+            bk.leg_post(plan, cfg, g, B);
         }
         // ---- CG update
         cg.p_old = ws.p[it & 1];

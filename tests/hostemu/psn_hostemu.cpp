@@ -34,7 +34,24 @@ struct HostBackend {
                 for (int tx = 0; tx < a.ntx; ++tx) psn_prologue_body(ctx, a, b, ty, tx);
     }
     void state_init(const PsnCgArgs& a, long long B) { for (long long b = 0; b < B; ++b) psn_state_init(a, b); }
-    void tile_pre(const PsnPlan& plan, const PsnTileArgs& t, long long B) {
+    template <int NU>
+    void strip_leg(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post) {
+        PsnWarp w;
+        for (long long b = 0; b < B; ++b)
+            for (int band = 0; band < a.nbands; ++band)
+                for (int strip = 0; strip < a.nstrips; ++strip) {
+                    if (post) psn_strip_post_body<NU>(w, plan, a, b, band, strip);
+                    else psn_strip_pre_body<NU>(w, plan, a, b, band, strip);
+                }
+    }
+    void strip_dispatch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post) {
+        if (plan.nu == 1) strip_leg<1>(plan, a, B, post);
+        else if (plan.nu == 2) strip_leg<2>(plan, a, B, post);
+        else strip_leg<3>(plan, a, B, post);
+    }
+    void leg_pre(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
+        if (cfg.mode == 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, false), B, false); return; }
+        const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
             for (int ty = 0; ty < t.nty; ++ty)
@@ -44,7 +61,9 @@ struct HostBackend {
                     psn_tile_pre_body(ctx, plan, t, b, ty, tx, smem.data());
                 }
     }
-    void tile_post(const PsnPlan& plan, const PsnTileArgs& t, long long B) {
+    void leg_post(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
+        if (cfg.mode == 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, true), B, true); return; }
+        const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
             for (int ty = 0; ty < t.nty; ++ty)
@@ -128,11 +147,13 @@ int hostemu_solve_smem(int n, long long B, const double* theta, const double* f,
 // streamed solver (tile kernels + global CG kernels + coarse shared-memory V-cycle)
 int hostemu_solve_stream(int n, long long B, const double* theta, const double* f, const double* sx, const double* sy,
                          const double* k1, const double* k2, int mn, int step, double rtol, int max_iter, int nu,
-                         int TH, int TW, int ls, double* u, int32_t* iters, double* relres, int32_t* status) {
+                         int TH, int TW, int ls, int mode, int band, double* u, int32_t* iters, double* relres, int32_t* status) {
     HostPlan hp(n, nu);
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
-    PsnStreamCfg cfg{ls, TH, TW};
+    PsnStreamCfg cfg;
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = mode;
+    for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
     memset(&ws, 0, sizeof(ws));
     std::vector<std::vector<double>> keep;
@@ -145,10 +166,8 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
         ws.bl[l] = alloc(B * m); ws.ub[l] = alloc(B * m);
         if (l < ls) ws.ua[l] = alloc(B * m);
     }
-    int t0x, t0y;
-    psn_tile_counts(n, TH, TW, &t0x, &t0y);
     const int gx = (n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
-    ws.part_rz = alloc((size_t)B * t0x * t0y);
+    ws.part_rz = alloc((size_t)B * psn_rz_count(plan, cfg));
     ws.part_a = alloc((size_t)B * gx * gy);
     ws.part_b = alloc((size_t)B * gx * gy);
     std::vector<PsnSampleState> st(B);
@@ -179,6 +198,40 @@ int hostemu_vcycle(int n, int nu, const double* rin, double* zout) {
     psn_vcycle_smem(ctx, hp.plan, 0, sb, su, su + l0.size);
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) zout[i * n + j] = su[(i + 1) * l0.pitch + j + 1];
+    return 0;
+}
+
+// one streamed V-cycle z = M^{-1} r (levels 0..ls-1 by tile or strip kernels, the rest by the
+// shared-memory coarse kernel), single sample; for unit comparison with hostemu_vcycle
+int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int band, const double* rin, double* zout, double* rz) {
+    HostPlan hp(n, nu);
+    const PsnPlan& plan = hp.plan;
+    if (ls < 1 || ls >= plan.nlev) return -1;
+    PsnStreamCfg cfg;
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = mode;
+    for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
+    std::vector<std::vector<double>> keep;
+    auto alloc = [&](size_t cnt) { keep.emplace_back(cnt, std::nan("")); return keep.back().data(); };
+    double* bl[PSN_MAX_LEVELS]; double* ua[PSN_MAX_LEVELS]; double* ub[PSN_MAX_LEVELS];
+    for (int l = 0; l <= ls; ++l) {
+        size_t m = (size_t)plan.lv[l].n * plan.lv[l].n;
+        bl[l] = alloc(m); ua[l] = alloc(m); ub[l] = alloc(m);
+    }
+    memcpy(bl[0], rin, sizeof(double) * n * n);
+    std::vector<double> part(psn_rz_count(plan, cfg), std::nan(""));
+    HostBackend bk;
+    for (int l = 0; l < ls; ++l) {
+        PsnLegArgs g{l, bl[l], nullptr, ua[l], bl[l + 1], nullptr, nullptr, nullptr};
+        bk.leg_pre(plan, cfg, g, 1);
+    }
+    bk.coarse_vcycle(plan, ls, bl[ls], ub[ls], nullptr, 1);
+    for (int l = ls - 1; l >= 0; --l) {
+        PsnLegArgs g{l, bl[l], ua[l], ub[l], nullptr, ub[l + 1], l == 0 ? part.data() : nullptr, nullptr};
+        bk.leg_post(plan, cfg, g, 1);
+    }
+    memcpy(zout, ub[0], sizeof(double) * n * n);
+    double s = 0; for (double v : part) s += v;
+    *rz = s;
     return 0;
 }
 }

@@ -46,8 +46,10 @@ def test_odd_and_boundary_sizes_vs_oracle(gpu_lib, n):
         assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= TOL
 
 
-def test_streamed_path_matches_resident(gpu_lib):
-    """Force the streamed kernels on a grid the resident kernel also handles; both must agree."""
+@pytest.mark.parametrize("mode", [0, 1])
+def test_streamed_path_matches_resident(gpu_lib, mode):
+    """Force the streamed kernels (mode 0: shared-memory tiles, mode 1: warp strips) on a grid the
+    resident kernel also handles; both must agree."""
     n, B = 64, 5
     rs = np.random.RandomState(5)
     theta = rs.uniform(0.5, 2.0, size=(B, n, n))
@@ -58,14 +60,36 @@ def test_streamed_path_matches_resident(gpu_lib):
     try:
         gpu_lib.set_option("smem_max_n", -1)
         gpu_lib.set_option("tile", 32)
+        gpu_lib.set_option("vcycle_mode", mode)
         u_str, info = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
     finally:
         gpu_lib.set_option("smem_max_n", 0)
         gpu_lib.set_option("tile", 64)
+        gpu_lib.set_option("vcycle_mode", 1)
     assert (info.status <= 1).all()
     for b in range(B):
         assert O.rel_l2(u_str[b], u_res[b]) <= 1e-11
         assert O.rel_l2(u_res[b], O.solve_poisson(np.outer(sy[b], sx[b]), theta[b], n)) <= TOL
+
+
+@pytest.mark.parametrize("n,B", [(160, 40), (320, 3), (200, 7)])
+def test_tile_and_strip_vcycles_agree(gpu_lib, n, B):
+    """The two implementations of the streamed V-cycle legs run the same algorithm; small and large
+    batches exercise different band splits of the strip kernels."""
+    rs = np.random.RandomState(n)
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    k = rs.uniform(0.5, 12.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    try:
+        gpu_lib.set_option("vcycle_mode", 0)
+        u0, i0 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    finally:
+        gpu_lib.set_option("vcycle_mode", 1)
+    u1, i1 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    assert (i0.status <= 1).all() and (i1.status <= 1).all()
+    assert O.rel_l2(u1, u0) <= 1e-12
+    assert O.rel_l2(u1[0], O.solve_poisson(np.outer(sy[0], sx[0]), theta[0], n)) <= TOL
 
 
 def test_generate_dataset_matches_reference_fixture(gpu_lib):

@@ -55,13 +55,13 @@ def run_smem(he, n, theta, f=None, sx=None, sy=None, rtol=1e-12, maxit=100, nu=2
     return u, it, rr, st, outs
 
 
-def run_stream(he, n, theta, f, TH, TW, ls, rtol=1e-12, maxit=100, nu=2, mn=None, step=1):
+def run_stream(he, n, theta, f, TH, TW, ls, rtol=1e-12, maxit=100, nu=2, mn=None, step=1, mode=0, band=64):
     B = f.shape[0]
     u = np.full((B, n, n), np.nan)
     it, rr, st = np.zeros(B, np.int32), np.zeros(B), np.zeros(B, np.int32)
     rc = he.hostemu_solve_stream(ctypes.c_int(n), ctypes.c_longlong(B), P(theta), P(f), None, None, None, None,
                                  ctypes.c_int(mn or n), ctypes.c_int(step), ctypes.c_double(rtol), ctypes.c_int(maxit), ctypes.c_int(nu),
-                                 ctypes.c_int(TH), ctypes.c_int(TW), ctypes.c_int(ls), P(u), PI(it), P(rr), PI(st))
+                                 ctypes.c_int(TH), ctypes.c_int(TW), ctypes.c_int(ls), ctypes.c_int(mode), ctypes.c_int(band), P(u), PI(it), P(rr), PI(st))
     assert rc > 0
     return u, it, rr, st
 
@@ -119,6 +119,35 @@ def test_streamed_bodies_match_oracle(he, n, TH, TW, ls):
     assert (st <= 1).all() and it.max() <= 12
     for b in range(3):
         assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= 1e-10
+
+
+@pytest.mark.parametrize("n,ls,band,nu", [(96, 1, 96, 2), (100, 1, 34, 2), (131, 1, 64, 2), (160, 2, 48, 2), (160, 1, 64, 1),
+                                           (160, 2, 32, 3), (45, 1, 16, 2), (200, 2, 200, 2)])
+def test_warp_strip_bodies_match_oracle(he, n, ls, band, nu):
+    """Register-resident warp-strip V-cycle legs (mode 1), emulated with 32-lane vectors."""
+    f, theta = batch_inputs(n, 1)
+    u, it, rr, st = run_stream(he, n, theta, f, 64, 64, ls, mode=1, band=band, nu=nu)
+    u0, it0, _, _ = run_stream(he, n, theta, f, 64, 64, ls, mode=0, nu=nu)
+    assert (st <= 1).all() and (it == it0).all()
+    assert O.rel_l2(u, u0) <= 1e-13                      # same algorithm as the tile kernels
+    for b in range(3):
+        assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= 1e-10
+
+
+def test_warp_strip_vcycle_equals_resident_vcycle(he):
+    """One V-cycle through the streamed strip kernels == the shared-memory V-cycle, node by node."""
+    for n, nu, ls, band in ((96, 2, 1, 96), (160, 1, 1, 64), (131, 3, 1, 40), (257, 2, 2, 86), (45, 2, 1, 16)):
+        r = np.random.RandomState(n).randn(n, n)
+        zr = np.zeros((n, n))
+        he.hostemu_vcycle(ctypes.c_int(n), ctypes.c_int(nu), P(r), P(zr))
+        for mode in (0, 1):
+            z = np.full((n, n), np.nan)
+            rz = np.zeros(1)
+            rc = he.hostemu_stream_vcycle(ctypes.c_int(n), ctypes.c_int(nu), ctypes.c_int(64), ctypes.c_int(64), ctypes.c_int(ls),
+                                          ctypes.c_int(mode), ctypes.c_int(band), P(r), P(z), P(rz))
+            assert rc == 0
+            assert np.abs(z - zr).max() <= 1e-12 * np.abs(zr).max()
+            assert abs(rz[0] - (r * zr).sum()) <= 1e-12 * abs(rz[0])
 
 
 def test_streamed_tiling_is_exact(he):
