@@ -195,8 +195,10 @@ class ClockSampler:
 # compulsory HBM bytes per grid node and participating sample of each streamed kernel (DESIGN.md
 # section "Kernels and their rooflines"); `survey` = the same work in SURVEY.md 8(d)'s unfused model
 KERNEL_BYTES = {
-    "tile_pre_l0": {"own": 18.0, "survey": 66.0},      # read r; write u_pre, coarse rhs (1/4)
-    "tile_post_l0": {"own": 26.0, "survey": 66.0},     # read u_pre, r, coarse corr (1/4); write z
+    "strip_pre_l0": {"own": 18.0, "survey": 66.0},     # read r; write u_pre, coarse rhs (1/4)
+    "strip_post_l0": {"own": 26.0, "survey": 66.0},    # read u_pre, r, coarse corr (1/4); write z
+    "tile_pre_l0": {"own": 18.0, "survey": 66.0},      # (vcycle_mode 0: shared-memory tile variant)
+    "tile_post_l0": {"own": 26.0, "survey": 66.0},
     "dir_apply_dot": {"own": 32.0, "survey": 40.0},    # read z, p; write p, q
     "update_norm": {"own": 48.0, "survey": 48.0},      # read p, q, x, r; write x, r
 }

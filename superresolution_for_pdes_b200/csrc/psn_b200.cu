@@ -552,6 +552,7 @@ int solve_internal(const Problem& P) {
     if (!resident) {
         if (P.sub > 0) return psn_fail(PSN_ERR_UNSUPPORTED, "fused sub-domain epilogue needs the resident path (n=%d too large)", P.n);
         scfg.ls = stream_ls(plan);
+        if (scfg.ls >= 1 && !psn_strip_ok(plan, scfg.ls)) scfg.mode = 0;   // odd level sizes: shared-memory tile kernels
         if (scfg.ls < 1) return psn_fail(PSN_ERR_UNSUPPORTED, "no shared-memory coarse level for n=%d", P.n);
     }
 

@@ -30,6 +30,12 @@ struct PsnLegArgs {
     const PsnSampleState* state;
 };
 
+// the warp-strip kernels use 128-bit pair accesses: every streamed level must have an even size
+static inline bool psn_strip_ok(const PsnPlan& plan, int ls) {
+    for (int l = 0; l < ls; ++l)
+        if (plan.lv[l].n & 1) return false;
+    return true;
+}
 static inline int psn_strip_count(int n, int use) { return (n + use - 1) / use; }
 static inline int psn_band_count(int n, int band) { return (n + band - 1) / band; }
 // number of <r,z> partials per sample produced by the level-0 up-leg

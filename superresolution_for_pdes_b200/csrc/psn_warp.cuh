@@ -55,6 +55,20 @@ PSN_FN void w_st2(double* row, wi col, wb m0, wb m1, bool vec, wd a, wd b) {
         if (m1) row[col + 1] = b;
     }
 }
+// raw neighbour-lane values (edge lanes receive their own value; callers only use these where the
+// edge lane's result is halo / out-of-domain data)
+PSN_FN wd w_up_raw(wd v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+PSN_FN wd w_down_raw(wd v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+// predicated 128-bit pair access: both elements valid or none (even n, even column)
+PSN_FN void w_ldp(const double* row, wi col, wb m, wd& a, wd& b) {
+    double2 v = make_double2(0.0, 0.0);
+    if (m) v = *reinterpret_cast<const double2*>(row + col);
+    a = v.x;
+    b = v.y;
+}
+PSN_FN void w_stp(double* row, wi col, wb m, wd a, wd b) {
+    if (m) *reinterpret_cast<double2*>(row + col) = make_double2(a, b);
+}
 PSN_FN wd w_ld1(const double* row, wi idx, wb m) { return m ? row[idx] : 0.0; }
 PSN_FN void w_st1(double* row, wi idx, wb m, wd v) {
     if (m) row[idx] = v;
@@ -105,22 +119,39 @@ inline void w_st2(double* row, const wi& col, const wb& m0, const wb& m1, bool, 
         if (m1.v[l_]) row[col.v[l_] + 1] = b.v[l_];
     }
 }
+inline wd w_up_raw(const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 0 ? v.v[0] : v.v[l_ - 1]; return r; }
+inline wd w_down_raw(const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 31 ? v.v[31] : v.v[l_ + 1]; return r; }
+inline void w_ldp(const double* row, const wi& col, const wb& m, wd& a, wd& b) {
+    PSN_W_FOR {
+        a.v[l_] = m.v[l_] ? row[col.v[l_]] : 0.0;
+        b.v[l_] = m.v[l_] ? row[col.v[l_] + 1] : 0.0;
+    }
+}
+inline void w_stp(double* row, const wi& col, const wb& m, const wd& a, const wd& b) {
+    PSN_W_FOR if (m.v[l_]) { row[col.v[l_]] = a.v[l_]; row[col.v[l_] + 1] = b.v[l_]; }
+}
 inline wd w_ld1(const double* row, const wi& idx, const wb& m) { wd r; PSN_W_FOR r.v[l_] = m.v[l_] ? row[idx.v[l_]] : 0.0; return r; }
 inline void w_st1(double* row, const wi& idx, const wb& m, const wd& v) { PSN_W_FOR if (m.v[l_]) row[idx.v[l_]] = v.v[l_]; }
 
 #endif
 
 // ----------------------------------------------------------------------------- strip kernels
-// One warp owns a strip of 64 columns (lane l: columns c0+2l, c0+2l+1, c0 even) and marches down
-// the rows of its band.  A rolling window of W = 2*NU+2 rows lives in registers; at time t the
-// pipeline applies
+// One warp owns a strip of PSN_STRIP_COLS = 128 columns (lane l: the 4 columns c0+4l .. c0+4l+3,
+// c0 even) and marches down the rows of its band.  A rolling window of W = 2*NU+2 rows lives in
+// registers; at time t the pipeline applies
 //     pre : R(t) [zero guess], B(t-1), R(t-2), ..., B(t-2NU+1), residual(t-2NU) -> restriction
 //     post: prolong(t), B(t-1), R(t-2), ..., R(t-2NU)                           -> <b,u> partial
 // so every sweep of a V-cycle leg is done in ONE pass over the rows, with vertical neighbours in
-// registers and horizontal neighbours through one shuffle per stage.  Row parity works out so that
-// at time t every stage touches the SAME register slot P = t & 1 of its row.  The validity window
-// shrinks by one column per stage from the strip edges (halo), exactly as in the tiled version, so
-// the result is identical to the untiled algorithm.
+// registers and horizontal neighbours in registers or through ONE shuffle per stage.  Row parity
+// works out so that at time t every stage touches the SAME register offsets {P, P+2}, P = t & 1.
+// The validity window shrinks by one column per stage from the strip edges (halo) exactly as in
+// the tiled version, so the result is identical to the untiled algorithm.  Out-of-domain columns
+// are kept at zero by a zero reciprocal diagonal (no per-stage masks); rows are handled by a
+// checked chunk at the band ends and a branch-free chunk in the steady state.
+// Requires even n (every 2-column pair is entirely inside or outside the domain, 128-bit accesses).
+#define PSN_STRIP_COLS 128
+#define PSN_STRIP_CPL 4
+
 struct PsnStripArgs {
     int level;
     int band;            // output rows per task (even)
@@ -134,18 +165,122 @@ struct PsnStripArgs {
     const PsnSampleState* state;
 };
 
-PSN_HDFN int psn_strip_use_pre(int nu) { return 64 - (4 * nu + 2); }
-// (the up-leg needs two more halo columns on the left: the prolongation onto an even column
-// reads the coarse value of the lane to the left)
-PSN_HDFN int psn_strip_use_post(int nu) { return 64 - (4 * nu + 2); }
+// useful (output) columns per strip: pre needs 2NU halo columns left and 2NU+1 right; post needs
+// 2NU+2 left (the prolongation onto an even column reads the coarse value one lane to the left)
+// and 2NU right
+PSN_HDFN int psn_strip_use_pre(int nu) { return PSN_STRIP_COLS - (4 * nu + 2); }
+PSN_HDFN int psn_strip_use_post(int nu) { return PSN_STRIP_COLS - (4 * nu + 2); }
+
+// horizontal neighbour sum of offset e (static) in a row held as v[0..3]
+#define PSN_LR(v, e, upv, dnv) \
+    (((e) == 0 ? (upv) : (v)[((e) + PSN_STRIP_CPL - 1) % PSN_STRIP_CPL]) + ((e) == PSN_STRIP_CPL - 1 ? (dnv) : (v)[((e) + 1) % PSN_STRIP_CPL]))
+
+template <int NU>
+struct PsnStripGeom {
+    static constexpr int NS = 2 * NU;
+    static constexpr int W = NS + 2;
+    static constexpr int PF = W / 2;
+};
+
+template <int NU, bool FAST>
+PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc,
+                                int i0, int i1, int I0, int I1,
+                                wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], wd (&pf)[NU + 1][4], wd (&acc)[2],
+                                const wd (&rdA)[4], const wd (&rdB)[4], const wd (&dA)[4], const wd (&dB)[4], const wd (&mk)[4],
+                                const double* bg, double* ug, double* cg, const wi& col0, const wb (&mp)[2], const wb (&so)[2],
+                                const wi& cj, const wb (&sc)[2]) {
+    constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
+    const wd zero = w_bcast(0.0);
+#pragma unroll
+    for (int tt = 0; tt < W; ++tt) {
+        const int tc = t + tt;
+        if (!FAST && tc > tend) break;
+        const int P = tt & 1;
+        const int k0 = tt;
+        // ---- new row: rhs from the prefetch ring; first red half sweep from the zero guess
+#pragma unroll
+        for (int e = 0; e < 4; ++e) bb[k0][e] = pf[tt % PF][e];
+        if (FAST || tc + PF <= tload) {
+            const double* rowp = bg + (long long)(tc + PF) * n;
+            w_ldp(rowp, col0, mp[0], pf[tt % PF][0], pf[tt % PF][1]);
+            w_ldp(rowp, col0 + 2, mp[1], pf[tt % PF][2], pf[tt % PF][3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pf[tt % PF][e] = zero;
+        }
+        if (FAST || tc <= last) {
+            const bool lastrow = !FAST && tc == last;
+            val[k0][P] = bb[k0][P] * (lastrow ? rdB[P] : rdA[P]);
+            val[k0][P + 2] = bb[k0][P + 2] * (lastrow ? rdB[P + 2] : rdA[P + 2]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) bb[k0][e] = zero;
+            val[k0][P] = val[k0][P + 2] = zero;
+        }
+        val[k0][1 - P] = val[k0][3 - P] = zero;
+        // ---- smoothing stages 1 .. NS-1 on rows tc-1 .. tc-NS+1
+#pragma unroll
+        for (int s = 1; s < NS; ++s) {
+            const int r = tc - s;
+            if (FAST || (r >= ts && r <= last)) {
+                const int ks = (tt - s + 2 * W) % W, ku = (tt - s - 1 + 2 * W) % W, kd = (tt - s + 1 + 2 * W) % W;
+                const bool lastrow = !FAST && r == last;
+                const wd upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
+                const wd dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
+                const wd sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
+                const wd sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
+                val[ks][P] = (bb[ks][P] + sa) * (lastrow ? rdB[P] : rdA[P]);
+                val[ks][P + 2] = (bb[ks][P + 2] + sb) * (lastrow ? rdB[P + 2] : rdA[P + 2]);
+            }
+        }
+        // ---- residual on the red nodes of row tc-NS, accumulate the restriction
+        {
+            const int r = tc - NS;
+            wd ra = zero, rb = zero;
+            if (FAST || (r >= ts && r <= last)) {
+                const int ks = (tt - NS + 2 * W) % W, ku = (tt - NS - 1 + 2 * W) % W, kd = (tt - NS + 1 + 2 * W) % W;
+                const bool lastrow = !FAST && r == last;
+                const wd upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
+                const wd dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
+                const wd sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
+                const wd sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
+                ra = mk[P] * (bb[ks][P] - ((lastrow ? dB[P] : dA[P]) * val[ks][P] - sa));
+                rb = mk[P + 2] * (bb[ks][P + 2] - ((lastrow ? dB[P + 2] : dA[P + 2]) * val[ks][P + 2] - sb));
+            }
+            if (P == 0) {  // even row 2I: corners of coarse rows I-1 (bottom) and I (top); lane holds J = cj, cj+1
+                const wd c0v = 0.25 * (ra + rb);
+                const wd c1v = 0.25 * (rb + w_down_raw(ra));
+                const int I = (r >> 1) - 1;
+                if (FAST || (r >= 2 && I >= I0 && I < I1)) {
+                    double* crow = cg + (long long)I * nc;
+                    w_st1(crow, cj, sc[0], acc[0] + c0v);
+                    w_st1(crow, cj + 1, sc[1], acc[1] + c1v);
+                }
+                acc[0] = c0v;
+                acc[1] = c1v;
+            } else {       // odd row 2I+1: centres
+                acc[0] = acc[0] + ra;
+                acc[1] = acc[1] + rb;
+            }
+        }
+        // ---- row tc-NS+1 is final after its last black half sweep
+        {
+            const int ro = tc - (NS - 1);
+            if (FAST || (ro >= i0 && ro < i1)) {
+                const int ko = (tt - (NS - 1) + 2 * W) % W;
+                double* rowp = ug + (long long)ro * n;
+                w_stp(rowp, col0, so[0], val[ko][0], val[ko][1]);
+                w_stp(rowp, col0 + 2, so[1], val[ko][2], val[ko][3]);
+            }
+        }
+    }
+}
 
 template <int NU>
 PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
-    constexpr int NS = 2 * NU;   // smoothing stages; the residual is stage NS
-    constexpr int W = NS + 2;    // window rows
-    constexpr int PF = W / 2;    // rows prefetched ahead
-    const int USE = 64 - (2 * NS + 2);
+    constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
+    const int USE = PSN_STRIP_COLS - (2 * NS + 2);
     const PsnLevel& lv = plan.lv[a.level];
     const PsnLevel& lc = plan.lv[a.level + 1];
     const int n = lv.n, nc = lc.n, last = n - 1;
@@ -154,20 +289,26 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
     const int i0 = band * a.band, i1 = psn_imin(i0 + a.band, n);
     const int I0 = i0 >> 1, I1 = psn_imin(i1 >> 1, nc);
     const int J0 = a0 >> 1, J1 = psn_imin(a1 >> 1, nc);
-    const bool vec = (n & 1) == 0;
 
-    const wi col0 = w_lane(w) * 2 + c0;
-    const wi col1 = col0 + 1;
-    const wb m[2] = {(col0 >= 0) && (col0 < n), (col1 >= 0) && (col1 < n)};
-    const wb lastc[2] = {col0 == last, col1 == last};
-    const wd rdA[2] = {w_sel(lastc[0], w_bcast(lv.rd1), w_bcast(lv.rd0)), w_sel(lastc[1], w_bcast(lv.rd1), w_bcast(lv.rd0))};
-    const wd rdB[2] = {w_sel(lastc[0], w_bcast(lv.rd2), w_bcast(lv.rd1)), w_sel(lastc[1], w_bcast(lv.rd2), w_bcast(lv.rd1))};
-    const wd dA[2] = {w_sel(lastc[0], w_bcast(4.0 + lv.gam), w_bcast(4.0)), w_sel(lastc[1], w_bcast(4.0 + lv.gam), w_bcast(4.0))};
-    const wd dB[2] = {w_sel(lastc[0], w_bcast(4.0 + 2.0 * lv.gam), w_bcast(4.0 + lv.gam)), w_sel(lastc[1], w_bcast(4.0 + 2.0 * lv.gam), w_bcast(4.0 + lv.gam))};
-    // store masks
-    const wb so[2] = {m[0] && (col0 >= a0) && (col0 < a1), m[1] && (col1 >= a0) && (col1 < a1)};
-    const wi cj = w_lane(w) + (c0 >> 1);   // coarse column held by this lane (c0 even, may be negative)
-    const wb sc = (cj >= J0) && (cj < J1);
+    const wi col0 = w_lane(w) * 4 + c0;
+    const wi col2 = col0 + 2;
+    const wb mp[2] = {(col0 >= 0) && (col0 < n), (col2 >= 0) && (col2 < n)};
+    const wb so[2] = {mp[0] && (col0 >= a0) && (col0 < a1), mp[1] && (col2 >= a0) && (col2 < a1)};
+    const wi cj = w_lane(w) * 2 + (c0 >> 1);
+    const wb sc[2] = {(cj >= J0) && (cj < J1), (cj + 1 >= J0) && (cj + 1 < J1)};
+    const wd zero = w_bcast(0.0);
+    wd rdA[4], rdB[4], dA[4], dB[4], mk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const wi ce = col0 + e;
+        const wb in = (e < 2) ? mp[0] : mp[1];
+        const wb lc_ = ce == last;
+        rdA[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd1), w_bcast(lv.rd0)), zero);
+        rdB[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd2), w_bcast(lv.rd1)), zero);
+        dA[e] = w_sel(lc_, w_bcast(4.0 + lv.gam), w_bcast(4.0));
+        dB[e] = w_sel(lc_, w_bcast(4.0 + 2.0 * lv.gam), w_bcast(4.0 + lv.gam));
+        mk[e] = w_sel(in, w_bcast(1.0), zero);
+    }
 
     const int ts = psn_imax(i0 - NS, 0);
     const int tload = psn_imin(i1 + NS, last);
@@ -175,78 +316,117 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
     const double* bg = a.b + b * (long long)n * n;
     double* ug = a.uout + b * (long long)n * n;
     double* cg = a.bc + b * (long long)nc * nc;
-    const wd zero = w_bcast(0.0);
 
-    wd val[W][2], bb[W][2], pf[PF][2];
+    wd val[W][4], bb[W][4], pf[PF][4], acc[2];
 #pragma unroll
-    for (int k = 0; k < W; ++k) val[k][0] = val[k][1] = bb[k][0] = bb[k][1] = zero;
+    for (int k = 0; k < W; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) val[k][e] = bb[k][e] = zero;
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
-        pf[k][0] = pf[k][1] = zero;
-        if (ts + k <= tload) w_ld2(bg + (long long)(ts + k) * n, col0, m[0], m[1], vec, pf[k][0], pf[k][1]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pf[k][e] = zero;
+        if (ts + k <= tload) {
+            w_ldp(bg + (long long)(ts + k) * n, col0, mp[0], pf[k][0], pf[k][1]);
+            w_ldp(bg + (long long)(ts + k) * n, col2, mp[1], pf[k][2], pf[k][3]);
+        }
     }
-    wd acc = zero;
+    acc[0] = acc[1] = zero;
 
     for (int t = ts; t <= tend; t += W) {
+        // steady state: every row touched by this chunk is an interior row of the band
+        const bool fast = (t - NS - 1 >= ts) && (t - NS >= 2) && (t + W - 1 + PF <= tload) && (t + W - 1 < last) &&
+                          (t - (NS - 1) >= i0) && (t + W - 1 - (NS - 1) < i1) &&
+                          (((t - NS) >> 1) - 1 >= I0) && (((t + W - 1 - NS) >> 1) - 1 < I1);
+        if (fast)
+            psn_strip_pre_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, pf, acc, rdA, rdB, dA, dB, mk,
+                                          bg, ug, cg, col0, mp, so, cj, sc);
+        else
+            psn_strip_pre_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, pf, acc, rdA, rdB, dA, dB, mk,
+                                           bg, ug, cg, col0, mp, so, cj, sc);
+    }
+}
+
+template <int NU, bool FAST>
+PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc, int i0, int i1,
+                                 wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], wd (&pfb)[NU + 1][4], wd (&pfu)[NU + 1][4],
+                                 wd (&eprev)[2], wd& dot, const wd (&rdA)[4], const wd (&rdB)[4], const wd (&mk)[4],
+                                 const double* bg, const double* uig, const double* eg, double* ug, const wi& col0,
+                                 const wb (&mp)[2], const wb (&so)[2], const wd (&sok)[4], const wi& cj, const wb (&mc)[2], bool want_dot) {
+    constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
+    const wd zero = w_bcast(0.0);
 #pragma unroll
-        for (int tt = 0; tt < W; ++tt) {
-            const int tc = t + tt;
-            if (tc > tend) break;
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int P = tt & 1;  // ts and W are even: parity of row tc
-            const int k0 = tt;     // window slot of row tc
-            // ---- new row: right-hand side from the prefetch ring, first red half sweep (zero guess)
-            bb[k0][0] = pf[tt % PF][0];
-            bb[k0][1] = pf[tt % PF][1];
-            pf[tt % PF][0] = pf[tt % PF][1] = zero;
-            if (tc + PF <= tload) w_ld2(bg + (long long)(tc + PF) * n, col0, m[0], m[1], vec, pf[tt % PF][0], pf[tt % PF][1]);
-            if (tc <= last) {
-                val[k0][P] = w_sel(m[P], bb[k0][P] * (tc == last ? rdB[P] : rdA[P]), zero);
-            } else {
-                bb[k0][0] = bb[k0][1] = zero;
-                val[k0][P] = zero;
-            }
-            val[k0][1 - P] = zero;
-            // ---- smoothing stages 1 .. NS-1 on rows tc-1 .. tc-NS+1
+    for (int tt = 0; tt < W; ++tt) {
+        const int tc = t + tt;
+        if (!FAST && tc > tend) break;
+        const int P = tt & 1;
+        const int k0 = tt;
+        // ---- new row: rhs and pre-smoothed iterate, then the prolongated correction on the red nodes
 #pragma unroll
-            for (int s = 1; s < NS; ++s) {
-                const int r = tc - s;
-                if (r >= ts && r <= last) {
-                    const int ks = (tt - s + 2 * W) % W, ku = (tt - s - 1 + 2 * W) % W, kd = (tt - s + 1 + 2 * W) % W;
-                    const wd other = val[ks][1 - P];
-                    const wd lr = (P == 0) ? (w_up(w, other) + other) : (other + w_down(w, other));
-                    const wd s4 = (val[ku][P] + val[kd][P]) + lr;
-                    val[ks][P] = w_sel(m[P], (bb[ks][P] + s4) * (r == last ? rdB[P] : rdA[P]), zero);
+        for (int e = 0; e < 4; ++e) {
+            bb[k0][e] = pfb[tt % PF][e];
+            val[k0][e] = pfu[tt % PF][e];
+        }
+        if (FAST || tc + PF <= tload) {
+            const double* rb_ = bg + (long long)(tc + PF) * n;
+            const double* ru_ = uig + (long long)(tc + PF) * n;
+            w_ldp(rb_, col0, mp[0], pfb[tt % PF][0], pfb[tt % PF][1]);
+            w_ldp(rb_, col0 + 2, mp[1], pfb[tt % PF][2], pfb[tt % PF][3]);
+            w_ldp(ru_, col0, mp[0], pfu[tt % PF][0], pfu[tt % PF][1]);
+            w_ldp(ru_, col0 + 2, mp[1], pfu[tt % PF][2], pfu[tt % PF][3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pfb[tt % PF][e] = pfu[tt % PF][e] = zero;
+        }
+        if (FAST || tc <= last) {
+            if (P == 0) {  // even row 2I, red = even columns: mean of coarse (I-1,J-1), (I-1,J), (I,J-1), (I,J)
+                const int I = tc >> 1;
+                wd enew[2] = {zero, zero};
+                if (FAST || I < nc) {
+                    const double* erow = eg + (long long)I * nc;
+                    enew[0] = w_ld1(erow, cj, mc[0]);
+                    enew[1] = w_ld1(erow, cj + 1, mc[1]);
                 }
+                const wd s0 = eprev[0] + enew[0], s1 = eprev[1] + enew[1];   // column sums J = cj, cj+1
+                const wd sl = w_up_raw(s1);                                     // column J = cj-1
+                val[k0][0] = mk[0] * (val[k0][0] + 0.25 * (sl + s0));
+                val[k0][2] = mk[2] * (val[k0][2] + 0.25 * (s0 + s1));
+                eprev[0] = enew[0];
+                eprev[1] = enew[1];
+            } else {       // odd row 2I+1, red = odd columns: coincide with coarse (I, J)
+                val[k0][1] = mk[1] * (val[k0][1] + eprev[0]);
+                val[k0][3] = mk[3] * (val[k0][3] + eprev[1]);
             }
-            // ---- residual on the red node of row tc-NS, accumulate the restriction
-            {
-                const int r = tc - NS;
-                wd rho = zero;
-                if (r >= ts && r <= last) {
-                    const int ks = (tt - NS + 2 * W) % W, ku = (tt - NS - 1 + 2 * W) % W, kd = (tt - NS + 1 + 2 * W) % W;
-                    const wd other = val[ks][1 - P];
-                    const wd lr = (P == 0) ? (w_up(w, other) + other) : (other + w_down(w, other));
-                    const wd s4 = (val[ku][P] + val[kd][P]) + lr;
-                    rho = w_sel(m[P], bb[ks][P] - ((r == last ? dB[P] : dA[P]) * val[ks][P] - s4), zero);
-                }
-                if (P == 0) {  // even row 2I: corner weights of coarse rows I-1 (bottom) and I (top)
-                    const wd cs = 0.25 * (rho + w_down(w, rho));
-                    const int I = (r >> 1) - 1;
-                    if (r >= 2 && I >= I0 && I < I1) w_st1(cg + (long long)I * nc, cj, sc, acc + cs);
-                    acc = cs;
-                } else {       // odd row 2I+1: centre of coarse row I
-                    acc = acc + rho;
-                }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) val[k0][e] = bb[k0][e] = zero;
+        }
+        // ---- smoothing stages 1 .. NS (black first) on rows tc-1 .. tc-NS
+#pragma unroll
+        for (int s = 1; s <= NS; ++s) {
+            const int r = tc - s;
+            if (FAST || (r >= ts && r <= last)) {
+                const int ks = (tt - s + 2 * W) % W, ku = (tt - s - 1 + 2 * W) % W, kd = (tt - s + 1 + 2 * W) % W;
+                const bool lastrow = !FAST && r == last;
+                const wd upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
+                const wd dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
+                const wd sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
+                const wd sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
+                val[ks][P] = (bb[ks][P] + sa) * (lastrow ? rdB[P] : rdA[P]);
+                val[ks][P + 2] = (bb[ks][P + 2] + sb) * (lastrow ? rdB[P + 2] : rdA[P + 2]);
             }
-            // ---- row tc-NS+1 is final after its last black half sweep
-            {
-                const int ro = tc - (NS - 1);
-                if (ro >= i0 && ro < i1) {
-                    const int ko = (tt - (NS - 1) + 2 * W) % W;
-                    w_st2(ug + (long long)ro * n, col0, so[0], so[1], vec, val[ko][0], val[ko][1]);
-                }
+        }
+        // ---- row tc-NS is final
+        {
+            const int ro = tc - NS;
+            if (FAST || (ro >= i0 && ro < i1)) {
+                const int ko = (tt - NS + 2 * W) % W;
+                double* rowp = ug + (long long)ro * n;
+                w_stp(rowp, col0, so[0], val[ko][0], val[ko][1]);
+                w_stp(rowp, col0 + 2, so[1], val[ko][2], val[ko][3]);
+                if (want_dot)
+                    dot = dot + ((sok[0] * val[ko][0]) * bb[ko][0] + (sok[1] * val[ko][1]) * bb[ko][1]) +
+                          ((sok[2] * val[ko][2]) * bb[ko][2] + (sok[3] * val[ko][3]) * bb[ko][3]);
             }
         }
     }
@@ -255,27 +435,33 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
 template <int NU>
 PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
-    constexpr int NS = 2 * NU;
-    constexpr int W = NS + 2;
-    constexpr int PF = W / 2;
-    const int USE = 64 - (2 * NS + 2);
+    constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
+    const int USE = PSN_STRIP_COLS - (2 * NS + 2);
     const PsnLevel& lv = plan.lv[a.level];
     const PsnLevel& lc = plan.lv[a.level + 1];
     const int n = lv.n, nc = lc.n, last = n - 1;
     const int a0 = strip * USE, a1 = psn_imin(a0 + USE, n);
     const int c0 = a0 - NS - 2;   // even; NS + 2 halo columns on the left, NS on the right
     const int i0 = band * a.band, i1 = psn_imin(i0 + a.band, n);
-    const bool vec = (n & 1) == 0;
 
-    const wi col0 = w_lane(w) * 2 + c0;
-    const wi col1 = col0 + 1;
-    const wb m[2] = {(col0 >= 0) && (col0 < n), (col1 >= 0) && (col1 < n)};
-    const wb lastc[2] = {col0 == last, col1 == last};
-    const wd rdA[2] = {w_sel(lastc[0], w_bcast(lv.rd1), w_bcast(lv.rd0)), w_sel(lastc[1], w_bcast(lv.rd1), w_bcast(lv.rd0))};
-    const wd rdB[2] = {w_sel(lastc[0], w_bcast(lv.rd2), w_bcast(lv.rd1)), w_sel(lastc[1], w_bcast(lv.rd2), w_bcast(lv.rd1))};
-    const wb so[2] = {m[0] && (col0 >= a0) && (col0 < a1), m[1] && (col1 >= a0) && (col1 < a1)};
-    const wi cj = w_lane(w) + (c0 >> 1);
-    const wb mc = (cj >= 0) && (cj < nc);
+    const wi col0 = w_lane(w) * 4 + c0;
+    const wi col2 = col0 + 2;
+    const wb mp[2] = {(col0 >= 0) && (col0 < n), (col2 >= 0) && (col2 < n)};
+    const wb so[2] = {mp[0] && (col0 >= a0) && (col0 < a1), mp[1] && (col2 >= a0) && (col2 < a1)};
+    const wi cj = w_lane(w) * 2 + (c0 >> 1);
+    const wb mc[2] = {(cj >= 0) && (cj < nc), (cj + 1 >= 0) && (cj + 1 < nc)};
+    const wd zero = w_bcast(0.0);
+    wd rdA[4], rdB[4], mk[4], sok[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const wi ce = col0 + e;
+        const wb in = (e < 2) ? mp[0] : mp[1];
+        const wb lc_ = ce == last;
+        rdA[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd1), w_bcast(lv.rd0)), zero);
+        rdB[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd2), w_bcast(lv.rd1)), zero);
+        mk[e] = w_sel(in, w_bcast(1.0), zero);
+        sok[e] = w_sel((e < 2) ? so[0] : so[1], w_bcast(1.0), zero);
+    }
 
     const int ts = psn_imax(i0 - NS, 0);
     const int tload = psn_imin(i1 - 1 + NS, last);
@@ -284,81 +470,46 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const double* uig = a.uin + b * (long long)n * n;
     const double* eg = a.ec + b * (long long)nc * nc;
     double* ug = a.uout + b * (long long)n * n;
-    const wd zero = w_bcast(0.0);
 
-    wd val[W][2], bb[W][2], pfb[PF][2], pfu[PF][2];
+    wd val[W][4], bb[W][4], pfb[PF][4], pfu[PF][4], eprev[2];
 #pragma unroll
-    for (int k = 0; k < W; ++k) val[k][0] = val[k][1] = bb[k][0] = bb[k][1] = zero;
+    for (int k = 0; k < W; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) val[k][e] = bb[k][e] = zero;
 #pragma unroll
     for (int k = 0; k < PF; ++k) {
-        pfb[k][0] = pfb[k][1] = pfu[k][0] = pfu[k][1] = zero;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pfb[k][e] = pfu[k][e] = zero;
         if (ts + k <= tload) {
-            w_ld2(bg + (long long)(ts + k) * n, col0, m[0], m[1], vec, pfb[k][0], pfb[k][1]);
-            w_ld2(uig + (long long)(ts + k) * n, col0, m[0], m[1], vec, pfu[k][0], pfu[k][1]);
+            w_ldp(bg + (long long)(ts + k) * n, col0, mp[0], pfb[k][0], pfb[k][1]);
+            w_ldp(bg + (long long)(ts + k) * n, col2, mp[1], pfb[k][2], pfb[k][3]);
+            w_ldp(uig + (long long)(ts + k) * n, col0, mp[0], pfu[k][0], pfu[k][1]);
+            w_ldp(uig + (long long)(ts + k) * n, col2, mp[1], pfu[k][2], pfu[k][3]);
         }
     }
     // coarse correction rows: eprev = row ts/2 - 1 (zero above the grid)
-    wd eprev = zero, dot = zero;
+    eprev[0] = eprev[1] = zero;
+    wd dot = zero;
     {
         const int Ip = (ts >> 1) - 1;
-        if (Ip >= 0 && Ip < nc) eprev = w_ld1(eg + (long long)Ip * nc, cj, mc);
-    }
-
-    for (int t = ts; t <= tend; t += W) {
-#pragma unroll
-        for (int tt = 0; tt < W; ++tt) {
-            const int tc = t + tt;
-            if (tc > tend) break;
-            const int P = tt & 1;
-            const int k0 = tt;
-            // ---- new row: rhs and pre-smoothed iterate, then add the prolongated correction on the red node
-            bb[k0][0] = pfb[tt % PF][0];
-            bb[k0][1] = pfb[tt % PF][1];
-            val[k0][0] = pfu[tt % PF][0];
-            val[k0][1] = pfu[tt % PF][1];
-            pfb[tt % PF][0] = pfb[tt % PF][1] = pfu[tt % PF][0] = pfu[tt % PF][1] = zero;
-            if (tc + PF <= tload) {
-                w_ld2(bg + (long long)(tc + PF) * n, col0, m[0], m[1], vec, pfb[tt % PF][0], pfb[tt % PF][1]);
-                w_ld2(uig + (long long)(tc + PF) * n, col0, m[0], m[1], vec, pfu[tt % PF][0], pfu[tt % PF][1]);
-            }
-            if (tc <= last) {
-                if (P == 0) {  // even row 2I, red = even column: mean of coarse (I-1,J-1), (I-1,J), (I,J-1), (I,J)
-                    const int I = tc >> 1;
-                    wd enew = zero;
-                    if (I < nc) enew = w_ld1(eg + (long long)I * nc, cj, mc);
-                    const wd corr = 0.25 * ((w_up(w, eprev) + eprev) + (w_up(w, enew) + enew));
-                    val[k0][0] = w_sel(m[0], val[k0][0] + corr, zero);
-                    eprev = enew;
-                } else {       // odd row 2I+1, red = odd column: coincides with coarse (I, J)
-                    val[k0][1] = w_sel(m[1], val[k0][1] + eprev, zero);
-                }
-            } else {
-                val[k0][0] = val[k0][1] = bb[k0][0] = bb[k0][1] = zero;
-            }
-            // ---- smoothing stages 1 .. NS (black first) on rows tc-1 .. tc-NS
-#pragma unroll
-            for (int s = 1; s <= NS; ++s) {
-                const int r = tc - s;
-                if (r >= ts && r <= last) {
-                    const int ks = (tt - s + 2 * W) % W, ku = (tt - s - 1 + 2 * W) % W, kd = (tt - s + 1 + 2 * W) % W;
-                    const wd other = val[ks][1 - P];
-                    const wd lr = (P == 0) ? (w_up(w, other) + other) : (other + w_down(w, other));
-                    const wd s4 = (val[ku][P] + val[kd][P]) + lr;
-                    val[ks][P] = w_sel(m[P], (bb[ks][P] + s4) * (r == last ? rdB[P] : rdA[P]), zero);
-                }
-            }
-            // ---- row tc-NS is final
-            {
-                const int ro = tc - NS;
-                if (ro >= i0 && ro < i1) {
-                    const int ko = (tt - NS + 2 * W) % W;
-                    w_st2(ug + (long long)ro * n, col0, so[0], so[1], vec, val[ko][0], val[ko][1]);
-                    if (a.part) dot = dot + (w_sel(so[0], val[ko][0] * bb[ko][0], zero) + w_sel(so[1], val[ko][1] * bb[ko][1], zero));
-                }
-            }
+        if (Ip >= 0 && Ip < nc) {
+            eprev[0] = w_ld1(eg + (long long)Ip * nc, cj, mc[0]);
+            eprev[1] = w_ld1(eg + (long long)Ip * nc, cj + 1, mc[1]);
         }
     }
-    if (a.part) {
+    const bool want_dot = a.part != nullptr;
+
+    for (int t = ts; t <= tend; t += W) {
+        const bool fast = (t - NS - 1 >= ts) && (t + W - 1 + PF <= tload) && (t + W - 1 < last) && (((t + W - 1) >> 1) < nc) &&
+                          (t - NS >= i0) && (t + W - 1 - NS < i1);
+        if (fast)
+            psn_strip_post_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, pfb, pfu, eprev, dot, rdA, rdB, mk,
+                                           bg, uig, eg, ug, col0, mp, so, sok, cj, mc, want_dot);
+        else
+            psn_strip_post_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, pfb, pfu, eprev, dot, rdA, rdB, mk,
+                                            bg, uig, eg, ug, col0, mp, so, sok, cj, mc, want_dot);
+    }
+    if (want_dot) {
         const double s = w_sum(dot);
         if (w_lane0(w)) a.part[b * (long long)(a.nstrips * a.nbands) + (long long)band * a.nstrips + strip] = s;
     }

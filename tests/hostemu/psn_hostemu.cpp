@@ -152,7 +152,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
     PsnStreamCfg cfg;
-    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = mode;
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode == 1 && psn_strip_ok(plan, ls)) ? 1 : 0;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
     memset(&ws, 0, sizeof(ws));
@@ -208,7 +208,7 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
     PsnStreamCfg cfg;
-    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = mode;
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode == 1 && psn_strip_ok(plan, ls)) ? 1 : 0;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     std::vector<std::vector<double>> keep;
     auto alloc = [&](size_t cnt) { keep.emplace_back(cnt, std::nan("")); return keep.back().data(); };
