@@ -14,7 +14,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsn_b200.so")
+# PSN_B200_LIB lets kernel experiments load an alternative build of the SAME CUDA library (never a CPU path)
+LIB_PATH = os.environ.get("PSN_B200_LIB") or os.path.join(_HERE, "libpsn_b200.so")
 
 PSN_OK = 0
 STATUS_CONVERGED, STATUS_FP64_FLOOR, STATUS_MAXITER, STATUS_BREAKDOWN = 0, 1, 2, 3

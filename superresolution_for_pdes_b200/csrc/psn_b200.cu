@@ -74,18 +74,35 @@ __global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_post_kernel(const _
 
 // register-resident warp-strip V-cycle legs: one warp per (sample, band, strip) task, no shared memory
 #define PSN_STRIP_WARPS 4
-template <int NU, bool POST>
-__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32) psn_strip_kernel(const __grid_constant__ PsnPlan plan,
-                                                                        const __grid_constant__ PsnStripArgs a, long long ntasks) {
-    const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + (threadIdx.x >> 5);
+#ifndef PSN_STRIP_MINB
+#define PSN_STRIP_MINB 2
+#endif
+#ifndef PSN_STRIP_MINB_TMA
+#define PSN_STRIP_MINB_TMA 3
+#endif
+template <int NU, bool POST, bool TMA>
+__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, TMA ? PSN_STRIP_MINB_TMA : PSN_STRIP_MINB)
+psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ PsnStripArgs a, long long ntasks) {
+    extern __shared__ __align__(128) unsigned char strip_smem[];
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
     if (task >= ntasks) return;
     const int per = a.nstrips * a.nbands;
     const long long b = task / per;
     const int rem = (int)(task - b * per);
     const int band = rem / a.nstrips, strip = rem - band * a.nstrips;
     const PsnWarp w{(int)(threadIdx.x & 31)};
-    if (POST) psn_strip_post_body<NU>(w, plan, a, b, band, strip);
-    else psn_strip_pre_body<NU>(w, plan, a, b, band, strip);
+    constexpr int NARR = POST ? 2 : 1;
+    if constexpr (TMA) {
+        PsnTmaFeeder<NU, NARR> fd;
+        fd.attach(strip_smem + (size_t)warp * PsnTmaFeeder<NU, NARR>::smem_bytes());
+        if constexpr (POST) psn_strip_post_body<NU>(w, plan, a, b, band, strip, fd);
+        else psn_strip_pre_body<NU>(w, plan, a, b, band, strip, fd);
+    } else {
+        PsnRegFeeder<NU, NARR> fd;
+        if constexpr (POST) psn_strip_post_body<NU>(w, plan, a, b, band, strip, fd);
+        else psn_strip_pre_body<NU>(w, plan, a, b, band, strip, fd);
+    }
 }
 
 __global__ void __launch_bounds__(PSN_COARSE_THREADS) psn_coarse_vcycle_kernel(const __grid_constant__ PsnPlan plan, int l0,
@@ -182,7 +199,7 @@ struct Context {
     int tile = 64;
     long long ws_bytes = 16ll << 30;
     int smem_max_n = 0;
-    int vcycle_mode = 1;   // 0: shared-memory tile kernels, 1: register-resident warp strips
+    int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     bool attrs_set = false;
     bool profiling = false;
     std::vector<ProfRec> prof;
@@ -332,18 +349,36 @@ struct CudaBackend {
         psn_state_init_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B);
         chk();
     }
-    template <bool POST>
-    void strip_launch(const PsnPlan& plan, const PsnStripArgs& a, long long B) {
+    template <int NU, bool POST, bool TMA>
+    void strip_launch_nu(const PsnPlan& plan, const PsnStripArgs& a, long long B) {
         const long long ntasks = B * a.nstrips * a.nbands;
         const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
-        if (plan.nu == 1) psn_strip_kernel<1, POST><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(plan, a, ntasks);
-        else if (plan.nu == 2) psn_strip_kernel<2, POST><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(plan, a, ntasks);
-        else psn_strip_kernel<3, POST><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(plan, a, ntasks);
+        const size_t smem = TMA ? (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<NU, POST ? 2 : 1>::smem_bytes() : 0;
+        if (TMA) {
+            static bool attr_done = false;   // one flag per template instantiation
+            if (!attr_done) {
+                cudaFuncSetAttribute(psn_strip_kernel<NU, POST, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_done = true;
+            }
+        }
+        psn_strip_kernel<NU, POST, TMA><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(plan, a, ntasks);
+    }
+    template <bool POST>
+    void strip_launch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool tma) {
+        if (tma) {
+            if (plan.nu == 1) strip_launch_nu<1, POST, true>(plan, a, B);
+            else if (plan.nu == 2) strip_launch_nu<2, POST, true>(plan, a, B);
+            else strip_launch_nu<3, POST, true>(plan, a, B);
+        } else {
+            if (plan.nu == 1) strip_launch_nu<1, POST, false>(plan, a, B);
+            else if (plan.nu == 2) strip_launch_nu<2, POST, false>(plan, a, B);
+            else strip_launch_nu<3, POST, false>(plan, a, B);
+        }
     }
     void leg_pre(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
-        if (cfg.mode == 1) {
+        if (cfg.mode >= 1) {
             ProfScope p(g.level == 0 ? "strip_pre_l0" : "strip_pre_coarse", s);
-            strip_launch<false>(plan, psn_leg_to_strip(plan, cfg, g, false), B);
+            strip_launch<false>(plan, psn_leg_to_strip(plan, cfg, g, false), B, cfg.mode == 2);
         } else {
             const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
             ProfScope p(t.level == 0 ? "tile_pre_l0" : "tile_pre_coarse", s);
@@ -353,9 +388,9 @@ struct CudaBackend {
         chk();
     }
     void leg_post(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
-        if (cfg.mode == 1) {
+        if (cfg.mode >= 1) {
             ProfScope p(g.level == 0 ? "strip_post_l0" : "strip_post_coarse", s);
-            strip_launch<true>(plan, psn_leg_to_strip(plan, cfg, g, true), B);
+            strip_launch<true>(plan, psn_leg_to_strip(plan, cfg, g, true), B, cfg.mode == 2);
         } else {
             const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
             ProfScope p(t.level == 0 ? "tile_post_l0" : "tile_post_coarse", s);
@@ -457,7 +492,7 @@ int copy_back(cudaStream_t s, T* host_dst, MemKind kind, long long offset, size_
 
 // upper bound of the <r,z> partial count over every band choice (smallest band = 16 rows)
 int psn_rz_max(const PsnPlan& plan, const PsnStreamCfg& cfg) {
-    if (cfg.mode != 1) return psn_rz_count(plan, cfg);
+    if (cfg.mode < 1) return psn_rz_count(plan, cfg);
     return psn_strip_count(plan.n, psn_strip_use_post(plan.nu)) * psn_band_count(plan.n, 16);
 }
 
@@ -847,7 +882,7 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "smem_max_n")) {
         g.smem_max_n = (int)value;
     } else if (!strcmp(name, "vcycle_mode")) {
-        if (value != 0 && value != 1) return psn_fail(PSN_ERR_INVALID, "vcycle_mode must be 0 (tiles) or 1 (warp strips)");
+        if (value < 0 || value > 2) return psn_fail(PSN_ERR_INVALID, "vcycle_mode must be 0 (tiles), 1 (warp strips, register prefetch) or 2 (warp strips, TMA ring)");
         g.vcycle_mode = (int)value;
     } else {
         return psn_fail(PSN_ERR_INVALID, "unknown option '%s'", name);

@@ -14,7 +14,8 @@
 struct PsnStreamCfg {
     int ls;       // first level handled by the shared-memory coarse kernel (levels 0..ls-1 are streamed)
     int TH, TW;   // interior tile of the shared-memory tile kernels (mode 0)
-    int mode;     // V-cycle legs: 0 = shared-memory tiles, 1 = register-resident warp strips
+    int mode;     // V-cycle legs: 0 = shared-memory tiles, 1 = warp strips fed by register prefetch,
+                  //               2 = warp strips fed by TMA bulk copies through a shared-memory ring
     int band[PSN_MAX_LEVELS];  // mode 1: output rows per warp task on each streamed level (even)
 };
 
@@ -41,7 +42,7 @@ static inline int psn_band_count(int n, int band) { return (n + band - 1) / band
 // number of <r,z> partials per sample produced by the level-0 up-leg
 static inline int psn_rz_count(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     const int n = plan.n;
-    if (cfg.mode == 1) return psn_strip_count(n, psn_strip_use_post(plan.nu)) * psn_band_count(n, cfg.band[0]);
+    if (cfg.mode >= 1) return psn_strip_count(n, psn_strip_use_post(plan.nu)) * psn_band_count(n, cfg.band[0]);
     return ((n + cfg.TW - 1) / cfg.TW) * ((n + cfg.TH - 1) / cfg.TH);
 }
 

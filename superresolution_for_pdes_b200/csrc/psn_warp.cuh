@@ -7,6 +7,7 @@
 // lane-dependent goes through w_sel().
 #pragma once
 #include "psn_core.cuh"
+#include <string.h>
 
 #if defined(__CUDACC__)
 
@@ -69,9 +70,59 @@ PSN_FN void w_ldp(const double* row, wi col, wb m, wd& a, wd& b) {
 PSN_FN void w_stp(double* row, wi col, wb m, wd a, wd b) {
     if (m) *reinterpret_cast<double2*>(row + col) = make_double2(a, b);
 }
+// hint: pull the lane's 32 bytes of a future row into L2 (no register cost)
+PSN_FN void w_prefetch_l2(const double* row, wi col, wb m) {
+    if (m) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + col));
+}
 PSN_FN wd w_ld1(const double* row, wi idx, wb m) { return m ? row[idx] : 0.0; }
 PSN_FN void w_st1(double* row, wi idx, wb m, wd v) {
     if (m) row[idx] = v;
+}
+
+// ---- per-warp asynchronous row staging: bulk global->shared copies (TMA engine, 1-D) completing on
+// an mbarrier.  One lane issues, every lane waits.  A protocol error traps instead of hanging.
+PSN_FN unsigned psn_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+PSN_FN void w_bar_init(const PsnWarp& w, unsigned long long* bars, int count) {
+    if (w.lane == 0) {
+        for (int i = 0; i < count; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(psn_smem_addr(bars + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // generic-proxy initialisation of the ring (zero fill) must be visible to the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+}
+PSN_FN void w_sync(const PsnWarp&) { __syncwarp(); }
+// lane 0: arm the barrier with the byte count of the copies that follow
+PSN_FN void w_bar_expect(const PsnWarp& w, unsigned long long* bar, unsigned bytes) {
+    if (w.lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(psn_smem_addr(bar)), "r"(bytes) : "memory");
+}
+PSN_FN void w_bulk_g2s(const PsnWarp& w, void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    if (w.lane == 0)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(psn_smem_addr(dst)), "l"(src), "r"(bytes), "r"(psn_smem_addr(bar)) : "memory");
+}
+PSN_FN void w_bar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = psn_smem_addr(bar);
+    unsigned done = 0;
+    long long t0 = 0;
+    for (unsigned spin = 0;; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        if (spin == 64) t0 = clock64();
+        if (spin > 64 && (spin & 1023) == 0 && clock64() - t0 > 4000000000ll) __trap();   // ~2 s: protocol error
+    }
+}
+// the lane's 4 doubles (columns 4*lane .. 4*lane+3) of a staged row
+PSN_FN void w_lds4(const PsnWarp& w, const double* row, wd (&out)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(row + 4 * w.lane);
+    const double2 b = *reinterpret_cast<const double2*>(row + 4 * w.lane + 2);
+    out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+}
+PSN_FN void w_zero_smem(const PsnWarp& w, double* p, int count) {
+    for (int i = w.lane; i < count; i += 32) p[i] = 0.0;
 }
 
 #else  // ------------------------------------------------------------------ host emulation
@@ -130,8 +181,19 @@ inline void w_ldp(const double* row, const wi& col, const wb& m, wd& a, wd& b) {
 inline void w_stp(double* row, const wi& col, const wb& m, const wd& a, const wd& b) {
     PSN_W_FOR if (m.v[l_]) { row[col.v[l_]] = a.v[l_]; row[col.v[l_] + 1] = b.v[l_]; }
 }
+inline void w_prefetch_l2(const double*, const wi&, const wb&) {}
 inline wd w_ld1(const double* row, const wi& idx, const wb& m) { wd r; PSN_W_FOR r.v[l_] = m.v[l_] ? row[idx.v[l_]] : 0.0; return r; }
 inline void w_st1(double* row, const wi& idx, const wb& m, const wd& v) { PSN_W_FOR if (m.v[l_]) row[idx.v[l_]] = v.v[l_]; }
+
+inline void w_bar_init(const PsnWarp&, unsigned long long*, int) {}
+inline void w_sync(const PsnWarp&) {}
+inline void w_bar_expect(const PsnWarp&, unsigned long long*, unsigned) {}
+inline void w_bulk_g2s(const PsnWarp&, void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+inline void w_bar_wait(unsigned long long*, unsigned) {}
+inline void w_lds4(const PsnWarp&, const double* row, wd (&out)[4]) {
+    PSN_W_FOR for (int e = 0; e < 4; ++e) out[e].v[l_] = row[4 * l_ + e];
+}
+inline void w_zero_smem(const PsnWarp&, double* p, int count) { for (int i = 0; i < count; ++i) p[i] = 0.0; }
 
 #endif
 
@@ -151,6 +213,7 @@ inline void w_st1(double* row, const wi& idx, const wb& m, const wd& v) { PSN_W_
 // Requires even n (every 2-column pair is entirely inside or outside the domain, 128-bit accesses).
 #define PSN_STRIP_COLS 128
 #define PSN_STRIP_CPL 4
+#define PSN_STRIP_L2_AHEAD 16   // rows ahead of the march that are pulled into L2
 
 struct PsnStripArgs {
     int level;
@@ -182,31 +245,150 @@ struct PsnStripGeom {
     static constexpr int PF = W / 2;
 };
 
-template <int NU, bool FAST>
+
+// ---- row feeders: how the next rows of the streamed arrays reach the warp
+// PsnRegFeeder: prefetch ring of PF rows in registers + L2 prefetch hints further ahead.
+// PsnTmaFeeder: ring of W rows per array in shared memory, filled W-1 rows ahead by 1-D bulk
+//               copies (TMA engine) that complete on one mbarrier per ring slot; no registers are
+//               tied up by loads in flight, so the prefetch distance is 2-3x deeper.
+template <int NU, int NARR>
+struct PsnRegFeeder {
+    static constexpr int W = 2 * NU + 2, PF = W / 2;
+    wd pf[NARR][PF][4];
+    const double* base[NARR];
+    int n, tload;
+    wi col0;
+    wb mp[2];
+    PSN_FN void prime(const PsnWarp&, int ts) {
+#pragma unroll
+        for (int a = 0; a < NARR; ++a)
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pf[a][k][e] = w_bcast(0.0);
+                if (ts + k <= tload) {
+                    w_ldp(base[a] + (long long)(ts + k) * n, col0, mp[0], pf[a][k][0], pf[a][k][1]);
+                    w_ldp(base[a] + (long long)(ts + k) * n, col0 + 2, mp[1], pf[a][k][2], pf[a][k][3]);
+                }
+            }
+    }
+    // values of row tc (zero beyond tload); starts the load of row tc + PF
+    template <bool FAST>
+    PSN_FN void fetch(const PsnWarp&, int tt, int tc, int /*par*/, wd (&out)[NARR][4]) {
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) out[a][e] = pf[a][tt % PF][e];
+            if (FAST || tc + PF <= tload) {
+                const double* rowp = base[a] + (long long)(tc + PF) * n;
+                w_ldp(rowp, col0, mp[0], pf[a][tt % PF][0], pf[a][tt % PF][1]);
+                w_ldp(rowp, col0 + 2, mp[1], pf[a][tt % PF][2], pf[a][tt % PF][3]);
+                if (tc + PSN_STRIP_L2_AHEAD <= tload) w_prefetch_l2(base[a] + (long long)(tc + PSN_STRIP_L2_AHEAD) * n, col0, mp[0]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pf[a][tt % PF][e] = w_bcast(0.0);
+            }
+        }
+    }
+};
+
+template <int NU, int NARR>
+struct PsnTmaFeeder {
+    static constexpr int W = 2 * NU + 2, D = W - 1;
+    double* ring[NARR];          // [W][PSN_STRIP_COLS] each, shared memory of this warp
+    unsigned long long* bar;     // [W]
+    const double* base[NARR];
+    int n, tload, ts;
+    int cA, cB, c0;              // in-domain column range [cA, cB) of the strip, strip origin
+#if defined(__CUDACC__)
+    __host__ __device__
+#endif
+    static constexpr int smem_bytes() { return NARR * W * PSN_STRIP_COLS * 8 + W * 8 + (128 - (W * 8) % 128) % 128; }
+    PSN_FN void attach(unsigned char* mem) {
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) ring[a] = reinterpret_cast<double*>(mem + (size_t)a * W * PSN_STRIP_COLS * 8);
+        bar = reinterpret_cast<unsigned long long*>(mem + (size_t)NARR * W * PSN_STRIP_COLS * 8);
+    }
+    PSN_FN void issue(const PsnWarp& w, int row, int slot) {
+        const unsigned bytes = (unsigned)(cB - cA) * 8u;
+        w_bar_expect(w, bar + slot, bytes * NARR);
+#pragma unroll
+        for (int a = 0; a < NARR; ++a)
+            w_bulk_g2s(w, ring[a] + slot * PSN_STRIP_COLS + (cA - c0), base[a] + (long long)row * n + cA, bytes, bar + slot);
+    }
+    PSN_FN void prime(const PsnWarp& w, int ts_) {
+        ts = ts_;
+#pragma unroll
+        for (int a = 0; a < NARR; ++a) w_zero_smem(w, ring[a], W * PSN_STRIP_COLS);   // out-of-domain columns stay zero
+        w_bar_init(w, bar, W);
+        for (int k = 0; k < D; ++k)
+            if (ts + k <= tload) issue(w, ts + k, k);
+    }
+    template <bool FAST>
+    PSN_FN void fetch(const PsnWarp& w, int tt, int tc, int par, wd (&out)[NARR][4]) {
+        // every lane has finished reading the slot of row tc-1 (previous time step): refill it with row tc+D
+        w_sync(w);
+        if (FAST || tc + D <= tload) issue(w, tc + D, (tt + W - 1) % W);
+        if (FAST || tc <= tload) {
+            w_bar_wait(bar + tt, (unsigned)par);
+#pragma unroll
+            for (int a = 0; a < NARR; ++a) w_lds4(w, ring[a] + tt * PSN_STRIP_COLS, out[a]);
+        } else {
+#pragma unroll
+            for (int a = 0; a < NARR; ++a)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) out[a][e] = w_bcast(0.0);
+        }
+    }
+};
+
+template <int NU, int NARR>
+PSN_FN void psn_feeder_geom(PsnRegFeeder<NU, NARR>& fd, const wi& col0, const wb (&mp)[2], int, int) {
+    fd.col0 = col0;
+    fd.mp[0] = mp[0];
+    fd.mp[1] = mp[1];
+}
+template <int NU, int NARR>
+PSN_FN void psn_feeder_geom(PsnTmaFeeder<NU, NARR>& fd, const wi&, const wb (&)[2], int c0, int n) {
+    fd.c0 = c0;
+    fd.cA = psn_imax(c0, 0);
+    fd.cB = psn_imin(c0 + PSN_STRIP_COLS, n);
+}
+
+template <int NU, bool FAST, class Feeder>
 PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc,
                                 int i0, int i1, int I0, int I1,
-                                wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], wd (&pf)[NU + 1][4], wd (&acc)[2],
-                                const wd (&rdA)[4], const wd (&rdB)[4], const wd (&dA)[4], const wd (&dB)[4], const wd (&mk)[4],
+                                wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], Feeder& fd, int par, wd (&acc)[2],
+                                const wd (&rdA)[4], const wd (&dA)[4], const wd (&mk)[4], const PsnLevel& lv,
                                 const double* bg, double* ug, double* cg, const wi& col0, const wb (&mp)[2], const wb (&so)[2],
                                 const wi& cj, const wb (&sc)[2]) {
     constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
     const wd zero = w_bcast(0.0);
+    // last-row diagonals are only needed by the checked chunk at the bottom of the grid: build them on demand
+    wd rdB[4], dB[4];
+    if (!FAST) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const wb lc_ = (col0 + e) == last;
+            rdB[e] = mk[e] * w_sel(lc_, w_bcast(lv.rd2), w_bcast(lv.rd1));
+            dB[e] = w_sel(lc_, w_bcast(4.0 + 2.0 * lv.gam), w_bcast(4.0 + lv.gam));
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rdB[e] = dB[e] = zero;
+    }
 #pragma unroll
     for (int tt = 0; tt < W; ++tt) {
         const int tc = t + tt;
         if (!FAST && tc > tend) break;
         const int P = tt & 1;
         const int k0 = tt;
-        // ---- new row: rhs from the prefetch ring; first red half sweep from the zero guess
+        // ---- new row: rhs from the feeder; first red half sweep from the zero guess
+        {
+            wd rowv[1][4];
+            fd.template fetch<FAST>(w, tt, tc, par, rowv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) bb[k0][e] = pf[tt % PF][e];
-        if (FAST || tc + PF <= tload) {
-            const double* rowp = bg + (long long)(tc + PF) * n;
-            w_ldp(rowp, col0, mp[0], pf[tt % PF][0], pf[tt % PF][1]);
-            w_ldp(rowp, col0 + 2, mp[1], pf[tt % PF][2], pf[tt % PF][3]);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pf[tt % PF][e] = zero;
+            for (int e = 0; e < 4; ++e) bb[k0][e] = rowv[0][e];
         }
         if (FAST || tc <= last) {
             const bool lastrow = !FAST && tc == last;
@@ -276,8 +458,8 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
     }
 }
 
-template <int NU>
-PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip) {
+template <int NU, class Feeder>
+PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip, Feeder& fd) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
     constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
     const int USE = PSN_STRIP_COLS - (2 * NS + 2);
@@ -297,16 +479,14 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
     const wi cj = w_lane(w) * 2 + (c0 >> 1);
     const wb sc[2] = {(cj >= J0) && (cj < J1), (cj + 1 >= J0) && (cj + 1 < J1)};
     const wd zero = w_bcast(0.0);
-    wd rdA[4], rdB[4], dA[4], dB[4], mk[4];
+    wd rdA[4], dA[4], mk[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const wi ce = col0 + e;
         const wb in = (e < 2) ? mp[0] : mp[1];
         const wb lc_ = ce == last;
         rdA[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd1), w_bcast(lv.rd0)), zero);
-        rdB[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd2), w_bcast(lv.rd1)), zero);
         dA[e] = w_sel(lc_, w_bcast(4.0 + lv.gam), w_bcast(4.0));
-        dB[e] = w_sel(lc_, w_bcast(4.0 + 2.0 * lv.gam), w_bcast(4.0 + lv.gam));
         mk[e] = w_sel(in, w_bcast(1.0), zero);
     }
 
@@ -317,44 +497,49 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
     double* ug = a.uout + b * (long long)n * n;
     double* cg = a.bc + b * (long long)nc * nc;
 
-    wd val[W][4], bb[W][4], pf[PF][4], acc[2];
+    wd val[W][4], bb[W][4], acc[2];
 #pragma unroll
     for (int k = 0; k < W; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) val[k][e] = bb[k][e] = zero;
-#pragma unroll
-    for (int k = 0; k < PF; ++k) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) pf[k][e] = zero;
-        if (ts + k <= tload) {
-            w_ldp(bg + (long long)(ts + k) * n, col0, mp[0], pf[k][0], pf[k][1]);
-            w_ldp(bg + (long long)(ts + k) * n, col2, mp[1], pf[k][2], pf[k][3]);
-        }
-    }
+    fd.base[0] = bg;
+    fd.n = n;
+    fd.tload = tload;
+    psn_feeder_geom(fd, col0, mp, c0, n);
+    fd.prime(w, ts);
     acc[0] = acc[1] = zero;
 
     for (int t = ts; t <= tend; t += W) {
         // steady state: every row touched by this chunk is an interior row of the band
-        const bool fast = (t - NS - 1 >= ts) && (t - NS >= 2) && (t + W - 1 + PF <= tload) && (t + W - 1 < last) &&
+        const bool fast = (t - NS - 1 >= ts) && (t - NS >= 2) && (t + W - 1 + (W - 1) <= tload) && (t + W - 1 < last) &&
                           (t - (NS - 1) >= i0) && (t + W - 1 - (NS - 1) < i1) &&
                           (((t - NS) >> 1) - 1 >= I0) && (((t + W - 1 - NS) >> 1) - 1 < I1);
+        const int par = ((t - ts) / W) & 1;
         if (fast)
-            psn_strip_pre_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, pf, acc, rdA, rdB, dA, dB, mk,
+            psn_strip_pre_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
                                           bg, ug, cg, col0, mp, so, cj, sc);
         else
-            psn_strip_pre_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, pf, acc, rdA, rdB, dA, dB, mk,
+            psn_strip_pre_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
                                            bg, ug, cg, col0, mp, so, cj, sc);
     }
 }
 
-template <int NU, bool FAST>
+template <int NU, bool FAST, class Feeder>
 PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc, int i0, int i1,
-                                 wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], wd (&pfb)[NU + 1][4], wd (&pfu)[NU + 1][4],
-                                 wd (&eprev)[2], wd& dot, const wd (&rdA)[4], const wd (&rdB)[4], const wd (&mk)[4],
+                                 wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], Feeder& fd, int par,
+                                 wd (&eprev)[2], wd (&enext)[2], wd& dot, const wd (&rdA)[4], const wd (&mk)[4], const PsnLevel& lv,
                                  const double* bg, const double* uig, const double* eg, double* ug, const wi& col0,
-                                 const wb (&mp)[2], const wb (&so)[2], const wd (&sok)[4], const wi& cj, const wb (&mc)[2], bool want_dot) {
+                                 const wb (&mp)[2], const wb (&so)[2], const wi& cj, const wb (&mc)[2], bool want_dot) {
     constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
     const wd zero = w_bcast(0.0);
+    wd rdB[4];
+    if (!FAST) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rdB[e] = mk[e] * w_sel((col0 + e) == last, w_bcast(lv.rd2), w_bcast(lv.rd1));
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rdB[e] = zero;
+    }
 #pragma unroll
     for (int tt = 0; tt < W; ++tt) {
         const int tc = t + tt;
@@ -362,30 +547,26 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
         const int P = tt & 1;
         const int k0 = tt;
         // ---- new row: rhs and pre-smoothed iterate, then the prolongated correction on the red nodes
+        {
+            wd rowv[2][4];
+            fd.template fetch<FAST>(w, tt, tc, par, rowv);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            bb[k0][e] = pfb[tt % PF][e];
-            val[k0][e] = pfu[tt % PF][e];
-        }
-        if (FAST || tc + PF <= tload) {
-            const double* rb_ = bg + (long long)(tc + PF) * n;
-            const double* ru_ = uig + (long long)(tc + PF) * n;
-            w_ldp(rb_, col0, mp[0], pfb[tt % PF][0], pfb[tt % PF][1]);
-            w_ldp(rb_, col0 + 2, mp[1], pfb[tt % PF][2], pfb[tt % PF][3]);
-            w_ldp(ru_, col0, mp[0], pfu[tt % PF][0], pfu[tt % PF][1]);
-            w_ldp(ru_, col0 + 2, mp[1], pfu[tt % PF][2], pfu[tt % PF][3]);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pfb[tt % PF][e] = pfu[tt % PF][e] = zero;
+            for (int e = 0; e < 4; ++e) {
+                bb[k0][e] = rowv[0][e];
+                val[k0][e] = rowv[1][e];
+            }
         }
         if (FAST || tc <= last) {
             if (P == 0) {  // even row 2I, red = even columns: mean of coarse (I-1,J-1), (I-1,J), (I,J-1), (I,J)
                 const int I = tc >> 1;
-                wd enew[2] = {zero, zero};
-                if (FAST || I < nc) {
-                    const double* erow = eg + (long long)I * nc;
-                    enew[0] = w_ld1(erow, cj, mc[0]);
-                    enew[1] = w_ld1(erow, cj + 1, mc[1]);
+                // coarse row I was requested two fine rows ago (enext); request row I+1 now
+                const wd enew[2] = {enext[0], enext[1]};
+                enext[0] = enext[1] = zero;
+                if (FAST || I + 1 < nc) {
+                    const double* erow = eg + (long long)(I + 1) * nc;
+                    enext[0] = w_ld1(erow, cj, mc[0]);
+                    enext[1] = w_ld1(erow, cj + 1, mc[1]);
+                    if (I + 9 < nc) w_prefetch_l2(eg + (long long)(I + 9) * nc, cj, mc[0]);
                 }
                 const wd s0 = eprev[0] + enew[0], s1 = eprev[1] + enew[1];   // column sums J = cj, cj+1
                 const wd sl = w_up_raw(s1);                                     // column J = cj-1
@@ -425,15 +606,15 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
                 w_stp(rowp, col0, so[0], val[ko][0], val[ko][1]);
                 w_stp(rowp, col0 + 2, so[1], val[ko][2], val[ko][3]);
                 if (want_dot)
-                    dot = dot + ((sok[0] * val[ko][0]) * bb[ko][0] + (sok[1] * val[ko][1]) * bb[ko][1]) +
-                          ((sok[2] * val[ko][2]) * bb[ko][2] + (sok[3] * val[ko][3]) * bb[ko][3]);
+                    dot = dot + w_sel(so[0], val[ko][0] * bb[ko][0] + val[ko][1] * bb[ko][1], zero) +
+                          w_sel(so[1], val[ko][2] * bb[ko][2] + val[ko][3] * bb[ko][3], zero);
             }
         }
     }
 }
 
-template <int NU>
-PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip) {
+template <int NU, class Feeder>
+PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip, Feeder& fd) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
     constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
     const int USE = PSN_STRIP_COLS - (2 * NS + 2);
@@ -451,16 +632,14 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const wi cj = w_lane(w) * 2 + (c0 >> 1);
     const wb mc[2] = {(cj >= 0) && (cj < nc), (cj + 1 >= 0) && (cj + 1 < nc)};
     const wd zero = w_bcast(0.0);
-    wd rdA[4], rdB[4], mk[4], sok[4];
+    wd rdA[4], mk[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const wi ce = col0 + e;
         const wb in = (e < 2) ? mp[0] : mp[1];
         const wb lc_ = ce == last;
         rdA[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd1), w_bcast(lv.rd0)), zero);
-        rdB[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd2), w_bcast(lv.rd1)), zero);
         mk[e] = w_sel(in, w_bcast(1.0), zero);
-        sok[e] = w_sel((e < 2) ? so[0] : so[1], w_bcast(1.0), zero);
     }
 
     const int ts = psn_imax(i0 - NS, 0);
@@ -471,24 +650,19 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const double* eg = a.ec + b * (long long)nc * nc;
     double* ug = a.uout + b * (long long)n * n;
 
-    wd val[W][4], bb[W][4], pfb[PF][4], pfu[PF][4], eprev[2];
+    wd val[W][4], bb[W][4], eprev[2], enext[2];
 #pragma unroll
     for (int k = 0; k < W; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) val[k][e] = bb[k][e] = zero;
-#pragma unroll
-    for (int k = 0; k < PF; ++k) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) pfb[k][e] = pfu[k][e] = zero;
-        if (ts + k <= tload) {
-            w_ldp(bg + (long long)(ts + k) * n, col0, mp[0], pfb[k][0], pfb[k][1]);
-            w_ldp(bg + (long long)(ts + k) * n, col2, mp[1], pfb[k][2], pfb[k][3]);
-            w_ldp(uig + (long long)(ts + k) * n, col0, mp[0], pfu[k][0], pfu[k][1]);
-            w_ldp(uig + (long long)(ts + k) * n, col2, mp[1], pfu[k][2], pfu[k][3]);
-        }
-    }
-    // coarse correction rows: eprev = row ts/2 - 1 (zero above the grid)
-    eprev[0] = eprev[1] = zero;
+    fd.base[0] = bg;
+    fd.base[1] = uig;
+    fd.n = n;
+    fd.tload = tload;
+    psn_feeder_geom(fd, col0, mp, c0, n);
+    fd.prime(w, ts);
+    // coarse correction rows: eprev = row ts/2 - 1 (zero above the grid), enext = row ts/2
+    eprev[0] = eprev[1] = enext[0] = enext[1] = zero;
     wd dot = zero;
     {
         const int Ip = (ts >> 1) - 1;
@@ -496,18 +670,23 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
             eprev[0] = w_ld1(eg + (long long)Ip * nc, cj, mc[0]);
             eprev[1] = w_ld1(eg + (long long)Ip * nc, cj + 1, mc[1]);
         }
+        if (Ip + 1 < nc) {
+            enext[0] = w_ld1(eg + (long long)(Ip + 1) * nc, cj, mc[0]);
+            enext[1] = w_ld1(eg + (long long)(Ip + 1) * nc, cj + 1, mc[1]);
+        }
     }
     const bool want_dot = a.part != nullptr;
 
     for (int t = ts; t <= tend; t += W) {
-        const bool fast = (t - NS - 1 >= ts) && (t + W - 1 + PF <= tload) && (t + W - 1 < last) && (((t + W - 1) >> 1) < nc) &&
+        const bool fast = (t - NS - 1 >= ts) && (t + W - 1 + (W - 1) <= tload) && (t + W - 1 < last) && (((t + W - 1) >> 1) + 1 < nc) &&
                           (t - NS >= i0) && (t + W - 1 - NS < i1);
+        const int par = ((t - ts) / W) & 1;
         if (fast)
-            psn_strip_post_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, pfb, pfu, eprev, dot, rdA, rdB, mk,
-                                           bg, uig, eg, ug, col0, mp, so, sok, cj, mc, want_dot);
+            psn_strip_post_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
+                                           bg, uig, eg, ug, col0, mp, so, cj, mc, want_dot);
         else
-            psn_strip_post_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, pfb, pfu, eprev, dot, rdA, rdB, mk,
-                                            bg, uig, eg, ug, col0, mp, so, sok, cj, mc, want_dot);
+            psn_strip_post_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
+                                            bg, uig, eg, ug, col0, mp, so, cj, mc, want_dot);
     }
     if (want_dot) {
         const double s = w_sum(dot);

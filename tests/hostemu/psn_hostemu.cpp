@@ -35,22 +35,29 @@ struct HostBackend {
     }
     void state_init(const PsnCgArgs& a, long long B) { for (long long b = 0; b < B; ++b) psn_state_init(a, b); }
     template <int NU>
-    void strip_leg(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post) {
+    void strip_leg(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post, bool tma) {
         PsnWarp w;
+        std::vector<unsigned char> ring(PsnTmaFeeder<NU, 2>::smem_bytes() + 256);
         for (long long b = 0; b < B; ++b)
             for (int band = 0; band < a.nbands; ++band)
                 for (int strip = 0; strip < a.nstrips; ++strip) {
-                    if (post) psn_strip_post_body<NU>(w, plan, a, b, band, strip);
-                    else psn_strip_pre_body<NU>(w, plan, a, b, band, strip);
+                    std::fill(ring.begin(), ring.end(), (unsigned char)0xff);   // NaN-poison the staging ring
+                    if (post) {
+                        if (tma) { PsnTmaFeeder<NU, 2> fd; fd.attach(ring.data()); psn_strip_post_body<NU>(w, plan, a, b, band, strip, fd); }
+                        else { PsnRegFeeder<NU, 2> fd; psn_strip_post_body<NU>(w, plan, a, b, band, strip, fd); }
+                    } else {
+                        if (tma) { PsnTmaFeeder<NU, 1> fd; fd.attach(ring.data()); psn_strip_pre_body<NU>(w, plan, a, b, band, strip, fd); }
+                        else { PsnRegFeeder<NU, 1> fd; psn_strip_pre_body<NU>(w, plan, a, b, band, strip, fd); }
+                    }
                 }
     }
-    void strip_dispatch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post) {
-        if (plan.nu == 1) strip_leg<1>(plan, a, B, post);
-        else if (plan.nu == 2) strip_leg<2>(plan, a, B, post);
-        else strip_leg<3>(plan, a, B, post);
+    void strip_dispatch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post, bool tma) {
+        if (plan.nu == 1) strip_leg<1>(plan, a, B, post, tma);
+        else if (plan.nu == 2) strip_leg<2>(plan, a, B, post, tma);
+        else strip_leg<3>(plan, a, B, post, tma);
     }
     void leg_pre(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
-        if (cfg.mode == 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, false), B, false); return; }
+        if (cfg.mode >= 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, false), B, false, cfg.mode == 2); return; }
         const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
@@ -62,7 +69,7 @@ struct HostBackend {
                 }
     }
     void leg_post(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
-        if (cfg.mode == 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, true), B, true); return; }
+        if (cfg.mode >= 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, true), B, true, cfg.mode == 2); return; }
         const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
@@ -152,7 +159,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
     PsnStreamCfg cfg;
-    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode == 1 && psn_strip_ok(plan, ls)) ? 1 : 0;
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? mode : 0;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
     memset(&ws, 0, sizeof(ws));
@@ -208,7 +215,7 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
     PsnStreamCfg cfg;
-    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode == 1 && psn_strip_ok(plan, ls)) ? 1 : 0;
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? mode : 0;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     std::vector<std::vector<double>> keep;
     auto alloc = [&](size_t cnt) { keep.emplace_back(cnt, std::nan("")); return keep.back().data(); };

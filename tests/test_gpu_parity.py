@@ -46,7 +46,7 @@ def test_odd_and_boundary_sizes_vs_oracle(gpu_lib, n):
         assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= TOL
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_streamed_path_matches_resident(gpu_lib, mode):
     """Force the streamed kernels (mode 0: shared-memory tiles, mode 1: warp strips) on a grid the
     resident kernel also handles; both must agree."""
@@ -65,7 +65,7 @@ def test_streamed_path_matches_resident(gpu_lib, mode):
     finally:
         gpu_lib.set_option("smem_max_n", 0)
         gpu_lib.set_option("tile", 64)
-        gpu_lib.set_option("vcycle_mode", 1)
+        gpu_lib.set_option("vcycle_mode", 2)
     assert (info.status <= 1).all()
     for b in range(B):
         assert O.rel_l2(u_str[b], u_res[b]) <= 1e-11
@@ -84,11 +84,14 @@ def test_tile_and_strip_vcycles_agree(gpu_lib, n, B):
     try:
         gpu_lib.set_option("vcycle_mode", 0)
         u0, i0 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
-    finally:
         gpu_lib.set_option("vcycle_mode", 1)
+        u2, i2 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    finally:
+        gpu_lib.set_option("vcycle_mode", 2)
     u1, i1 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
-    assert (i0.status <= 1).all() and (i1.status <= 1).all()
+    assert (i0.status <= 1).all() and (i1.status <= 1).all() and (i2.status <= 1).all()
     assert O.rel_l2(u1, u0) <= 1e-12
+    assert np.array_equal(u1, u2)     # register-fed and TMA-fed strips do identical arithmetic
     assert O.rel_l2(u1[0], O.solve_poisson(np.outer(sy[0], sx[0]), theta[0], n)) <= TOL
 
 

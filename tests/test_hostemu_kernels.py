@@ -128,19 +128,21 @@ def test_warp_strip_bodies_match_oracle(he, n, ls, band, nu):
     f, theta = batch_inputs(n, 1)
     u, it, rr, st = run_stream(he, n, theta, f, 64, 64, ls, mode=1, band=band, nu=nu)
     u0, it0, _, _ = run_stream(he, n, theta, f, 64, 64, ls, mode=0, nu=nu)
+    u2, it2, _, _ = run_stream(he, n, theta, f, 64, 64, ls, mode=2, band=band, nu=nu)
     assert (st <= 1).all() and (it == it0).all()
     assert O.rel_l2(u, u0) <= 1e-13                      # same algorithm as the tile kernels
+    assert np.array_equal(u2, u)                         # the shared-memory ring feeder changes nothing
     for b in range(3):
         assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= 1e-10
 
 
 def test_warp_strip_vcycle_equals_resident_vcycle(he):
     """One V-cycle through the streamed strip kernels == the shared-memory V-cycle, node by node."""
-    for n, nu, ls, band in ((96, 2, 1, 96), (160, 1, 1, 64), (131, 3, 1, 40), (257, 2, 2, 86), (45, 2, 1, 16)):
+    for n, nu, ls, band in ((96, 2, 1, 96), (160, 1, 1, 64), (132, 3, 1, 40), (256, 2, 2, 86), (46, 2, 1, 16), (640, 2, 3, 80)):
         r = np.random.RandomState(n).randn(n, n)
         zr = np.zeros((n, n))
         he.hostemu_vcycle(ctypes.c_int(n), ctypes.c_int(nu), P(r), P(zr))
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             z = np.full((n, n), np.nan)
             rz = np.zeros(1)
             rc = he.hostemu_stream_vcycle(ctypes.c_int(n), ctypes.c_int(nu), ctypes.c_int(64), ctypes.c_int(64), ctypes.c_int(ls),
