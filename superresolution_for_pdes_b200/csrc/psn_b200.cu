@@ -169,6 +169,8 @@ struct PlanEntry {
     double* d_inv;
 };
 
+#define PSN_NSLOTS 3
+
 struct Arena {
     char* base = nullptr;
     size_t cap = 0, off = 0;
@@ -193,12 +195,16 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     size_t smem_optin = 0;
-    Slot slots[2];
+    Slot slots[PSN_NSLOTS];
+    cudaEvent_t ws_free = nullptr;
+    char* h_info = nullptr;          // pinned bounce buffer for iters / relres / status of host callers
+    size_t h_info_cap = 0;   // recorded after the last kernel that touches the shared streamed workspace
     std::map<long long, PlanEntry> plans;  // key = n * 16 + nu
     int nu = 2;
     int tile = 64;
     long long ws_bytes = 16ll << 30;
     int smem_max_n = 0;
+    int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 3 streamed / 8 resident)
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     bool attrs_set = false;
     bool profiling = false;
@@ -629,78 +635,141 @@ int solve_internal(const Problem& P) {
         if (cap > 65535 && !resident) cap = 65535;   // gridDim.z
         if (any_host) {
             // at least ~8 chunks so that copies overlap the solve, but keep chunks large enough to fill the GPU
-            long long want = (P.B + 7) / 8;
+            const int hc = g.host_chunks > 0 ? g.host_chunks : (resident ? 8 : 3);
+            long long want = (P.B + hc - 1) / hc;
             const long long floor_ = resident ? 4ll * g.sm_count : 64;
             if (want < floor_) want = floor_;
             if (cap > want) cap = want;
         }
         if (Bc > cap) Bc = cap;
     }
-    const int nslots = any_host ? 2 : 1;
+    const int nslots = any_host ? PSN_NSLOTS : 1;
     if (any_host) CU_TRY(cudaStreamSynchronize(P.stream));  // device inputs may still be in flight on the caller's stream
 
-    long long chunk_idx = 0;
-    for (long long b0 = 0; b0 < P.B; b0 += Bc, ++chunk_idx) {
-        const long long bc = (P.B - b0 < Bc) ? (P.B - b0) : Bc;
-        Slot& slot = g.slots[chunk_idx % nslots];
-        cudaStream_t s = any_host ? slot.stream : P.stream;
-        if (chunk_idx < nslots) {
-            rc = arena_reserve(slot.arena, pad256(stage_ps * Bc) + 64 * 256 + (size_t)Bc * 64);
-            if (rc) return rc;
-            if (!resident) {
-                rc = arena_reserve(slot.ws_arena, ws_ps * Bc + 64 * 256 + pad256((size_t)(P.max_iter + 8) * 4));
-                if (rc) return rc;
-                if (slot.h_counters_cap < P.max_iter + 8) {
-                    if (slot.h_counters) cudaFreeHost(slot.h_counters);
-                    CU_TRY(cudaMallocHost(&slot.h_counters, sizeof(int) * (P.max_iter + 8)));
-                    slot.h_counters_cap = P.max_iter + 8;
-                }
-            }
-        } else {
-            slot.arena.off = 0;   // stream order on slot.stream protects reuse
-        }
-        Arena& ar = slot.arena;
-
+    // Software pipeline over chunks (host buffers): the H2D staging of chunk c+1 is enqueued on its own
+    // slot stream BEFORE the (host-blocking) solve of chunk c, and the D2H of chunk c-1 drains on a third
+    // stream, so copies in both directions overlap the solve.  The streamed-path workspace is shared by
+    // all slots (solves are serialised by an event chain); staging buffers are per slot.
+    struct ChunkCtx {
+        long long b0, bc;
+        Slot* slot;
+        cudaStream_t s;
         PsnRhs rhs;
-        rhs.mn = P.mn;
-        rhs.step = P.step;
-        if ((rc = stage_in(ar, s, P.theta, k_theta, b0 * (long long)mm, bc * mm, &rhs.theta))) return rc;
-        if ((rc = stage_in(ar, s, P.f, k_f, b0 * (long long)mm, bc * mm, &rhs.f))) return rc;
-        if ((rc = stage_in(ar, s, P.sx, k_sx, b0 * (long long)P.mn, bc * (size_t)P.mn, &rhs.sx))) return rc;
-        if ((rc = stage_in(ar, s, P.sy, k_sy, b0 * (long long)P.mn, bc * (size_t)P.mn, &rhs.sy))) return rc;
-        if ((rc = stage_in(ar, s, P.k1, k_k1, b0, (size_t)bc, &rhs.k1))) return rc;
-        if ((rc = stage_in(ar, s, P.k2, k_k2, b0, (size_t)bc, &rhs.k2))) return rc;
+        double* d_u;
+        int32_t* d_it;
+        double* d_rr;
+        int32_t* d_st;
+        PsnSolveArgs a;
+    };
+    // chunk schedule: equal chunks of Bc for device callers; for host callers the first and last chunks
+    // are shorter (1/4, 1/2, 1 ... 1, 1/2, 1/4 of Bc) so that pipeline fill (first H2D) and drain (last D2H) are short
+    std::vector<long long> bounds;
+    bounds.push_back(0);
+    if (any_host && P.B > 2 * Bc) {
+        const long long ramp[2] = {Bc / 4 > 0 ? Bc / 4 : 1, Bc / 2 > 0 ? Bc / 2 : 1};
+        long long pos = 0;
+        for (int k = 0; k < 2; ++k) { pos += ramp[k]; bounds.push_back(pos); }
+        const long long tail = ramp[0] + ramp[1];
+        while (P.B - tail - pos > Bc) { pos += Bc; bounds.push_back(pos); }
+        if (P.B - tail > pos) { pos = P.B - tail; bounds.push_back(pos); }
+        pos += ramp[1]; bounds.push_back(pos);
+        bounds.push_back(P.B);
+    } else {
+        for (long long pos = Bc; pos < P.B; pos += Bc) bounds.push_back(pos);
+        bounds.push_back(P.B);
+    }
+    const long long nchunks = (long long)bounds.size() - 1;
+    Slot& ws_slot = g.slots[0];
+    if (!resident) {
+        rc = arena_reserve(ws_slot.ws_arena, ws_ps * Bc + 64 * 256 + pad256((size_t)(P.max_iter + 8) * 4));
+        if (rc) return rc;
+        if (ws_slot.h_counters_cap < P.max_iter + 8) {
+            if (ws_slot.h_counters) cudaFreeHost(ws_slot.h_counters);
+            ws_slot.h_counters = nullptr;
+            CU_TRY(cudaMallocHost(&ws_slot.h_counters, sizeof(int) * (P.max_iter + 8)));
+            ws_slot.h_counters_cap = P.max_iter + 8;
+        }
+    }
 
-        double* d_u = nullptr;
-        int32_t* d_it = nullptr;
-        double* d_rr = nullptr;
-        int32_t* d_st = nullptr;
-        if ((rc = stage_out(ar, P.u, k_u, b0 * (long long)nn, bc * nn, &d_u, !resident))) return rc;
-        if ((rc = stage_out(ar, P.iters, k_it, b0, (size_t)bc, &d_it, false))) return rc;
-        if ((rc = stage_out(ar, P.relres, k_rr, b0, (size_t)bc, &d_rr, false))) return rc;
-        if ((rc = stage_out(ar, P.status, k_st, b0, (size_t)bc, &d_st, false))) return rc;
+    // Small per-sample outputs of host callers go through a pinned bounce buffer: an async D2H into
+    // pageable memory would block the host until the whole chunk (including its multi-MB copies) has
+    // drained, which serialises the pipeline.
+    int32_t* hb_it = nullptr;
+    double* hb_rr = nullptr;
+    int32_t* hb_st = nullptr;
+    if (any_host && (k_it == MEM_HOST || k_rr == MEM_HOST || k_st == MEM_HOST)) {
+        const size_t need = (size_t)P.B * 16;
+        if (g.h_info_cap < need) {
+            if (g.h_info) cudaFreeHost(g.h_info);
+            g.h_info = nullptr;
+            g.h_info_cap = 0;
+            CU_TRY(cudaMallocHost(&g.h_info, need));
+            g.h_info_cap = need;
+        }
+        hb_rr = reinterpret_cast<double*>(g.h_info);
+        hb_it = reinterpret_cast<int32_t*>(g.h_info + (size_t)P.B * 8);
+        hb_st = reinterpret_cast<int32_t*>(g.h_info + (size_t)P.B * 12);
+    }
 
+    auto prepare = [&](long long c, ChunkCtx& cx) -> int {
+        int rc2;
+        cx.b0 = bounds[c];
+        cx.bc = bounds[c + 1] - bounds[c];
+        cx.slot = &g.slots[c % nslots];
+        cx.s = any_host ? cx.slot->stream : P.stream;
+        const long long b0 = cx.b0, bc = cx.bc;
+        cudaStream_t s = cx.s;
+        if (c < nslots) {
+            rc2 = arena_reserve(cx.slot->arena, pad256(stage_ps * Bc) + 64 * 256 + (size_t)Bc * 64);
+            if (rc2) return rc2;
+        } else {
+            cx.slot->arena.off = 0;   // stream order on the slot's stream protects reuse
+        }
+        Arena& ar = cx.slot->arena;
+        cx.rhs.mn = P.mn;
+        cx.rhs.step = P.step;
+        if ((rc2 = stage_in(ar, s, P.theta, k_theta, b0 * (long long)mm, bc * mm, &cx.rhs.theta))) return rc2;
+        if ((rc2 = stage_in(ar, s, P.f, k_f, b0 * (long long)mm, bc * mm, &cx.rhs.f))) return rc2;
+        if ((rc2 = stage_in(ar, s, P.sx, k_sx, b0 * (long long)P.mn, bc * (size_t)P.mn, &cx.rhs.sx))) return rc2;
+        if ((rc2 = stage_in(ar, s, P.sy, k_sy, b0 * (long long)P.mn, bc * (size_t)P.mn, &cx.rhs.sy))) return rc2;
+        if ((rc2 = stage_in(ar, s, P.k1, k_k1, b0, (size_t)bc, &cx.rhs.k1))) return rc2;
+        if ((rc2 = stage_in(ar, s, P.k2, k_k2, b0, (size_t)bc, &cx.rhs.k2))) return rc2;
+        cx.d_u = nullptr; cx.d_it = nullptr; cx.d_rr = nullptr; cx.d_st = nullptr;
+        if ((rc2 = stage_out(ar, P.u, k_u, b0 * (long long)nn, bc * nn, &cx.d_u, !resident))) return rc2;
+        if ((rc2 = stage_out(ar, P.iters, k_it, b0, (size_t)bc, &cx.d_it, false))) return rc2;
+        if ((rc2 = stage_out(ar, P.relres, k_rr, b0, (size_t)bc, &cx.d_rr, false))) return rc2;
+        if ((rc2 = stage_out(ar, P.status, k_st, b0, (size_t)bc, &cx.d_st, false))) return rc2;
         if (resident) {
-            PsnSolveArgs a;
+            PsnSolveArgs& a = cx.a;
             memset(&a, 0, sizeof(a));
-            a.rhs = rhs;
+            a.rhs = cx.rhs;
             a.rtol = P.rtol;
             a.max_iter = P.max_iter;
-            a.u = d_u;
-            a.iters = d_it;
-            a.relres = d_rr;
-            a.status = d_st;
+            a.u = cx.d_u;
+            a.iters = cx.d_it;
+            a.relres = cx.d_rr;
+            a.status = cx.d_st;
             a.sub = P.sub;
             if (P.sub > 0) {
-                if ((rc = stage_in(ar, s, P.start_x, k_x0, b0, (size_t)bc, &a.start_x))) return rc;
-                if ((rc = stage_in(ar, s, P.start_y, k_y0, b0, (size_t)bc, &a.start_y))) return rc;
-                if ((rc = stage_out(ar, P.u_fine, k_uf, b0 * (long long)ss, bc * ss, &a.u_fine, false))) return rc;
-                if ((rc = stage_out(ar, P.f_fine, k_ff, b0 * (long long)ss, bc * ss, &a.f_fine, false))) return rc;
-                if ((rc = stage_out(ar, P.th_fine, k_tf, b0 * (long long)ss, bc * ss, &a.th_fine, false))) return rc;
-                if ((rc = stage_out(ar, P.u_coarse, k_uc, b0 * (long long)scc, bc * scc, &a.u_coarse, false))) return rc;
-                if ((rc = stage_out(ar, P.f_coarse, k_fc, b0 * (long long)scc, bc * scc, &a.f_coarse, false))) return rc;
-                if ((rc = stage_out(ar, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, &a.th_coarse, false))) return rc;
+                if ((rc2 = stage_in(ar, s, P.start_x, k_x0, b0, (size_t)bc, &a.start_x))) return rc2;
+                if ((rc2 = stage_in(ar, s, P.start_y, k_y0, b0, (size_t)bc, &a.start_y))) return rc2;
+                if ((rc2 = stage_out(ar, P.u_fine, k_uf, b0 * (long long)ss, bc * ss, &a.u_fine, false))) return rc2;
+                if ((rc2 = stage_out(ar, P.f_fine, k_ff, b0 * (long long)ss, bc * ss, &a.f_fine, false))) return rc2;
+                if ((rc2 = stage_out(ar, P.th_fine, k_tf, b0 * (long long)ss, bc * ss, &a.th_fine, false))) return rc2;
+                if ((rc2 = stage_out(ar, P.u_coarse, k_uc, b0 * (long long)scc, bc * scc, &a.u_coarse, false))) return rc2;
+                if ((rc2 = stage_out(ar, P.f_coarse, k_fc, b0 * (long long)scc, bc * scc, &a.f_coarse, false))) return rc2;
+                if ((rc2 = stage_out(ar, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, &a.th_coarse, false))) return rc2;
             }
+        }
+        return PSN_OK;
+    };
+
+    auto run = [&](long long c, ChunkCtx& cx) -> int {
+        int rc2;
+        cudaStream_t s = cx.s;
+        const long long b0 = cx.b0, bc = cx.bc;
+        if (resident) {
+            const PsnSolveArgs& a = cx.a;
             {
                 ProfScope pr("smem_solve", s);
                 const unsigned grid = (unsigned)bc;
@@ -711,34 +780,50 @@ int solve_internal(const Problem& P) {
             }
             CU_TRY(cudaGetLastError());
             if (P.sub > 0) {
-                if ((rc = copy_back(s, P.u_fine, k_uf, b0 * (long long)ss, bc * ss, a.u_fine))) return rc;
-                if ((rc = copy_back(s, P.f_fine, k_ff, b0 * (long long)ss, bc * ss, a.f_fine))) return rc;
-                if ((rc = copy_back(s, P.th_fine, k_tf, b0 * (long long)ss, bc * ss, a.th_fine))) return rc;
-                if ((rc = copy_back(s, P.u_coarse, k_uc, b0 * (long long)scc, bc * scc, a.u_coarse))) return rc;
-                if ((rc = copy_back(s, P.f_coarse, k_fc, b0 * (long long)scc, bc * scc, a.f_coarse))) return rc;
-                if ((rc = copy_back(s, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, a.th_coarse))) return rc;
+                if ((rc2 = copy_back(s, P.u_fine, k_uf, b0 * (long long)ss, bc * ss, a.u_fine))) return rc2;
+                if ((rc2 = copy_back(s, P.f_fine, k_ff, b0 * (long long)ss, bc * ss, a.f_fine))) return rc2;
+                if ((rc2 = copy_back(s, P.th_fine, k_tf, b0 * (long long)ss, bc * ss, a.th_fine))) return rc2;
+                if ((rc2 = copy_back(s, P.u_coarse, k_uc, b0 * (long long)scc, bc * scc, a.u_coarse))) return rc2;
+                if ((rc2 = copy_back(s, P.f_coarse, k_fc, b0 * (long long)scc, bc * scc, a.f_coarse))) return rc2;
+                if ((rc2 = copy_back(s, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, a.th_coarse))) return rc2;
             }
         } else {
-            slot.ws_arena.off = 0;
+            // the shared workspace is free once the previous chunk's last kernel has run
+            if (c > 0 && any_host) CU_TRY(cudaStreamWaitEvent(s, g.ws_free, 0));
+            ws_slot.ws_arena.off = 0;
             PsnStreamWs ws;
-            if ((rc = carve_stream_ws(slot.ws_arena, plan, scfg, bc, P.max_iter, &ws))) return rc;
+            if ((rc2 = carve_stream_ws(ws_slot.ws_arena, plan, scfg, bc, P.max_iter, &ws))) return rc2;
             choose_bands(plan, &scfg, bc);
-            CudaBackend bk{s, &slot};
-            psn_stream_solve(bk, plan, scfg, rhs, bc, P.rtol, P.max_iter, d_u, ws);
+            CudaBackend bk{s, &ws_slot};
+            psn_stream_solve(bk, plan, scfg, cx.rhs, bc, P.rtol, P.max_iter, cx.d_u, ws);
             if (bk.err != cudaSuccess) return psn_fail(PSN_ERR_CUDA, "streamed solve failed: %s", cudaGetErrorString(bk.err));
             {
                 ProfScope pr("state", s);
-                psn_finalize_kernel<<<(unsigned)((bc + 127) / 128), 128, 0, s>>>(ws.state, bc, d_it, d_rr, d_st);
+                psn_finalize_kernel<<<(unsigned)((bc + 127) / 128), 128, 0, s>>>(ws.state, bc, cx.d_it, cx.d_rr, cx.d_st);
             }
             CU_TRY(cudaGetLastError());
+            if (any_host) CU_TRY(cudaEventRecord(g.ws_free, s));
         }
-        if ((rc = copy_back(s, P.u, k_u, b0 * (long long)nn, bc * nn, d_u))) return rc;
-        if ((rc = copy_back(s, P.iters, k_it, b0, (size_t)bc, d_it))) return rc;
-        if ((rc = copy_back(s, P.relres, k_rr, b0, (size_t)bc, d_rr))) return rc;
-        if ((rc = copy_back(s, P.status, k_st, b0, (size_t)bc, d_st))) return rc;
+        if ((rc2 = copy_back(s, P.u, k_u, b0 * (long long)nn, bc * nn, cx.d_u))) return rc2;
+        if ((rc2 = copy_back(s, hb_it ? hb_it : P.iters, k_it, b0, (size_t)bc, cx.d_it))) return rc2;
+        if ((rc2 = copy_back(s, hb_rr ? hb_rr : P.relres, k_rr, b0, (size_t)bc, cx.d_rr))) return rc2;
+        if ((rc2 = copy_back(s, hb_st ? hb_st : P.status, k_st, b0, (size_t)bc, cx.d_st))) return rc2;
+        return PSN_OK;
+    };
+
+    ChunkCtx cur, nxt;
+    if ((rc = prepare(0, cur))) return rc;
+    for (long long c = 0; c < nchunks; ++c) {
+        const bool more = c + 1 < nchunks;
+        if (more && (rc = prepare(c + 1, nxt))) return rc;
+        if ((rc = run(c, cur))) return rc;
+        if (more) cur = nxt;
     }
     if (any_host) {
         for (int i = 0; i < nslots; ++i) CU_TRY(cudaStreamSynchronize(g.slots[i].stream));
+        if (hb_it && k_it == MEM_HOST) memcpy(P.iters, hb_it, (size_t)P.B * 4);
+        if (hb_rr && k_rr == MEM_HOST) memcpy(P.relres, hb_rr, (size_t)P.B * 8);
+        if (hb_st && k_st == MEM_HOST) memcpy(P.status, hb_st, (size_t)P.B * 4);
     }
     return PSN_OK;
 }
@@ -775,7 +860,8 @@ int psn_init(int device) {
     g.device = cur;
     g.sm_count = prop.multiProcessorCount;
     g.smem_optin = prop.sharedMemPerBlockOptin;
-    for (int i = 0; i < 2; ++i) {
+    CU_TRY(cudaEventCreateWithFlags(&g.ws_free, cudaEventDisableTiming));
+    for (int i = 0; i < PSN_NSLOTS; ++i) {
         CU_TRY(cudaStreamCreateWithFlags(&g.slots[i].stream, cudaStreamNonBlocking));
         for (int k = 0; k < 4; ++k) CU_TRY(cudaEventCreateWithFlags(&g.slots[i].ev[k], cudaEventDisableTiming));
     }
@@ -791,7 +877,12 @@ void psn_shutdown(void) {
     cudaDeviceSynchronize();
     for (auto& kv : g.plans) cudaFree(kv.second.d_inv);
     g.plans.clear();
-    for (int i = 0; i < 2; ++i) {
+    if (g.ws_free) cudaEventDestroy(g.ws_free);
+    g.ws_free = nullptr;
+    if (g.h_info) cudaFreeHost(g.h_info);
+    g.h_info = nullptr;
+    g.h_info_cap = 0;
+    for (int i = 0; i < PSN_NSLOTS; ++i) {
         Slot& s = g.slots[i];
         if (s.arena.base) cudaFree(s.arena.base);
         if (s.ws_arena.base) cudaFree(s.ws_arena.base);
@@ -881,6 +972,9 @@ int psn_set_option(const char* name, int64_t value) {
         g.ws_bytes = value;
     } else if (!strcmp(name, "smem_max_n")) {
         g.smem_max_n = (int)value;
+    } else if (!strcmp(name, "host_chunks")) {
+        if (value < 0 || value > 1024) return psn_fail(PSN_ERR_INVALID, "host_chunks must be in 0..1024");
+        g.host_chunks = (int)value;
     } else if (!strcmp(name, "vcycle_mode")) {
         if (value < 0 || value > 2) return psn_fail(PSN_ERR_INVALID, "vcycle_mode must be 0 (tiles), 1 (warp strips, register prefetch) or 2 (warp strips, TMA ring)");
         g.vcycle_mode = (int)value;

@@ -362,7 +362,7 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
                                 const wd (&rdA)[4], const wd (&dA)[4], const wd (&mk)[4], const PsnLevel& lv,
                                 const double* bg, double* ug, double* cg, const wi& col0, const wb (&mp)[2], const wb (&so)[2],
                                 const wi& cj, const wb (&sc)[2]) {
-    constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
+    constexpr int NS = 2 * NU, W = NS + 2;
     const wd zero = w_bcast(0.0);
     // last-row diagonals are only needed by the checked chunk at the bottom of the grid: build them on demand
     wd rdB[4], dB[4];
@@ -461,7 +461,7 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
 template <int NU, class Feeder>
 PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip, Feeder& fd) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
-    constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
+    constexpr int NS = 2 * NU, W = NS + 2;
     const int USE = PSN_STRIP_COLS - (2 * NS + 2);
     const PsnLevel& lv = plan.lv[a.level];
     const PsnLevel& lc = plan.lv[a.level + 1];
@@ -530,7 +530,7 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
                                  wd (&eprev)[2], wd (&enext)[2], wd& dot, const wd (&rdA)[4], const wd (&mk)[4], const PsnLevel& lv,
                                  const double* bg, const double* uig, const double* eg, double* ug, const wi& col0,
                                  const wb (&mp)[2], const wb (&so)[2], const wi& cj, const wb (&mc)[2], bool want_dot) {
-    constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
+    constexpr int NS = 2 * NU, W = NS + 2;
     const wd zero = w_bcast(0.0);
     wd rdB[4];
     if (!FAST) {
@@ -616,7 +616,7 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
 template <int NU, class Feeder>
 PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip, Feeder& fd) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
-    constexpr int NS = 2 * NU, W = NS + 2, PF = W / 2;
+    constexpr int NS = 2 * NU, W = NS + 2;
     const int USE = PSN_STRIP_COLS - (2 * NS + 2);
     const PsnLevel& lv = plan.lv[a.level];
     const PsnLevel& lc = plan.lv[a.level + 1];
