@@ -204,6 +204,7 @@ struct Context {
     int tile = 64;
     long long ws_bytes = 16ll << 30;
     int smem_max_n = 0;
+    int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
     int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 3 streamed / 8 resident)
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     bool attrs_set = false;
@@ -280,10 +281,16 @@ ResidentCfg resident_cfg(const PsnPlan& plan) {
     if (g.smem_max_n < 0) return c;
     c.smem = (size_t)psn_smem_solver_doubles(plan) * sizeof(double);
     if (c.smem + 1024 > g.smem_optin) return c;
-    if (nn <= 128 * 4) { c.T = 128; c.XPT = 4; }
-    else if (nn <= 256 * 8) { c.T = 256; c.XPT = 8; }
-    else if (nn <= 512 * 8) { c.T = 512; c.XPT = 8; }
-    else if (nn <= 512 * 16) { c.T = 512; c.XPT = 16; }
+    // compiled (threads, values-per-thread) variants; "res_threads" forces a thread count for experiments
+    // order = preference (measured on B200: 20^2 best with 128 threads, 40^2 with 512x4, 80^2 with 512x16)
+    static const int variants[][2] = {{128, 4}, {256, 4}, {512, 4}, {256, 8}, {512, 8}, {1024, 4}, {512, 16}, {1024, 8}};
+    for (auto& v : variants) {
+        if (g.res_threads > 0 && v[0] != g.res_threads) continue;
+        if (nn <= v[0] * v[1]) { c.T = v[0]; c.XPT = v[1]; break; }
+    }
+    if (c.T == 0 && g.res_threads > 0)
+        for (auto& v : variants)
+            if (nn <= v[0] * v[1]) { c.T = v[0]; c.XPT = v[1]; break; }
     return c;
 }
 
@@ -299,10 +306,10 @@ int stream_ls(const PsnPlan& plan) {
 int set_kernel_attrs() {
     if (g.attrs_set) return PSN_OK;
     const int mx = (int)g.smem_optin - 1024;  // leave room for the static reduction scratch
-    CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<256, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<512, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+#define PSN_RES_ATTR(T_, X_) CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<T_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
+    PSN_RES_ATTR(128, 4); PSN_RES_ATTR(256, 4); PSN_RES_ATTR(256, 8); PSN_RES_ATTR(512, 4);
+    PSN_RES_ATTR(512, 8); PSN_RES_ATTR(1024, 4); PSN_RES_ATTR(512, 16); PSN_RES_ATTR(1024, 8);
+#undef PSN_RES_ATTR
     CU_TRY(cudaFuncSetAttribute(psn_tile_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CU_TRY(cudaFuncSetAttribute(psn_tile_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CU_TRY(cudaFuncSetAttribute(psn_coarse_vcycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -773,10 +780,11 @@ int solve_internal(const Problem& P) {
             {
                 ProfScope pr("smem_solve", s);
                 const unsigned grid = (unsigned)bc;
-                if (rcfg.T == 128) psn_smem_solve_kernel<128, 4><<<grid, 128, rcfg.smem, s>>>(plan, a);
-                else if (rcfg.T == 256) psn_smem_solve_kernel<256, 8><<<grid, 256, rcfg.smem, s>>>(plan, a);
-                else if (rcfg.XPT == 8) psn_smem_solve_kernel<512, 8><<<grid, 512, rcfg.smem, s>>>(plan, a);
-                else psn_smem_solve_kernel<512, 16><<<grid, 512, rcfg.smem, s>>>(plan, a);
+#define PSN_RES_LAUNCH(T_, X_) \
+    if (rcfg.T == T_ && rcfg.XPT == X_) psn_smem_solve_kernel<T_, X_><<<grid, T_, rcfg.smem, s>>>(plan, a)
+                PSN_RES_LAUNCH(128, 4); PSN_RES_LAUNCH(256, 4); PSN_RES_LAUNCH(256, 8); PSN_RES_LAUNCH(512, 4);
+                PSN_RES_LAUNCH(512, 8); PSN_RES_LAUNCH(1024, 4); PSN_RES_LAUNCH(512, 16); PSN_RES_LAUNCH(1024, 8);
+#undef PSN_RES_LAUNCH
             }
             CU_TRY(cudaGetLastError());
             if (P.sub > 0) {
@@ -972,6 +980,9 @@ int psn_set_option(const char* name, int64_t value) {
         g.ws_bytes = value;
     } else if (!strcmp(name, "smem_max_n")) {
         g.smem_max_n = (int)value;
+    } else if (!strcmp(name, "res_threads")) {
+        if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
+        g.res_threads = (int)value;
     } else if (!strcmp(name, "host_chunks")) {
         if (value < 0 || value > 1024) return psn_fail(PSN_ERR_INVALID, "host_chunks must be in 0..1024");
         g.host_chunks = (int)value;

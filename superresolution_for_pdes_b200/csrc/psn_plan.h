@@ -28,9 +28,14 @@
 
 struct PsnLevel {
     int n;       // nodes per side
-    int pitch;   // shared-memory pitch (n + 1: one shared zero ghost column)
-    int size;    // doubles in one shared-memory level array: (n + 2) * pitch + 1, rounded up to even
+    int pitch;   // shared-memory pitch n + 2 (zero ghost column on both sides).  For even n the pitch is even,
+                 // so a step along a grid diagonal is an ODD number of doubles: diagonal thread mappings of the
+                 // red-black sweeps are bank-conflict free
+    int size;    // doubles in one shared-memory level array: (n + 2)^2, rounded up to even
     int half;    // ceil(n / 2): slots per row and colour
+    int off;     // offset (doubles) of this level's rhs array in a shared pool that starts at level 1
+    unsigned nmagic;  // ceil(2^32 / n): exact idx / n by multiply-high (0 for n == 1)
+    unsigned hmagic;  // same for `half`
     double gam;  // extra diagonal weight on the last row / last column
     double rd0;  // 1 / 4
     double rd1;  // 1 / (4 + gam)
@@ -47,9 +52,8 @@ struct PsnPlan {
 };
 
 static inline int psn_level_size(int n) {
-    // +1: the bilinear prolongation onto an odd-sized parent reads the (n, n) corner ghost,
-    // which aliases one element past the last ghost row
-    int s = (n + 2) * (n + 1) + 1;
+    // full zero ghost ring: (n + 2) x (n + 2), element (i, j) at (i + 1) * (n + 2) + (j + 1)
+    int s = (n + 2) * (n + 2);
     return (s + 1) & ~1;
 }
 
@@ -65,9 +69,12 @@ static inline void psn_plan_levels(PsnPlan* p, int n, int nu) {
     for (;;) {
         PsnLevel& L = p->lv[nl];
         L.n = cur;
-        L.pitch = cur + 1;
+        L.pitch = cur + 2;
         L.size = psn_level_size(cur);
         L.half = (cur + 1) / 2;
+        L.off = 0;
+        L.nmagic = cur > 1 ? (0xFFFFFFFFu / (unsigned)cur + 1u) : 0u;
+        L.hmagic = L.half > 1 ? (0xFFFFFFFFu / (unsigned)L.half + 1u) : 0u;
         L.gam = gam;
         L.rd0 = 0.25;
         L.rd1 = 1.0 / (4.0 + gam);
@@ -78,6 +85,7 @@ static inline void psn_plan_levels(PsnPlan* p, int n, int nu) {
         cur = cur / 2;
     }
     p->nlev = nl;
+    for (int l = 2; l < nl; ++l) p->lv[l].off = p->lv[l - 1].off + 2 * p->lv[l - 1].size;
     p->coarse_inv = nullptr;
 }
 
