@@ -105,6 +105,28 @@ psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ P
     }
 }
 
+template <bool TMA>
+__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
+psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
+    extern __shared__ __align__(128) unsigned char strip_smem[];
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
+    if (task >= ntasks) return;
+    const int per = a.dir_nstrips * a.dir_nbands;
+    const long long b = task / per;
+    const int rem = (int)(task - b * per);
+    const int band = rem / a.dir_nstrips, strip = rem - band * a.dir_nstrips;
+    const PsnWarp w{(int)(threadIdx.x & 31)};
+    if constexpr (TMA) {
+        PsnTmaFeeder<2, 2> fd;
+        fd.attach(strip_smem + (size_t)warp * PsnTmaFeeder<2, 2>::smem_bytes());
+        psn_dir_strip_body(w, a, b, band, strip, fd);
+    } else {
+        PsnRegFeeder<2, 2> fd;
+        psn_dir_strip_body(w, a, b, band, strip, fd);
+    }
+}
+
 __global__ void __launch_bounds__(PSN_COARSE_THREADS) psn_coarse_vcycle_kernel(const __grid_constant__ PsnPlan plan, int l0,
                                                                                const double* bg, double* ug,
                                                                                const PsnSampleState* state) {
@@ -204,6 +226,7 @@ struct Context {
     int tile = 64;
     long long ws_bytes = 16ll << 30;
     int smem_max_n = 0;
+    int coarse_max_n = 40; // largest level handed to the shared-memory coarse V-cycle kernel (0: as large as fits)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
     int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 3 streamed / 8 resident)
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
@@ -298,6 +321,7 @@ ResidentCfg resident_cfg(const PsnPlan& plan) {
 int stream_ls(const PsnPlan& plan) {
     for (int l = 1; l < plan.nlev; ++l) {
         size_t bytes = ((size_t)2 * plan.lv[l].size + psn_pool_doubles(plan, l)) * sizeof(double);
+        if (g.coarse_max_n > 0 && plan.lv[l].n > g.coarse_max_n && l + 1 < plan.nlev) continue;
         if (bytes + 1024 <= g.smem_optin) return l;
     }
     return -1;
@@ -420,7 +444,23 @@ struct CudaBackend {
     }
     void dir_apply(const PsnCgArgs& a, long long B) {
         ProfScope p("dir_apply_dot", s);
-        psn_dir_apply_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        if (a.dir_mode >= 1) {
+            const long long ntasks = B * a.dir_nstrips * a.dir_nbands;
+            const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
+            if (a.dir_mode == 2) {
+                const size_t smem = (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<2, 2>::smem_bytes();
+                static bool attr_done = false;
+                if (!attr_done) {
+                    cudaFuncSetAttribute(psn_dir_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attr_done = true;
+                }
+                psn_dir_strip_kernel<true><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(a, ntasks);
+            } else {
+                psn_dir_strip_kernel<false><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(a, ntasks);
+            }
+        } else {
+            psn_dir_apply_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        }
         chk();
     }
     void update(const PsnCgArgs& a, long long B) {
@@ -535,7 +575,7 @@ size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) 
         b += (l < cfg.ls ? 3 : 2) * m;
     }
     const int gx = (plan.n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (plan.n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
-    b += ((size_t)psn_rz_max(plan, cfg) + 2 * (size_t)gx * gy) * sizeof(double) + sizeof(PsnSampleState);
+    b += ((size_t)psn_rz_max(plan, cfg) + (size_t)psn_pq_max(plan.n) + 2 * (size_t)gx * gy) * sizeof(double) + sizeof(PsnSampleState);
     return b + 4096 / 16;
 }
 
@@ -562,10 +602,11 @@ int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, lon
     const int gx = (plan.n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (plan.n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
     ws->part_rz = arena_take<double>(ar, (size_t)Bc * psn_rz_max(plan, cfg));
     ws->part_a = arena_take<double>(ar, (size_t)Bc * gx * gy);
+    ws->part_pq = arena_take<double>(ar, (size_t)Bc * psn_pq_max(plan.n));
     ws->part_b = arena_take<double>(ar, (size_t)Bc * gx * gy);
     ws->state = arena_take<PsnSampleState>(ar, Bc);
     ws->counters = arena_take<int>(ar, max_iter + 8);
-    ok = ok && ws->part_rz && ws->part_a && ws->part_b && ws->state && ws->counters;
+    ok = ok && ws->part_rz && ws->part_a && ws->part_pq && ws->part_b && ws->state && ws->counters;
     return ok ? PSN_OK : psn_fail(PSN_ERR_NOMEM, "workspace arena exhausted");
 }
 
@@ -980,6 +1021,9 @@ int psn_set_option(const char* name, int64_t value) {
         g.ws_bytes = value;
     } else if (!strcmp(name, "smem_max_n")) {
         g.smem_max_n = (int)value;
+    } else if (!strcmp(name, "coarse_max_n")) {
+        if (value < 0) return psn_fail(PSN_ERR_INVALID, "coarse_max_n must be >= 0");
+        g.coarse_max_n = (int)value;
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;

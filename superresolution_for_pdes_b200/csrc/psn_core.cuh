@@ -749,7 +749,11 @@ struct PsnCgArgs {
     double* p_new;
     double* q;
     double* part_rz;         // [B, ntiles_rz]
-    double* part_a;          // [B, ntx*nty]   <p,q> partials / ||b||^2 partials
+    double* part_a;          // [B, ntx*nty]   ||b||^2 partials (prologue)
+    double* part_pq;         // [B, npq]       <p,q> partials
+    int npq;                 // partials per sample written by the direction kernel
+    int dir_mode;            // 0: 2-D tile kernel, 1: warp strips + register prefetch, 2: warp strips + TMA ring
+    int dir_band, dir_nstrips, dir_nbands;   // strip decomposition of the direction kernel
     double* part_b;          // [B, ntx*nty]   ||r||^2 partials
     PsnSampleState* state;   // [B]
     double rtol;
@@ -831,7 +835,7 @@ PSN_FN void psn_dir_apply_body(Ctx& ctx, const PsnCgArgs& a, long long b, int ty
     })
     const double s = ctx.block_sum(acc);
     if (ctx.tid == 0) {
-        a.part_a[b * (long long)(a.ntx * a.nty) + (long long)ty * a.ntx + tx] = s;
+        a.part_pq[b * (long long)a.npq + (long long)ty * a.ntx + tx] = s;
         if (ty == 0 && tx == 0) a.state[b].rz = rz;
     }
 }
@@ -841,7 +845,7 @@ template <class Ctx>
 PSN_FN void psn_update_body(Ctx& ctx, const PsnCgArgs& a, long long b, int ty, int tx) {
     const PsnSampleState st = a.state[b];
     if (st.phase != PSN_PHASE_ITER) return;
-    const double pq = psn_sum_partials(ctx, a.part_a + b * (long long)(a.ntx * a.nty), a.ntx * a.nty);
+    const double pq = psn_sum_partials(ctx, a.part_pq + b * (long long)a.npq, a.npq);
     const double alpha = (pq > 0.0) ? st.rz / pq : 0.0;
     const int n = a.n;
     const long long base = b * (long long)n * n;

@@ -39,6 +39,12 @@ static inline bool psn_strip_ok(const PsnPlan& plan, int ls) {
 }
 static inline int psn_strip_count(int n, int use) { return (n + use - 1) / use; }
 static inline int psn_band_count(int n, int band) { return (n + band - 1) / band; }
+// upper bound of the <p,q> partial count per sample (any band choice >= 16 rows, or the 2-D tiles)
+static inline int psn_pq_max(int n) {
+    const int strips = ((n + PSN_DIR_USE - 1) / PSN_DIR_USE) * ((n + 15) / 16);
+    const int tiles = ((n + PSN_GT_COLS - 1) / PSN_GT_COLS) * ((n + PSN_GT_ROWS - 1) / PSN_GT_ROWS);
+    return strips > tiles ? strips : tiles;
+}
 // number of <r,z> partials per sample produced by the level-0 up-leg
 static inline int psn_rz_count(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     const int n = plan.n;
@@ -58,6 +64,7 @@ struct PsnStreamWs {
     double* ub[PSN_MAX_LEVELS];  // levels 1..ls: corrected iterate
     double* part_rz;
     double* part_a;
+    double* part_pq;
     double* part_b;
     PsnSampleState* state;
     int* counters;               // [max_iter + 8] active-sample count per outer iteration
@@ -108,6 +115,12 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.p_new = ws.p[1];
     cg.part_rz = ws.part_rz;
     cg.part_a = ws.part_a;
+    cg.part_pq = ws.part_pq;
+    cg.dir_mode = (cfg.mode >= 1 && (n & 1) == 0) ? cfg.mode : 0;
+    cg.dir_band = cfg.band[0];
+    cg.dir_nstrips = (n + PSN_DIR_USE - 1) / PSN_DIR_USE;
+    cg.dir_nbands = psn_band_count(n, cg.dir_band);
+    cg.npq = cg.dir_mode ? cg.dir_nstrips * cg.dir_nbands : cg.ntx * cg.nty;
     cg.part_b = ws.part_b;
     cg.state = ws.state;
     cg.rtol = rtol;

@@ -693,3 +693,95 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
         if (w_lane0(w)) a.part[b * (long long)(a.nstrips * a.nbands) + (long long)band * a.nstrips + strip] = s;
     }
 }
+
+
+// ----------------------------------------------------------------------------- direction kernel, strip form
+// p_new = z + beta p_old;  q = At p_new;  partial <p_new, q>  -- one warp marches down a 128-column strip
+// (2 halo columns per side) with a 3-row window of p_new in registers; z and p_old rows arrive through
+// the same feeders as the V-cycle strips.
+#define PSN_DIR_USE (PSN_STRIP_COLS - 4)
+
+PSN_FN double psn_warp_sum_partials(const PsnWarp& w, const double* part, int count) {
+    wd acc = w_bcast(0.0);
+    const wi lane = w_lane(w);
+    for (int k0 = 0; k0 < count; k0 += 32) acc = acc + w_ld1(part + k0, lane, lane < (count - k0));
+    return w_sum(acc);
+}
+
+template <class Feeder>
+PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b, int band, int strip, Feeder& fd) {
+    const PsnSampleState st = a.state[b];
+    if (st.phase != PSN_PHASE_ITER) return;
+    constexpr int W = Feeder::W;
+    static_assert(W % 3 == 0, "the 3-row window rotates inside one ring period");
+    const double rz = psn_warp_sum_partials(w, a.part_rz + b * (long long)a.ntiles_rz, a.ntiles_rz);
+    const bool fresh = st.restart != 0;
+    const wd beta = w_bcast(fresh ? 0.0 : rz / st.rz_old);
+    const int n = a.n, last = n - 1;
+    const int a0 = strip * PSN_DIR_USE, a1 = psn_imin(a0 + PSN_DIR_USE, n);
+    const int c0 = a0 - 2;
+    const int i0 = band * a.dir_band, i1 = psn_imin(i0 + a.dir_band, n);
+    const wi col0 = w_lane(w) * 4 + c0;
+    const wi col2 = col0 + 2;
+    const wb mp[2] = {(col0 >= 0) && (col0 < n), (col2 >= 0) && (col2 < n)};
+    const wb so[2] = {mp[0] && (col0 >= a0) && (col0 < a1), mp[1] && (col2 >= a0) && (col2 < a1)};
+    const long long base = b * (long long)n * n;
+    const wd zero = w_bcast(0.0);
+
+    const int ts = psn_imax(i0 - 1, 0);
+    const int tload = psn_imin(i1, last);
+    const int tend = i1;   // q(row r) is formed at time r + 1; row n reads as zero
+    fd.base[0] = a.z + base;
+    fd.base[1] = a.p_old + base;
+    fd.n = n;
+    fd.tload = tload;
+    psn_feeder_geom(fd, col0, mp, c0, n);
+    fd.prime(w, ts);
+
+    wd pn[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) pn[k][e] = zero;
+    wd dot = zero;
+    double* pg = a.p_new + base;
+    double* qg = a.q + base;
+
+    for (int t = ts; t <= tend; t += W) {
+        const int par = ((t - ts) / W) & 1;
+#pragma unroll
+        for (int tt = 0; tt < W; ++tt) {
+            const int tc = t + tt;
+            if (tc > tend) break;
+            const int k0 = tt % 3, k1 = (tt + 2) % 3, k2 = (tt + 1) % 3;   // rows tc, tc-1, tc-2
+            wd rowv[2][4];
+            fd.template fetch<false>(w, tt, tc, par, rowv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pn[k0][e] = fresh ? rowv[0][e] : rowv[0][e] + beta * rowv[1][e];
+            if (tc >= i0 && tc < i1) {
+                double* rowp = pg + (long long)tc * n;
+                w_stp(rowp, col0, so[0], pn[k0][0], pn[k0][1]);
+                w_stp(rowp, col2, so[1], pn[k0][2], pn[k0][3]);
+            }
+            const int r = tc - 1;
+            if (r >= i0 && r < i1) {
+                const wd upv = w_up_raw(pn[k1][3]);
+                const wd dnv = w_down_raw(pn[k1][0]);
+                wd q[4];
+                q[0] = 4.0 * pn[k1][0] - ((pn[k0][0] + pn[k2][0]) + (upv + pn[k1][1]));
+                q[1] = 4.0 * pn[k1][1] - ((pn[k0][1] + pn[k2][1]) + (pn[k1][0] + pn[k1][2]));
+                q[2] = 4.0 * pn[k1][2] - ((pn[k0][2] + pn[k2][2]) + (pn[k1][1] + pn[k1][3]));
+                q[3] = 4.0 * pn[k1][3] - ((pn[k0][3] + pn[k2][3]) + (pn[k1][2] + dnv));
+                double* rowq = qg + (long long)r * n;
+                w_stp(rowq, col0, so[0], q[0], q[1]);
+                w_stp(rowq, col2, so[1], q[2], q[3]);
+                dot = dot + w_sel(so[0], pn[k1][0] * q[0] + pn[k1][1] * q[1], zero) + w_sel(so[1], pn[k1][2] * q[2] + pn[k1][3] * q[3], zero);
+            }
+        }
+    }
+    const double s = w_sum(dot);
+    if (w_lane0(w)) {
+        a.part_pq[b * (long long)a.npq + (long long)band * a.dir_nstrips + strip] = s;
+        if (band == 0 && strip == 0) a.state[b].rz = rz;
+    }
+}

@@ -84,6 +84,18 @@ struct HostBackend {
         for (long long b = 0; b < B; ++b) psn_coarse_vcycle_body(ctx, plan, l0, bg, ug, st, b, smem.data());
     }
     void dir_apply(const PsnCgArgs& a, long long B) {
+        if (a.dir_mode >= 1) {
+            PsnWarp w;
+            std::vector<unsigned char> ring(PsnTmaFeeder<2, 2>::smem_bytes() + 256);
+            for (long long b = 0; b < B; ++b)
+                for (int band = 0; band < a.dir_nbands; ++band)
+                    for (int strip = 0; strip < a.dir_nstrips; ++strip) {
+                        std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
+                        if (a.dir_mode == 2) { PsnTmaFeeder<2, 2> fd; fd.attach(ring.data()); psn_dir_strip_body(w, a, b, band, strip, fd); }
+                        else { PsnRegFeeder<2, 2> fd; psn_dir_strip_body(w, a, b, band, strip, fd); }
+                    }
+            return;
+        }
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
             for (int ty = 0; ty < a.nty; ++ty)
@@ -176,6 +188,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     const int gx = (n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
     ws.part_rz = alloc((size_t)B * psn_rz_count(plan, cfg));
     ws.part_a = alloc((size_t)B * gx * gy);
+    ws.part_pq = alloc((size_t)B * psn_pq_max(n));
     ws.part_b = alloc((size_t)B * gx * gy);
     std::vector<PsnSampleState> st(B);
     ws.state = st.data();
