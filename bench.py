@@ -348,8 +348,18 @@ def run_own(args):
             # every sample takes part in exactly iters[b] launches of each per-iteration kernel (per step)
             total_bytes = KERNEL_BYTES[top]["own"] * n * n * sample_iters * args.steps
             ach = total_bytes / (rec["ms"] / 1000.0) / 1e9
+            # measured DRAM traffic of that kernel (ncu --set full capture summarised under profiles/), scaled to
+            # the nodes one launch of this run processes; null if the kernel was not captured
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))["bytes_per_level0_node"]
+                if top in tj:
+                    traffic = tj[top] * n * n * B
+            except Exception:
+                pass
             roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "avg_launch_ms": rec["ms"] / rec["launches"],
+                    "traffic": traffic, "algorithmic_bytes_per_launch": KERNEL_BYTES[top]["own"] * n * n * B,
+                    "avg_launch_ms": rec["ms"] / rec["launches"],
                     "bytes_per_node": KERNEL_BYTES[top]["own"], "peak_source": peak_src,
                     "achieved_survey_model": KERNEL_BYTES[top]["survey"] * n * n * sample_iters * args.steps / (rec["ms"] / 1000.0) / 1e9,
                     "all_kernels_GBps": {k: KERNEL_BYTES[k]["own"] * n * n * sample_iters * args.steps / (prof[k]["ms"] / 1000.0) / 1e9

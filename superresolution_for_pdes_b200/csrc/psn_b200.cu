@@ -179,6 +179,30 @@ __global__ void psn_finalize_kernel(const PsnSampleState* state, long long B, in
     if (relres) relres[b] = st.bb > 0.0 ? sqrt(st.rr / st.bb) : 0.0;
     if (status) status[b] = st.phase == PSN_PHASE_DONE ? st.status : PSN_ST_MAXITER;
 }
+// Sub-domain epilogue of the STREAMED path (the resident kernel fuses it): window extract + stride-2
+// downsample of u, f, theta for one sample per blockIdx.y  (src/enhanced_data_generation.py:141-148)
+__global__ void psn_window_kernel(const __grid_constant__ PsnSolveArgs a, int n, const double* u) {
+    const long long b = blockIdx.y;
+    const int s = a.sub, sc = (s + 1) >> 1;
+    const int x0 = a.start_x[b], y0 = a.start_y[b];
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < s * s; idx += gridDim.x * blockDim.x) {
+        const int wi = idx / s, wj = idx - wi * s;
+        const int i = y0 + wi, j = x0 + wj;
+        const double uv = u[(b * n + i) * (long long)n + j];
+        const double fv = psn_forcing(a.rhs, b, i, j);
+        const double tv = a.rhs.theta ? a.rhs.theta[(b * a.rhs.mn + (long long)i * a.rhs.step) * a.rhs.mn + (long long)j * a.rhs.step] : 1.0;
+        const long long o = (b * s + wi) * s + wj;
+        if (a.u_fine) a.u_fine[o] = uv;
+        if (a.f_fine) a.f_fine[o] = fv;
+        if (a.th_fine) a.th_fine[o] = tv;
+        if (((wi | wj) & 1) == 0) {
+            const long long oc = (b * sc + (wi >> 1)) * sc + (wj >> 1);
+            if (a.u_coarse) a.u_coarse[oc] = uv;
+            if (a.f_coarse) a.f_coarse[oc] = fv;
+            if (a.th_coarse) a.th_coarse[oc] = tv;
+        }
+    }
+}
 __global__ void psn_fill_kernel(double* p, long long cnt, double v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -639,7 +663,6 @@ int solve_internal(const Problem& P) {
     scfg.TH = scfg.TW = g.tile;
     scfg.mode = g.vcycle_mode;
     if (!resident) {
-        if (P.sub > 0) return psn_fail(PSN_ERR_UNSUPPORTED, "fused sub-domain epilogue needs the resident path (n=%d too large)", P.n);
         scfg.ls = stream_ls(plan);
         if (scfg.ls >= 1 && !psn_strip_ok(plan, scfg.ls)) scfg.mode = 0;   // odd level sizes: shared-memory tile kernels
         if (scfg.ls < 1) return psn_fail(PSN_ERR_UNSUPPORTED, "no shared-memory coarse level for n=%d", P.n);
@@ -787,7 +810,7 @@ int solve_internal(const Problem& P) {
         if ((rc2 = stage_out(ar, P.iters, k_it, b0, (size_t)bc, &cx.d_it, false))) return rc2;
         if ((rc2 = stage_out(ar, P.relres, k_rr, b0, (size_t)bc, &cx.d_rr, false))) return rc2;
         if ((rc2 = stage_out(ar, P.status, k_st, b0, (size_t)bc, &cx.d_st, false))) return rc2;
-        if (resident) {
+        if (resident || P.sub > 0) {
             PsnSolveArgs& a = cx.a;
             memset(&a, 0, sizeof(a));
             a.rhs = cx.rhs;
@@ -851,6 +874,17 @@ int solve_internal(const Problem& P) {
                 psn_finalize_kernel<<<(unsigned)((bc + 127) / 128), 128, 0, s>>>(ws.state, bc, cx.d_it, cx.d_rr, cx.d_st);
             }
             CU_TRY(cudaGetLastError());
+            if (P.sub > 0) {
+                const PsnSolveArgs& a = cx.a;
+                psn_window_kernel<<<dim3((unsigned)((P.sub * P.sub + 255) / 256), (unsigned)bc), 256, 0, s>>>(a, P.n, cx.d_u);
+                CU_TRY(cudaGetLastError());
+                if ((rc2 = copy_back(s, P.u_fine, k_uf, b0 * (long long)ss, bc * ss, a.u_fine))) return rc2;
+                if ((rc2 = copy_back(s, P.f_fine, k_ff, b0 * (long long)ss, bc * ss, a.f_fine))) return rc2;
+                if ((rc2 = copy_back(s, P.th_fine, k_tf, b0 * (long long)ss, bc * ss, a.th_fine))) return rc2;
+                if ((rc2 = copy_back(s, P.u_coarse, k_uc, b0 * (long long)scc, bc * scc, a.u_coarse))) return rc2;
+                if ((rc2 = copy_back(s, P.f_coarse, k_fc, b0 * (long long)scc, bc * scc, a.f_coarse))) return rc2;
+                if ((rc2 = copy_back(s, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, a.th_coarse))) return rc2;
+            }
             if (any_host) CU_TRY(cudaEventRecord(g.ws_free, s));
         }
         if ((rc2 = copy_back(s, P.u, k_u, b0 * (long long)nn, bc * nn, cx.d_u))) return rc2;

@@ -142,6 +142,22 @@ def test_generate_subdomain_dataset_matches_reference_fixture(gpu_lib):
     assert np.allclose(norms, meta["u_fine_norms"], rtol=1e-10, atol=0)
 
 
+def test_subdomain_dataset_on_a_streamed_superfine_grid(gpu_lib):
+    """n_superfine = 120 is too large for the resident kernel: the window / downsample epilogue then
+    runs as a separate gather kernel after the streamed solve.  Same results as the oracle."""
+    from superresolution_for_pdes_b200 import EnhancedPoissonSolver
+    np.random.seed(11)
+    es = EnhancedPoissonSolver(n_coarse=30, n_fine=60, n_superfine=120)
+    ds = es.generate_subdomain_dataset(3, k_range=(0.5, 9.0))
+    np.random.seed(11)
+    ref = O.generate_subdomain_dataset(3, k_range=(0.5, 9.0), n_coarse=30, n_fine=60, n_superfine=120)
+    for k in ("k1", "k2", "f_coarse", "f_fine", "theta_coarse", "theta_fine", "is_subdomain"):
+        assert np.array_equal(ds[k], ref[k]), k
+    for k in ("u_coarse", "u_fine"):
+        assert ds[k].shape == ref[k].shape
+        assert O.rel_l2(ds[k], ref[k]) <= TOL
+
+
 def test_multires_chain_matches_reference_fixture(gpu_lib):
     from superresolution_for_pdes_b200 import solve_multi_resolution
     gold = np.load(os.path.join(GOLDEN, "multires_seed2.npz"))
