@@ -18,6 +18,7 @@
 
 #include "../../include/psn_b200.h"
 #include "psn_stream_driver.h"
+#include "psn_block.cuh"
 
 #define PSN_VERSION 100
 
@@ -50,6 +51,16 @@ __global__ void __launch_bounds__(T) psn_smem_solve_kernel(const __grid_constant
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, T, red, 0};
     psn_smem_solve_body<XPT>(ctx, plan, a, (long long)blockIdx.x, smem);
+}
+
+// register-blocked resident solver (n = 4*BX): one CTA per sample, 4x4 nodes per thread in registers
+template <int BX>
+__global__ void __launch_bounds__(PsnBlockGeom<BX>::NTPAD, 1) psn_block_solve_kernel(const __grid_constant__ PsnPlan plan,
+                                                                                     const __grid_constant__ PsnSolveArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PsnBlockGeom<BX>::NTPAD, red, 0};
+    psn_block_solve_body<BX>(ctx, plan, a, (long long)blockIdx.x, smem);
 }
 
 #define PSN_TILE_THREADS 256
@@ -251,6 +262,7 @@ struct Context {
     long long ws_bytes = 16ll << 30;
     int smem_max_n = 0;
     int coarse_max_n = 40; // largest level handed to the shared-memory coarse V-cycle kernel (0: as large as fits)
+    int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
     int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 3 streamed / 8 resident)
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
@@ -355,6 +367,7 @@ int set_kernel_attrs() {
     if (g.attrs_set) return PSN_OK;
     const int mx = (int)g.smem_optin - 1024;  // leave room for the static reduction scratch
 #define PSN_RES_ATTR(T_, X_) CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<T_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
+    CU_TRY(cudaFuncSetAttribute(psn_block_solve_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     PSN_RES_ATTR(128, 4); PSN_RES_ATTR(256, 4); PSN_RES_ATTR(256, 8); PSN_RES_ATTR(512, 4);
     PSN_RES_ATTR(512, 8); PSN_RES_ATTR(1024, 4); PSN_RES_ATTR(512, 16); PSN_RES_ATTR(1024, 8);
 #undef PSN_RES_ATTR
@@ -844,11 +857,16 @@ int solve_internal(const Problem& P) {
             {
                 ProfScope pr("smem_solve", s);
                 const unsigned grid = (unsigned)bc;
+                if (g.res_block && plan.n == 80) {
+                    const size_t bsm = (size_t)psn_block_smem_doubles<20>(plan) * sizeof(double);
+                    psn_block_solve_kernel<20><<<grid, PsnBlockGeom<20>::NTPAD, bsm, s>>>(plan, a);
+                } else {
 #define PSN_RES_LAUNCH(T_, X_) \
     if (rcfg.T == T_ && rcfg.XPT == X_) psn_smem_solve_kernel<T_, X_><<<grid, T_, rcfg.smem, s>>>(plan, a)
                 PSN_RES_LAUNCH(128, 4); PSN_RES_LAUNCH(256, 4); PSN_RES_LAUNCH(256, 8); PSN_RES_LAUNCH(512, 4);
                 PSN_RES_LAUNCH(512, 8); PSN_RES_LAUNCH(1024, 4); PSN_RES_LAUNCH(512, 16); PSN_RES_LAUNCH(1024, 8);
 #undef PSN_RES_LAUNCH
+                }
             }
             CU_TRY(cudaGetLastError());
             if (P.sub > 0) {
@@ -1058,6 +1076,8 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "coarse_max_n")) {
         if (value < 0) return psn_fail(PSN_ERR_INVALID, "coarse_max_n must be >= 0");
         g.coarse_max_n = (int)value;
+    } else if (!strcmp(name, "res_block")) {
+        g.res_block = value ? 1 : 0;
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;

@@ -1,0 +1,748 @@
+// psn_block.cuh -- register-blocked resident solver for n = 4*BX (the 80x80 "super-fine" grid: BX = 20).
+//
+// One CTA solves one sample.  Thread (bx, by) owns the 4x4 block of finest-level nodes
+// rows 4by..4by+3, cols 4bx..4bx+3 and keeps r (residual = V-cycle rhs), z (V-cycle iterate) and
+// p (search direction) of that block in REGISTERS; x sits in shared memory in a [16][thread] layout.
+// A red-black half sweep updates 8 nodes per thread with neighbours taken from registers, except the
+// 8 block-edge neighbours, which come from four shared-memory edge buffers ([slot][thread] layout:
+// lanes are contiguous, so every access is bank-conflict free) that the owning thread re-publishes
+// after each half sweep.  Red and black edge slots alternate, so a half sweep reads only slots of the
+// other colour while it writes its own: one __syncthreads per half sweep, no double buffering.
+// Compared with the generic shared-memory kernel (psn_smem_solve_body) a node update drops from
+// 5 LDS + 1 STS + ~12 integer instructions to 1 LDS + 1 STS amortised and no index arithmetic.
+// Levels >= 1 (40^2 ... 5^2) reuse the shared-memory V-cycle of psn_core.cuh.
+//
+// Dual build like the rest of the bodies: nvcc compiles one thread's view (state arrays of extent 1);
+// the host emulation (tests/hostemu) keeps the state of all threads and runs every phase as a loop
+// over the virtual thread ids.
+#pragma once
+#include "psn_core.cuh"
+
+#ifndef PSN_BLOCK_DEEP
+#define PSN_BLOCK_DEEP 1
+#endif
+
+#if defined(__CUDACC__)
+#define PSN_BK_TS 1
+#define PSN_BK_FOR(ctx, NT) for (int t_ = (ctx).tid, once_ = 1; once_; once_ = 0)
+#define PSN_BK_TI 0
+#else
+#define PSN_BK_TS NTPAD
+#define PSN_BK_FOR(ctx, NT) for (int t_ = 0; t_ < (NT); ++t_)
+#define PSN_BK_TI t_
+#endif
+
+// Shared-memory array of doubles addressed by a 32-bit shared-space address (device): every access is
+// one ld.shared / st.shared with an immediate offset.  (With generic double* members the compiler
+// re-derived the cluster-window base -- S2UR SR_CgaCtaId + ULEA -- in front of almost every access:
+// 18 % of all executed instructions and a long-latency link in every dependency chain.)
+#if defined(__CUDACC__)
+struct PsnShF64 {
+    unsigned base;
+    __device__ __forceinline__ explicit PsnShF64(double* p) : base((unsigned)__cvta_generic_to_shared(p)) {}
+    __device__ __forceinline__ PsnShF64 at(int off) const { PsnShF64 r(*this); r.base = base + 8u * (unsigned)off; return r; }
+    __device__ __forceinline__ double ld(int i) const {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + 8u * (unsigned)i) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void st(int i, double v) const {
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + 8u * (unsigned)i), "d"(v) : "memory");
+    }
+    __device__ __forceinline__ void add(int i, double v) const { st(i, ld(i) + v); }
+};
+#else
+struct PsnShF64 {
+    double* base;
+    explicit PsnShF64(double* p) : base(p) {}
+    PsnShF64 at(int off) const { return PsnShF64(base + off); }
+    double ld(int i) const { return base[i]; }
+    void st(int i, double v) const { base[i] = v; }
+    void add(int i, double v) const { base[i] += v; }
+};
+#endif
+
+template <int BX>
+struct PsnBlockGeom {
+    static constexpr int N = 4 * BX;
+    static constexpr int NT = BX * BX;
+    static constexpr int NTPAD = (NT + 31) & ~31;
+    // shared memory (doubles): x[16][NTPAD], edges[4 sides][4 slots][NTPAD]
+    static constexpr int XS = 16 * NTPAD;
+    static constexpr int ES = 16 * NTPAD;
+};
+
+// doubles of dynamic shared memory the block kernel needs (x, edge buffers, coarse levels >= 1)
+template <int BX>
+PSN_HDFN int psn_block_smem_doubles(const PsnPlan& plan) {
+    return PsnBlockGeom<BX>::XS + PsnBlockGeom<BX>::ES + psn_pool_doubles(plan, 0);
+}
+
+template <int BX, class Ctx>
+struct PsnBlockSolver {
+    typedef PsnBlockGeom<BX> G;
+    static constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
+    enum { TOP = 0, BOT = 1, LEFT = 2, RIGHT = 3 };
+
+    Ctx& ctx;
+    PsnShF64 xs;     // [16][NTPAD]
+    PsnShF64 edge;   // [4][4][NTPAD]
+    double z[PSN_BK_TS][16], r[PSN_BK_TS][16], p[PSN_BK_TS][16];
+
+    PSN_FN PsnBlockSolver(Ctx& c, double* smem) : ctx(c), xs(smem), edge(smem + G::XS) {}   // (explicit PsnShF64 ctors)
+
+    // element t of edge buffer (side, slot)
+    PSN_FN double EL(int side, int slot, int t) const { return edge.ld((side * 4 + slot) * NTPAD + t); }
+    PSN_FN void ES(int side, int slot, int t, double v) const { edge.st((side * 4 + slot) * NTPAD + t, v); }
+
+    // halo values of field v needed by a half sweep of colour `col` (slots of the other colour)
+    PSN_FN void load_halo(int t, int col, double (&hT)[4], double (&hB)[4], double (&hL)[4], double (&hR)[4]) {
+        const int bx = t % BX, by = t / BX;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hT[k] = hB[k] = hL[k] = hR[k] = 0.0;
+            if ((k & 1) == col) {           // (0,k) and (k,0) have colour col: they need the node above / left
+                if (by > 0) hT[k] = EL(BOT, k, t - BX);
+                if (bx > 0) hL[k] = EL(RIGHT, k, t - 1);
+            } else {                        // (3,k) and (k,3) have colour col: they need the node below / right
+                if (by < BX - 1) hB[k] = EL(TOP, k, t + BX);
+                if (bx < BX - 1) hR[k] = EL(LEFT, k, t + 1);
+            }
+        }
+    }
+    // all 16 halo values (both colours)
+    PSN_FN void load_halo_all(int t, double (&hT)[4], double (&hB)[4], double (&hL)[4], double (&hR)[4]) {
+        const int bx = t % BX, by = t / BX;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hT[k] = (by > 0) ? EL(BOT, k, t - BX) : 0.0;
+            hB[k] = (by < BX - 1) ? EL(TOP, k, t + BX) : 0.0;
+            hL[k] = (bx > 0) ? EL(RIGHT, k, t - 1) : 0.0;
+            hR[k] = (bx < BX - 1) ? EL(LEFT, k, t + 1) : 0.0;
+        }
+    }
+    // publish the edge values of colour `col` (col < 0: both colours) of field v
+    PSN_FN void publish(int t, const double (&v)[16], int col) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (col < 0 || (k & 1) == col) {        // (0,k), (k,0) have colour k&1
+                ES(TOP, k, t, v[k]);
+                ES(LEFT, k, t, v[4 * k]);
+            }
+            if (col < 0 || (k & 1) != col) {        // (3,k), (k,3) have colour (k+1)&1
+                ES(BOT, k, t, v[12 + k]);
+                ES(RIGHT, k, t, v[4 * k + 3]);
+            }
+        }
+    }
+    // sum of the four neighbours of local node (a, c)
+    PSN_FN static double nbsum(const double (&v)[16], int a, int c, const double (&hT)[4], const double (&hB)[4],
+                               const double (&hL)[4], const double (&hR)[4]) {
+        const double up = (a > 0) ? v[4 * (a - 1) + c] : hT[c];
+        const double dn = (a < 3) ? v[4 * (a + 1) + c] : hB[c];
+        const double lf = (c > 0) ? v[4 * a + c - 1] : hL[a];
+        const double rt = (c < 3) ? v[4 * a + c + 1] : hR[a];
+        return (up + dn) + (lf + rt);
+    }
+
+    // one RB-GS half sweep on z with rhs r; ends with the edges of colour `col` published and a sync
+    PSN_FN void half_sweep(int col, bool first) {
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                double (&zz)[16] = z[PSN_BK_TI];
+                const double (&rr)[16] = r[PSN_BK_TI];
+                double hT[4], hB[4], hL[4], hR[4];
+                if (!first) load_halo(t_, col, hT, hB, hL, hR);
+                double nv[16];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (((a + c) & 1) == col)
+                            nv[4 * a + c] = (rr[4 * a + c] + (first ? 0.0 : nbsum(zz, a, c, hT, hB, hL, hR))) * 0.25;
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if ((((k >> 2) + (k & 3)) & 1) == col) zz[k] = nv[k];
+                publish(t_, zz, col);
+            }
+        }
+        ctx.sync();
+    }
+
+    // restricted residual of level 0 -> shared rhs array of level 1 (ghost-ringed layout); needs the black edges of z
+    PSN_FN void residual_restrict(const PsnLevel& l1, double* b1) {
+        // red residuals in registers; publish the ones other blocks need as corners (row 0 / col 0, even slots)
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const double (&zz)[16] = z[PSN_BK_TI];
+                const double (&rr)[16] = r[PSN_BK_TI];
+                double (&pp)[16] = rho[PSN_BK_TI];
+                double hT[4], hB[4], hL[4], hR[4];
+                load_halo(t_, 0, hT, hB, hL, hR);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (((a + c) & 1) == 0) pp[4 * a + c] = rr[4 * a + c] - (4.0 * zz[4 * a + c] - nbsum(zz, a, c, hT, hB, hL, hR));
+            }
+        }
+        ctx.sync();   // everybody has read the black edges of z before the red slots are reused for rho
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const double (&pp)[16] = rho[PSN_BK_TI];
+                ES(TOP, 0, t_, pp[0]);
+                ES(TOP, 2, t_, pp[2]);
+                ES(LEFT, 0, t_, pp[0]);
+                ES(LEFT, 2, t_, pp[8]);
+            }
+        }
+        ctx.sync();
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const double (&pp)[16] = rho[PSN_BK_TI];
+                const int bx = t_ % BX, by = t_ / BX;
+                const bool hasR = bx < BX - 1, hasB = by < BX - 1;
+                const double r04 = hasR ? EL(LEFT, 0, t_ + 1) : 0.0, r24 = hasR ? EL(LEFT, 2, t_ + 1) : 0.0;
+                const double r40 = hasB ? EL(TOP, 0, t_ + BX) : 0.0, r42 = hasB ? EL(TOP, 2, t_ + BX) : 0.0;
+                const double r44 = (hasR && hasB) ? EL(TOP, 0, t_ + BX + 1) : 0.0;
+                const int P1 = l1.pitch;
+                double* o = b1 + (2 * by + 1) * P1 + (2 * bx + 1);
+                o[0] = pp[5] + 0.25 * ((pp[0] + pp[2]) + (pp[8] + pp[10]));
+                o[1] = pp[7] + 0.25 * ((pp[2] + r04) + (pp[10] + r24));
+                o[P1] = pp[13] + 0.25 * ((pp[8] + pp[10]) + (r40 + r42));
+                o[P1 + 1] = pp[15] + 0.25 * ((pp[10] + r24) + (r42 + r44));
+            }
+        }
+        ctx.sync();
+    }
+
+    // z += P u1 on the red nodes; ends with the red edges of z published and a sync
+    PSN_FN void prolong(const PsnLevel& l1, const double* u1) {
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                double (&zz)[16] = z[PSN_BK_TI];
+                const int bx = t_ % BX, by = t_ / BX;
+                const int P1 = l1.pitch;
+                const double* e = u1 + (2 * by + 1) * P1 + (2 * bx + 1);   // coarse (2by, 2bx)
+                const double e00 = e[0], e01 = e[1], e10 = e[P1], e11 = e[P1 + 1];
+                const double em0 = e[-P1], em1 = e[-P1 + 1], emm = e[-P1 - 1], e0m = e[-1], e1m = e[P1 - 1];
+                zz[5] += e00;
+                zz[7] += e01;
+                zz[13] += e10;
+                zz[15] += e11;
+                zz[0] += 0.25 * ((emm + em0) + (e0m + e00));
+                zz[2] += 0.25 * ((em0 + em1) + (e00 + e01));
+                zz[8] += 0.25 * ((e0m + e00) + (e1m + e10));
+                zz[10] += 0.25 * ((e00 + e01) + (e10 + e11));
+                publish(t_, zz, 0);
+            }
+        }
+        ctx.sync();
+    }
+
+    double rho[PSN_BK_TS][16];
+
+    // z = M^{-1} r : V(nu,nu) with level 0 in registers
+    PSN_FN void vcycle(const PsnPlan& plan, double* pool) {
+        const int nu = plan.nu;
+        const PsnLevel& l1 = plan.lv[1];
+        double* b1 = pool;              // pool layout of psn_vcycle_smem: level-1 rhs, then level-1 solution
+        double* u1 = pool + l1.size;
+        half_sweep(0, true);
+        half_sweep(1, false);
+        for (int s = 1; s < nu; ++s) {
+            half_sweep(0, false);
+            half_sweep(1, false);
+        }
+        residual_restrict(l1, b1);
+        psn_vcycle_smem(ctx, plan, 1, b1, u1, pool + 2 * l1.size);
+        prolong(l1, u1);
+        for (int s = 0; s < nu; ++s) {
+            half_sweep(1, false);
+            half_sweep(0, false);
+        }
+    }
+
+    // ------------------------------------------------------------------ three register-blocked levels
+    // Level 1 (2 BX)^2: each thread owns the 2x2 block under its fine block; level 2 (BX)^2: one node per
+    // thread.  Same edge-buffer exchange (slots k < block size); levels >= 3 stay in the shared-memory code.
+    double z1[PSN_BK_TS][4], r1[PSN_BK_TS][4], z2[PSN_BK_TS][1], r2[PSN_BK_TS][1];
+
+    template <int BS>
+    PSN_FN void load_halo_bs(int t, int col, double (&hT)[BS], double (&hB)[BS], double (&hL)[BS], double (&hR)[BS]) {
+        const int bx = t % BX, by = t / BX;
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+            hT[k] = hB[k] = hL[k] = hR[k] = 0.0;
+            if (col < 0 || (k & 1) == col) {
+                if (by > 0) hT[k] = EL(BOT, k, t - BX);
+                if (bx > 0) hL[k] = EL(RIGHT, k, t - 1);
+            }
+            if (col < 0 || (k & 1) != col) {
+                if (by < BX - 1) hB[k] = EL(TOP, k, t + BX);
+                if (bx < BX - 1) hR[k] = EL(LEFT, k, t + 1);
+            }
+        }
+    }
+    template <int BS>
+    PSN_FN void publish_bs(int t, const double (&v)[BS * BS], int col) {
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+            if (col < 0 || (k & 1) == col) {
+                ES(TOP, k, t, v[k]);
+                ES(LEFT, k, t, v[BS * k]);
+            }
+            if (col < 0 || (k & 1) != col) {
+                ES(BOT, k, t, v[BS * (BS - 1) + k]);
+                ES(RIGHT, k, t, v[BS * k + BS - 1]);
+            }
+        }
+    }
+    template <int BS>
+    PSN_FN static double nbsum_bs(const double (&v)[BS * BS], int a, int c, const double (&hT)[BS], const double (&hB)[BS],
+                                  const double (&hL)[BS], const double (&hR)[BS]) {
+        const double up = (a > 0) ? v[BS * (a - 1) + c] : hT[c];
+        const double dn = (a < BS - 1) ? v[BS * (a + 1) + c] : hB[c];
+        const double lf = (c > 0) ? v[BS * a + c - 1] : hL[a];
+        const double rt = (c < BS - 1) ? v[BS * a + c + 1] : hR[a];
+        return (up + dn) + (lf + rt);
+    }
+    // diagonal weight of local node (a, c) of a BS-blocked level (extra weight gam on the last grid row / column)
+    template <int BS>
+    PSN_FN static double diag_bs(const PsnLevel& lv, int t, int a, int c) {
+        const int bx = t % BX, by = t / BX;
+        const bool lr = (by == BX - 1) && (a == BS - 1), lc = (bx == BX - 1) && (c == BS - 1);
+        return 4.0 + (lr ? lv.gam : 0.0) + (lc ? lv.gam : 0.0);
+    }
+    template <int BS>
+    PSN_FN static double rdiag_bs(const PsnLevel& lv, int t, int a, int c) {
+        const int bx = t % BX, by = t / BX;
+        const bool lr = (by == BX - 1) && (a == BS - 1), lc = (bx == BX - 1) && (c == BS - 1);
+        return lr ? (lc ? lv.rd2 : lv.rd1) : (lc ? lv.rd1 : lv.rd0);
+    }
+    // half sweep of a BS-blocked level held in zz / rr (thread t_); publishes the updated colour
+    template <int BS>
+    PSN_FN void half_sweep_bs(int t, const PsnLevel& lv, double (&zz)[BS * BS], const double (&rr)[BS * BS], int col, bool first) {
+        double hT[BS], hB[BS], hL[BS], hR[BS];
+        if (!first) load_halo_bs<BS>(t, col, hT, hB, hL, hR);
+        double nv[BS * BS];
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int c = 0; c < BS; ++c)
+                if (((a + c) & 1) == col)
+                    nv[BS * a + c] = (rr[BS * a + c] + (first ? 0.0 : nbsum_bs<BS>(zz, a, c, hT, hB, hL, hR))) * rdiag_bs<BS>(lv, t, a, c);
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+#pragma unroll
+            for (int c = 0; c < BS; ++c)
+                if (((a + c) & 1) == col) zz[BS * a + c] = nv[BS * a + c];
+        publish_bs<BS>(t, zz, col);
+    }
+    // level 2: one node per thread, colour (bx + by) & 1; all four sides read the single slot TOP[0]
+    PSN_FN double nb2(int t) {
+        const int bx = t % BX, by = t / BX;
+        const double up = (by > 0) ? EL(TOP, 0, t - BX) : 0.0, dn = (by < BX - 1) ? EL(TOP, 0, t + BX) : 0.0;
+        const double lf = (bx > 0) ? EL(TOP, 0, t - 1) : 0.0, rt = (bx < BX - 1) ? EL(TOP, 0, t + 1) : 0.0;
+        return (up + dn) + (lf + rt);
+    }
+    PSN_FN void half_sweep_2(const PsnLevel& lv, int col, bool first) {
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT && (((t_ % BX) + (t_ / BX)) & 1) == col) {
+                const double v = (r2[PSN_BK_TI][0] + (first ? 0.0 : nb2(t_))) * rdiag_bs<1>(lv, t_, 0, 0);
+                z2[PSN_BK_TI][0] = v;
+                ES(TOP, 0, t_, v);
+            }
+        }
+        ctx.sync();
+    }
+
+    // z = M^{-1} r with levels 0, 1, 2 in registers (n = 4 BX, 2 BX, BX) and levels >= 3 in shared memory
+    PSN_FN void vcycle3(const PsnPlan& plan, double* pool) {
+        const int nu = plan.nu;
+        const PsnLevel& l1 = plan.lv[1];
+        const PsnLevel& l2 = plan.lv[2];
+        const PsnLevel& l3 = plan.lv[3];
+        double* b3 = pool;
+        double* u3 = pool + l3.size;
+        double* pool4 = pool + 2 * l3.size;
+        // ---------------- level 0 down
+        half_sweep(0, true);
+        half_sweep(1, false);
+        for (int s = 1; s < nu; ++s) {
+            half_sweep(0, false);
+            half_sweep(1, false);
+        }
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const double (&zz)[16] = z[PSN_BK_TI];
+                const double (&rr)[16] = r[PSN_BK_TI];
+                double (&pp)[16] = rho[PSN_BK_TI];
+                double hT[4], hB[4], hL[4], hR[4];
+                load_halo(t_, 0, hT, hB, hL, hR);
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (((a + c) & 1) == 0) pp[4 * a + c] = rr[4 * a + c] - (4.0 * zz[4 * a + c] - nbsum(zz, a, c, hT, hB, hL, hR));
+                // (reads above: black slots; writes below: red slots of TOP / LEFT -> no barrier needed in between)
+                ES(TOP, 0, t_, pp[0]);
+                ES(TOP, 2, t_, pp[2]);
+                ES(LEFT, 0, t_, pp[0]);
+                ES(LEFT, 2, t_, pp[8]);
+            }
+        }
+        ctx.sync();
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const double (&pp)[16] = rho[PSN_BK_TI];
+                const int bx = t_ % BX, by = t_ / BX;
+                const bool hasR = bx < BX - 1, hasB = by < BX - 1;
+                const double r04 = hasR ? EL(LEFT, 0, t_ + 1) : 0.0, r24 = hasR ? EL(LEFT, 2, t_ + 1) : 0.0;
+                const double r40 = hasB ? EL(TOP, 0, t_ + BX) : 0.0, r42 = hasB ? EL(TOP, 2, t_ + BX) : 0.0;
+                const double r44 = (hasR && hasB) ? EL(TOP, 0, t_ + BX + 1) : 0.0;
+                double (&q)[4] = r1[PSN_BK_TI];
+                q[0] = pp[5] + 0.25 * ((pp[0] + pp[2]) + (pp[8] + pp[10]));
+                q[1] = pp[7] + 0.25 * ((pp[2] + r04) + (pp[10] + r24));
+                q[2] = pp[13] + 0.25 * ((pp[8] + pp[10]) + (r40 + r42));
+                q[3] = pp[15] + 0.25 * ((pp[10] + r24) + (r42 + r44));
+            }
+        }
+        ctx.sync();
+        // ---------------- level 1 down (2x2 per thread)
+        for (int s = 0; s < nu; ++s) {
+            PSN_BK_FOR(ctx, NT) { if (t_ < NT) half_sweep_bs<2>(t_, l1, z1[PSN_BK_TI], r1[PSN_BK_TI], 0, s == 0); }
+            ctx.sync();
+            PSN_BK_FOR(ctx, NT) { if (t_ < NT) half_sweep_bs<2>(t_, l1, z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
+            ctx.sync();
+        }
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const double (&zz)[4] = z1[PSN_BK_TI];
+                const double (&rr)[4] = r1[PSN_BK_TI];
+                double hT[2], hB[2], hL[2], hR[2];
+                load_halo_bs<2>(t_, 0, hT, hB, hL, hR);
+                const double rho00 = rr[0] - (diag_bs<2>(l1, t_, 0, 0) * zz[0] - nbsum_bs<2>(zz, 0, 0, hT, hB, hL, hR));
+                const double rho11 = rr[3] - (diag_bs<2>(l1, t_, 1, 1) * zz[3] - nbsum_bs<2>(zz, 1, 1, hT, hB, hL, hR));
+                rho[PSN_BK_TI][0] = rho00;
+                rho[PSN_BK_TI][1] = rho11;
+                ES(TOP, 0, t_, rho00);   // red slot of TOP: not read by this phase
+            }
+        }
+        ctx.sync();
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const int bx = t_ % BX, by = t_ / BX;
+                const bool hasR = bx < BX - 1, hasB = by < BX - 1;
+                const double c02 = hasR ? EL(TOP, 0, t_ + 1) : 0.0, c20 = hasB ? EL(TOP, 0, t_ + BX) : 0.0;
+                const double c22 = (hasR && hasB) ? EL(TOP, 0, t_ + BX + 1) : 0.0;
+                r2[PSN_BK_TI][0] = rho[PSN_BK_TI][1] + 0.25 * ((rho[PSN_BK_TI][0] + c02) + (c20 + c22));
+            }
+        }
+        ctx.sync();
+        // ---------------- level 2 down (one node per thread)
+        for (int s = 0; s < nu; ++s) {
+            half_sweep_2(l2, 0, s == 0);
+            half_sweep_2(l2, 1, false);
+        }
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {   // residual on red nodes -> BOT[0] (TOP[0] is being read by the neighbours)
+                double rh = 0.0;
+                if ((((t_ % BX) + (t_ / BX)) & 1) == 0) rh = r2[PSN_BK_TI][0] - (diag_bs<1>(l2, t_, 0, 0) * z2[PSN_BK_TI][0] - nb2(t_));
+                rho[PSN_BK_TI][0] = rh;
+                ES(BOT, 0, t_, rh);
+            }
+        }
+        ctx.sync();
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const int bx = t_ % BX, by = t_ / BX;
+                if ((bx & 1) && (by & 1)) {   // centre of coarse node ((by-1)/2, (bx-1)/2) of level 3
+                    const bool hasR = bx < BX - 1, hasB = by < BX - 1;
+                    const double c00 = EL(BOT, 0, t_ - BX - 1), c02 = hasR ? EL(BOT, 0, t_ - BX + 1) : 0.0;
+                    const double c20 = hasB ? EL(BOT, 0, t_ + BX - 1) : 0.0, c22 = (hasR && hasB) ? EL(BOT, 0, t_ + BX + 1) : 0.0;
+                    b3[(((by - 1) >> 1) + 1) * l3.pitch + ((bx - 1) >> 1) + 1] = rho[PSN_BK_TI][0] + 0.25 * ((c00 + c02) + (c20 + c22));
+                }
+            }
+        }
+        ctx.sync();
+        // ---------------- levels >= 3 in shared memory (all warps; running them on a single warp with
+        // __syncwarp instead of CTA barriers was measured 7 % slower)
+        psn_vcycle_smem(ctx, plan, 3, b3, u3, pool4);
+        // ---------------- level 2 up
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const int bx = t_ % BX, by = t_ / BX;
+                if (((bx + by) & 1) == 0) {
+                    const int P3 = l3.pitch;
+                    double add;
+                    if (by & 1) {
+                        add = u3[(((by - 1) >> 1) + 1) * P3 + ((bx - 1) >> 1) + 1];
+                    } else {
+                        const double* e = u3 + ((by >> 1) + 1) * P3 + (bx >> 1) + 1;
+                        add = 0.25 * ((e[-P3 - 1] + e[-P3]) + (e[-1] + e[0]));
+                    }
+                    z2[PSN_BK_TI][0] += add;
+                    ES(TOP, 0, t_, z2[PSN_BK_TI][0]);
+                }
+            }
+        }
+        ctx.sync();
+        for (int s = 0; s < nu; ++s) {
+            half_sweep_2(l2, 1, false);
+            half_sweep_2(l2, 0, false);
+        }
+        // ---------------- level 1 up: corrections from z2 (TOP[0] holds every thread's current z2)
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                const int bx = t_ % BX, by = t_ / BX;
+                const double e00 = z2[PSN_BK_TI][0];
+                const double em0 = (by > 0) ? EL(TOP, 0, t_ - BX) : 0.0, e0m = (bx > 0) ? EL(TOP, 0, t_ - 1) : 0.0;
+                const double emm = (by > 0 && bx > 0) ? EL(TOP, 0, t_ - BX - 1) : 0.0;
+                z1[PSN_BK_TI][3] += e00;
+                z1[PSN_BK_TI][0] += 0.25 * ((emm + em0) + (e0m + e00));
+            }
+        }
+        ctx.sync();   // TOP[0] is about to be overwritten by the edges of z1
+        PSN_BK_FOR(ctx, NT) { if (t_ < NT) publish_bs<2>(t_, z1[PSN_BK_TI], 0); }
+        ctx.sync();
+        for (int s = 0; s < nu; ++s) {
+            PSN_BK_FOR(ctx, NT) { if (t_ < NT) half_sweep_bs<2>(t_, l1, z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
+            ctx.sync();
+            PSN_BK_FOR(ctx, NT) { if (t_ < NT) half_sweep_bs<2>(t_, l1, z1[PSN_BK_TI], r1[PSN_BK_TI], 0, false); }
+            ctx.sync();
+        }
+        // ---------------- level 0 up: corrections from z1 (every edge of z1 is current in the buffers)
+        PSN_BK_FOR(ctx, NT) {
+            if (t_ < NT) {
+                double (&zz)[16] = z[PSN_BK_TI];
+                const double (&ee)[4] = z1[PSN_BK_TI];
+                const int bx = t_ % BX, by = t_ / BX;
+                const double e00 = ee[0], e01 = ee[1], e10 = ee[2], e11 = ee[3];
+                const double em0 = (by > 0) ? EL(BOT, 0, t_ - BX) : 0.0, em1 = (by > 0) ? EL(BOT, 1, t_ - BX) : 0.0;
+                const double e0m = (bx > 0) ? EL(RIGHT, 0, t_ - 1) : 0.0, e1m = (bx > 0) ? EL(RIGHT, 1, t_ - 1) : 0.0;
+                const double emm = (by > 0 && bx > 0) ? EL(BOT, 1, t_ - BX - 1) : 0.0;
+                zz[5] += e00;
+                zz[7] += e01;
+                zz[13] += e10;
+                zz[15] += e11;
+                zz[0] += 0.25 * ((emm + em0) + (e0m + e00));
+                zz[2] += 0.25 * ((em0 + em1) + (e00 + e01));
+                zz[8] += 0.25 * ((e0m + e00) + (e1m + e10));
+                zz[10] += 0.25 * ((e00 + e01) + (e10 + e11));
+            }
+        }
+        ctx.sync();   // the z1 edges have been read; the buffers now take the red edges of z
+        PSN_BK_FOR(ctx, NT) { if (t_ < NT) publish(t_, z[PSN_BK_TI], 0); }
+        ctx.sync();
+        for (int s = 0; s < nu; ++s) {
+            half_sweep(1, false);
+            half_sweep(0, false);
+        }
+    }
+
+    // block-wide sum of per-thread partials (device: acc[0] of every thread; host: all entries)
+    PSN_FN double tsum(const double (&acc)[PSN_BK_TS]) {
+#if defined(__CUDACC__)
+        return ctx.block_sum(acc[0]);
+#else
+        double s = 0.0;
+        for (int t = 0; t < NT; ++t) s += acc[t];
+        return s;
+#endif
+    }
+};
+
+// Whole solve of sample b.  smem: dynamic shared memory (psn_block_smem_doubles doubles).
+template <int BX, class Ctx>
+PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveArgs& a, long long b, double* smem) {
+    typedef PsnBlockGeom<BX> G;
+    constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
+    PsnBlockSolver<BX, Ctx> S(ctx, smem);
+    double* pool = smem + G::XS + G::ES;
+    const int pool_n = psn_pool_doubles(plan, 0);
+    for (int idx = ctx.tid; idx < pool_n; idx += ctx.nthreads) pool[idx] = 0.0;   // ghost rings of the coarse levels
+    double acc[PSN_BK_TS];
+    // levels 1 and 2 in registers as well when the hierarchy is n, n/2, n/4, ... with at least 4 levels
+    const bool deep = (a.sub >= -1) && plan.nlev >= 4 && plan.lv[1].n == 2 * BX && plan.lv[2].n == BX && PSN_BLOCK_DEEP;
+
+    // ---- prologue: r = bt, x = 0
+    PSN_BK_FOR(ctx, NT) {
+        acc[PSN_BK_TI] = 0.0;
+        if (t_ < NT) {
+            const int bx = t_ % BX, by = t_ / BX;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const double v = psn_rhs(a.rhs, b, 4 * by + (k >> 2), 4 * bx + (k & 3), plan.h2);
+                S.r[PSN_BK_TI][k] = v;
+                S.p[PSN_BK_TI][k] = 0.0;
+                S.xs.st(k * NTPAD + t_, 0.0);
+                s += v * v;
+            }
+            acc[PSN_BK_TI] = s;
+        }
+    }
+    ctx.sync();
+    const double bb = S.tsum(acc);
+    const double tol2 = a.rtol * a.rtol * bb;
+
+    int it = 0, status = PSN_ST_MAXITER, nrestart = 0;
+    bool restart = true;
+    double rz_old = 1.0, prev_true = 0.0, rr_final = bb;
+    if (!(bb > 0.0)) {
+        status = (bb == 0.0) ? PSN_ST_CONVERGED : PSN_ST_BREAKDOWN;
+        rr_final = 0.0;
+    } else {
+        for (;;) {
+            if (deep) S.vcycle3(plan, pool + plan.lv[3].off); else S.vcycle(plan, pool);
+            PSN_BK_FOR(ctx, NT) {
+                acc[PSN_BK_TI] = 0.0;
+                if (t_ < NT) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) s += S.r[PSN_BK_TI][k] * S.z[PSN_BK_TI][k];
+                    acc[PSN_BK_TI] = s;
+                }
+            }
+            const double rz = S.tsum(acc);      // (device: block_sum syncs, so every thread is past its last edge read)
+            const double beta = restart ? 0.0 : rz / rz_old;
+            restart = false;
+            rz_old = rz;
+            // p = z + beta p, publish every edge of p
+            PSN_BK_FOR(ctx, NT) {
+                if (t_ < NT) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) S.p[PSN_BK_TI][k] = S.z[PSN_BK_TI][k] + beta * S.p[PSN_BK_TI][k];
+                    S.publish(t_, S.p[PSN_BK_TI], -1);
+                }
+            }
+            ctx.sync();
+            // q = At p (kept in z), <p, q>
+            PSN_BK_FOR(ctx, NT) {
+                acc[PSN_BK_TI] = 0.0;
+                if (t_ < NT) {
+                    double hT[4], hB[4], hL[4], hR[4];
+                    S.load_halo_all(t_, hT, hB, hL, hR);
+                    double s = 0.0;
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const double pc = S.p[PSN_BK_TI][4 * aa + c];
+                            const double q = 4.0 * pc - PsnBlockSolver<BX, Ctx>::nbsum(S.p[PSN_BK_TI], aa, c, hT, hB, hL, hR);
+                            S.z[PSN_BK_TI][4 * aa + c] = q;
+                            s += pc * q;
+                        }
+                    acc[PSN_BK_TI] = s;
+                }
+            }
+            const double pq = S.tsum(acc);
+            if (!(pq > 0.0)) {
+                status = PSN_ST_BREAKDOWN;
+                break;
+            }
+            const double alpha = rz / pq;
+            PSN_BK_FOR(ctx, NT) {
+                acc[PSN_BK_TI] = 0.0;
+                if (t_ < NT) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        S.xs.add(k * NTPAD + t_, alpha * S.p[PSN_BK_TI][k]);
+                        const double rv = S.r[PSN_BK_TI][k] - alpha * S.z[PSN_BK_TI][k];
+                        S.r[PSN_BK_TI][k] = rv;
+                        s += rv * rv;
+                    }
+                    acc[PSN_BK_TI] = s;
+                }
+            }
+            const double rr = S.tsum(acc);
+            rr_final = rr;
+            ++it;
+            if (rr <= tol2 || it >= a.max_iter) {
+                // true residual r = bt - At x: x block into z, publish, stencil
+                PSN_BK_FOR(ctx, NT) {
+                    if (t_ < NT) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) S.z[PSN_BK_TI][k] = S.xs.ld(k * NTPAD + t_);
+                        S.publish(t_, S.z[PSN_BK_TI], -1);
+                    }
+                }
+                ctx.sync();
+                PSN_BK_FOR(ctx, NT) {
+                    acc[PSN_BK_TI] = 0.0;
+                    if (t_ < NT) {
+                        const int bx = t_ % BX, by = t_ / BX;
+                        double hT[4], hB[4], hL[4], hR[4];
+                        S.load_halo_all(t_, hT, hB, hL, hR);
+                        double s = 0.0;
+#pragma unroll
+                        for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                const double bt = psn_rhs(a.rhs, b, 4 * by + aa, 4 * bx + c, plan.h2);
+                                const double rv = bt - (4.0 * S.z[PSN_BK_TI][4 * aa + c] -
+                                                        PsnBlockSolver<BX, Ctx>::nbsum(S.z[PSN_BK_TI], aa, c, hT, hB, hL, hR));
+                                S.r[PSN_BK_TI][4 * aa + c] = rv;
+                                s += rv * rv;
+                            }
+                        acc[PSN_BK_TI] = s;
+                    }
+                }
+                const double rt = S.tsum(acc);
+                rr_final = rt;
+                if (rt <= tol2) { status = PSN_ST_CONVERGED; break; }
+                if (nrestart >= 1 && rt > prev_true * 0.0625) { status = PSN_ST_FP64_FLOOR; break; }
+                if (it >= a.max_iter) { status = PSN_ST_MAXITER; break; }
+                prev_true = rt;
+                ++nrestart;
+                restart = true;
+            }
+        }
+    }
+
+    // ---- epilogue: u and / or the fused window + downsample outputs
+    PSN_BK_FOR(ctx, NT) {
+        if (t_ < NT) {
+            const int bx = t_ % BX, by = t_ / BX;
+            double xv[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) xv[k] = S.xs.ld(k * NTPAD + t_);
+            if (a.u) {
+                double* ug = a.u + b * (long long)(N * N);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) ug[(4 * by + (k >> 2)) * N + 4 * bx + (k & 3)] = xv[k];
+            }
+            if (a.sub > 0) {
+                const int s = a.sub, sc = (s + 1) >> 1;
+                const int x0 = a.start_x[b], y0 = a.start_y[b];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int i = 4 * by + (k >> 2), j = 4 * bx + (k & 3);
+                    const int wi = i - y0, wj = j - x0;
+                    if (wi >= 0 && wi < s && wj >= 0 && wj < s) {
+                        const double fv = psn_forcing(a.rhs, b, i, j);
+                        const double tv = a.rhs.theta
+                            ? a.rhs.theta[(b * a.rhs.mn + (long long)i * a.rhs.step) * a.rhs.mn + (long long)j * a.rhs.step] : 1.0;
+                        const long long o = (b * s + wi) * s + wj;
+                        if (a.u_fine) a.u_fine[o] = xv[k];
+                        if (a.f_fine) a.f_fine[o] = fv;
+                        if (a.th_fine) a.th_fine[o] = tv;
+                        if (((wi | wj) & 1) == 0) {
+                            const long long oc = (b * sc + (wi >> 1)) * sc + (wj >> 1);
+                            if (a.u_coarse) a.u_coarse[oc] = xv[k];
+                            if (a.f_coarse) a.f_coarse[oc] = fv;
+                            if (a.th_coarse) a.th_coarse[oc] = tv;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (ctx.tid == 0) {
+        if (a.iters) a.iters[b] = it;
+        if (a.relres) a.relres[b] = (bb > 0.0) ? sqrt(rr_final / bb) : 0.0;
+        if (a.status) a.status[b] = status;
+    }
+}

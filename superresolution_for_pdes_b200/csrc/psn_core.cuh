@@ -135,6 +135,15 @@ struct PsnDevCtx {
 };
 #endif
 
+#if defined(__CUDACC__)
+// One warp acting as a (small) CTA: used for the tiny coarse levels, where a CTA-wide barrier per half
+// sweep costs far more than the sweep itself.
+struct PsnWarpCtxDev {
+    int tid, nthreads;
+    __device__ __forceinline__ void sync() { __syncwarp(); }
+};
+#endif
+
 // ----------------------------------------------------------------------------- forcing / rhs
 PSN_FN double psn_forcing(const PsnRhs& s, long long b, int i, int j) {
     const long long mi = (long long)i * s.step, mj = (long long)j * s.step;

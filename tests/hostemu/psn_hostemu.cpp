@@ -9,6 +9,7 @@
 #include <cstring>
 #include <vector>
 #include "../../superresolution_for_pdes_b200/csrc/psn_stream_driver.h"
+#include "../../superresolution_for_pdes_b200/csrc/psn_block.cuh"
 
 namespace {
 
@@ -252,6 +253,29 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     memcpy(zout, ub[0], sizeof(double) * n * n);
     double s = 0; for (double v : part) s += v;
     *rz = s;
+    return 0;
+}
+
+// register-blocked resident solver (n = 80), all threads of the CTA emulated phase by phase
+int hostemu_solve_block(int n, long long B, const double* theta, const double* f, const double* sx, const double* sy,
+                        int mn, int step, double rtol, int max_iter, int nu,
+                        double* u, int32_t* iters, double* relres, int32_t* status,
+                        int sub, const int32_t* start_x, const int32_t* start_y,
+                        double* u_fine, double* f_fine, double* u_coarse, double* f_coarse) {
+    if (n != 80) return -1;
+    HostPlan hp(n, nu);
+    PsnSolveArgs a;
+    a.rhs = make_rhs(theta, f, sx, sy, nullptr, nullptr, mn, step);
+    a.rtol = rtol; a.max_iter = max_iter; a.u = u; a.iters = iters; a.relres = relres; a.status = status;
+    a.sub = sub; a.start_x = start_x; a.start_y = start_y;
+    a.u_fine = u_fine; a.f_fine = f_fine; a.u_coarse = u_coarse; a.f_coarse = f_coarse;
+    a.th_fine = nullptr; a.th_coarse = nullptr;
+    std::vector<double> smem(psn_block_smem_doubles<20>(hp.plan) + 64);
+    PsnHostCtx ctx;
+    for (long long b = 0; b < B; ++b) {
+        std::fill(smem.begin(), smem.end(), std::nan(""));
+        psn_block_solve_body<20>(ctx, hp.plan, a, b, smem.data());
+    }
     return 0;
 }
 }
