@@ -286,26 +286,30 @@ def run_own(args):
         return ms, info, prof, u
 
     def timed_e2e(n_, B_, theta, k1, k2, steps, warmup):
-        # host-resident, pinned: theta + host-evaluated sine factors in, u out, all through the C ABI
+        # The call a user makes: host-resident (pinned) theta in, u out, through the C ABI.  The forcing is
+        # passed the way the drop-in shims pass it -- 2n host-evaluated sines per sample (bit-exact f) -- and
+        # that numpy evaluation is INSIDE the timed region, as are all H2D / D2H copies.
         x = np.linspace(0, 1, n_)
         th_h = torch.empty((B_, n_, n_), dtype=torch.float64, pin_memory=True)
         th_h.copy_(theta)
         k1h, k2h = k1.cpu().numpy(), k2.cpu().numpy()
-        sx_h = torch.from_numpy(np.sin((2 * np.pi * k1h)[:, None] * x[None, :])).pin_memory()
-        sy_h = torch.from_numpy(np.sin((2 * np.pi * k2h)[:, None] * x[None, :])).pin_memory()
         u_h = torch.empty((B_, n_, n_), dtype=torch.float64, pin_memory=True)
+
+        def one_call():
+            return _lib.solve_from_wavenumbers(n_, k1h, k2h, theta=th_h.numpy(), out=u_h.numpy(), rtol=args.rtol)[1]
+
         info = None
         for _ in range(max(1, min(warmup, 2))):
-            _, info = _lib.solve_batch(n_, B_, theta=th_h, sin_x=sx_h, sin_y=sy_h, out=u_h, rtol=args.rtol)
+            info = one_call()
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            _, info = _lib.solve_batch(n_, B_, theta=th_h, sin_x=sx_h, sin_y=sy_h, out=u_h, rtol=args.rtol)
+            info = one_call()
         torch.cuda.synchronize()
         sec = max_over_ranks(time.perf_counter() - t0)
         if (info.status > 1).any():
             raise SystemExit("bench.py: e2e samples did not converge")
-        h2d = th_h.numel() * 8 + sx_h.numel() * 8 + sy_h.numel() * 8
+        h2d = th_h.numel() * 8 + 2 * B_ * n_ * 8
         d2h = u_h.numel() * 8 + B_ * 16
         return sec, h2d, d2h, float(u_h[0, n_ // 2, n_ // 2])
 

@@ -118,10 +118,9 @@ class PoissonSolver:
         ks = np.random.uniform(*k_range, size=(n_samples, 2))  # same stream order as k1, k2 per sample
         k1 = ks[:, 0].copy()
         k2 = ks[:, 1].copy()
-        sxf, syf = sine_factors(k1, k2, self.x_fine)
-        sxc, syc = sine_factors(k1, k2, self.x_coarse)
-        u_fine, info_f = _lib.solve_batch(self.n_fine, n_samples, sin_x=sxf, sin_y=syf, rtol=self.rtol, max_iter=self.max_iter)
-        u_coarse, info_c = _lib.solve_batch(self.n_coarse, n_samples, sin_x=sxc, sin_y=syc, rtol=self.rtol, max_iter=self.max_iter)
+        # sine factors on the host (bit-exact forcing) overlapped with the GPU solves of the previous chunk
+        u_fine, info_f, sxf, syf = _lib.solve_from_wavenumbers(self.n_fine, k1, k2, rtol=self.rtol, max_iter=self.max_iter)
+        u_coarse, info_c, sxc, syc = _lib.solve_from_wavenumbers(self.n_coarse, k1, k2, rtol=self.rtol, max_iter=self.max_iter)
         self.last_info = info_f
         info_f.raise_if_failed("generate_dataset (fine)")
         info_c.raise_if_failed("generate_dataset (coarse)")

@@ -256,3 +256,33 @@ def test_large_batch_properties_640(gpu_lib):
     perm = rs.permutation(B)
     u2, _ = gpu_lib.solve_batch(n, B, theta=theta[perm], sin_x=sx[perm], sin_y=sy[perm])
     assert np.array_equal(u2, u[perm])    # deterministic, batch-order independent
+
+
+def test_repeated_runs_are_bit_identical(gpu_lib):
+    """The kernels use fixed-order reductions and no atomics on floating-point data, so repeated runs of
+    the same batch must agree bit for bit -- a cheap detector of data races (missing barriers show up as
+    run-to-run differences) on the register-blocked 80x80 kernel, the generic resident kernel and the
+    streamed path."""
+    rs = np.random.RandomState(21)
+    for n, B in ((80, 1500), (40, 3000), (36, 500), (160, 300)):
+        theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+        k = rs.uniform(0.5, 12.0, size=(B, 2))
+        x = np.linspace(0, 1, n)
+        sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+        u0, i0 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+        assert (i0.status <= 1).all()
+        for _ in range(3):
+            u1, i1 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+            assert np.array_equal(u1, u0) and np.array_equal(i1.iters, i0.iters)
+    # generic resident kernel (register-blocked kernel switched off) gives the same answer at 80x80
+    n, B = 80, 64
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    f = np.stack([O.forcing_term(*rs.uniform(0.5, 12.0, size=2), n) for _ in range(B)])
+    ub, _ = gpu_lib.solve_batch(n, B, theta=theta, f=f)
+    try:
+        gpu_lib.set_option("res_block", 0)
+        ug, _ = gpu_lib.solve_batch(n, B, theta=theta, f=f)
+    finally:
+        gpu_lib.set_option("res_block", 1)
+    assert O.rel_l2(ub, ug) <= 1e-13
+    assert O.rel_l2(ub[0], O.solve_poisson(f[0], theta[0], n)) <= TOL
