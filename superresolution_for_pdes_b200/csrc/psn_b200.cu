@@ -253,7 +253,7 @@ struct Context {
     int sm_count = 0;
     size_t smem_optin = 0;
     Slot slots[PSN_NSLOTS];
-    cudaEvent_t ws_free = nullptr;
+    cudaEvent_t ws_free[2] = {nullptr, nullptr};   // recorded after the last kernel that touches streamed workspace k
     char* h_info = nullptr;          // pinned bounce buffer for iters / relres / status of host callers
     size_t h_info_cap = 0;   // recorded after the last kernel that touches the shared streamed workspace
     std::map<long long, PlanEntry> plans;  // key = n * 16 + nu
@@ -262,6 +262,7 @@ struct Context {
     long long ws_bytes = 16ll << 30;
     int smem_max_n = 0;
     int coarse_max_n = 40; // largest level handed to the shared-memory coarse V-cycle kernel (0: as large as fits)
+    int serialize_solves = 0;
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
     int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 3 streamed / 8 resident)
@@ -746,34 +747,54 @@ int solve_internal(const Problem& P) {
         PsnSolveArgs a;
     };
     // chunk schedule: equal chunks of Bc for device callers; for host callers the first and last chunks
-    // are shorter (1/4, 1/2, 1 ... 1, 1/2, 1/4 of Bc) so that pipeline fill (first H2D) and drain (last D2H) are short
+    // are shorter (1/4 of Bc) so that pipeline fill (first H2D) and drain (last D2H) are short
     std::vector<long long> bounds;
     bounds.push_back(0);
     if (any_host && P.B > 2 * Bc) {
-        const long long ramp[2] = {Bc / 4 > 0 ? Bc / 4 : 1, Bc / 2 > 0 ? Bc / 2 : 1};
-        long long pos = 0;
-        for (int k = 0; k < 2; ++k) { pos += ramp[k]; bounds.push_back(pos); }
-        const long long tail = ramp[0] + ramp[1];
-        while (P.B - tail - pos > Bc) { pos += Bc; bounds.push_back(pos); }
-        if (P.B - tail > pos) { pos = P.B - tail; bounds.push_back(pos); }
-        pos += ramp[1]; bounds.push_back(pos);
+        // short first / last chunk (pipeline fill = first H2D, drain = last D2H), equal chunks <= Bc in between
+        const long long e = Bc / 4 > 0 ? Bc / 4 : 1;
+        const long long mid = P.B - 2 * e;
+        const long long parts = (mid + Bc - 1) / Bc;
+        bounds.push_back(e);
+        for (long long k = 1; k < parts; ++k) bounds.push_back(e + (mid * k) / parts);
+        bounds.push_back(P.B - e);
         bounds.push_back(P.B);
     } else {
         for (long long pos = Bc; pos < P.B; pos += Bc) bounds.push_back(pos);
         bounds.push_back(P.B);
     }
     const long long nchunks = (long long)bounds.size() - 1;
-    Slot& ws_slot = g.slots[0];
+    // Streamed path with host buffers: two workspaces (slots 0 / 1) alternate between chunks, so that a chunk can
+    // be enqueued completely (expected iteration count, no polling) while the previous one is still running;
+    // its convergence is verified one chunk later, before its workspace is reused.
+    const int nws = (!resident && any_host) ? 2 : 1;
     if (!resident) {
-        rc = arena_reserve(ws_slot.ws_arena, ws_ps * Bc + 64 * 256 + pad256((size_t)(P.max_iter + 8) * 4));
-        if (rc) return rc;
-        if (ws_slot.h_counters_cap < P.max_iter + 8) {
-            if (ws_slot.h_counters) cudaFreeHost(ws_slot.h_counters);
-            ws_slot.h_counters = nullptr;
-            CU_TRY(cudaMallocHost(&ws_slot.h_counters, sizeof(int) * (P.max_iter + 8)));
-            ws_slot.h_counters_cap = P.max_iter + 8;
+        for (int k = 0; k < nws; ++k) {
+            Slot& wsl = g.slots[k];
+            rc = arena_reserve(wsl.ws_arena, ws_ps * Bc + 64 * 256 + pad256((size_t)(P.max_iter + 8) * 4));
+            if (rc) return rc;
+            if (wsl.h_counters_cap < P.max_iter + 8) {
+                if (wsl.h_counters) cudaFreeHost(wsl.h_counters);
+                wsl.h_counters = nullptr;
+                CU_TRY(cudaMallocHost(&wsl.h_counters, sizeof(int) * (P.max_iter + 8)));
+                wsl.h_counters_cap = P.max_iter + 8;
+            }
         }
     }
+    struct Pending {
+        bool active = false;
+        long long b0 = 0, bc = 0;
+        cudaStream_t s = nullptr;
+        PsnRhs rhs;
+        double* d_u = nullptr;
+        int32_t* d_it = nullptr;
+        double* d_rr = nullptr;
+        int32_t* d_st = nullptr;
+        PsnStreamWs ws;
+        PsnStreamCfg cfg;
+        int it_end = 0;
+    } pending[2];
+    int est_iters = 0;   // outer iterations the previous chunks needed (0: unknown -> poll)
 
     // Small per-sample outputs of host callers go through a pinned bounce buffer: an async D2H into
     // pageable memory would block the host until the whole chunk (including its multi-MB copies) has
@@ -878,20 +899,38 @@ int solve_internal(const Problem& P) {
                 if ((rc2 = copy_back(s, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, a.th_coarse))) return rc2;
             }
         } else {
-            // the shared workspace is free once the previous chunk's last kernel has run
-            if (c > 0 && any_host) CU_TRY(cudaStreamWaitEvent(s, g.ws_free, 0));
-            ws_slot.ws_arena.off = 0;
+            const int wk = (nws == 2) ? (int)(c & 1) : 0;
+            Slot& wsl = g.slots[wk];
+            // workspace wk is free once the last kernel of the chunk that used it before has run
+            if (c >= nws && any_host) CU_TRY(cudaStreamWaitEvent(s, g.ws_free[wk], 0));
+            // solves run back to back (the other workspace's chunk first): interleaving two chunks' kernels was
+            // measured slower than keeping each chunk's working set to itself
+            if (c >= 1 && any_host && nws == 2 && g.serialize_solves) CU_TRY(cudaStreamWaitEvent(s, g.ws_free[wk ^ 1], 0));
+            wsl.ws_arena.off = 0;
             PsnStreamWs ws;
-            if ((rc2 = carve_stream_ws(ws_slot.ws_arena, plan, scfg, bc, P.max_iter, &ws))) return rc2;
+            if ((rc2 = carve_stream_ws(wsl.ws_arena, plan, scfg, bc, P.max_iter, &ws))) return rc2;
             choose_bands(plan, &scfg, bc);
-            CudaBackend bk{s, &ws_slot};
-            psn_stream_solve(bk, plan, scfg, cx.rhs, bc, P.rtol, P.max_iter, cx.d_u, ws);
+            CudaBackend bk{s, &wsl};
+            // After the first chunk has told us how many outer iterations this workload needs, later chunks are
+            // enqueued with that count (+1 spare) without the host waiting on the device; stragglers are caught by
+            // the deferred check (resolve) and resumed.
+            const bool speculative = any_host && nws == 2 && P.sub == 0 && est_iters > 0;
+            const int it_end = psn_stream_solve(bk, plan, scfg, cx.rhs, bc, P.rtol, P.max_iter, cx.d_u, ws, 0,
+                                                speculative ? est_iters + 1 : 0);
             if (bk.err != cudaSuccess) return psn_fail(PSN_ERR_CUDA, "streamed solve failed: %s", cudaGetErrorString(bk.err));
+            if (!speculative && it_end - PSN_COUNTER_LAG > est_iters) est_iters = it_end - PSN_COUNTER_LAG;
             {
                 ProfScope pr("state", s);
                 psn_finalize_kernel<<<(unsigned)((bc + 127) / 128), 128, 0, s>>>(ws.state, bc, cx.d_it, cx.d_rr, cx.d_st);
             }
             CU_TRY(cudaGetLastError());
+            if (speculative) {
+                Pending& pd = pending[wk];
+                pd.active = true;
+                pd.b0 = b0; pd.bc = bc; pd.s = s; pd.rhs = cx.rhs;
+                pd.d_u = cx.d_u; pd.d_it = cx.d_it; pd.d_rr = cx.d_rr; pd.d_st = cx.d_st;
+                pd.ws = ws; pd.cfg = scfg; pd.it_end = it_end;
+            }
             if (P.sub > 0) {
                 const PsnSolveArgs& a = cx.a;
                 psn_window_kernel<<<dim3((unsigned)((P.sub * P.sub + 255) / 256), (unsigned)bc), 256, 0, s>>>(a, P.n, cx.d_u);
@@ -903,7 +942,7 @@ int solve_internal(const Problem& P) {
                 if ((rc2 = copy_back(s, P.f_coarse, k_fc, b0 * (long long)scc, bc * scc, a.f_coarse))) return rc2;
                 if ((rc2 = copy_back(s, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, a.th_coarse))) return rc2;
             }
-            if (any_host) CU_TRY(cudaEventRecord(g.ws_free, s));
+            if (any_host) CU_TRY(cudaEventRecord(g.ws_free[wk], s));
         }
         if ((rc2 = copy_back(s, P.u, k_u, b0 * (long long)nn, bc * nn, cx.d_u))) return rc2;
         if ((rc2 = copy_back(s, hb_it ? hb_it : P.iters, k_it, b0, (size_t)bc, cx.d_it))) return rc2;
@@ -912,13 +951,43 @@ int solve_internal(const Problem& P) {
         return PSN_OK;
     };
 
+    // deferred convergence check of a speculatively enqueued chunk; resumes it (polling) if samples are still active
+    auto resolve = [&](int k) -> int {
+        Pending& pd = pending[k];
+        if (!pd.active) return PSN_OK;
+        pd.active = false;
+        Slot& wsl = g.slots[k];
+        CudaBackend bk{pd.s, &wsl};
+        const int left = bk.wait_counter(pd.it_end - 1);
+        if (bk.err != cudaSuccess) return psn_fail(PSN_ERR_CUDA, "streamed solve failed: %s", cudaGetErrorString(bk.err));
+        if (left == 0) return PSN_OK;
+        const int it2 = psn_stream_solve(bk, plan, pd.cfg, pd.rhs, pd.bc, P.rtol, P.max_iter, pd.d_u, pd.ws, pd.it_end, 0);
+        if (bk.err != cudaSuccess) return psn_fail(PSN_ERR_CUDA, "streamed solve failed: %s", cudaGetErrorString(bk.err));
+        if (it2 - PSN_COUNTER_LAG > est_iters) est_iters = it2 - PSN_COUNTER_LAG;
+        psn_finalize_kernel<<<(unsigned)((pd.bc + 127) / 128), 128, 0, pd.s>>>(pd.ws.state, pd.bc, pd.d_it, pd.d_rr, pd.d_st);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(g.ws_free[k], pd.s));
+        int rc2;
+        if ((rc2 = copy_back(pd.s, P.u, k_u, pd.b0 * (long long)nn, pd.bc * nn, pd.d_u))) return rc2;
+        if ((rc2 = copy_back(pd.s, hb_it ? hb_it : P.iters, k_it, pd.b0, (size_t)pd.bc, pd.d_it))) return rc2;
+        if ((rc2 = copy_back(pd.s, hb_rr ? hb_rr : P.relres, k_rr, pd.b0, (size_t)pd.bc, pd.d_rr))) return rc2;
+        if ((rc2 = copy_back(pd.s, hb_st ? hb_st : P.status, k_st, pd.b0, (size_t)pd.bc, pd.d_st))) return rc2;
+        return PSN_OK;
+    };
+
     ChunkCtx cur, nxt;
     if ((rc = prepare(0, cur))) return rc;
     for (long long c = 0; c < nchunks; ++c) {
         const bool more = c + 1 < nchunks;
+        // chunk c-2 used the workspace (and chunk c+1 reuses the staging slot) that are about to be recycled
+        if (nws == 2 && (rc = resolve((int)(c & 1)))) return rc;
         if (more && (rc = prepare(c + 1, nxt))) return rc;
         if ((rc = run(c, cur))) return rc;
         if (more) cur = nxt;
+    }
+    if (nws == 2) {
+        if ((rc = resolve(0))) return rc;
+        if ((rc = resolve(1))) return rc;
     }
     if (any_host) {
         for (int i = 0; i < nslots; ++i) CU_TRY(cudaStreamSynchronize(g.slots[i].stream));
@@ -961,7 +1030,7 @@ int psn_init(int device) {
     g.device = cur;
     g.sm_count = prop.multiProcessorCount;
     g.smem_optin = prop.sharedMemPerBlockOptin;
-    CU_TRY(cudaEventCreateWithFlags(&g.ws_free, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) CU_TRY(cudaEventCreateWithFlags(&g.ws_free[k], cudaEventDisableTiming));
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         CU_TRY(cudaStreamCreateWithFlags(&g.slots[i].stream, cudaStreamNonBlocking));
         for (int k = 0; k < 4; ++k) CU_TRY(cudaEventCreateWithFlags(&g.slots[i].ev[k], cudaEventDisableTiming));
@@ -978,8 +1047,10 @@ void psn_shutdown(void) {
     cudaDeviceSynchronize();
     for (auto& kv : g.plans) cudaFree(kv.second.d_inv);
     g.plans.clear();
-    if (g.ws_free) cudaEventDestroy(g.ws_free);
-    g.ws_free = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        if (g.ws_free[k]) cudaEventDestroy(g.ws_free[k]);
+        g.ws_free[k] = nullptr;
+    }
     if (g.h_info) cudaFreeHost(g.h_info);
     g.h_info = nullptr;
     g.h_info_cap = 0;
@@ -1076,6 +1147,8 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "coarse_max_n")) {
         if (value < 0) return psn_fail(PSN_ERR_INVALID, "coarse_max_n must be >= 0");
         g.coarse_max_n = (int)value;
+    } else if (!strcmp(name, "serialize_solves")) {
+        g.serialize_solves = value ? 1 : 0;
     } else if (!strcmp(name, "res_block")) {
         g.res_block = value ? 1 : 0;
     } else if (!strcmp(name, "res_threads")) {

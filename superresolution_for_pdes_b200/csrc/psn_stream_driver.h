@@ -95,10 +95,15 @@ static inline PsnStripArgs psn_leg_to_strip(const PsnPlan& plan, const PsnStream
     return a;
 }
 
-// x: [B, n, n] device array that receives the solution.  Returns the number of outer iterations run.
+// x: [B, n, n] device array that receives the solution.
+// start_it == 0: fresh solve (prologue + state init); > 0: resume an earlier call at that outer iteration.
+// fixed_iters == 0: poll the active-sample counter (lag PSN_COUNTER_LAG) and stop when every sample is done;
+// fixed_iters  > 0: enqueue exactly that many outer iterations WITHOUT waiting on the device (iterations after a
+//                   sample's convergence are no-ops for it); the caller checks counter[returned - 1] later.
+// Returns the index of the next outer iteration.
 template <class BK>
 int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnRhs& rhs, long long B,
-                     double rtol, int max_iter, double* x, PsnStreamWs& ws) {
+                     double rtol, int max_iter, double* x, PsnStreamWs& ws, int start_it = 0, int fixed_iters = 0) {
     const int n = plan.n;
     PsnCgArgs cg;
     cg.n = n;
@@ -126,12 +131,14 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.rtol = rtol;
     cg.max_iter = max_iter;
 
-    bk.zero_counters(ws.counters, max_iter + 8);
-    bk.prologue(cg, B);
-    bk.state_init(cg, B);
+    if (start_it == 0) {
+        bk.zero_counters(ws.counters, max_iter + 8);
+        bk.prologue(cg, B);
+        bk.state_init(cg, B);
+    }
 
     const int max_outer = max_iter + 4;  // every check/restart costs at most one extra outer pass
-    int it = 0;
+    int it = start_it;
     for (; it < max_outer; ++it) {
         // ---- z = M^{-1} r : one V(nu,nu) cycle
         for (int l = 0; l < cfg.ls; ++l) {
@@ -168,7 +175,12 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
         bk.true_residual(cg, B);
         bk.state_after_check(cg, B, ws.counters + it);
         bk.fetch_counter_async(ws.counters + it, it);
-        if (it >= PSN_COUNTER_LAG && bk.wait_counter(it - PSN_COUNTER_LAG) == 0) {
+        if (fixed_iters > 0) {
+            if (it + 1 >= start_it + fixed_iters) {
+                ++it;
+                break;
+            }
+        } else if (it >= PSN_COUNTER_LAG && bk.wait_counter(it - PSN_COUNTER_LAG) == 0) {
             ++it;
             break;
         }
