@@ -134,6 +134,23 @@ int psn_multires(int n_finest, const int32_t* resolutions, int n_res, int64_t ba
                  double* const* u_out, int32_t* iters, double* relres, int32_t* status,
                  void* stream);
 
+/* Training-tensor prologue of the path's immediate consumer ("next" row f1 of SURVEY.md section 8).
+ *
+ * Replaces PDEDataset.__init__ / __getitem__ (src/models.py:132-203): float32 cast, global mean and unbiased
+ * std of u_fine / f_fine / theta_fine, z-score (theta is passed through unchanged when its std < 1e-6,
+ * src/models.py:162-179), bilinear upsample of the normalised coarse solution n_coarse -> n_fine with
+ * align_corners = True (src/models.py:182-187; the reference hard-codes 40x40) and the channel concat
+ * [u_coarse_up, theta, f] (src/models.py:192-203).
+ *
+ *   u_coarse [n, n_coarse, n_coarse], u_fine / f_fine / theta_fine [n, n_fine, n_fine]  float64, host or device
+ *   x [n, 3, n_fine, n_fine] float32 out, y [n, 1, n_fine, n_fine] float32 out          host or device
+ *   stats [8] float64 out (host or device, may be NULL):
+ *         u_mean, u_std, f_mean, f_std, theta_mean, theta_std, theta_is_constant (0/1), 0
+ */
+int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine,
+                        const double* u_coarse, const double* u_fine, const double* f_fine, const double* theta_fine,
+                        float* x, float* y, double* stats, void* stream);
+
 /* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg, default 2), "tile" (interior
  * tile edge of the streamed kernels, default 64), "ws_bytes" (workspace budget per pipeline slot),
  * "smem_max_n" (largest n solved fully in shared memory; 0 = as large as fits). */

@@ -10,8 +10,9 @@ There is no CPU fallback.
 from . import _lib
 from ._lib import PsnError
 from .data_generation import PoissonSolver
+from .dataset_tensors import PDEDataset
 from .enhanced_data_generation import EnhancedPoissonSolver
 from .resolution_comparison import solve_multi_resolution, solve_multi_resolution_batch
 
-__all__ = ["PoissonSolver", "EnhancedPoissonSolver", "solve_multi_resolution",
+__all__ = ["PoissonSolver", "EnhancedPoissonSolver", "PDEDataset", "solve_multi_resolution",
            "solve_multi_resolution_batch", "PsnError", "_lib"]

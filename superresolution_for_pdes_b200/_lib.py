@@ -23,7 +23,7 @@ STATUS_CONVERGED, STATUS_FP64_FLOOR, STATUS_MAXITER, STATUS_BREAKDOWN = 0, 1, 2,
 EXPORTED_SYMBOLS = (
     "psn_version", "psn_get_device_count", "psn_init", "psn_shutdown", "psn_last_error",
     "psn_solve_batch", "psn_subdomain_batch", "psn_multires", "psn_set_option",
-    "psn_profile_begin", "psn_profile_read", "psn_profile_end", "psn_describe",
+    "psn_profile_begin", "psn_profile_read", "psn_profile_end", "psn_describe", "psn_dataset_tensors",
 )
 
 
@@ -69,6 +69,9 @@ def load() -> ctypes.CDLL:
     lib.psn_profile_read.argtypes = [ctypes.c_char_p, ctypes.c_int64]
     lib.psn_profile_read.restype = ctypes.c_int
     lib.psn_profile_end.restype = ctypes.c_int
+    lib.psn_dataset_tensors.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
+                                        ctypes.c_void_p]
+    lib.psn_dataset_tensors.restype = ctypes.c_int
     lib.psn_describe.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
     lib.psn_describe.restype = ctypes.c_int
     _lib = lib
@@ -308,3 +311,25 @@ def solve_from_wavenumbers(n: int, k1, k2, *, theta=None, out=None, chunks: Opti
                 dst[...] = u_c
             iters[lo:hi], relres[lo:hi], status[lo:hi] = info.iters, info.relres, info.status
     return out, SolveInfo(iters, relres, status), sx, sy
+
+
+def dataset_tensors(u_coarse, u_fine, f_fine, theta_fine, *, x=None, y=None, stream: int = 0):
+    """float32 training tensors of the reference's PDEDataset (src/models.py:132-203) from float64 dataset arrays.
+    Inputs: numpy arrays or torch CUDA float64 tensors; outputs follow `x` / `y` if given, else numpy float32.
+    Returns (x [N,3,nf,nf], y [N,1,nf,nf], stats[8] as numpy)."""
+    lib = load()
+    N, nc = int(u_coarse.shape[0]), int(u_coarse.shape[-1])
+    nf = int(u_fine.shape[-1])
+    u_coarse = _f64(u_coarse, (N, nc, nc), "u_coarse")
+    u_fine = _f64(u_fine, (N, nf, nf), "u_fine")
+    f_fine = _f64(f_fine, (N, nf, nf), "f_fine")
+    theta_fine = _f64(theta_fine, (N, nf, nf), "theta_fine")
+    if x is None:
+        x = np.empty((N, 3, nf, nf), dtype=np.float32)
+    if y is None:
+        y = np.empty((N, 1, nf, nf), dtype=np.float32)
+    stats = np.zeros(8, dtype=np.float64)
+    rc = lib.psn_dataset_tensors(N, nc, nf, _ptr(u_coarse), _ptr(u_fine), _ptr(f_fine), _ptr(theta_fine), _ptr(x), _ptr(y),
+                                 _ptr(stats), ctypes.c_void_p(stream))
+    _check(rc)
+    return x, y, stats

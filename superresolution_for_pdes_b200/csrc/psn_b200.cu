@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -216,6 +217,80 @@ __global__ void psn_window_kernel(const __grid_constant__ PsnSolveArgs a, int n,
 }
 __global__ void psn_fill_kernel(double* p, long long cnt, double v) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+
+// ----------------------------------------------------------------------------- consumer prologue (row f1)
+// moments of the float32-cast data: per-block partial (sum, sum of squares) in double, fixed-order final sum
+#define PSN_MOM_BLOCKS 592
+__global__ void __launch_bounds__(256) psn_moments_kernel(const double* a, long long cnt, double* partial) {
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, 256, red, 0};
+    double s = 0.0, s2 = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < cnt; i += (long long)gridDim.x * 256) {
+        const double v = (double)(float)a[i];
+        s += v;
+        s2 += v * v;
+    }
+    const double ts = ctx.block_sum(s);
+    const double ts2 = ctx.block_sum(s2);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = ts;
+        partial[2 * blockIdx.x + 1] = ts2;
+    }
+}
+// stats[2k] = mean, stats[2k+1] = unbiased std of array k (k = 0: u_fine, 1: f_fine, 2: theta_fine)
+__global__ void psn_moments_final_kernel(const double* partial, int nblocks, long long cnt, double* stats) {
+    const int k = threadIdx.x;
+    if (k >= 3) return;
+    const double* p = partial + (size_t)k * 2 * nblocks;
+    double s = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+        s += p[2 * b];
+        s2 += p[2 * b + 1];
+    }
+    const double mean = s / (double)cnt;
+    const double var = cnt > 1 ? fmax(0.0, (s2 - (double)cnt * mean * mean) / (double)(cnt - 1)) : 0.0;
+    stats[2 * k] = mean;
+    stats[2 * k + 1] = sqrt(var);
+    if (k == 2) {
+        const bool constant = sqrt(var) < 1e-6;
+        stats[6] = constant ? 1.0 : 0.0;
+        stats[7] = 0.0;
+        if (constant) {   // src/models.py:163-165: theta passes through unchanged
+            stats[4] = 0.0;
+            stats[5] = 1.0;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) psn_tensor_kernel(long long n, int nc, int nf, const double* uc, const double* uf,
+                                                         const double* ff, const double* th, const double* stats,
+                                                         float* x, float* y) {
+    const long long total = n * nf * nf;
+    const float um = (float)stats[0], us = (float)stats[1], fm = (float)stats[2], fs = (float)stats[3];
+    const float tm = (float)stats[4], ts = (float)stats[5];
+    const bool tconst = stats[6] != 0.0;
+    const float scale = nf > 1 ? (float)(nc - 1) / (float)(nf - 1) : 0.f;   // align_corners = True
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const long long b = idx / (nf * nf);
+        const int rem = (int)(idx - b * nf * nf);
+        const int i = rem / nf, j = rem - i * nf;
+        // bilinear sample of the normalised coarse solution
+        const float sy = scale * (float)i, sx = scale * (float)j;
+        const int i0 = (int)sy, j0 = (int)sx;
+        const int i1 = min(i0 + 1, nc - 1), j1 = min(j0 + 1, nc - 1);
+        const float ly = sy - (float)i0, lx = sx - (float)j0;
+        const double* c = uc + b * (long long)nc * nc;
+        const float v00 = ((float)c[i0 * nc + j0] - um) / us, v01 = ((float)c[i0 * nc + j1] - um) / us;
+        const float v10 = ((float)c[i1 * nc + j0] - um) / us, v11 = ((float)c[i1 * nc + j1] - um) / us;
+        const float up = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+        const float tv = (float)th[idx];
+        float* xo = x + (b * 3) * (long long)nf * nf + rem;
+        xo[0] = up;
+        xo[(long long)nf * nf] = tconst ? tv : (tv - tm) / ts;
+        xo[2ll * nf * nf] = ((float)ff[idx] - fm) / fs;
+        y[idx] = ((float)uf[idx] - um) / us;
+    }
 }
 
 // ----------------------------------------------------------------------------- library context
@@ -1127,6 +1202,60 @@ int psn_multires(int n_finest, const int32_t* resolutions, int n_res, int64_t ba
         int rc = solve_internal(P);
         if (rc) return rc;
     }
+    return PSN_OK;
+}
+
+int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine, const double* u_coarse, const double* u_fine,
+                        const double* f_fine, const double* theta_fine, float* x, float* y, double* stats, void* stream) {
+    g_err[0] = 0;
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (n_samples < 0 || n_coarse < 1 || n_fine < 1) return psn_fail(PSN_ERR_INVALID, "bad sizes");
+    if (!u_coarse || !u_fine || !f_fine || !theta_fine || !x || !y) return psn_fail(PSN_ERR_INVALID, "NULL array");
+    if (n_samples == 0) return PSN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t cc = (size_t)n_samples * n_coarse * n_coarse, cf = (size_t)n_samples * n_fine * n_fine;
+    const MemKind k_uc = classify(u_coarse), k_uf = classify(u_fine), k_ff = classify(f_fine), k_th = classify(theta_fine),
+                  k_x = classify(x), k_y = classify(y), k_s = classify(stats);
+    Arena& ar = g.slots[0].arena;
+    size_t need = 64 * 256 + pad256((size_t)3 * 2 * PSN_MOM_BLOCKS * 8) + 256;
+    if (k_uc == MEM_HOST) need += pad256(cc * 8);
+    if (k_uf == MEM_HOST) need += pad256(cf * 8);
+    if (k_ff == MEM_HOST) need += pad256(cf * 8);
+    if (k_th == MEM_HOST) need += pad256(cf * 8);
+    if (k_x == MEM_HOST) need += pad256(cf * 3 * 4);
+    if (k_y == MEM_HOST) need += pad256(cf * 4);
+    if ((rc = arena_reserve(ar, need))) return rc;
+    const double *d_uc, *d_uf, *d_ff, *d_th;
+    if ((rc = stage_in(ar, s, u_coarse, k_uc, 0, cc, &d_uc))) return rc;
+    if ((rc = stage_in(ar, s, u_fine, k_uf, 0, cf, &d_uf))) return rc;
+    if ((rc = stage_in(ar, s, f_fine, k_ff, 0, cf, &d_ff))) return rc;
+    if ((rc = stage_in(ar, s, theta_fine, k_th, 0, cf, &d_th))) return rc;
+    float *d_x, *d_y;
+    if ((rc = stage_out(ar, x, k_x, 0, cf * 3, &d_x, true))) return rc;
+    if ((rc = stage_out(ar, y, k_y, 0, cf, &d_y, true))) return rc;
+    double* d_part = arena_take<double>(ar, (size_t)3 * 2 * PSN_MOM_BLOCKS);
+    double* d_stats = (k_s == MEM_DEVICE) ? stats : arena_take<double>(ar, 8);
+    if (!d_part || !d_stats) return psn_fail(PSN_ERR_NOMEM, "staging arena exhausted");
+    const double* arrs[3] = {d_uf, d_ff, d_th};
+    for (int k = 0; k < 3; ++k) {
+        ProfScope pr("dataset_moments", s);
+        psn_moments_kernel<<<PSN_MOM_BLOCKS, 256, 0, s>>>(arrs[k], (long long)cf, d_part + (size_t)k * 2 * PSN_MOM_BLOCKS);
+    }
+    psn_moments_final_kernel<<<1, 32, 0, s>>>(d_part, PSN_MOM_BLOCKS, (long long)cf, d_stats);
+    {
+        ProfScope pr("dataset_tensors", s);
+        const unsigned grid = (unsigned)std::min<size_t>((cf + 255) / 256, (size_t)g.sm_count * 16);
+        psn_tensor_kernel<<<grid, 256, 0, s>>>((long long)n_samples, n_coarse, n_fine, d_uc, d_uf, d_ff, d_th, d_stats, d_x, d_y);
+    }
+    CU_TRY(cudaGetLastError());
+    if ((rc = copy_back(s, x, k_x, 0, cf * 3, d_x))) return rc;
+    if ((rc = copy_back(s, y, k_y, 0, cf, d_y))) return rc;
+    if (k_s == MEM_HOST) CU_TRY(cudaMemcpyAsync(stats, d_stats, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    const MemKind kinds[] = {k_uc, k_uf, k_ff, k_th, k_x, k_y, k_s};
+    bool any_host = false;
+    for (MemKind k : kinds) any_host = any_host || (k == MEM_HOST);
+    if (any_host) CU_TRY(cudaStreamSynchronize(s));
     return PSN_OK;
 }
 

@@ -286,3 +286,32 @@ def test_repeated_runs_are_bit_identical(gpu_lib):
         gpu_lib.set_option("res_block", 1)
     assert O.rel_l2(ub, ug) <= 1e-13
     assert O.rel_l2(ub[0], O.solve_poisson(f[0], theta[0], n)) <= TOL
+
+
+@pytest.mark.parametrize("random_theta", [False, True])
+def test_dataset_tensor_prologue_matches_reference_semantics(gpu_lib, random_theta):
+    """Row f1: the consumer's float32 tensors (src/models.py:132-203) built by psn_dataset_tensors against the
+    torch-CPU restatement (oracle/dataset_oracle.py, itself bit-equal to the live reference class).
+    Tolerance: float32 arithmetic -- 2e-6 relative on the statistics, 2e-5 absolute on the z-scored tensors."""
+    import torch
+    from oracle.dataset_oracle import dataset_tensors as oracle_tensors
+    from superresolution_for_pdes_b200 import PDEDataset, PoissonSolver
+    np.random.seed(0)
+    ds = PoissonSolver().generate_dataset(64, k_range=(0.5, 5.0))
+    if random_theta:
+        ds = dict(ds)
+        ds["theta_fine"] = np.random.RandomState(1).uniform(0.5, 2.0, size=ds["theta_fine"].shape)
+    ref = oracle_tensors(ds)
+    # through the C ABI with host arrays ...
+    x, y, stats = gpu_lib.dataset_tensors(ds["u_coarse"], ds["u_fine"], ds["f_fine"], ds["theta_fine"])
+    assert x.dtype == np.float32 and x.shape == ref["x"].shape and y.shape == ref["y"].shape
+    assert np.allclose(stats[:6], ref["stats"][:6], rtol=2e-6, atol=1e-12) and stats[6] == ref["stats"][6]
+    assert np.abs(x - ref["x"]).max() <= 2e-5 and np.abs(y - ref["y"]).max() <= 2e-5
+    # ... and through the reference-signature class with device-resident tensors
+    d = PDEDataset(ds, device="cuda:0")
+    assert len(d) == 64 and d.theta_is_constant == (not random_theta)
+    xi, yi = d[5]
+    assert tuple(xi.shape) == (3, 40, 40) and tuple(yi.shape) == (1, 40, 40) and xi.dtype == torch.float32
+    assert np.abs(xi.cpu().numpy() - ref["x"][5]).max() <= 2e-5 and np.abs(yi.cpu().numpy() - ref["y"][5]).max() <= 2e-5
+    back = d.denormalize(d.u_fine_norm[3]).cpu().numpy()
+    assert np.abs(back - ds["u_fine"][3]).max() <= 1e-6 * np.abs(ds["u_fine"][3]).max() + 1e-9

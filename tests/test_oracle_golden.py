@@ -71,3 +71,14 @@ def test_structural_facts_of_the_reference_operator():
     x = np.linspace(0, 1, n)
     k1, k2 = 2.3, 3.7
     assert np.array_equal(np.outer(np.sin(2 * np.pi * k2 * x), np.sin(2 * np.pi * k1 * x)), O.forcing_term(k1, k2, n))
+
+
+def test_dataset_tensor_oracle_against_golden():
+    """oracle/dataset_oracle.py against outputs of the LIVE reference PDEDataset (fixture made by
+    tests/golden/make_golden_tensors.py in the build container)."""
+    from oracle.dataset_oracle import dataset_tensors
+    gold = np.load(os.path.join(GOLDEN, "dataset_tensors_seed0.npz"))
+    ds = np.load(os.path.join(GOLDEN, "dataset_standard_seed0.npz"))
+    out = dataset_tensors({k: ds[k] for k in ds.files})
+    assert np.abs(out["x"] - gold["x"]).max() <= 1e-6 and np.abs(out["y"] - gold["y"]).max() <= 1e-6
+    assert np.allclose(out["stats"][:4], gold["stats"][:4], rtol=1e-6)
