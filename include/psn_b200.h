@@ -151,6 +151,18 @@ int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine,
                         const double* u_coarse, const double* u_fine, const double* f_fine, const double* theta_fine,
                         float* x, float* y, double* stats, void* stream);
 
+/* Interpolation baselines of the evaluation scripts ("next" row f4 of SURVEY.md section 8).
+ *
+ * Replaces bilinear_multi_level_upscale / cubic_multi_level_upscale
+ * (src/resolution_comparison_enhanced.py:19-65): `levels` successive x2 upsamplings with
+ * F.interpolate(mode = 'bilinear' | 'bicubic', align_corners = True) in float32 (the reference casts the
+ * float64 solution to float32 first and every level rounds to float32).
+ *
+ *   mode 0 = bilinear, 1 = bicubic (cubic convolution, A = -0.75, border-clamped taps: torch's definition)
+ *   u_in [batch, n_in, n_in] float64;  out [batch, n_in * 2^levels, n_in * 2^levels] float32;  host or device
+ */
+int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const double* u_in, float* out, void* stream);
+
 /* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg, default 2), "tile" (interior
  * tile edge of the streamed kernels, default 64), "ws_bytes" (workspace budget per pipeline slot),
  * "smem_max_n" (largest n solved fully in shared memory; 0 = as large as fits). */

@@ -12,7 +12,8 @@ from ._lib import PsnError
 from .data_generation import PoissonSolver
 from .dataset_tensors import PDEDataset
 from .enhanced_data_generation import EnhancedPoissonSolver
-from .resolution_comparison import solve_multi_resolution, solve_multi_resolution_batch
+from .resolution_comparison import (bilinear_multi_level_upscale, cubic_multi_level_upscale, solve_multi_resolution,
+                                    solve_multi_resolution_batch, split_into_subdomains, stitch_subdomains)
 
 __all__ = ["PoissonSolver", "EnhancedPoissonSolver", "PDEDataset", "solve_multi_resolution",
            "solve_multi_resolution_batch", "PsnError", "_lib"]

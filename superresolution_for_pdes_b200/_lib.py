@@ -23,7 +23,7 @@ STATUS_CONVERGED, STATUS_FP64_FLOOR, STATUS_MAXITER, STATUS_BREAKDOWN = 0, 1, 2,
 EXPORTED_SYMBOLS = (
     "psn_version", "psn_get_device_count", "psn_init", "psn_shutdown", "psn_last_error",
     "psn_solve_batch", "psn_subdomain_batch", "psn_multires", "psn_set_option",
-    "psn_profile_begin", "psn_profile_read", "psn_profile_end", "psn_describe", "psn_dataset_tensors",
+    "psn_profile_begin", "psn_profile_read", "psn_profile_end", "psn_describe", "psn_dataset_tensors", "psn_upscale_cascade",
 )
 
 
@@ -72,6 +72,8 @@ def load() -> ctypes.CDLL:
     lib.psn_dataset_tensors.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp, _c_dp,
                                         ctypes.c_void_p]
     lib.psn_dataset_tensors.restype = ctypes.c_int
+    lib.psn_upscale_cascade.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _c_dp, _c_dp, ctypes.c_void_p]
+    lib.psn_upscale_cascade.restype = ctypes.c_int
     lib.psn_describe.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
     lib.psn_describe.restype = ctypes.c_int
     _lib = lib
@@ -333,3 +335,17 @@ def dataset_tensors(u_coarse, u_fine, f_fine, theta_fine, *, x=None, y=None, str
                                  _ptr(stats), ctypes.c_void_p(stream))
     _check(rc)
     return x, y, stats
+
+
+def upscale_cascade(u, levels: int, mode: str = "bilinear", out=None, stream: int = 0):
+    """`levels` successive x2 upsamplings (align_corners=True, float32) of u [B, n, n] (float64).
+    mode: 'bilinear' | 'bicubic'.  Returns float32 [B, n*2^levels, n*2^levels]."""
+    lib = load()
+    B, n = int(u.shape[0]), int(u.shape[-1])
+    u = _f64(u, (B, n, n), "u")
+    m = n << levels
+    if out is None:
+        out = np.empty((B, m, m), dtype=np.float32)
+    rc = lib.psn_upscale_cascade({"bilinear": 0, "bicubic": 1}[mode], n, int(levels), B, _ptr(u), _ptr(out), ctypes.c_void_p(stream))
+    _check(rc)
+    return out

@@ -293,6 +293,60 @@ __global__ void __launch_bounds__(256) psn_tensor_kernel(long long n, int nc, in
     }
 }
 
+
+// ----------------------------------------------------------------------------- interpolation baselines (row f4)
+__device__ __forceinline__ void psn_cubic_coeffs(float t, float (&w)[4]) {
+    const float A = -0.75f;
+    float x = t + 1.f;
+    w[0] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+    x = t;
+    w[1] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    x = 1.f - t;
+    w[2] = ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f;
+    x = 2.f - t;
+    w[3] = ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A;
+}
+// one x2 level, align_corners = True; SRC = double for the first level (cast to float32 on load), float after
+template <class SRC>
+__global__ void __launch_bounds__(256) psn_upscale2_kernel(int mode, int n, long long batch, const SRC* in, float* out) {
+    const int m = 2 * n;
+    const long long total = batch * m * m;
+    const float scale = (float)(n - 1) / (float)(m - 1);
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+        const long long b = idx / ((long long)m * m);
+        const int rem = (int)(idx - b * (long long)m * m);
+        const int oy = rem / m, ox = rem - oy * m;
+        const SRC* p = in + b * (long long)n * n;
+        const float ry = scale * (float)oy, rx = scale * (float)ox;
+        float v;
+        if (mode == 0) {
+            const int y0 = (int)ry, x0 = (int)rx;
+            const int y1 = min(y0 + 1, n - 1), x1 = min(x0 + 1, n - 1);
+            const float ly = ry - (float)y0, lx = rx - (float)x0;
+            v = (1.f - ly) * ((1.f - lx) * (float)p[y0 * n + x0] + lx * (float)p[y0 * n + x1]) +
+                ly * ((1.f - lx) * (float)p[y1 * n + x0] + lx * (float)p[y1 * n + x1]);
+        } else {
+            const int iy = (int)floorf(ry), ix = (int)floorf(rx);
+            float wy[4], wx[4];
+            psn_cubic_coeffs(ry - (float)iy, wy);
+            psn_cubic_coeffs(rx - (float)ix, wx);
+            v = 0.f;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int yy = min(max(iy - 1 + a, 0), n - 1);
+                float row = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int xx = min(max(ix - 1 + c, 0), n - 1);
+                    row += wx[c] * (float)p[yy * n + xx];
+                }
+                v += wy[a] * row;
+            }
+        }
+        out[idx] = v;
+    }
+}
+
 // ----------------------------------------------------------------------------- library context
 namespace {
 
@@ -1256,6 +1310,46 @@ int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine, const doubl
     bool any_host = false;
     for (MemKind k : kinds) any_host = any_host || (k == MEM_HOST);
     if (any_host) CU_TRY(cudaStreamSynchronize(s));
+    return PSN_OK;
+}
+
+int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const double* u_in, float* out, void* stream) {
+    g_err[0] = 0;
+    int rc = ensure_init();
+    if (rc) return rc;
+    if ((mode != 0 && mode != 1) || n_in < 2 || levels < 1 || levels > 8 || batch < 0) return psn_fail(PSN_ERR_INVALID, "bad arguments");
+    if (!u_in || !out) return psn_fail(PSN_ERR_INVALID, "NULL array");
+    if (batch == 0) return PSN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const long long n_out = (long long)n_in << levels;
+    const size_t c_in = (size_t)batch * n_in * n_in, c_out = (size_t)batch * n_out * n_out;
+    const MemKind k_in = classify(u_in), k_out = classify(out);
+    Arena& ar = g.slots[0].arena;
+    size_t need = 64 * 256 + 2 * pad256(c_out * 4);
+    if (k_in == MEM_HOST) need += pad256(c_in * 8);
+    if ((rc = arena_reserve(ar, need))) return rc;
+    const double* d_in;
+    if ((rc = stage_in(ar, s, u_in, k_in, 0, c_in, &d_in))) return rc;
+    float* buf[2] = {arena_take<float>(ar, c_out), arena_take<float>(ar, c_out)};
+    if (!buf[0] || !buf[1]) return psn_fail(PSN_ERR_NOMEM, "staging arena exhausted");
+    int n = n_in;
+    const float* cur = nullptr;
+    for (int l = 0; l < levels; ++l) {
+        const bool last = l == levels - 1;
+        float* dst = (last && k_out == MEM_DEVICE) ? out : buf[l & 1];
+        const size_t cnt = (size_t)batch * (2 * n) * (2 * n);
+        const unsigned grid = (unsigned)std::min<size_t>((cnt + 255) / 256, (size_t)g.sm_count * 32);
+        ProfScope pr("upscale2", s);
+        if (l == 0) psn_upscale2_kernel<double><<<grid, 256, 0, s>>>(mode, n, (long long)batch, d_in, dst);
+        else psn_upscale2_kernel<float><<<grid, 256, 0, s>>>(mode, n, (long long)batch, cur, dst);
+        cur = dst;
+        n *= 2;
+    }
+    CU_TRY(cudaGetLastError());
+    if (k_out == MEM_HOST) {
+        CU_TRY(cudaMemcpyAsync(out, cur, c_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    if (k_in == MEM_HOST || k_out == MEM_HOST) CU_TRY(cudaStreamSynchronize(s));
     return PSN_OK;
 }
 

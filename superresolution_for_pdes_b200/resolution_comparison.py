@@ -88,3 +88,45 @@ def solve_multi_resolution_batch(n_examples: int, n_coarse: int = 40, resolution
     us, info = _lib.multires(n_finest, all_res, n_examples, theta, sx, sy, rtol=rtol, max_iter=max_iter)
     info.raise_if_failed("solve_multi_resolution_batch")
     return {'k1': k1, 'k2': k2, 'theta_finest': theta, 'sin_x': sx, 'sin_y': sy, 'u': us, 'info': info}
+
+
+# --------------------------------------------------------------------------- interpolation baselines (row f4)
+def _cascade(data: dict, target_resolution: int, mode: str) -> np.ndarray:
+    current_res = 40
+    levels = 0
+    while current_res < target_resolution:
+        current_res *= 2
+        levels += 1
+    u40 = np.asarray(data['u'][40])
+    if levels == 0:
+        return u40
+    return _lib.upscale_cascade(u40[None], levels, mode)[0]
+
+
+def bilinear_multi_level_upscale(data: dict, target_resolution: int) -> np.ndarray:
+    """src/resolution_comparison_enhanced.py:19-41: 40 -> 80 -> ... -> target by x2 bilinear steps
+    (align_corners=True, float32), all levels in one GPU call."""
+    return _cascade(data, target_resolution, "bilinear")
+
+
+def cubic_multi_level_upscale(data: dict, target_resolution: int) -> np.ndarray:
+    """src/resolution_comparison_enhanced.py:43-65: the same cascade with bicubic steps."""
+    return _cascade(data, target_resolution, "bicubic")
+
+
+def split_into_subdomains(array: np.ndarray, subdomain_size: int) -> list:
+    """src/resolution_comparison.py:123-139 (host-side views, as in the reference)."""
+    n = array.shape[0] // subdomain_size
+    return [[array[i * subdomain_size:(i + 1) * subdomain_size, j * subdomain_size:(j + 1) * subdomain_size]
+             for j in range(n)] for i in range(n)]
+
+
+def stitch_subdomains(subdomains: list) -> np.ndarray:
+    """src/resolution_comparison.py:141-158"""
+    n_rows, n_cols = len(subdomains), len(subdomains[0])
+    size = subdomains[0][0].shape[0]
+    result = np.zeros((n_rows * size, n_rows * size))
+    for i in range(n_rows):
+        for j in range(n_cols):
+            result[i * size:(i + 1) * size, j * size:(j + 1) * size] = subdomains[i][j]
+    return result

@@ -315,3 +315,34 @@ def test_dataset_tensor_prologue_matches_reference_semantics(gpu_lib, random_the
     assert np.abs(xi.cpu().numpy() - ref["x"][5]).max() <= 2e-5 and np.abs(yi.cpu().numpy() - ref["y"][5]).max() <= 2e-5
     back = d.denormalize(d.u_fine_norm[3]).cpu().numpy()
     assert np.abs(back - ds["u_fine"][3]).max() <= 1e-6 * np.abs(ds["u_fine"][3]).max() + 1e-9
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "bicubic"])
+def test_upscale_cascades_match_reference_semantics(gpu_lib, mode):
+    """Row f4: psn_upscale_cascade against the torch-CPU restatement (oracle/upscale_oracle.py, bit-equal to the
+    live reference functions) and against the committed golden outputs of the reference.
+    Tolerance: float32 arithmetic with a different summation order -- 4 ulp of the field's maximum per level."""
+    from oracle import upscale_oracle as uo
+    import superresolution_for_pdes_b200 as P
+    gold = np.load(os.path.join(GOLDEN, "upscale_seed2.npz"))
+    u40 = np.load(os.path.join(GOLDEN, "multires_seed2.npz"))["u40"]
+    data = {"u": {40: u40}}
+    fn = P.bilinear_multi_level_upscale if mode == "bilinear" else P.cubic_multi_level_upscale
+    scale = float(np.abs(u40).max())
+    for target, levels in ((80, 1), (160, 2), (320, 3), (640, 4)):
+        out = fn(data, target)
+        assert out.dtype == np.float32 and out.shape == (target, target)
+        tol = 4 * levels * np.finfo(np.float32).eps * scale
+        assert np.abs(out - uo.multi_level_upscale(data, target, mode)).max() <= tol
+        if target <= 160:
+            assert np.abs(out - gold[f"{mode}_{target}"]).max() <= tol
+    assert fn(data, 40) is not None and fn(data, 40).shape == (40, 40)
+    # batched, odd start size, through the C ABI
+    rng = np.random.RandomState(3)
+    u = rng.standard_normal((5, 23, 23))
+    out = gpu_lib.upscale_cascade(u, 2, mode)
+    ref = uo.upscale_batch(u, 2, mode)
+    assert out.shape == (5, 92, 92) and np.abs(out - ref).max() <= 16 * np.finfo(np.float32).eps * np.abs(u).max()
+    # the tiling helpers of the evaluation scripts round-trip
+    parts = P.split_into_subdomains(u40, 10)
+    assert np.array_equal(P.stitch_subdomains(parts), u40)

@@ -82,3 +82,21 @@ def test_dataset_tensor_oracle_against_golden():
     out = dataset_tensors({k: ds[k] for k in ds.files})
     assert np.abs(out["x"] - gold["x"]).max() <= 1e-6 and np.abs(out["y"] - gold["y"]).max() <= 1e-6
     assert np.allclose(out["stats"][:4], gold["stats"][:4], rtol=1e-6)
+
+
+def test_upscale_oracle_against_golden():
+    """oracle/upscale_oracle.py against outputs of the LIVE reference cascades (fixture made by
+    tests/golden/make_golden_upscale.py in the build container).  float32 kernels of torch may differ in the
+    last bits between CPUs (vectorised paths), hence 1e-6 absolute on O(0.01..1) values."""
+    from oracle import upscale_oracle as uo
+    gold = np.load(os.path.join(GOLDEN, "upscale_seed2.npz"))
+    u40 = np.load(os.path.join(GOLDEN, "multires_seed2.npz"))["u40"]
+    data = {"u": {40: u40}}
+    for target in (80, 160):
+        for mode in ("bilinear", "bicubic"):
+            out = uo.multi_level_upscale(data, target, mode)
+            assert out.dtype == np.float32 and out.shape == (target, target)
+            assert np.abs(out - gold[f"{mode}_{target}"]).max() <= 1e-6 * max(1.0, np.abs(u40).max())
+    assert uo.multi_level_upscale(data, 40, "bilinear").shape == (40, 40)
+    parts = uo.split_into_subdomains(u40, 10)
+    assert len(parts) == 4 and len(parts[0]) == 4 and np.array_equal(uo.stitch_subdomains(parts), u40)
