@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <map>
 #include <string>
+#include <chrono>
 #include <vector>
 
 #include "../../include/psn_b200.h"
@@ -182,6 +183,15 @@ __global__ void psn_state_after_check_kernel(const __grid_constant__ PsnCgArgs a
     if (b < B) active = psn_state_after_check(a, b);
     const unsigned m = __ballot_sync(0xffffffffu, active);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(counter, __popc(m));
+}
+// The convergence counter goes to the host through mapped pinned memory, not through a D2H copy: a copy would
+// queue behind the multi-hundred-MB result copies of the previous chunk on the same copy engine and stall the solve.
+__global__ void psn_publish_counter_kernel(const int* counter, int* host_slot) {
+    *reinterpret_cast<volatile int*>(host_slot) = *counter;
+    __threadfence_system();
+}
+__global__ void psn_zero_ints_kernel(int* p, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0;
 }
 __global__ void psn_finalize_kernel(const PsnSampleState* state, long long B, int32_t* iters, double* relres, int32_t* status) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -366,7 +376,8 @@ struct Slot {
     cudaStream_t stream = nullptr;
     Arena arena;      // staging buffers (per chunk)
     Arena ws_arena;   // streamed-path workspace
-    int* h_counters = nullptr;  // pinned
+    int* h_counters = nullptr;  // pinned, mapped into the device address space
+    int* d_counters_map = nullptr;   // device alias of h_counters
     int h_counters_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -529,6 +540,48 @@ struct ProfScope {
     }
 };
 
+// ---- chunk timeline of the host-buffer pipeline (PSN_TRACE=1: one line per chunk on stderr, ms since call start)
+struct TraceMark {
+    const char* what;
+    long long chunk;
+    cudaEvent_t ev;
+    double host_ms;
+};
+struct Trace {
+    bool on = false;
+    std::vector<TraceMark> marks;
+    std::chrono::steady_clock::time_point t0;
+    void begin(cudaStream_t s) {
+        const char* e = getenv("PSN_TRACE");
+        on = e && atoi(e) > 0;
+        if (!on) return;
+        marks.clear();
+        t0 = std::chrono::steady_clock::now();
+        mark("call", -1, s);
+    }
+    void mark(const char* what, long long chunk, cudaStream_t s) {
+        if (!on) return;
+        TraceMark m{what, chunk, nullptr, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()};
+        cudaEventCreate(&m.ev);
+        cudaEventRecord(m.ev, s);
+        marks.push_back(m);
+    }
+    void dump() {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const double host_end = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[0].ev, marks[i].ev);
+            fprintf(stderr, "[psn trace] chunk %2lld %-10s device %8.3f ms   enqueued at host %8.3f ms\n", marks[i].chunk, marks[i].what, ms,
+                    marks[i].host_ms);
+        }
+        fprintf(stderr, "[psn trace] call returns at host %8.3f ms\n", host_end);
+        for (auto& m : marks) cudaEventDestroy(m.ev);
+        marks.clear();
+    }
+};
+
 // ---- CUDA backend of the streamed driver
 struct CudaBackend {
     cudaStream_t s;
@@ -540,8 +593,8 @@ struct CudaBackend {
     }
     dim3 cg_grid(const PsnCgArgs& a, long long B) { return dim3(a.ntx, a.nty, (unsigned)B); }
     void zero_counters(int* c, int cnt) {
-        cudaError_t e = cudaMemsetAsync(c, 0, sizeof(int) * cnt, s);
-        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        psn_zero_ints_kernel<<<1, 128, 0, s>>>(c, cnt);
+        chk();
     }
     void prologue(const PsnCgArgs& a, long long B) {
         ProfScope p("prologue", s);
@@ -651,8 +704,9 @@ struct CudaBackend {
         chk();
     }
     void fetch_counter_async(const int* c, int it) {
-        cudaError_t e = cudaMemcpyAsync(slot->h_counters + it, c, sizeof(int), cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaEventRecord(slot->ev[it & 3], s);
+        psn_publish_counter_kernel<<<1, 1, 0, s>>>(c, slot->d_counters_map + it);
+        chk();
+        cudaError_t e = cudaEventRecord(slot->ev[it & 3], s);
         if (e != cudaSuccess && err == cudaSuccess) err = e;
     }
     int wait_counter(int it) {
@@ -858,7 +912,9 @@ int solve_internal(const Problem& P) {
         if (Bc > cap) Bc = cap;
     }
     const int nslots = any_host ? PSN_NSLOTS : 1;
-    if (any_host) CU_TRY(cudaStreamSynchronize(P.stream));  // device inputs may still be in flight on the caller's stream
+    if (any_host) CU_TRY(cudaStreamSynchronize(P.stream));
+    Trace trace;
+    if (any_host) trace.begin(g.slots[0].stream);  // device inputs may still be in flight on the caller's stream
 
     // Software pipeline over chunks (host buffers): the H2D staging of chunk c+1 is enqueued on its own
     // slot stream BEFORE the (host-blocking) solve of chunk c, and the D2H of chunk c-1 drains on a third
@@ -905,7 +961,8 @@ int solve_internal(const Problem& P) {
             if (wsl.h_counters_cap < P.max_iter + 8) {
                 if (wsl.h_counters) cudaFreeHost(wsl.h_counters);
                 wsl.h_counters = nullptr;
-                CU_TRY(cudaMallocHost(&wsl.h_counters, sizeof(int) * (P.max_iter + 8)));
+                CU_TRY(cudaHostAlloc(&wsl.h_counters, sizeof(int) * (P.max_iter + 8), cudaHostAllocMapped));
+                CU_TRY(cudaHostGetDevicePointer(&wsl.d_counters_map, wsl.h_counters, 0));
                 wsl.h_counters_cap = P.max_iter + 8;
             }
         }
@@ -960,6 +1017,7 @@ int solve_internal(const Problem& P) {
             cx.slot->arena.off = 0;   // stream order on the slot's stream protects reuse
         }
         Arena& ar = cx.slot->arena;
+        trace.mark("h2d_begin", c, s);
         cx.rhs.mn = P.mn;
         cx.rhs.step = P.step;
         if ((rc2 = stage_in(ar, s, P.theta, k_theta, b0 * (long long)mm, bc * mm, &cx.rhs.theta))) return rc2;
@@ -995,6 +1053,7 @@ int solve_internal(const Problem& P) {
                 if ((rc2 = stage_out(ar, P.th_coarse, k_tc, b0 * (long long)scc, bc * scc, &a.th_coarse, false))) return rc2;
             }
         }
+        trace.mark("h2d_end", c, s);
         return PSN_OK;
     };
 
@@ -1002,6 +1061,7 @@ int solve_internal(const Problem& P) {
         int rc2;
         cudaStream_t s = cx.s;
         const long long b0 = cx.b0, bc = cx.bc;
+        if (resident) trace.mark("solve_begin", c, s);
         if (resident) {
             const PsnSolveArgs& a = cx.a;
             {
@@ -1036,6 +1096,7 @@ int solve_internal(const Problem& P) {
             // measured slower than keeping each chunk's working set to itself
             if (c >= 1 && any_host && nws == 2 && g.serialize_solves) CU_TRY(cudaStreamWaitEvent(s, g.ws_free[wk ^ 1], 0));
             wsl.ws_arena.off = 0;
+            trace.mark("solve_begin", c, s);
             PsnStreamWs ws;
             if ((rc2 = carve_stream_ws(wsl.ws_arena, plan, scfg, bc, P.max_iter, &ws))) return rc2;
             choose_bands(plan, &scfg, bc);
@@ -1073,10 +1134,12 @@ int solve_internal(const Problem& P) {
             }
             if (any_host) CU_TRY(cudaEventRecord(g.ws_free[wk], s));
         }
+        trace.mark("solve_end", c, s);
         if ((rc2 = copy_back(s, P.u, k_u, b0 * (long long)nn, bc * nn, cx.d_u))) return rc2;
         if ((rc2 = copy_back(s, hb_it ? hb_it : P.iters, k_it, b0, (size_t)bc, cx.d_it))) return rc2;
         if ((rc2 = copy_back(s, hb_rr ? hb_rr : P.relres, k_rr, b0, (size_t)bc, cx.d_rr))) return rc2;
         if ((rc2 = copy_back(s, hb_st ? hb_st : P.status, k_st, b0, (size_t)bc, cx.d_st))) return rc2;
+        trace.mark("d2h_end", c, s);
         return PSN_OK;
     };
 
@@ -1123,6 +1186,7 @@ int solve_internal(const Problem& P) {
         if (hb_it && k_it == MEM_HOST) memcpy(P.iters, hb_it, (size_t)P.B * 4);
         if (hb_rr && k_rr == MEM_HOST) memcpy(P.relres, hb_rr, (size_t)P.B * 8);
         if (hb_st && k_st == MEM_HOST) memcpy(P.status, hb_st, (size_t)P.B * 4);
+        trace.dump();
     }
     return PSN_OK;
 }
