@@ -203,7 +203,7 @@ class ClockSampler:
 # --------------------------------------------------------------------------- own arm
 # compulsory HBM bytes per grid node and participating sample of each streamed kernel (DESIGN.md
 # section "Kernels and their rooflines"); `survey` = the same work in SURVEY.md 8(d)'s unfused model
-KERNEL_BYTES = {
+KERNEL_BYTES_F64 = {
     "strip_pre_l0": {"own": 18.0, "survey": 66.0},     # read r; write u_pre, coarse rhs (1/4)
     "strip_post_l0": {"own": 26.0, "survey": 66.0},    # read u_pre, r, coarse corr (1/4); write z
     "tile_pre_l0": {"own": 18.0, "survey": 66.0},      # (vcycle_mode 0: shared-memory tile variant)
@@ -211,6 +211,14 @@ KERNEL_BYTES = {
     "dir_apply_dot": {"own": 32.0, "survey": 40.0},    # read z, p; write p, q
     "update_norm": {"own": 48.0, "survey": 48.0},      # read p, q, x, r; write x, r
 }
+# V-cycle intermediates stored as float (describe()["vcycle_f32"]): u_pre, z, coarse rhs / correction are 4 bytes
+KERNEL_BYTES_F32 = {
+    "strip_pre_l0": {"own": 13.0, "survey": 66.0},     # read r (8); write u_pre (4), coarse rhs (4/4)
+    "strip_post_l0": {"own": 17.0, "survey": 66.0},    # read r (8), u_pre (4), coarse corr (4/4); write z (4)
+    "dir_apply_dot": {"own": 28.0, "survey": 40.0},    # read z (4), p (8); write p, q (16)
+    "update_norm": {"own": 48.0, "survey": 48.0},
+}
+KERNEL_BYTES = KERNEL_BYTES_F64
 
 
 def run_own(args):
@@ -337,6 +345,8 @@ def run_own(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     sample_iters = float(info.iters.sum())
     desc = _lib.describe(n)
+    global KERNEL_BYTES
+    KERNEL_BYTES = KERNEL_BYTES_F32 if desc.get("vcycle_f32") else KERNEL_BYTES_F64
     roof = None
     kernels = {}
     if prof:
@@ -410,7 +420,9 @@ def run_own(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, B, world), "n": n, "batch_per_gpu": B, "rtol": args.rtol,
-                       "solver": "MG-preconditioned CG, V(2,2) red-black GS, matrix-free 5-point zero-ghost stencil",
+                       "solver": "MG-preconditioned CG, V(2,2) red-black GS, matrix-free 5-point zero-ghost stencil; fp64 "
+                                 "arithmetic, CG vectors and inner products" + ("; preconditioner intermediates stored as float"
+                                                                                if desc.get("vcycle_f32") else ""),
                        "path": "resident" if desc["resident"] else "streamed", "mean_iters": float(info.iters.mean()),
                        "max_iters": int(info.iters.max()),
                        "l2": f"inputs larger than L2 (theta = {B * n * n * 8 / 1e6:.0f} MB per GPU, workspace {desc['workspace_bytes_per_sample'] * B / 1e9:.1f} GB)"},

@@ -165,7 +165,11 @@ int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const dou
 
 /* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg, default 2), "tile" (interior
  * tile edge of the streamed kernels, default 64), "ws_bytes" (workspace budget per pipeline slot),
- * "smem_max_n" (largest n solved fully in shared memory; 0 = as large as fits). */
+ * "smem_max_n" (largest n solved fully in shared memory; 0 = as large as fits), "vcycle_mode" (streamed V-cycle
+ * legs: 0 shared-memory tiles, 1 register-fed warp strips, 2 TMA-fed warp strips = default), "vcycle_f32"
+ * (default 1: with vcycle_mode 2 and grid sizes divisible by 4 on every streamed level, the preconditioner's
+ * intermediate arrays are stored as float; x, r, p, q, every inner product and all arithmetic stay fp64, so the
+ * accuracy of the solution is unchanged), "coarse_max_n", "host_chunks", "res_block", "serialize_solves". */
 int psn_set_option(const char* name, int64_t value);
 
 /* Per-kernel device timing (CUDA events around every launch).  Off by default because the event
@@ -178,7 +182,8 @@ int psn_profile_end(void);
 
 /* Which path a grid size takes and what it costs: fills info[0..7] =
  * {resident(1)/streamed(0), levels, first shared-memory level, threads per CTA,
- *  dynamic shared memory bytes of the dominant kernel, tile edge, workspace bytes per sample, 0}. */
+ *  dynamic shared memory bytes of the dominant kernel, tile edge, workspace bytes per sample,
+ *  1 if the V-cycle intermediates of this size are stored as float (option "vcycle_f32", streamed path)}. */
 int psn_describe(int n, int64_t* info);
 
 #ifdef __cplusplus

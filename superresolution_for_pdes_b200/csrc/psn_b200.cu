@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_post_kernel(const _
 #ifndef PSN_STRIP_MINB_TMA
 #define PSN_STRIP_MINB_TMA 3
 #endif
-template <int NU, bool POST, bool TMA>
+// TB / TV: element types of the right-hand side and of the V-cycle intermediates (see PsnStripArgs)
+template <int NU, bool POST, bool TMA, class TB, class TV>
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, TMA ? PSN_STRIP_MINB_TMA : PSN_STRIP_MINB)
 psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ PsnStripArgs a, long long ntasks) {
     extern __shared__ __align__(128) unsigned char strip_smem[];
@@ -107,18 +108,19 @@ psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ P
     const PsnWarp w{(int)(threadIdx.x & 31)};
     constexpr int NARR = POST ? 2 : 1;
     if constexpr (TMA) {
-        PsnTmaFeeder<NU, NARR> fd;
-        fd.attach(strip_smem + (size_t)warp * PsnTmaFeeder<NU, NARR>::smem_bytes());
-        if constexpr (POST) psn_strip_post_body<NU>(w, plan, a, b, band, strip, fd);
-        else psn_strip_pre_body<NU>(w, plan, a, b, band, strip, fd);
+        typedef typename PsnStripFeederSel<NU, POST, TB, TV>::type Feeder;
+        Feeder fd;
+        fd.attach(strip_smem + (size_t)warp * Feeder::smem_bytes());
+        if constexpr (POST) psn_strip_post_body<NU, TB, TV>(w, plan, a, b, band, strip, fd);
+        else psn_strip_pre_body<NU, TB, TV>(w, plan, a, b, band, strip, fd);
     } else {
         PsnRegFeeder<NU, NARR> fd;
-        if constexpr (POST) psn_strip_post_body<NU>(w, plan, a, b, band, strip, fd);
-        else psn_strip_pre_body<NU>(w, plan, a, b, band, strip, fd);
+        if constexpr (POST) psn_strip_post_body<NU, TB, TV>(w, plan, a, b, band, strip, fd);
+        else psn_strip_pre_body<NU, TB, TV>(w, plan, a, b, band, strip, fd);
     }
 }
 
-template <bool TMA>
+template <bool TMA, class TZ>
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
 psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     extern __shared__ __align__(128) unsigned char strip_smem[];
@@ -131,17 +133,18 @@ psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     const int band = rem / a.dir_nstrips, strip = rem - band * a.dir_nstrips;
     const PsnWarp w{(int)(threadIdx.x & 31)};
     if constexpr (TMA) {
-        PsnTmaFeeder<2, 2> fd;
-        fd.attach(strip_smem + (size_t)warp * PsnTmaFeeder<2, 2>::smem_bytes());
-        psn_dir_strip_body(w, a, b, band, strip, fd);
+        PsnTmaFeeder<2, TZ, double> fd;
+        fd.attach(strip_smem + (size_t)warp * PsnTmaFeeder<2, TZ, double>::smem_bytes());
+        psn_dir_strip_body<TZ>(w, a, b, band, strip, fd);
     } else {
         PsnRegFeeder<2, 2> fd;
-        psn_dir_strip_body(w, a, b, band, strip, fd);
+        psn_dir_strip_body<TZ>(w, a, b, band, strip, fd);
     }
 }
 
+template <class TV>
 __global__ void __launch_bounds__(PSN_COARSE_THREADS) psn_coarse_vcycle_kernel(const __grid_constant__ PsnPlan plan, int l0,
-                                                                               const double* bg, double* ug,
+                                                                               const TV* bg, TV* ug,
                                                                                const PsnSampleState* state) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[64];
@@ -380,7 +383,10 @@ struct Slot {
     int* d_counters_map = nullptr;   // device alias of h_counters
     int h_counters_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t staging_free = nullptr;   // recorded after the last copy of the chunk that used the staging arena
 };
+
+#define PSN_NCHUNK_STREAMS 6
 
 struct ProfRec {
     const char* name;
@@ -388,6 +394,10 @@ struct ProfRec {
 };
 
 struct Context {
+    // Host-buffer pipeline: chunk c runs on chunk_stream[c % 6], created with DEcreasing priority, so that of two
+    // overlapping chunks the earlier one wins the SMs (it finishes, and its result copy starts, as early as it
+    // would alone) while the later one fills the gaps.
+    cudaStream_t chunk_stream[PSN_NCHUNK_STREAMS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ready = false;
     int device = -1;
     int sm_count = 0;
@@ -405,6 +415,10 @@ struct Context {
     int serialize_solves = 0;
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
+    int band0 = 0;         // rows per warp task on level 0 (0 = automatic)
+    int band_target = 32;  // V-cycle strip tasks per SM the band split aims for
+    int dir_band = 0;      // rows per warp task of the direction kernel (0: same as level 0 of the V-cycle)
+    int vcycle_f32 = 1;    // streamed path: store V-cycle intermediates as float where the grid sizes allow (PsnStreamCfg::vf32)
     int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 3 streamed / 8 resident)
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     bool attrs_set = false;
@@ -514,7 +528,8 @@ int set_kernel_attrs() {
 #undef PSN_RES_ATTR
     CU_TRY(cudaFuncSetAttribute(psn_tile_pre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CU_TRY(cudaFuncSetAttribute(psn_tile_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CU_TRY(cudaFuncSetAttribute(psn_coarse_vcycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_coarse_vcycle_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_coarse_vcycle_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     g.attrs_set = true;
     return PSN_OK;
 }
@@ -606,36 +621,42 @@ struct CudaBackend {
         psn_state_init_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B);
         chk();
     }
-    template <int NU, bool POST, bool TMA>
-    void strip_launch_nu(const PsnPlan& plan, const PsnStripArgs& a, long long B) {
+    template <int NU, bool POST, bool TMA, class TB, class TV>
+    void strip_launch_t(const PsnPlan& plan, const PsnStripArgs& a, long long B) {
         const long long ntasks = B * a.nstrips * a.nbands;
         const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
-        const size_t smem = TMA ? (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<NU, POST ? 2 : 1>::smem_bytes() : 0;
-        if (TMA) {
+        size_t smem = 0;
+        if constexpr (TMA) {
+            smem = (size_t)PSN_STRIP_WARPS * PsnStripFeederSel<NU, POST, TB, TV>::type::smem_bytes();
             static bool attr_done = false;   // one flag per template instantiation
             if (!attr_done) {
-                cudaFuncSetAttribute(psn_strip_kernel<NU, POST, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                cudaFuncSetAttribute(psn_strip_kernel<NU, POST, TMA, TB, TV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 attr_done = true;
             }
         }
-        psn_strip_kernel<NU, POST, TMA><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(plan, a, ntasks);
+        psn_strip_kernel<NU, POST, TMA, TB, TV><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(plan, a, ntasks);
+    }
+    template <int NU, bool POST>
+    void strip_launch_nu(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool tma, bool f32) {
+        if (tma && f32) {
+            if (a.level == 0) strip_launch_t<NU, POST, true, double, float>(plan, a, B);
+            else strip_launch_t<NU, POST, true, float, float>(plan, a, B);
+        } else if (tma) {
+            strip_launch_t<NU, POST, true, double, double>(plan, a, B);
+        } else {
+            strip_launch_t<NU, POST, false, double, double>(plan, a, B);
+        }
     }
     template <bool POST>
-    void strip_launch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool tma) {
-        if (tma) {
-            if (plan.nu == 1) strip_launch_nu<1, POST, true>(plan, a, B);
-            else if (plan.nu == 2) strip_launch_nu<2, POST, true>(plan, a, B);
-            else strip_launch_nu<3, POST, true>(plan, a, B);
-        } else {
-            if (plan.nu == 1) strip_launch_nu<1, POST, false>(plan, a, B);
-            else if (plan.nu == 2) strip_launch_nu<2, POST, false>(plan, a, B);
-            else strip_launch_nu<3, POST, false>(plan, a, B);
-        }
+    void strip_launch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool tma, bool f32) {
+        if (plan.nu == 1) strip_launch_nu<1, POST>(plan, a, B, tma, f32);
+        else if (plan.nu == 2) strip_launch_nu<2, POST>(plan, a, B, tma, f32);
+        else strip_launch_nu<3, POST>(plan, a, B, tma, f32);
     }
     void leg_pre(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
         if (cfg.mode >= 1) {
             ProfScope p(g.level == 0 ? "strip_pre_l0" : "strip_pre_coarse", s);
-            strip_launch<false>(plan, psn_leg_to_strip(plan, cfg, g, false), B, cfg.mode == 2);
+            strip_launch<false>(plan, psn_leg_to_strip(plan, cfg, g, false), B, cfg.mode == 2, cfg.mode == 2 && cfg.vf32);
         } else {
             const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
             ProfScope p(t.level == 0 ? "tile_pre_l0" : "tile_pre_coarse", s);
@@ -647,7 +668,7 @@ struct CudaBackend {
     void leg_post(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
         if (cfg.mode >= 1) {
             ProfScope p(g.level == 0 ? "strip_post_l0" : "strip_post_coarse", s);
-            strip_launch<true>(plan, psn_leg_to_strip(plan, cfg, g, true), B, cfg.mode == 2);
+            strip_launch<true>(plan, psn_leg_to_strip(plan, cfg, g, true), B, cfg.mode == 2, cfg.mode == 2 && cfg.vf32);
         } else {
             const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
             ProfScope p(t.level == 0 ? "tile_post_l0" : "tile_post_coarse", s);
@@ -656,10 +677,15 @@ struct CudaBackend {
         }
         chk();
     }
-    void coarse_vcycle(const PsnPlan& plan, int l0, const double* bg, double* ug, const PsnSampleState* st, long long B) {
+    void coarse_vcycle(const PsnPlan& plan, const PsnStreamCfg& cfg, const double* bg, double* ug, const PsnSampleState* st, long long B) {
         ProfScope p("coarse_vcycle", s);
+        const int l0 = cfg.ls;
         const size_t smem = ((size_t)2 * plan.lv[l0].size + psn_pool_doubles(plan, l0)) * sizeof(double);
-        psn_coarse_vcycle_kernel<<<(unsigned)B, PSN_COARSE_THREADS, smem, s>>>(plan, l0, bg, ug, st);
+        if (cfg.mode == 2 && cfg.vf32)
+            psn_coarse_vcycle_kernel<float><<<(unsigned)B, PSN_COARSE_THREADS, smem, s>>>(plan, l0, reinterpret_cast<const float*>(bg),
+                                                                                         reinterpret_cast<float*>(ug), st);
+        else
+            psn_coarse_vcycle_kernel<double><<<(unsigned)B, PSN_COARSE_THREADS, smem, s>>>(plan, l0, bg, ug, st);
         chk();
     }
     void dir_apply(const PsnCgArgs& a, long long B) {
@@ -667,16 +693,24 @@ struct CudaBackend {
         if (a.dir_mode >= 1) {
             const long long ntasks = B * a.dir_nstrips * a.dir_nbands;
             const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
-            if (a.dir_mode == 2) {
-                const size_t smem = (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<2, 2>::smem_bytes();
+            if (a.dir_mode == 2 && a.vf32) {
+                const size_t smem = (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<2, float, double>::smem_bytes();
                 static bool attr_done = false;
                 if (!attr_done) {
-                    cudaFuncSetAttribute(psn_dir_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    cudaFuncSetAttribute(psn_dir_strip_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     attr_done = true;
                 }
-                psn_dir_strip_kernel<true><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(a, ntasks);
+                psn_dir_strip_kernel<true, float><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(a, ntasks);
+            } else if (a.dir_mode == 2) {
+                const size_t smem = (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<2, double, double>::smem_bytes();
+                static bool attr_done = false;
+                if (!attr_done) {
+                    cudaFuncSetAttribute(psn_dir_strip_kernel<true, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    attr_done = true;
+                }
+                psn_dir_strip_kernel<true, double><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(a, ntasks);
             } else {
-                psn_dir_strip_kernel<false><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(a, ntasks);
+                psn_dir_strip_kernel<false, double><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(a, ntasks);
             }
         } else {
             psn_dir_apply_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
@@ -767,17 +801,17 @@ int copy_back(cudaStream_t s, T* host_dst, MemKind kind, long long offset, size_
 // upper bound of the <r,z> partial count over every band choice (smallest band = 16 rows)
 int psn_rz_max(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     if (cfg.mode < 1) return psn_rz_count(plan, cfg);
-    return psn_strip_count(plan.n, psn_strip_use_post(plan.nu)) * psn_band_count(plan.n, 16);
+    return psn_strip_count(plan.n, psn_strip_use_post(plan.nu, cfg.vf32)) * psn_band_count(plan.n, 16);
 }
 
 // rows per warp task on every streamed level: full columns when the batch alone fills the GPU,
 // shorter bands (more tasks, a little halo re-computation) for small batches
 void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg->band[l] = 16;
-    const long long target = (long long)g.sm_count * 32;
+    const long long target = (long long)g.sm_count * g.band_target;
     for (int l = 0; l < cfg->ls; ++l) {
         const int n = plan.lv[l].n;
-        const long long strips = psn_strip_count(n, psn_strip_use_pre(plan.nu));
+        const long long strips = psn_strip_count(n, psn_strip_use_pre(plan.nu, cfg->vf32));
         long long nb = (target + Bc * strips - 1) / (Bc * strips);
         if (nb < 1) nb = 1;
         if (nb > n / 16) nb = n / 16 > 0 ? n / 16 : 1;
@@ -786,6 +820,8 @@ void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
         if (band < 16) band = 16;
         cfg->band[l] = band;
     }
+    if (g.band0 >= 16 && cfg->ls >= 1) cfg->band[0] = (g.band0 + 1) & ~1;   // experiment knob
+    cfg->dir_band = g.dir_band >= 16 ? ((g.dir_band + 1) & ~1) : cfg->band[0];
 }
 
 size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) {
@@ -862,6 +898,7 @@ int solve_internal(const Problem& P) {
     if (!resident) {
         scfg.ls = stream_ls(plan);
         if (scfg.ls >= 1 && !psn_strip_ok(plan, scfg.ls)) scfg.mode = 0;   // odd level sizes: shared-memory tile kernels
+        scfg.vf32 = (scfg.mode == 2 && g.vcycle_f32 && scfg.ls >= 1 && psn_vf32_ok(plan, scfg.ls)) ? 1 : 0;
         if (scfg.ls < 1) return psn_fail(PSN_ERR_UNSUPPORTED, "no shared-memory coarse level for n=%d", P.n);
     }
 
@@ -914,7 +951,7 @@ int solve_internal(const Problem& P) {
     const int nslots = any_host ? PSN_NSLOTS : 1;
     if (any_host) CU_TRY(cudaStreamSynchronize(P.stream));
     Trace trace;
-    if (any_host) trace.begin(g.slots[0].stream);  // device inputs may still be in flight on the caller's stream
+    if (any_host) trace.begin(g.chunk_stream[0]);  // device inputs may still be in flight on the caller's stream
 
     // Software pipeline over chunks (host buffers): the H2D staging of chunk c+1 is enqueued on its own
     // slot stream BEFORE the (host-blocking) solve of chunk c, and the D2H of chunk c-1 drains on a third
@@ -979,6 +1016,7 @@ int solve_internal(const Problem& P) {
         PsnStreamWs ws;
         PsnStreamCfg cfg;
         int it_end = 0;
+        Slot* staging = nullptr;
     } pending[2];
     int est_iters = 0;   // outer iterations the previous chunks needed (0: unknown -> poll)
 
@@ -1007,14 +1045,15 @@ int solve_internal(const Problem& P) {
         cx.b0 = bounds[c];
         cx.bc = bounds[c + 1] - bounds[c];
         cx.slot = &g.slots[c % nslots];
-        cx.s = any_host ? cx.slot->stream : P.stream;
+        cx.s = any_host ? g.chunk_stream[c % PSN_NCHUNK_STREAMS] : P.stream;
         const long long b0 = cx.b0, bc = cx.bc;
         cudaStream_t s = cx.s;
         if (c < nslots) {
             rc2 = arena_reserve(cx.slot->arena, pad256(stage_ps * Bc) + 64 * 256 + (size_t)Bc * 64);
             if (rc2) return rc2;
         } else {
-            cx.slot->arena.off = 0;   // stream order on the slot's stream protects reuse
+            cx.slot->arena.off = 0;
+            CU_TRY(cudaStreamWaitEvent(s, cx.slot->staging_free, 0));   // chunk c - nslots has left the staging buffers
         }
         Arena& ar = cx.slot->arena;
         trace.mark("h2d_begin", c, s);
@@ -1119,7 +1158,7 @@ int solve_internal(const Problem& P) {
                 pd.active = true;
                 pd.b0 = b0; pd.bc = bc; pd.s = s; pd.rhs = cx.rhs;
                 pd.d_u = cx.d_u; pd.d_it = cx.d_it; pd.d_rr = cx.d_rr; pd.d_st = cx.d_st;
-                pd.ws = ws; pd.cfg = scfg; pd.it_end = it_end;
+                pd.ws = ws; pd.cfg = scfg; pd.it_end = it_end; pd.staging = cx.slot;
             }
             if (P.sub > 0) {
                 const PsnSolveArgs& a = cx.a;
@@ -1140,6 +1179,7 @@ int solve_internal(const Problem& P) {
         if ((rc2 = copy_back(s, hb_rr ? hb_rr : P.relres, k_rr, b0, (size_t)bc, cx.d_rr))) return rc2;
         if ((rc2 = copy_back(s, hb_st ? hb_st : P.status, k_st, b0, (size_t)bc, cx.d_st))) return rc2;
         trace.mark("d2h_end", c, s);
+        if (any_host) CU_TRY(cudaEventRecord(cx.slot->staging_free, s));
         return PSN_OK;
     };
 
@@ -1164,6 +1204,7 @@ int solve_internal(const Problem& P) {
         if ((rc2 = copy_back(pd.s, hb_it ? hb_it : P.iters, k_it, pd.b0, (size_t)pd.bc, pd.d_it))) return rc2;
         if ((rc2 = copy_back(pd.s, hb_rr ? hb_rr : P.relres, k_rr, pd.b0, (size_t)pd.bc, pd.d_rr))) return rc2;
         if ((rc2 = copy_back(pd.s, hb_st ? hb_st : P.status, k_st, pd.b0, (size_t)pd.bc, pd.d_st))) return rc2;
+        CU_TRY(cudaEventRecord(pd.staging->staging_free, pd.s));
         return PSN_OK;
     };
 
@@ -1182,7 +1223,7 @@ int solve_internal(const Problem& P) {
         if ((rc = resolve(1))) return rc;
     }
     if (any_host) {
-        for (int i = 0; i < nslots; ++i) CU_TRY(cudaStreamSynchronize(g.slots[i].stream));
+        for (int i = 0; i < PSN_NCHUNK_STREAMS; ++i) CU_TRY(cudaStreamSynchronize(g.chunk_stream[i]));
         if (hb_it && k_it == MEM_HOST) memcpy(P.iters, hb_it, (size_t)P.B * 4);
         if (hb_rr && k_rr == MEM_HOST) memcpy(P.relres, hb_rr, (size_t)P.B * 8);
         if (hb_st && k_st == MEM_HOST) memcpy(P.status, hb_st, (size_t)P.B * 4);
@@ -1226,7 +1267,17 @@ int psn_init(int device) {
     for (int k = 0; k < 2; ++k) CU_TRY(cudaEventCreateWithFlags(&g.ws_free[k], cudaEventDisableTiming));
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         CU_TRY(cudaStreamCreateWithFlags(&g.slots[i].stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&g.slots[i].staging_free, cudaEventDisableTiming));
         for (int k = 0; k < 4; ++k) CU_TRY(cudaEventCreateWithFlags(&g.slots[i].ev[k], cudaEventDisableTiming));
+    }
+    {
+        int prio_lo = 0, prio_hi = 0;   // numerically lower = higher priority
+        CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        for (int i = 0; i < PSN_NCHUNK_STREAMS; ++i) {
+            int pr = prio_hi + i;
+            if (pr > prio_lo) pr = prio_lo;
+            CU_TRY(cudaStreamCreateWithPriority(&g.chunk_stream[i], cudaStreamNonBlocking, pr));
+        }
     }
     const char* env = getenv("PSN_WS_BYTES");
     if (env) g.ws_bytes = atoll(env);
@@ -1247,6 +1298,10 @@ void psn_shutdown(void) {
     if (g.h_info) cudaFreeHost(g.h_info);
     g.h_info = nullptr;
     g.h_info_cap = 0;
+    for (int i = 0; i < PSN_NCHUNK_STREAMS; ++i) {
+        if (g.chunk_stream[i]) cudaStreamDestroy(g.chunk_stream[i]);
+        g.chunk_stream[i] = nullptr;
+    }
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         Slot& s = g.slots[i];
         if (s.arena.base) cudaFree(s.arena.base);
@@ -1255,6 +1310,7 @@ void psn_shutdown(void) {
         for (int k = 0; k < 4; ++k)
             if (s.ev[k]) cudaEventDestroy(s.ev[k]);
         if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.staging_free) cudaEventDestroy(s.staging_free);
         s = Slot();
     }
     for (auto& r : g.prof) {
@@ -1441,6 +1497,18 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;
+    } else if (!strcmp(name, "band_target")) {
+        if (value < 1 || value > 1024) return psn_fail(PSN_ERR_INVALID, "band_target must be in 1..1024");
+        g.band_target = (int)value;
+    } else if (!strcmp(name, "dir_band")) {
+        if (value < 0 || value > 65536) return psn_fail(PSN_ERR_INVALID, "dir_band must be 0 (automatic) or >= 16");
+        g.dir_band = (int)value;
+    } else if (!strcmp(name, "band0")) {
+        if (value < 0 || value > 65536) return psn_fail(PSN_ERR_INVALID, "band0 must be 0 (automatic) or >= 16");
+        g.band0 = (int)value;
+    } else if (!strcmp(name, "vcycle_f32")) {
+        if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "vcycle_f32 must be 0 or 1");
+        g.vcycle_f32 = (int)value;
     } else if (!strcmp(name, "host_chunks")) {
         if (value < 0 || value > 1024) return psn_fail(PSN_ERR_INVALID, "host_chunks must be in 0..1024");
         g.host_chunks = (int)value;
@@ -1517,6 +1585,9 @@ int psn_describe(int n, int64_t* info) {
         PsnStreamCfg sc;
         memset(&sc, 0, sizeof(sc));
         sc.ls = stream_ls(plan); sc.TH = sc.TW = g.tile; sc.mode = g.vcycle_mode;
+        if (sc.ls >= 1 && !psn_strip_ok(plan, sc.ls)) sc.mode = 0;
+        sc.vf32 = (sc.mode == 2 && g.vcycle_f32 && sc.ls >= 1 && psn_vf32_ok(plan, sc.ls)) ? 1 : 0;
+        info[7] = sc.vf32;
         info[0] = 0;
         info[2] = sc.ls;
         info[3] = PSN_TILE_THREADS;

@@ -718,8 +718,8 @@ PSN_FN void psn_tile_post_body(Ctx& ctx, const PsnPlan& plan, const PsnTileArgs&
 }
 
 // Coarse part of a streamed V-cycle: levels l0.. of one sample entirely in shared memory.
-template <class Ctx>
-PSN_FN void psn_coarse_vcycle_body(Ctx& ctx, const PsnPlan& plan, int l0, const double* bglob, double* uglob,
+template <class Ctx, class TV>
+PSN_FN void psn_coarse_vcycle_body(Ctx& ctx, const PsnPlan& plan, int l0, const TV* bglob, TV* uglob,
                                    const PsnSampleState* state, long long b, double* smem) {
     if (state && state[b].phase != PSN_PHASE_ITER) return;
     const PsnLevel& lv = plan.lv[l0];
@@ -731,12 +731,12 @@ PSN_FN void psn_coarse_vcycle_body(Ctx& ctx, const PsnPlan& plan, int l0, const 
     for (int idx = ctx.tid; idx < total; idx += ctx.nthreads) smem[idx] = 0.0;
     ctx.sync();
     const unsigned nmagic = lv.nmagic;
-    const double* bg = bglob + b * (long long)nn;
-    for (int idx = ctx.tid; idx < nn; idx += ctx.nthreads) sb[idx + 2 * (int)psn_fdiv((unsigned)idx, nmagic) + P + 1] = bg[idx];
+    const TV* bg = bglob + b * (long long)nn;
+    for (int idx = ctx.tid; idx < nn; idx += ctx.nthreads) sb[idx + 2 * (int)psn_fdiv((unsigned)idx, nmagic) + P + 1] = (double)bg[idx];
     ctx.sync();
     psn_vcycle_smem(ctx, plan, l0, sb, su, pool);
-    double* ug = uglob + b * (long long)nn;
-    for (int idx = ctx.tid; idx < nn; idx += ctx.nthreads) ug[idx] = su[idx + 2 * (int)psn_fdiv((unsigned)idx, nmagic) + P + 1];
+    TV* ug = uglob + b * (long long)nn;
+    for (int idx = ctx.tid; idx < nn; idx += ctx.nthreads) ug[idx] = (TV)su[idx + 2 * (int)psn_fdiv((unsigned)idx, nmagic) + P + 1];
 }
 
 // ----------------------------------------------------------------------------- streamed path: CG kernels (level 0, global memory)
@@ -763,6 +763,7 @@ struct PsnCgArgs {
     int npq;                 // partials per sample written by the direction kernel
     int dir_mode;            // 0: 2-D tile kernel, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     int dir_band, dir_nstrips, dir_nbands;   // strip decomposition of the direction kernel
+    int vf32;                // z is stored as float, scaled by psn_vscale(||r||^2) (PsnStreamCfg::vf32)
     double* part_b;          // [B, ntx*nty]   ||r||^2 partials
     PsnSampleState* state;   // [B]
     double rtol;

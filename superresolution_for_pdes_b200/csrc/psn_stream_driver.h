@@ -17,6 +17,11 @@ struct PsnStreamCfg {
     int mode;     // V-cycle legs: 0 = shared-memory tiles, 1 = warp strips fed by register prefetch,
                   //               2 = warp strips fed by TMA bulk copies through a shared-memory ring
     int band[PSN_MAX_LEVELS];  // mode 1: output rows per warp task on each streamed level (even)
+    int dir_band; // rows per warp task of the direction kernel (0: band[0])
+    int vf32;     // mode 2 only: V-cycle intermediates (iterates, restricted residuals, z) are STORED as float; all
+                  // arithmetic, the CG vectors x r p q and every inner product stay fp64.  The preconditioner only has
+                  // to be an approximate inverse, so CG converges in the same number of iterations (tests), while the
+                  // V-cycle legs move 30-35 % fewer bytes.  Needs n % 4 == 0 on every streamed level.
 };
 
 // one leg (down or up) of the V-cycle on one streamed level
@@ -37,18 +42,24 @@ static inline bool psn_strip_ok(const PsnPlan& plan, int ls) {
         if (plan.lv[l].n & 1) return false;
     return true;
 }
+// float rows are accessed in 16-byte quads: every streamed level needs n % 4 == 0
+static inline bool psn_vf32_ok(const PsnPlan& plan, int ls) {
+    for (int l = 0; l < ls; ++l)
+        if (plan.lv[l].n & 3) return false;
+    return true;
+}
 static inline int psn_strip_count(int n, int use) { return (n + use - 1) / use; }
 static inline int psn_band_count(int n, int band) { return (n + band - 1) / band; }
 // upper bound of the <p,q> partial count per sample (any band choice >= 16 rows, or the 2-D tiles)
 static inline int psn_pq_max(int n) {
-    const int strips = ((n + PSN_DIR_USE - 1) / PSN_DIR_USE) * ((n + 15) / 16);
+    const int strips = ((n + psn_dir_use(1) - 1) / psn_dir_use(1)) * ((n + 15) / 16);
     const int tiles = ((n + PSN_GT_COLS - 1) / PSN_GT_COLS) * ((n + PSN_GT_ROWS - 1) / PSN_GT_ROWS);
     return strips > tiles ? strips : tiles;
 }
 // number of <r,z> partials per sample produced by the level-0 up-leg
 static inline int psn_rz_count(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     const int n = plan.n;
-    if (cfg.mode >= 1) return psn_strip_count(n, psn_strip_use_post(plan.nu)) * psn_band_count(n, cfg.band[0]);
+    if (cfg.mode >= 1) return psn_strip_count(n, psn_strip_use_post(plan.nu, cfg.vf32)) * psn_band_count(n, cfg.band[0]);
     return ((n + cfg.TW - 1) / cfg.TW) * ((n + cfg.TH - 1) / cfg.TH);
 }
 
@@ -89,7 +100,7 @@ static inline PsnStripArgs psn_leg_to_strip(const PsnPlan& plan, const PsnStream
     const int n = plan.lv[g.level].n;
     a.level = g.level;
     a.band = cfg.band[g.level];
-    a.nstrips = psn_strip_count(n, post ? psn_strip_use_post(plan.nu) : psn_strip_use_pre(plan.nu));
+    a.nstrips = psn_strip_count(n, post ? psn_strip_use_post(plan.nu, cfg.vf32) : psn_strip_use_pre(plan.nu, cfg.vf32));
     a.nbands = psn_band_count(n, a.band);
     a.b = g.b; a.uin = g.uin; a.uout = g.uout; a.bc = g.bc; a.ec = g.ec; a.part = g.part; a.state = g.state;
     return a;
@@ -122,8 +133,9 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.part_a = ws.part_a;
     cg.part_pq = ws.part_pq;
     cg.dir_mode = (cfg.mode >= 1 && (n & 1) == 0) ? cfg.mode : 0;
-    cg.dir_band = cfg.band[0];
-    cg.dir_nstrips = (n + PSN_DIR_USE - 1) / PSN_DIR_USE;
+    cg.dir_band = cfg.dir_band >= 16 ? cfg.dir_band : cfg.band[0];
+    cg.vf32 = (cg.dir_mode == 2) ? cfg.vf32 : 0;
+    cg.dir_nstrips = (n + psn_dir_use(cg.vf32) - 1) / psn_dir_use(cg.vf32);
     cg.dir_nbands = psn_band_count(n, cg.dir_band);
     cg.npq = cg.dir_mode ? cg.dir_nstrips * cg.dir_nbands : cg.ntx * cg.nty;
     cg.part_b = ws.part_b;
@@ -153,7 +165,7 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
             g.state = ws.state;
             bk.leg_pre(plan, cfg, g, B);
         }
-        bk.coarse_vcycle(plan, cfg.ls, ws.bl[cfg.ls], ws.ub[cfg.ls], ws.state, B);
+        bk.coarse_vcycle(plan, cfg, ws.bl[cfg.ls], ws.ub[cfg.ls], ws.state, B);
         for (int l = cfg.ls - 1; l >= 0; --l) {
             PsnLegArgs g;
             g.level = l;

@@ -124,6 +124,33 @@ PSN_FN void w_lds4(const PsnWarp& w, const double* row, wd (&out)[4]) {
 PSN_FN void w_zero_smem(const PsnWarp& w, double* p, int count) {
     for (int i = w.lane; i < count; i += 32) p[i] = 0.0;
 }
+// float-storage overloads (V-cycle intermediates kept in fp32 in HBM; registers and arithmetic stay fp64)
+PSN_FN void w_stp(float* row, wi col, wb m, wd a, wd b) {
+    if (m) *reinterpret_cast<float2*>(row + col) = make_float2((float)a, (float)b);
+}
+PSN_FN void w_prefetch_l2(const float* row, wi col, wb m) {
+    if (m) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + col));
+}
+PSN_FN wd w_ld1(const float* row, wi idx, wb m) { return m ? (double)row[idx] : 0.0; }
+PSN_FN void w_st1(float* row, wi idx, wb m, wd v) {
+    if (m) row[idx] = (float)v;
+}
+PSN_FN void w_lds4(const PsnWarp& w, const float* row, wd (&out)[4]) {
+    const float4 v = *reinterpret_cast<const float4*>(row + 4 * w.lane);
+    out[0] = (double)v.x; out[1] = (double)v.y; out[2] = (double)v.z; out[3] = (double)v.w;
+}
+PSN_FN void w_zero_smem(const PsnWarp& w, float* p, int count) {
+    for (int i = w.lane; i < count; i += 32) p[i] = 0.f;
+}
+// the lane's four outputs of a row: two pair stores (double) or one 128-bit store (float; strip geometry
+// guarantees that both pairs of a lane are inside or outside the owned range together)
+PSN_FN void w_stq(double* row, wi col0, wb m0, wb m1, const wd (&v)[4]) {
+    w_stp(row, col0, m0, v[0], v[1]);
+    w_stp(row, col0 + 2, m1, v[2], v[3]);
+}
+PSN_FN void w_stq(float* row, wi col0, wb m0, wb, const wd (&v)[4]) {
+    if (m0) *reinterpret_cast<float4*>(row + col0) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+}
 
 #else  // ------------------------------------------------------------------ host emulation
 
@@ -194,6 +221,27 @@ inline void w_lds4(const PsnWarp&, const double* row, wd (&out)[4]) {
     PSN_W_FOR for (int e = 0; e < 4; ++e) out[e].v[l_] = row[4 * l_ + e];
 }
 inline void w_zero_smem(const PsnWarp&, double* p, int count) { for (int i = 0; i < count; ++i) p[i] = 0.0; }
+inline void w_stp(float* row, const wi& col, const wb& m, const wd& a, const wd& b) {
+    PSN_W_FOR if (m.v[l_]) { row[col.v[l_]] = (float)a.v[l_]; row[col.v[l_] + 1] = (float)b.v[l_]; }
+}
+inline void w_prefetch_l2(const float*, const wi&, const wb&) {}
+inline wd w_ld1(const float* row, const wi& idx, const wb& m) { wd r; PSN_W_FOR r.v[l_] = m.v[l_] ? (double)row[idx.v[l_]] : 0.0; return r; }
+inline void w_st1(float* row, const wi& idx, const wb& m, const wd& v) { PSN_W_FOR if (m.v[l_]) row[idx.v[l_]] = (float)v.v[l_]; }
+inline void w_lds4(const PsnWarp&, const float* row, wd (&out)[4]) {
+    PSN_W_FOR for (int e = 0; e < 4; ++e) out[e].v[l_] = (double)row[4 * l_ + e];
+}
+inline void w_zero_smem(const PsnWarp&, float* p, int count) { for (int i = 0; i < count; ++i) p[i] = 0.f; }
+inline void w_stq(double* row, const wi& col0, const wb& m0, const wb& m1, const wd (&v)[4]) {
+    w_stp(row, col0, m0, v[0], v[1]);
+    w_stp(row, col0 + 2, m1, v[2], v[3]);
+}
+inline void w_stq(float* row, const wi& col0, const wb& m0, const wb& m1, const wd (&v)[4]) {
+    PSN_W_FOR {
+        // mirrors the device's single 128-bit store: the two pair masks must agree
+        if (m0.v[l_] != m1.v[l_]) abort();
+        if (m0.v[l_]) for (int e = 0; e < 4; ++e) row[col0.v[l_] + e] = (float)v[e].v[l_];
+    }
+}
 
 #endif
 
@@ -215,15 +263,17 @@ inline void w_zero_smem(const PsnWarp&, double* p, int count) { for (int i = 0; 
 #define PSN_STRIP_CPL 4
 #define PSN_STRIP_L2_AHEAD 16   // rows ahead of the march that are pulled into L2
 
+// Element types: b is double on level 0 (the CG residual) and TV on coarse levels; every other grid array is TV,
+// the storage type of the V-cycle intermediates (double, or float when PsnStreamCfg::vf32 is set).
 struct PsnStripArgs {
     int level;
     int band;            // output rows per task (even)
     int nstrips, nbands; // tasks per sample = nstrips * nbands
-    const double* b;     // [B, n, n]
-    const double* uin;   // post
-    double* uout;
-    double* bc;          // pre:  [B, nc, nc] out
-    const double* ec;    // post: [B, nc, nc] in
+    const void* b;       // [B, n, n]
+    const void* uin;     // post
+    void* uout;
+    void* bc;            // pre:  [B, nc, nc] out
+    const void* ec;      // post: [B, nc, nc] in
     double* part;        // post, level 0: [B, nstrips*nbands] partial <b,u>
     const PsnSampleState* state;
 };
@@ -231,8 +281,27 @@ struct PsnStripArgs {
 // useful (output) columns per strip: pre needs 2NU halo columns left and 2NU+1 right; post needs
 // 2NU+2 left (the prolongation onto an even column reads the coarse value one lane to the left)
 // and 2NU right
-PSN_HDFN int psn_strip_use_pre(int nu) { return PSN_STRIP_COLS - (4 * nu + 2); }
-PSN_HDFN int psn_strip_use_post(int nu) { return PSN_STRIP_COLS - (4 * nu + 2); }
+// With fp32 storage (f32 != 0) every strip origin and owned range is a multiple of 4 columns, so that float rows
+// are accessed in whole 16-byte quads (bulk copies, 128-bit stores): the left halo is rounded up to a multiple of
+// 4 and the useful width down.
+PSN_HDFN int psn_strip_hl_pre(int nu, int f32) { return f32 ? ((2 * nu + 3) & ~3) : 2 * nu; }
+PSN_HDFN int psn_strip_hl_post(int nu, int f32) { return f32 ? ((2 * nu + 2 + 3) & ~3) : 2 * nu + 2; }
+PSN_HDFN int psn_strip_use_pre(int nu, int f32) {
+    const int u = PSN_STRIP_COLS - psn_strip_hl_pre(nu, f32) - (2 * nu + 1);
+    return f32 ? (u & ~3) : (u & ~1);
+}
+PSN_HDFN int psn_strip_use_post(int nu, int f32) {
+    const int u = PSN_STRIP_COLS - psn_strip_hl_post(nu, f32) - 2 * nu;
+    return f32 ? (u & ~3) : (u & ~1);
+}
+// power-of-two scale that brings a residual of squared norm rr to O(1) before it is rounded to fp32
+// (exact in fp64, makes the fp32-stored V-cycle independent of the magnitude of the data)
+PSN_HDFN double psn_vscale(double rr) {
+    if (!(rr > 0.0) || !(rr < 1e300)) return 1.0;
+    int e = 0;
+    frexp(rr, &e);
+    return ldexp(1.0, -(e / 2));
+}
 
 // horizontal neighbour sum of offset e (static) in a row held as v[0..3]
 #define PSN_LR(v, e, upv, dnv) \
@@ -259,6 +328,8 @@ struct PsnRegFeeder {
     int n, tload;
     wi col0;
     wb mp[2];
+    PSN_FN void set_base0(const double* p) { base[0] = p; }
+    PSN_FN void set_base1(const double* p) { base[NARR - 1] = p; }
     PSN_FN void prime(const PsnWarp&, int ts) {
 #pragma unroll
         for (int a = 0; a < NARR; ++a)
@@ -292,34 +363,56 @@ struct PsnRegFeeder {
     }
 };
 
-template <int NU, int NARR>
+template <class T>
+struct PsnElemOr {
+    typedef T type;
+    static constexpr int bytes = (int)sizeof(T);
+    static constexpr int narr = 1;
+};
+template <>
+struct PsnElemOr<void> {
+    typedef double type;
+    static constexpr int bytes = 0;
+    static constexpr int narr = 0;
+};
+
+// T0 / T1: element types of the one or two streamed arrays (T1 = void: one array)
+template <int NU, class T0, class T1 = void>
 struct PsnTmaFeeder {
+    typedef typename PsnElemOr<T1>::type U1;
+    static constexpr int NARR = 1 + PsnElemOr<T1>::narr;
     static constexpr int W = 2 * NU + 2, D = W - 1;
-    double* ring[NARR];          // [W][PSN_STRIP_COLS] each, shared memory of this warp
+    static constexpr int RING_BYTES = W * PSN_STRIP_COLS * ((int)sizeof(T0) + PsnElemOr<T1>::bytes);
+    T0* ring0;                   // [W][PSN_STRIP_COLS], shared memory of this warp
+    U1* ring1;
     unsigned long long* bar;     // [W]
-    const double* base[NARR];
+    const T0* base0;
+    const U1* base1;
     int n, tload, ts;
     int cA, cB, c0;              // in-domain column range [cA, cB) of the strip, strip origin
 #if defined(__CUDACC__)
     __host__ __device__
 #endif
-    static constexpr int smem_bytes() { return NARR * W * PSN_STRIP_COLS * 8 + W * 8 + (128 - (W * 8) % 128) % 128; }
+    static constexpr int smem_bytes() { return RING_BYTES + W * 8 + (128 - (W * 8) % 128) % 128; }
     PSN_FN void attach(unsigned char* mem) {
-#pragma unroll
-        for (int a = 0; a < NARR; ++a) ring[a] = reinterpret_cast<double*>(mem + (size_t)a * W * PSN_STRIP_COLS * 8);
-        bar = reinterpret_cast<unsigned long long*>(mem + (size_t)NARR * W * PSN_STRIP_COLS * 8);
+        ring0 = reinterpret_cast<T0*>(mem);
+        ring1 = reinterpret_cast<U1*>(mem + (size_t)W * PSN_STRIP_COLS * sizeof(T0));
+        bar = reinterpret_cast<unsigned long long*>(mem + RING_BYTES);
+        base1 = nullptr;
     }
+    PSN_FN void set_base0(const T0* p) { base0 = p; }
+    PSN_FN void set_base1(const U1* p) { base1 = p; }
     PSN_FN void issue(const PsnWarp& w, int row, int slot) {
-        const unsigned bytes = (unsigned)(cB - cA) * 8u;
-        w_bar_expect(w, bar + slot, bytes * NARR);
-#pragma unroll
-        for (int a = 0; a < NARR; ++a)
-            w_bulk_g2s(w, ring[a] + slot * PSN_STRIP_COLS + (cA - c0), base[a] + (long long)row * n + cA, bytes, bar + slot);
+        const unsigned cnt = (unsigned)(cB - cA);
+        w_bar_expect(w, bar + slot, cnt * (unsigned)(sizeof(T0) + PsnElemOr<T1>::bytes));
+        w_bulk_g2s(w, ring0 + slot * PSN_STRIP_COLS + (cA - c0), base0 + (long long)row * n + cA, cnt * (unsigned)sizeof(T0), bar + slot);
+        if (NARR == 2)
+            w_bulk_g2s(w, ring1 + slot * PSN_STRIP_COLS + (cA - c0), base1 + (long long)row * n + cA, cnt * (unsigned)sizeof(U1), bar + slot);
     }
     PSN_FN void prime(const PsnWarp& w, int ts_) {
         ts = ts_;
-#pragma unroll
-        for (int a = 0; a < NARR; ++a) w_zero_smem(w, ring[a], W * PSN_STRIP_COLS);   // out-of-domain columns stay zero
+        w_zero_smem(w, ring0, W * PSN_STRIP_COLS);   // out-of-domain columns stay zero
+        if (NARR == 2) w_zero_smem(w, ring1, W * PSN_STRIP_COLS);
         w_bar_init(w, bar, W);
         for (int k = 0; k < D; ++k)
             if (ts + k <= tload) issue(w, ts + k, k);
@@ -331,8 +424,8 @@ struct PsnTmaFeeder {
         if (FAST || tc + D <= tload) issue(w, tc + D, (tt + W - 1) % W);
         if (FAST || tc <= tload) {
             w_bar_wait(bar + tt, (unsigned)par);
-#pragma unroll
-            for (int a = 0; a < NARR; ++a) w_lds4(w, ring[a] + tt * PSN_STRIP_COLS, out[a]);
+            w_lds4(w, ring0 + tt * PSN_STRIP_COLS, out[0]);
+            if (NARR == 2) w_lds4(w, ring1 + tt * PSN_STRIP_COLS, out[NARR - 1]);
         } else {
 #pragma unroll
             for (int a = 0; a < NARR; ++a)
@@ -342,25 +435,35 @@ struct PsnTmaFeeder {
     }
 };
 
+// TMA feeder of a V-cycle leg: pre streams the rhs (TB); post streams the rhs (TB) and the pre-smoothed iterate (TV)
+template <int NU, bool POST, class TB, class TV>
+struct PsnStripFeederSel {
+    typedef PsnTmaFeeder<NU, TB, void> type;
+};
+template <int NU, class TB, class TV>
+struct PsnStripFeederSel<NU, true, TB, TV> {
+    typedef PsnTmaFeeder<NU, TB, TV> type;
+};
+
 template <int NU, int NARR>
 PSN_FN void psn_feeder_geom(PsnRegFeeder<NU, NARR>& fd, const wi& col0, const wb (&mp)[2], int, int) {
     fd.col0 = col0;
     fd.mp[0] = mp[0];
     fd.mp[1] = mp[1];
 }
-template <int NU, int NARR>
-PSN_FN void psn_feeder_geom(PsnTmaFeeder<NU, NARR>& fd, const wi&, const wb (&)[2], int c0, int n) {
+template <int NU, class T0, class T1>
+PSN_FN void psn_feeder_geom(PsnTmaFeeder<NU, T0, T1>& fd, const wi&, const wb (&)[2], int c0, int n) {
     fd.c0 = c0;
     fd.cA = psn_imax(c0, 0);
     fd.cB = psn_imin(c0 + PSN_STRIP_COLS, n);
 }
 
-template <int NU, bool FAST, class Feeder>
+template <int NU, bool FAST, bool SCALE, class TV, class Feeder>
 PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc,
                                 int i0, int i1, int I0, int I1,
                                 wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], Feeder& fd, int par, wd (&acc)[2],
                                 const wd (&rdA)[4], const wd (&dA)[4], const wd (&mk)[4], const PsnLevel& lv,
-                                const double* bg, double* ug, double* cg, const wi& col0, const wb (&mp)[2], const wb (&so)[2],
+                                const wd& bsc, TV* ug, TV* cg, const wi& col0, const wb (&mp)[2], const wb (&so)[2],
                                 const wi& cj, const wb (&sc)[2]) {
     constexpr int NS = 2 * NU, W = NS + 2;
     const wd zero = w_bcast(0.0);
@@ -388,7 +491,7 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
             wd rowv[1][4];
             fd.template fetch<FAST>(w, tt, tc, par, rowv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) bb[k0][e] = rowv[0][e];
+            for (int e = 0; e < 4; ++e) bb[k0][e] = SCALE ? rowv[0][e] * bsc : rowv[0][e];
         }
         if (FAST || tc <= last) {
             const bool lastrow = !FAST && tc == last;
@@ -434,7 +537,7 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
                 const wd c1v = 0.25 * (rb + w_down_raw(ra));
                 const int I = (r >> 1) - 1;
                 if (FAST || (r >= 2 && I >= I0 && I < I1)) {
-                    double* crow = cg + (long long)I * nc;
+                    TV* crow = cg + (long long)I * nc;
                     w_st1(crow, cj, sc[0], acc[0] + c0v);
                     w_st1(crow, cj + 1, sc[1], acc[1] + c1v);
                 }
@@ -450,24 +553,27 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
             const int ro = tc - (NS - 1);
             if (FAST || (ro >= i0 && ro < i1)) {
                 const int ko = (tt - (NS - 1) + 2 * W) % W;
-                double* rowp = ug + (long long)ro * n;
-                w_stp(rowp, col0, so[0], val[ko][0], val[ko][1]);
-                w_stp(rowp, col0 + 2, so[1], val[ko][2], val[ko][3]);
+                w_stq(ug + (long long)ro * n, col0, so[0], so[1], val[ko]);
             }
         }
     }
 }
 
-template <int NU, class Feeder>
+// TB: element type of the right-hand side (double on level 0, TV below); TV: storage type of the iterate and of the
+// restricted residual.  With TV = float the level-0 rhs is scaled by psn_vscale(||r||^2) on load.
+template <int NU, class TB, class TV, class Feeder>
 PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip, Feeder& fd) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
     constexpr int NS = 2 * NU, W = NS + 2;
-    const int USE = PSN_STRIP_COLS - (2 * NS + 2);
+    constexpr int F32 = sizeof(TV) == 4 ? 1 : 0;
+    constexpr bool SCALE = F32 && sizeof(TB) == 8;
+    const int USE = psn_strip_use_pre(NU, F32);
+    const int HL = psn_strip_hl_pre(NU, F32);
     const PsnLevel& lv = plan.lv[a.level];
     const PsnLevel& lc = plan.lv[a.level + 1];
     const int n = lv.n, nc = lc.n, last = n - 1;
     const int a0 = strip * USE, a1 = psn_imin(a0 + USE, n);
-    const int c0 = a0 - NS;
+    const int c0 = a0 - HL;
     const int i0 = band * a.band, i1 = psn_imin(i0 + a.band, n);
     const int I0 = i0 >> 1, I1 = psn_imin(i1 >> 1, nc);
     const int J0 = a0 >> 1, J1 = psn_imin(a1 >> 1, nc);
@@ -493,16 +599,17 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
     const int ts = psn_imax(i0 - NS, 0);
     const int tload = psn_imin(i1 + NS, last);
     const int tend = i1 + NS;
-    const double* bg = a.b + b * (long long)n * n;
-    double* ug = a.uout + b * (long long)n * n;
-    double* cg = a.bc + b * (long long)nc * nc;
+    const TB* bg = reinterpret_cast<const TB*>(a.b) + b * (long long)n * n;
+    TV* ug = reinterpret_cast<TV*>(a.uout) + b * (long long)n * n;
+    TV* cg = reinterpret_cast<TV*>(a.bc) + b * (long long)nc * nc;
+    const wd bsc = w_bcast((SCALE && a.state) ? psn_vscale(a.state[b].rr) : 1.0);
 
     wd val[W][4], bb[W][4], acc[2];
 #pragma unroll
     for (int k = 0; k < W; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) val[k][e] = bb[k][e] = zero;
-    fd.base[0] = bg;
+    fd.set_base0(bg);
     fd.n = n;
     fd.tload = tload;
     psn_feeder_geom(fd, col0, mp, c0, n);
@@ -516,19 +623,19 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
                           (((t - NS) >> 1) - 1 >= I0) && (((t + W - 1 - NS) >> 1) - 1 < I1);
         const int par = ((t - ts) / W) & 1;
         if (fast)
-            psn_strip_pre_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
-                                          bg, ug, cg, col0, mp, so, cj, sc);
+            psn_strip_pre_chunk<NU, true, SCALE>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
+                                                 bsc, ug, cg, col0, mp, so, cj, sc);
         else
-            psn_strip_pre_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
-                                           bg, ug, cg, col0, mp, so, cj, sc);
+            psn_strip_pre_chunk<NU, false, SCALE>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
+                                                  bsc, ug, cg, col0, mp, so, cj, sc);
     }
 }
 
-template <int NU, bool FAST, class Feeder>
+template <int NU, bool FAST, bool SCALE, class TV, class Feeder>
 PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc, int i0, int i1,
                                  wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], Feeder& fd, int par,
                                  wd (&eprev)[2], wd (&enext)[2], wd& dot, const wd (&rdA)[4], const wd (&mk)[4], const PsnLevel& lv,
-                                 const double* bg, const double* uig, const double* eg, double* ug, const wi& col0,
+                                 const wd& bsc, const TV* eg, TV* ug, const wi& col0,
                                  const wb (&mp)[2], const wb (&so)[2], const wi& cj, const wb (&mc)[2], bool want_dot) {
     constexpr int NS = 2 * NU, W = NS + 2;
     const wd zero = w_bcast(0.0);
@@ -552,7 +659,7 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
             fd.template fetch<FAST>(w, tt, tc, par, rowv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                bb[k0][e] = rowv[0][e];
+                bb[k0][e] = SCALE ? rowv[0][e] * bsc : rowv[0][e];
                 val[k0][e] = rowv[1][e];
             }
         }
@@ -563,7 +670,7 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
                 const wd enew[2] = {enext[0], enext[1]};
                 enext[0] = enext[1] = zero;
                 if (FAST || I + 1 < nc) {
-                    const double* erow = eg + (long long)(I + 1) * nc;
+                    const TV* erow = eg + (long long)(I + 1) * nc;
                     enext[0] = w_ld1(erow, cj, mc[0]);
                     enext[1] = w_ld1(erow, cj + 1, mc[1]);
                     if (I + 9 < nc) w_prefetch_l2(eg + (long long)(I + 9) * nc, cj, mc[0]);
@@ -602,9 +709,7 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
             const int ro = tc - NS;
             if (FAST || (ro >= i0 && ro < i1)) {
                 const int ko = (tt - NS + 2 * W) % W;
-                double* rowp = ug + (long long)ro * n;
-                w_stp(rowp, col0, so[0], val[ko][0], val[ko][1]);
-                w_stp(rowp, col0 + 2, so[1], val[ko][2], val[ko][3]);
+                w_stq(ug + (long long)ro * n, col0, so[0], so[1], val[ko]);
                 if (want_dot)
                     dot = dot + w_sel(so[0], val[ko][0] * bb[ko][0] + val[ko][1] * bb[ko][1], zero) +
                           w_sel(so[1], val[ko][2] * bb[ko][2] + val[ko][3] * bb[ko][3], zero);
@@ -613,16 +718,19 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
     }
 }
 
-template <int NU, class Feeder>
+template <int NU, class TB, class TV, class Feeder>
 PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip, Feeder& fd) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
     constexpr int NS = 2 * NU, W = NS + 2;
-    const int USE = PSN_STRIP_COLS - (2 * NS + 2);
+    constexpr int F32 = sizeof(TV) == 4 ? 1 : 0;
+    constexpr bool SCALE = F32 && sizeof(TB) == 8;
+    const int USE = psn_strip_use_post(NU, F32);
+    const int HL = psn_strip_hl_post(NU, F32);
     const PsnLevel& lv = plan.lv[a.level];
     const PsnLevel& lc = plan.lv[a.level + 1];
     const int n = lv.n, nc = lc.n, last = n - 1;
     const int a0 = strip * USE, a1 = psn_imin(a0 + USE, n);
-    const int c0 = a0 - NS - 2;   // even; NS + 2 halo columns on the left, NS on the right
+    const int c0 = a0 - HL;       // even; at least NS + 2 halo columns on the left, NS on the right
     const int i0 = band * a.band, i1 = psn_imin(i0 + a.band, n);
 
     const wi col0 = w_lane(w) * 4 + c0;
@@ -645,18 +753,20 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const int ts = psn_imax(i0 - NS, 0);
     const int tload = psn_imin(i1 - 1 + NS, last);
     const int tend = psn_imin(i1 - 1, last) + NS;
-    const double* bg = a.b + b * (long long)n * n;
-    const double* uig = a.uin + b * (long long)n * n;
-    const double* eg = a.ec + b * (long long)nc * nc;
-    double* ug = a.uout + b * (long long)n * n;
+    const TB* bg = reinterpret_cast<const TB*>(a.b) + b * (long long)n * n;
+    const TV* uig = reinterpret_cast<const TV*>(a.uin) + b * (long long)n * n;
+    const TV* eg = reinterpret_cast<const TV*>(a.ec) + b * (long long)nc * nc;
+    TV* ug = reinterpret_cast<TV*>(a.uout) + b * (long long)n * n;
+    const double bs = (SCALE && a.state) ? psn_vscale(a.state[b].rr) : 1.0;
+    const wd bsc = w_bcast(bs);
 
     wd val[W][4], bb[W][4], eprev[2], enext[2];
 #pragma unroll
     for (int k = 0; k < W; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) val[k][e] = bb[k][e] = zero;
-    fd.base[0] = bg;
-    fd.base[1] = uig;
+    fd.set_base0(bg);
+    fd.set_base1(uig);
     fd.n = n;
     fd.tload = tload;
     psn_feeder_geom(fd, col0, mp, c0, n);
@@ -682,14 +792,15 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
                           (t - NS >= i0) && (t + W - 1 - NS < i1);
         const int par = ((t - ts) / W) & 1;
         if (fast)
-            psn_strip_post_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
-                                           bg, uig, eg, ug, col0, mp, so, cj, mc, want_dot);
+            psn_strip_post_chunk<NU, true, SCALE>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
+                                                  bsc, eg, ug, col0, mp, so, cj, mc, want_dot);
         else
-            psn_strip_post_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
-                                            bg, uig, eg, ug, col0, mp, so, cj, mc, want_dot);
+            psn_strip_post_chunk<NU, false, SCALE>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
+                                                   bsc, eg, ug, col0, mp, so, cj, mc, want_dot);
     }
     if (want_dot) {
-        const double s = w_sum(dot);
+        // rhs and iterate both carry the scale: <r, z> = <s r, s z> / s^2 (exact, s is a power of two)
+        const double s = w_sum(dot) * ((1.0 / bs) * (1.0 / bs));
         if (w_lane0(w)) a.part[b * (long long)(a.nstrips * a.nbands) + (long long)band * a.nstrips + strip] = s;
     }
 }
@@ -700,6 +811,8 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
 // (2 halo columns per side) with a 3-row window of p_new in registers; z and p_old rows arrive through
 // the same feeders as the V-cycle strips.
 #define PSN_DIR_USE (PSN_STRIP_COLS - 4)
+PSN_HDFN int psn_dir_hl(int f32) { return f32 ? 4 : 2; }
+PSN_HDFN int psn_dir_use(int f32) { return f32 ? PSN_STRIP_COLS - 8 : PSN_DIR_USE; }
 
 PSN_FN double psn_warp_sum_partials(const PsnWarp& w, const double* part, int count) {
     wd acc = w_bcast(0.0);
@@ -708,7 +821,8 @@ PSN_FN double psn_warp_sum_partials(const PsnWarp& w, const double* part, int co
     return w_sum(acc);
 }
 
-template <class Feeder>
+// TZ: storage type of z (float: the value read is s z with s = psn_vscale(||r||^2), undone here)
+template <class TZ, class Feeder>
 PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b, int band, int strip, Feeder& fd) {
     const PsnSampleState st = a.state[b];
     if (st.phase != PSN_PHASE_ITER) return;
@@ -718,8 +832,10 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
     const bool fresh = st.restart != 0;
     const wd beta = w_bcast(fresh ? 0.0 : rz / st.rz_old);
     const int n = a.n, last = n - 1;
-    const int a0 = strip * PSN_DIR_USE, a1 = psn_imin(a0 + PSN_DIR_USE, n);
-    const int c0 = a0 - 2;
+    constexpr int F32 = sizeof(TZ) == 4 ? 1 : 0;
+    const int a0 = strip * psn_dir_use(F32), a1 = psn_imin(a0 + psn_dir_use(F32), n);
+    const int c0 = a0 - psn_dir_hl(F32);
+    const wd zinv = w_bcast(F32 ? 1.0 / psn_vscale(st.rr) : 1.0);
     const int i0 = band * a.dir_band, i1 = psn_imin(i0 + a.dir_band, n);
     const wi col0 = w_lane(w) * 4 + c0;
     const wi col2 = col0 + 2;
@@ -731,8 +847,8 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
     const int ts = psn_imax(i0 - 1, 0);
     const int tload = psn_imin(i1, last);
     const int tend = i1;   // q(row r) is formed at time r + 1; row n reads as zero
-    fd.base[0] = a.z + base;
-    fd.base[1] = a.p_old + base;
+    fd.set_base0(reinterpret_cast<const TZ*>(a.z) + base);
+    fd.set_base1(a.p_old + base);
     fd.n = n;
     fd.tload = tload;
     psn_feeder_geom(fd, col0, mp, c0, n);
@@ -757,7 +873,10 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
             wd rowv[2][4];
             fd.template fetch<false>(w, tt, tc, par, rowv);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pn[k0][e] = fresh ? rowv[0][e] : rowv[0][e] + beta * rowv[1][e];
+            for (int e = 0; e < 4; ++e) {
+                const wd zv = F32 ? rowv[0][e] * zinv : rowv[0][e];
+                pn[k0][e] = fresh ? zv : zv + beta * rowv[1][e];
+            }
             if (tc >= i0 && tc < i1) {
                 double* rowp = pg + (long long)tc * n;
                 w_stp(rowp, col0, so[0], pn[k0][0], pn[k0][1]);

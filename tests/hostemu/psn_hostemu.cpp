@@ -35,30 +35,39 @@ struct HostBackend {
                 for (int tx = 0; tx < a.ntx; ++tx) psn_prologue_body(ctx, a, b, ty, tx);
     }
     void state_init(const PsnCgArgs& a, long long B) { for (long long b = 0; b < B; ++b) psn_state_init(a, b); }
-    template <int NU>
-    void strip_leg(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post, bool tma) {
+    template <int NU, class TB, class TV>
+    void strip_leg_t(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post, bool tma) {
         PsnWarp w;
-        std::vector<unsigned char> ring(PsnTmaFeeder<NU, 2>::smem_bytes() + 256);
+        std::vector<unsigned char> ring(PsnTmaFeeder<NU, double, double>::smem_bytes() + 256);
         for (long long b = 0; b < B; ++b)
             for (int band = 0; band < a.nbands; ++band)
                 for (int strip = 0; strip < a.nstrips; ++strip) {
                     std::fill(ring.begin(), ring.end(), (unsigned char)0xff);   // NaN-poison the staging ring
                     if (post) {
-                        if (tma) { PsnTmaFeeder<NU, 2> fd; fd.attach(ring.data()); psn_strip_post_body<NU>(w, plan, a, b, band, strip, fd); }
-                        else { PsnRegFeeder<NU, 2> fd; psn_strip_post_body<NU>(w, plan, a, b, band, strip, fd); }
+                        if (tma) { PsnTmaFeeder<NU, TB, TV> fd; fd.attach(ring.data()); psn_strip_post_body<NU, TB, TV>(w, plan, a, b, band, strip, fd); }
+                        else if constexpr (sizeof(TV) == 8) { PsnRegFeeder<NU, 2> fd; psn_strip_post_body<NU, TB, TV>(w, plan, a, b, band, strip, fd); }
                     } else {
-                        if (tma) { PsnTmaFeeder<NU, 1> fd; fd.attach(ring.data()); psn_strip_pre_body<NU>(w, plan, a, b, band, strip, fd); }
-                        else { PsnRegFeeder<NU, 1> fd; psn_strip_pre_body<NU>(w, plan, a, b, band, strip, fd); }
+                        if (tma) { PsnTmaFeeder<NU, TB> fd; fd.attach(ring.data()); psn_strip_pre_body<NU, TB, TV>(w, plan, a, b, band, strip, fd); }
+                        else if constexpr (sizeof(TV) == 8) { PsnRegFeeder<NU, 1> fd; psn_strip_pre_body<NU, TB, TV>(w, plan, a, b, band, strip, fd); }
                     }
                 }
     }
-    void strip_dispatch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post, bool tma) {
-        if (plan.nu == 1) strip_leg<1>(plan, a, B, post, tma);
-        else if (plan.nu == 2) strip_leg<2>(plan, a, B, post, tma);
-        else strip_leg<3>(plan, a, B, post, tma);
+    template <int NU>
+    void strip_leg(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post, bool tma, bool f32) {
+        if (tma && f32) {
+            if (a.level == 0) strip_leg_t<NU, double, float>(plan, a, B, post, true);
+            else strip_leg_t<NU, float, float>(plan, a, B, post, true);
+        } else {
+            strip_leg_t<NU, double, double>(plan, a, B, post, tma);
+        }
+    }
+    void strip_dispatch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post, bool tma, bool f32) {
+        if (plan.nu == 1) strip_leg<1>(plan, a, B, post, tma, f32);
+        else if (plan.nu == 2) strip_leg<2>(plan, a, B, post, tma, f32);
+        else strip_leg<3>(plan, a, B, post, tma, f32);
     }
     void leg_pre(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
-        if (cfg.mode >= 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, false), B, false, cfg.mode == 2); return; }
+        if (cfg.mode >= 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, false), B, false, cfg.mode == 2, cfg.mode == 2 && cfg.vf32); return; }
         const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
@@ -70,7 +79,7 @@ struct HostBackend {
                 }
     }
     void leg_post(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
-        if (cfg.mode >= 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, true), B, true, cfg.mode == 2); return; }
+        if (cfg.mode >= 1) { strip_dispatch(plan, psn_leg_to_strip(plan, cfg, g, true), B, true, cfg.mode == 2, cfg.mode == 2 && cfg.vf32); return; }
         const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
@@ -80,20 +89,26 @@ struct HostBackend {
                     psn_tile_post_body(ctx, plan, t, b, ty, tx, smem.data());
                 }
     }
-    void coarse_vcycle(const PsnPlan& plan, int l0, const double* bg, double* ug, const PsnSampleState* st, long long B) {
+    void coarse_vcycle(const PsnPlan& plan, const PsnStreamCfg& cfg, const double* bg, double* ug, const PsnSampleState* st, long long B) {
         PsnHostCtx ctx;
-        for (long long b = 0; b < B; ++b) psn_coarse_vcycle_body(ctx, plan, l0, bg, ug, st, b, smem.data());
+        for (long long b = 0; b < B; ++b) {
+            if (cfg.mode == 2 && cfg.vf32)
+                psn_coarse_vcycle_body(ctx, plan, cfg.ls, reinterpret_cast<const float*>(bg), reinterpret_cast<float*>(ug), st, b, smem.data());
+            else
+                psn_coarse_vcycle_body(ctx, plan, cfg.ls, bg, ug, st, b, smem.data());
+        }
     }
     void dir_apply(const PsnCgArgs& a, long long B) {
         if (a.dir_mode >= 1) {
             PsnWarp w;
-            std::vector<unsigned char> ring(PsnTmaFeeder<2, 2>::smem_bytes() + 256);
+            std::vector<unsigned char> ring(PsnTmaFeeder<2, double, double>::smem_bytes() + 256);
             for (long long b = 0; b < B; ++b)
                 for (int band = 0; band < a.dir_nbands; ++band)
                     for (int strip = 0; strip < a.dir_nstrips; ++strip) {
                         std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
-                        if (a.dir_mode == 2) { PsnTmaFeeder<2, 2> fd; fd.attach(ring.data()); psn_dir_strip_body(w, a, b, band, strip, fd); }
-                        else { PsnRegFeeder<2, 2> fd; psn_dir_strip_body(w, a, b, band, strip, fd); }
+                        if (a.dir_mode == 2 && a.vf32) { PsnTmaFeeder<2, float, double> fd; fd.attach(ring.data()); psn_dir_strip_body<float>(w, a, b, band, strip, fd); }
+                        else if (a.dir_mode == 2) { PsnTmaFeeder<2, double, double> fd; fd.attach(ring.data()); psn_dir_strip_body<double>(w, a, b, band, strip, fd); }
+                        else { PsnRegFeeder<2, 2> fd; psn_dir_strip_body<double>(w, a, b, band, strip, fd); }
                     }
             return;
         }
@@ -172,7 +187,11 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
     PsnStreamCfg cfg;
-    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? mode : 0;
+    // mode 3 = mode 2 (TMA-fed strips) with float storage of the V-cycle intermediates
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? (mode == 3 ? 2 : mode) : 0;
+    cfg.vf32 = (mode == 3 && cfg.mode == 2 && psn_vf32_ok(plan, ls)) ? 1 : 0;
+    cfg.dir_band = 0;
+    if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
     memset(&ws, 0, sizeof(ws));
@@ -229,7 +248,11 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
     PsnStreamCfg cfg;
-    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? mode : 0;
+    // mode 3 = mode 2 (TMA-fed strips) with float storage of the V-cycle intermediates
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? (mode == 3 ? 2 : mode) : 0;
+    cfg.vf32 = (mode == 3 && cfg.mode == 2 && psn_vf32_ok(plan, ls)) ? 1 : 0;
+    cfg.dir_band = 0;
+    if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     std::vector<std::vector<double>> keep;
     auto alloc = [&](size_t cnt) { keep.emplace_back(cnt, std::nan("")); return keep.back().data(); };
@@ -245,12 +268,17 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
         PsnLegArgs g{l, bl[l], nullptr, ua[l], bl[l + 1], nullptr, nullptr, nullptr};
         bk.leg_pre(plan, cfg, g, 1);
     }
-    bk.coarse_vcycle(plan, ls, bl[ls], ub[ls], nullptr, 1);
+    bk.coarse_vcycle(plan, cfg, bl[ls], ub[ls], nullptr, 1);
     for (int l = ls - 1; l >= 0; --l) {
         PsnLegArgs g{l, bl[l], ua[l], ub[l], nullptr, ub[l + 1], l == 0 ? part.data() : nullptr, nullptr};
         bk.leg_post(plan, cfg, g, 1);
     }
-    memcpy(zout, ub[0], sizeof(double) * n * n);
+    if (cfg.vf32) {
+        const float* zf = reinterpret_cast<const float*>(ub[0]);
+        for (int i = 0; i < n * n; ++i) zout[i] = (double)zf[i];
+    } else {
+        memcpy(zout, ub[0], sizeof(double) * n * n);
+    }
     double s = 0; for (double v : part) s += v;
     *rz = s;
     return 0;

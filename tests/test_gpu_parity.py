@@ -86,13 +86,38 @@ def test_tile_and_strip_vcycles_agree(gpu_lib, n, B):
         u0, i0 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
         gpu_lib.set_option("vcycle_mode", 1)
         u2, i2 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+        gpu_lib.set_option("vcycle_mode", 2)
+        gpu_lib.set_option("vcycle_f32", 0)
+        u1, i1 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
     finally:
         gpu_lib.set_option("vcycle_mode", 2)
-    u1, i1 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+        gpu_lib.set_option("vcycle_f32", 1)
     assert (i0.status <= 1).all() and (i1.status <= 1).all() and (i2.status <= 1).all()
     assert O.rel_l2(u1, u0) <= 1e-12
     assert np.array_equal(u1, u2)     # register-fed and TMA-fed strips do identical arithmetic
     assert O.rel_l2(u1[0], O.solve_poisson(np.outer(sy[0], sx[0]), theta[0], n)) <= TOL
+    # default configuration: V-cycle intermediates stored as float where every streamed level is a multiple of 4
+    # (160, 320: yes; 200 -> 100 -> 50: no, stays fp64).  Same iteration counts, same accuracy bar.
+    u3, i3 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    assert (i3.status <= 1).all() and (i3.iters <= i1.iters + 1).all() and i3.iters.sum() <= i1.iters.sum() + 1
+    assert O.rel_l2(u3, u1) <= 1e-11
+    assert O.rel_l2(u3[0], O.solve_poisson(np.outer(sy[0], sx[0]), theta[0], n)) <= TOL
+    if n == 200:
+        assert np.array_equal(u3, u1)
+
+
+def test_float_stored_vcycle_is_scale_invariant(gpu_lib):
+    """The float copies of the V-cycle intermediates are rescaled by a power of two of the residual norm, so data of
+    any magnitude converges exactly like O(1) data (the reference's direct solve is scale-invariant too)."""
+    n, B = 160, 6
+    rs = np.random.RandomState(5)
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    f = rs.standard_normal((B, n, n))
+    u, info = gpu_lib.solve_batch(n, B, theta=theta, f=f)
+    for scale in (1e-40, 1e-25, 1e+25):
+        us, infos = gpu_lib.solve_batch(n, B, theta=theta, f=f * scale)
+        assert (infos.status <= 1).all() and (infos.iters <= info.iters + 1).all()
+        assert O.rel_l2(us / scale, u) <= 1e-10
 
 
 def test_generate_dataset_matches_reference_fixture(gpu_lib):

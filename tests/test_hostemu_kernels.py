@@ -23,7 +23,7 @@ IP = ctypes.POINTER(ctypes.c_int32)
 def he():
     srcs = [os.path.join(HE_DIR, "psn_hostemu.cpp")] + [
         os.path.join(ROOT, "superresolution_for_pdes_b200", "csrc", f)
-        for f in ("psn_core.cuh", "psn_plan.h", "psn_stream_driver.h")]
+        for f in ("psn_core.cuh", "psn_plan.h", "psn_stream_driver.h", "psn_warp.cuh", "psn_block.cuh")]
     if not os.path.exists(HE_LIB) or any(os.path.getmtime(s) > os.path.getmtime(HE_LIB) for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", HE_LIB, srcs[0]], check=True)
     return ctypes.CDLL(HE_LIB)
@@ -214,3 +214,40 @@ def test_register_blocked_resident_solver_matches_generic(he, nu):
         win = (slice(y0[b], y0[b] + 40), slice(x0[b], x0[b] + 40))
         assert np.array_equal(uf[b], u[b][win]) and np.array_equal(ff[b], f[b][win])
         assert np.array_equal(uc[b], u[b][win][::2, ::2]) and np.array_equal(fc[b], f[b][win][::2, ::2])
+
+
+@pytest.mark.parametrize("n,ls,band,nu", [(96, 1, 96, 2), (160, 2, 48, 2), (160, 1, 64, 1), (160, 2, 32, 3), (320, 3, 64, 2), (200, 1, 200, 2)])
+def test_float_storage_vcycle_is_as_good_a_preconditioner(he, n, ls, band, nu):
+    """Mode 3 = TMA-fed strips with the V-cycle intermediates STORED as float (arithmetic, CG vectors and dot
+    products fp64).  One V-cycle agrees with the fp64 V-cycle to float rounding, CG needs the same number of
+    iterations and the solution meets the same 1e-10 bar against the reference operator."""
+    r = np.random.RandomState(n).randn(n, n) * 3.7e-9          # arbitrary magnitude: the kernels rescale by 2^k
+    zr = np.zeros((n, n))
+    he.hostemu_vcycle(ctypes.c_int(n), ctypes.c_int(nu), P(r), P(zr))
+    z = np.full((n, n), np.nan)
+    rz = np.zeros(1)
+    rc = he.hostemu_stream_vcycle(ctypes.c_int(n), ctypes.c_int(nu), ctypes.c_int(64), ctypes.c_int(64), ctypes.c_int(ls),
+                                  ctypes.c_int(3), ctypes.c_int(band), P(r), P(z), P(rz))
+    assert rc == 0
+    # no per-sample state in this unit call => scale 1: the float copy of z carries ~6e-8 relative rounding per level
+    assert np.abs(z - zr).max() <= 2e-6 * np.abs(zr).max()
+    assert abs(rz[0] - (r * zr).sum()) <= 2e-6 * abs(rz[0])
+    f, theta = batch_inputs(n, 1)
+    u, it, rr, st = run_stream(he, n, theta, f, 64, 64, ls, mode=3, band=band, nu=nu)
+    u2, it2, _, _ = run_stream(he, n, theta, f, 64, 64, ls, mode=2, band=band, nu=nu)
+    assert (st <= 1).all() and (it <= it2 + 1).all() and it.sum() <= it2.sum() + 1
+    for b in range(3):
+        assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= 1e-10
+    # data of extreme magnitude: the power-of-two rescaling keeps the float copies in range
+    for scale in (1e-30, 1e+30):
+        us, its, _, sts = run_stream(he, n, theta[:1], f[:1] * scale, 64, 64, ls, mode=3, band=band, nu=nu)
+        assert (sts <= 1).all() and its[0] <= it2[0] + 1
+        assert O.rel_l2(us[0] / scale, u2[0]) <= 1e-10
+
+
+def test_float_storage_needs_multiples_of_four(he):
+    n = 100   # levels 100, 50: 50 % 4 != 0 on a streamed level
+    r = np.zeros((n, n)); z = np.zeros((n, n)); rz = np.zeros(1)
+    rc = he.hostemu_stream_vcycle(ctypes.c_int(n), ctypes.c_int(2), ctypes.c_int(64), ctypes.c_int(64), ctypes.c_int(2),
+                                  ctypes.c_int(3), ctypes.c_int(64), P(r), P(z), P(rz))
+    assert rc == -2
