@@ -93,9 +93,12 @@ __global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_post_kernel(const _
 #ifndef PSN_STRIP_MINB_TMA
 #define PSN_STRIP_MINB_TMA 3
 #endif
+#ifndef PSN_STRIP_MINB_F32
+#define PSN_STRIP_MINB_F32 4   // float strips hold half the register window: 4 CTAs (16 warps) per SM
+#endif
 // TB / TV: element types of the right-hand side and of the V-cycle intermediates (see PsnStripArgs)
 template <int NU, bool POST, bool TMA, class TB, class TV>
-__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, TMA ? PSN_STRIP_MINB_TMA : PSN_STRIP_MINB)
+__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, TMA ? (sizeof(TV) == 4 ? PSN_STRIP_MINB_F32 : PSN_STRIP_MINB_TMA) : PSN_STRIP_MINB)
 psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ PsnStripArgs a, long long ntasks) {
     extern __shared__ __align__(128) unsigned char strip_smem[];
     const int warp = threadIdx.x >> 5;
@@ -416,10 +419,11 @@ struct Context {
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
     int band0 = 0;         // rows per warp task on level 0 (0 = automatic)
-    int band_target = 32;  // V-cycle strip tasks per SM the band split aims for
-    int dir_band = 0;      // rows per warp task of the direction kernel (0: same as level 0 of the V-cycle)
+    int band_target = 8;   // V-cycle strip tasks per SM the band split aims for (long bands: the 2*nu halo rows of every band are recomputed)
+    int dir_band = 64;     // rows per warp task of the direction kernel (1 halo row per band: short bands balance better); 0: as level 0
+    int host_edge_div = 4; // first / last chunk of the host pipeline = regular chunk / host_edge_div
     int vcycle_f32 = 1;    // streamed path: store V-cycle intermediates as float where the grid sizes allow (PsnStreamCfg::vf32)
-    int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 3 streamed / 8 resident)
+    int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 5 streamed / 8 resident)
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     bool attrs_set = false;
     bool profiling = false;
@@ -940,7 +944,7 @@ int solve_internal(const Problem& P) {
         if (cap > 65535 && !resident) cap = 65535;   // gridDim.z
         if (any_host) {
             // at least ~8 chunks so that copies overlap the solve, but keep chunks large enough to fill the GPU
-            const int hc = g.host_chunks > 0 ? g.host_chunks : (resident ? 8 : 3);
+            const int hc = g.host_chunks > 0 ? g.host_chunks : (resident ? 8 : 5);
             long long want = (P.B + hc - 1) / hc;
             const long long floor_ = resident ? 4ll * g.sm_count : 64;
             if (want < floor_) want = floor_;
@@ -974,7 +978,7 @@ int solve_internal(const Problem& P) {
     bounds.push_back(0);
     if (any_host && P.B > 2 * Bc) {
         // short first / last chunk (pipeline fill = first H2D, drain = last D2H), equal chunks <= Bc in between
-        const long long e = Bc / 4 > 0 ? Bc / 4 : 1;
+        const long long e = Bc / g.host_edge_div > 0 ? Bc / g.host_edge_div : 1;
         const long long mid = P.B - 2 * e;
         const long long parts = (mid + Bc - 1) / Bc;
         bounds.push_back(e);
@@ -1497,6 +1501,9 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;
+    } else if (!strcmp(name, "host_edge_div")) {
+        if (value < 1 || value > 64) return psn_fail(PSN_ERR_INVALID, "host_edge_div must be in 1..64");
+        g.host_edge_div = (int)value;
     } else if (!strcmp(name, "band_target")) {
         if (value < 1 || value > 1024) return psn_fail(PSN_ERR_INVALID, "band_target must be in 1..1024");
         g.band_target = (int)value;

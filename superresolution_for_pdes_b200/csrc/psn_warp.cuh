@@ -12,6 +12,7 @@
 #if defined(__CUDACC__)
 
 typedef double wd;
+typedef float wf;
 typedef int wi;
 typedef bool wb;
 struct PsnWarp {
@@ -124,20 +125,21 @@ PSN_FN void w_lds4(const PsnWarp& w, const double* row, wd (&out)[4]) {
 PSN_FN void w_zero_smem(const PsnWarp& w, double* p, int count) {
     for (int i = w.lane; i < count; i += 32) p[i] = 0.0;
 }
-// float-storage overloads (V-cycle intermediates kept in fp32 in HBM; registers and arithmetic stay fp64)
-PSN_FN void w_stp(float* row, wi col, wb m, wd a, wd b) {
-    if (m) *reinterpret_cast<float2*>(row + col) = make_float2((float)a, (float)b);
-}
+// float overloads: V-cycle intermediates are kept in fp32 in HBM and the strip kernels that work on them compute in
+// fp32 as well (wf); the CG vectors, the level-0 right-hand side and every inner product stay fp64 (wd)
+PSN_FN wf w_sel(wb c, wf a, wf b) { return c ? a : b; }
+PSN_FN wf w_up_raw(wf v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+PSN_FN wf w_down_raw(wf v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 PSN_FN void w_prefetch_l2(const float* row, wi col, wb m) {
     if (m) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + col));
 }
-PSN_FN wd w_ld1(const float* row, wi idx, wb m) { return m ? (double)row[idx] : 0.0; }
-PSN_FN void w_st1(float* row, wi idx, wb m, wd v) {
-    if (m) row[idx] = (float)v;
+PSN_FN wf w_ld1(const float* row, wi idx, wb m) { return m ? row[idx] : 0.f; }
+PSN_FN void w_st1(float* row, wi idx, wb m, wf v) {
+    if (m) row[idx] = v;
 }
-PSN_FN void w_lds4(const PsnWarp& w, const float* row, wd (&out)[4]) {
+PSN_FN void w_lds4(const PsnWarp& w, const float* row, wf (&out)[4]) {
     const float4 v = *reinterpret_cast<const float4*>(row + 4 * w.lane);
-    out[0] = (double)v.x; out[1] = (double)v.y; out[2] = (double)v.z; out[3] = (double)v.w;
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
 }
 PSN_FN void w_zero_smem(const PsnWarp& w, float* p, int count) {
     for (int i = w.lane; i < count; i += 32) p[i] = 0.f;
@@ -148,15 +150,24 @@ PSN_FN void w_stq(double* row, wi col0, wb m0, wb m1, const wd (&v)[4]) {
     w_stp(row, col0, m0, v[0], v[1]);
     w_stp(row, col0 + 2, m1, v[2], v[3]);
 }
-PSN_FN void w_stq(float* row, wi col0, wb m0, wb, const wd (&v)[4]) {
-    if (m0) *reinterpret_cast<float4*>(row + col0) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+PSN_FN void w_stq(float* row, wi col0, wb m0, wb, const wf (&v)[4]) {
+    if (m0) *reinterpret_cast<float4*>(row + col0) = make_float4(v[0], v[1], v[2], v[3]);
 }
+template <class S> struct PsnWV;
+template <> struct PsnWV<double> { typedef wd type; };
+template <> struct PsnWV<float> { typedef wf type; };
+template <class S> PSN_FN typename PsnWV<S>::type w_bcastT(double s) { return (S)s; }
+template <class S> PSN_FN typename PsnWV<S>::type w_cvt(wd v) { return (S)v; }
+template <class S> PSN_FN typename PsnWV<S>::type w_cvt(wf v) { return (S)v; }
 
 #else  // ------------------------------------------------------------------ host emulation
 
-struct wd {
-    double v[32];
+template <class S>
+struct wvt {
+    S v[32];
 };
+typedef wvt<double> wd;
+typedef wvt<float> wf;
 struct wi {
     int v[32];
 };
@@ -170,9 +181,9 @@ struct PsnWarp {
 #define PSN_W_FOR for (int l_ = 0; l_ < 32; ++l_)
 inline wd w_bcast(double s) { wd r; PSN_W_FOR r.v[l_] = s; return r; }
 inline wi w_lane(const PsnWarp&) { wi r; PSN_W_FOR r.v[l_] = l_; return r; }
-inline wd operator+(const wd& a, const wd& b) { wd r; PSN_W_FOR r.v[l_] = a.v[l_] + b.v[l_]; return r; }
-inline wd operator-(const wd& a, const wd& b) { wd r; PSN_W_FOR r.v[l_] = a.v[l_] - b.v[l_]; return r; }
-inline wd operator*(const wd& a, const wd& b) { wd r; PSN_W_FOR r.v[l_] = a.v[l_] * b.v[l_]; return r; }
+template <class S> inline wvt<S> operator+(const wvt<S>& a, const wvt<S>& b) { wvt<S> r; PSN_W_FOR r.v[l_] = a.v[l_] + b.v[l_]; return r; }
+template <class S> inline wvt<S> operator-(const wvt<S>& a, const wvt<S>& b) { wvt<S> r; PSN_W_FOR r.v[l_] = a.v[l_] - b.v[l_]; return r; }
+template <class S> inline wvt<S> operator*(const wvt<S>& a, const wvt<S>& b) { wvt<S> r; PSN_W_FOR r.v[l_] = a.v[l_] * b.v[l_]; return r; }
 inline wd operator*(double a, const wd& b) { wd r; PSN_W_FOR r.v[l_] = a * b.v[l_]; return r; }
 inline wi operator*(const wi& a, int b) { wi r; PSN_W_FOR r.v[l_] = a.v[l_] * b; return r; }
 inline wi operator+(const wi& a, int b) { wi r; PSN_W_FOR r.v[l_] = a.v[l_] + b; return r; }
@@ -180,7 +191,7 @@ inline wb operator>=(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] >= 
 inline wb operator<(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] < b; return r; }
 inline wb operator==(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] == b; return r; }
 inline wb operator&&(const wb& a, const wb& b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] && b.v[l_]; return r; }
-inline wd w_sel(const wb& c, const wd& a, const wd& b) { wd r; PSN_W_FOR r.v[l_] = c.v[l_] ? a.v[l_] : b.v[l_]; return r; }
+template <class S> inline wvt<S> w_sel(const wb& c, const wvt<S>& a, const wvt<S>& b) { wvt<S> r; PSN_W_FOR r.v[l_] = c.v[l_] ? a.v[l_] : b.v[l_]; return r; }
 inline wd w_up(const PsnWarp&, const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 0 ? 0.0 : v.v[l_ - 1]; return r; }
 inline wd w_down(const PsnWarp&, const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 31 ? 0.0 : v.v[l_ + 1]; return r; }
 inline double w_sum(const wd& v) { double s = 0.0; PSN_W_FOR s += v.v[l_]; return s; }
@@ -197,8 +208,8 @@ inline void w_st2(double* row, const wi& col, const wb& m0, const wb& m1, bool, 
         if (m1.v[l_]) row[col.v[l_] + 1] = b.v[l_];
     }
 }
-inline wd w_up_raw(const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 0 ? v.v[0] : v.v[l_ - 1]; return r; }
-inline wd w_down_raw(const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 31 ? v.v[31] : v.v[l_ + 1]; return r; }
+template <class S> inline wvt<S> w_up_raw(const wvt<S>& v) { wvt<S> r; PSN_W_FOR r.v[l_] = l_ == 0 ? v.v[0] : v.v[l_ - 1]; return r; }
+template <class S> inline wvt<S> w_down_raw(const wvt<S>& v) { wvt<S> r; PSN_W_FOR r.v[l_] = l_ == 31 ? v.v[31] : v.v[l_ + 1]; return r; }
 inline void w_ldp(const double* row, const wi& col, const wb& m, wd& a, wd& b) {
     PSN_W_FOR {
         a.v[l_] = m.v[l_] ? row[col.v[l_]] : 0.0;
@@ -221,27 +232,27 @@ inline void w_lds4(const PsnWarp&, const double* row, wd (&out)[4]) {
     PSN_W_FOR for (int e = 0; e < 4; ++e) out[e].v[l_] = row[4 * l_ + e];
 }
 inline void w_zero_smem(const PsnWarp&, double* p, int count) { for (int i = 0; i < count; ++i) p[i] = 0.0; }
-inline void w_stp(float* row, const wi& col, const wb& m, const wd& a, const wd& b) {
-    PSN_W_FOR if (m.v[l_]) { row[col.v[l_]] = (float)a.v[l_]; row[col.v[l_] + 1] = (float)b.v[l_]; }
-}
 inline void w_prefetch_l2(const float*, const wi&, const wb&) {}
-inline wd w_ld1(const float* row, const wi& idx, const wb& m) { wd r; PSN_W_FOR r.v[l_] = m.v[l_] ? (double)row[idx.v[l_]] : 0.0; return r; }
-inline void w_st1(float* row, const wi& idx, const wb& m, const wd& v) { PSN_W_FOR if (m.v[l_]) row[idx.v[l_]] = (float)v.v[l_]; }
-inline void w_lds4(const PsnWarp&, const float* row, wd (&out)[4]) {
-    PSN_W_FOR for (int e = 0; e < 4; ++e) out[e].v[l_] = (double)row[4 * l_ + e];
+inline wf w_ld1(const float* row, const wi& idx, const wb& m) { wf r; PSN_W_FOR r.v[l_] = m.v[l_] ? row[idx.v[l_]] : 0.f; return r; }
+inline void w_st1(float* row, const wi& idx, const wb& m, const wf& v) { PSN_W_FOR if (m.v[l_]) row[idx.v[l_]] = v.v[l_]; }
+inline void w_lds4(const PsnWarp&, const float* row, wf (&out)[4]) {
+    PSN_W_FOR for (int e = 0; e < 4; ++e) out[e].v[l_] = row[4 * l_ + e];
 }
 inline void w_zero_smem(const PsnWarp&, float* p, int count) { for (int i = 0; i < count; ++i) p[i] = 0.f; }
 inline void w_stq(double* row, const wi& col0, const wb& m0, const wb& m1, const wd (&v)[4]) {
     w_stp(row, col0, m0, v[0], v[1]);
     w_stp(row, col0 + 2, m1, v[2], v[3]);
 }
-inline void w_stq(float* row, const wi& col0, const wb& m0, const wb& m1, const wd (&v)[4]) {
+inline void w_stq(float* row, const wi& col0, const wb& m0, const wb& m1, const wf (&v)[4]) {
     PSN_W_FOR {
         // mirrors the device's single 128-bit store: the two pair masks must agree
         if (m0.v[l_] != m1.v[l_]) abort();
-        if (m0.v[l_]) for (int e = 0; e < 4; ++e) row[col0.v[l_] + e] = (float)v[e].v[l_];
+        if (m0.v[l_]) for (int e = 0; e < 4; ++e) row[col0.v[l_] + e] = v[e].v[l_];
     }
 }
+template <class S> struct PsnWV { typedef wvt<S> type; };
+template <class S> inline wvt<S> w_bcastT(double s) { wvt<S> r; PSN_W_FOR r.v[l_] = (S)s; return r; }
+template <class S, class F> inline wvt<S> w_cvt(const wvt<F>& v) { wvt<S> r; PSN_W_FOR r.v[l_] = (S)v.v[l_]; return r; }
 
 #endif
 
@@ -322,6 +333,8 @@ struct PsnStripGeom {
 //               tied up by loads in flight, so the prefetch distance is 2-3x deeper.
 template <int NU, int NARR>
 struct PsnRegFeeder {
+    typedef wd V0;
+    typedef wd V1;
     static constexpr int W = 2 * NU + 2, PF = W / 2;
     wd pf[NARR][PF][4];
     const double* base[NARR];
@@ -343,13 +356,16 @@ struct PsnRegFeeder {
                 }
             }
     }
-    // values of row tc (zero beyond tload); starts the load of row tc + PF
+    // values of row tc (zero beyond tload) of array 0 (and 1); starts the load of row tc + PF
     template <bool FAST>
-    PSN_FN void fetch(const PsnWarp&, int tt, int tc, int /*par*/, wd (&out)[NARR][4]) {
+    PSN_FN void fetch(const PsnWarp&, int tt, int tc, int /*par*/, wd (&o0)[4], wd (&o1)[4]) {
 #pragma unroll
         for (int a = 0; a < NARR; ++a) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) out[a][e] = pf[a][tt % PF][e];
+            for (int e = 0; e < 4; ++e) {
+                if (a == 0) o0[e] = pf[a][tt % PF][e];
+                else o1[e] = pf[a][tt % PF][e];
+            }
             if (FAST || tc + PF <= tload) {
                 const double* rowp = base[a] + (long long)(tc + PF) * n;
                 w_ldp(rowp, col0, mp[0], pf[a][tt % PF][0], pf[a][tt % PF][1]);
@@ -380,6 +396,8 @@ struct PsnElemOr<void> {
 template <int NU, class T0, class T1 = void>
 struct PsnTmaFeeder {
     typedef typename PsnElemOr<T1>::type U1;
+    typedef typename PsnWV<T0>::type V0;   // register type the rows are delivered in: the array's own precision
+    typedef typename PsnWV<U1>::type V1;
     static constexpr int NARR = 1 + PsnElemOr<T1>::narr;
     static constexpr int W = 2 * NU + 2, D = W - 1;
     static constexpr int RING_BYTES = W * PSN_STRIP_COLS * ((int)sizeof(T0) + PsnElemOr<T1>::bytes);
@@ -418,19 +436,20 @@ struct PsnTmaFeeder {
             if (ts + k <= tload) issue(w, ts + k, k);
     }
     template <bool FAST>
-    PSN_FN void fetch(const PsnWarp& w, int tt, int tc, int par, wd (&out)[NARR][4]) {
+    PSN_FN void fetch(const PsnWarp& w, int tt, int tc, int par, V0 (&o0)[4], V1 (&o1)[4]) {
         // every lane has finished reading the slot of row tc-1 (previous time step): refill it with row tc+D
         w_sync(w);
         if (FAST || tc + D <= tload) issue(w, tc + D, (tt + W - 1) % W);
         if (FAST || tc <= tload) {
             w_bar_wait(bar + tt, (unsigned)par);
-            w_lds4(w, ring0 + tt * PSN_STRIP_COLS, out[0]);
-            if (NARR == 2) w_lds4(w, ring1 + tt * PSN_STRIP_COLS, out[NARR - 1]);
+            w_lds4(w, ring0 + tt * PSN_STRIP_COLS, o0);
+            if (NARR == 2) w_lds4(w, ring1 + tt * PSN_STRIP_COLS, o1);
         } else {
 #pragma unroll
-            for (int a = 0; a < NARR; ++a)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) out[a][e] = w_bcast(0.0);
+            for (int e = 0; e < 4; ++e) {
+                o0[e] = w_bcastT<T0>(0.0);
+                if (NARR == 2) o1[e] = w_bcastT<U1>(0.0);
+            }
         }
     }
 };
@@ -461,20 +480,24 @@ PSN_FN void psn_feeder_geom(PsnTmaFeeder<NU, T0, T1>& fd, const wi&, const wb (&
 template <int NU, bool FAST, bool SCALE, class TV, class Feeder>
 PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc,
                                 int i0, int i1, int I0, int I1,
-                                wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], Feeder& fd, int par, wd (&acc)[2],
-                                const wd (&rdA)[4], const wd (&dA)[4], const wd (&mk)[4], const PsnLevel& lv,
+                                typename PsnWV<TV>::type (&val)[2 * NU + 2][4], typename PsnWV<TV>::type (&bb)[2 * NU + 2][4],
+                                Feeder& fd, int par, typename PsnWV<TV>::type (&acc)[2],
+                                const typename PsnWV<TV>::type (&rdA)[4], const typename PsnWV<TV>::type (&dA)[4],
+                                const typename PsnWV<TV>::type (&mk)[4], const PsnLevel& lv,
                                 const wd& bsc, TV* ug, TV* cg, const wi& col0, const wb (&mp)[2], const wb (&so)[2],
                                 const wi& cj, const wb (&sc)[2]) {
     constexpr int NS = 2 * NU, W = NS + 2;
-    const wd zero = w_bcast(0.0);
+    typedef typename PsnWV<TV>::type WV;   // compute type of the sweeps = storage type of the iterate
+    const WV zero = w_bcastT<TV>(0.0);
+    const WV q25 = w_bcastT<TV>(0.25);
     // last-row diagonals are only needed by the checked chunk at the bottom of the grid: build them on demand
-    wd rdB[4], dB[4];
+    WV rdB[4], dB[4];
     if (!FAST) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const wb lc_ = (col0 + e) == last;
-            rdB[e] = mk[e] * w_sel(lc_, w_bcast(lv.rd2), w_bcast(lv.rd1));
-            dB[e] = w_sel(lc_, w_bcast(4.0 + 2.0 * lv.gam), w_bcast(4.0 + lv.gam));
+            rdB[e] = mk[e] * w_sel(lc_, w_bcastT<TV>(lv.rd2), w_bcastT<TV>(lv.rd1));
+            dB[e] = w_sel(lc_, w_bcastT<TV>(4.0 + 2.0 * lv.gam), w_bcastT<TV>(4.0 + lv.gam));
         }
     } else {
 #pragma unroll
@@ -488,10 +511,14 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
         const int k0 = tt;
         // ---- new row: rhs from the feeder; first red half sweep from the zero guess
         {
-            wd rowv[1][4];
-            fd.template fetch<FAST>(w, tt, tc, par, rowv);
+            typename Feeder::V0 r0[4];
+            typename Feeder::V1 r1[4];
+            fd.template fetch<FAST>(w, tt, tc, par, r0, r1);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) bb[k0][e] = SCALE ? rowv[0][e] * bsc : rowv[0][e];
+            for (int e = 0; e < 4; ++e) {
+                if constexpr (SCALE) bb[k0][e] = w_cvt<TV>(r0[e] * bsc);
+                else bb[k0][e] = w_cvt<TV>(r0[e]);
+            }
         }
         if (FAST || tc <= last) {
             const bool lastrow = !FAST && tc == last;
@@ -510,10 +537,10 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
             if (FAST || (r >= ts && r <= last)) {
                 const int ks = (tt - s + 2 * W) % W, ku = (tt - s - 1 + 2 * W) % W, kd = (tt - s + 1 + 2 * W) % W;
                 const bool lastrow = !FAST && r == last;
-                const wd upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
-                const wd dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
-                const wd sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
-                const wd sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
+                const WV upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
+                const WV dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
+                const WV sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
+                const WV sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
                 val[ks][P] = (bb[ks][P] + sa) * (lastrow ? rdB[P] : rdA[P]);
                 val[ks][P + 2] = (bb[ks][P + 2] + sb) * (lastrow ? rdB[P + 2] : rdA[P + 2]);
             }
@@ -521,20 +548,20 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
         // ---- residual on the red nodes of row tc-NS, accumulate the restriction
         {
             const int r = tc - NS;
-            wd ra = zero, rb = zero;
+            WV ra = zero, rb = zero;
             if (FAST || (r >= ts && r <= last)) {
                 const int ks = (tt - NS + 2 * W) % W, ku = (tt - NS - 1 + 2 * W) % W, kd = (tt - NS + 1 + 2 * W) % W;
                 const bool lastrow = !FAST && r == last;
-                const wd upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
-                const wd dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
-                const wd sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
-                const wd sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
+                const WV upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
+                const WV dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
+                const WV sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
+                const WV sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
                 ra = mk[P] * (bb[ks][P] - ((lastrow ? dB[P] : dA[P]) * val[ks][P] - sa));
                 rb = mk[P + 2] * (bb[ks][P + 2] - ((lastrow ? dB[P + 2] : dA[P + 2]) * val[ks][P + 2] - sb));
             }
             if (P == 0) {  // even row 2I: corners of coarse rows I-1 (bottom) and I (top); lane holds J = cj, cj+1
-                const wd c0v = 0.25 * (ra + rb);
-                const wd c1v = 0.25 * (rb + w_down_raw(ra));
+                const WV c0v = q25 * (ra + rb);
+                const WV c1v = q25 * (rb + w_down_raw(ra));
                 const int I = (r >> 1) - 1;
                 if (FAST || (r >= 2 && I >= I0 && I < I1)) {
                     TV* crow = cg + (long long)I * nc;
@@ -584,16 +611,17 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
     const wb so[2] = {mp[0] && (col0 >= a0) && (col0 < a1), mp[1] && (col2 >= a0) && (col2 < a1)};
     const wi cj = w_lane(w) * 2 + (c0 >> 1);
     const wb sc[2] = {(cj >= J0) && (cj < J1), (cj + 1 >= J0) && (cj + 1 < J1)};
-    const wd zero = w_bcast(0.0);
-    wd rdA[4], dA[4], mk[4];
+    typedef typename PsnWV<TV>::type WV;
+    const WV zero = w_bcastT<TV>(0.0);
+    WV rdA[4], dA[4], mk[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const wi ce = col0 + e;
         const wb in = (e < 2) ? mp[0] : mp[1];
         const wb lc_ = ce == last;
-        rdA[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd1), w_bcast(lv.rd0)), zero);
-        dA[e] = w_sel(lc_, w_bcast(4.0 + lv.gam), w_bcast(4.0));
-        mk[e] = w_sel(in, w_bcast(1.0), zero);
+        rdA[e] = w_sel(in, w_sel(lc_, w_bcastT<TV>(lv.rd1), w_bcastT<TV>(lv.rd0)), zero);
+        dA[e] = w_sel(lc_, w_bcastT<TV>(4.0 + lv.gam), w_bcastT<TV>(4.0));
+        mk[e] = w_sel(in, w_bcastT<TV>(1.0), zero);
     }
 
     const int ts = psn_imax(i0 - NS, 0);
@@ -604,7 +632,7 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
     TV* cg = reinterpret_cast<TV*>(a.bc) + b * (long long)nc * nc;
     const wd bsc = w_bcast((SCALE && a.state) ? psn_vscale(a.state[b].rr) : 1.0);
 
-    wd val[W][4], bb[W][4], acc[2];
+    WV val[W][4], bb[W][4], acc[2];
 #pragma unroll
     for (int k = 0; k < W; ++k)
 #pragma unroll
@@ -623,26 +651,30 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
                           (((t - NS) >> 1) - 1 >= I0) && (((t + W - 1 - NS) >> 1) - 1 < I1);
         const int par = ((t - ts) / W) & 1;
         if (fast)
-            psn_strip_pre_chunk<NU, true, SCALE>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
+            psn_strip_pre_chunk<NU, true, SCALE, TV>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
                                                  bsc, ug, cg, col0, mp, so, cj, sc);
         else
-            psn_strip_pre_chunk<NU, false, SCALE>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
+            psn_strip_pre_chunk<NU, false, SCALE, TV>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv,
                                                   bsc, ug, cg, col0, mp, so, cj, sc);
     }
 }
 
 template <int NU, bool FAST, bool SCALE, class TV, class Feeder>
 PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc, int i0, int i1,
-                                 wd (&val)[2 * NU + 2][4], wd (&bb)[2 * NU + 2][4], Feeder& fd, int par,
-                                 wd (&eprev)[2], wd (&enext)[2], wd& dot, const wd (&rdA)[4], const wd (&mk)[4], const PsnLevel& lv,
+                                 typename PsnWV<TV>::type (&val)[2 * NU + 2][4], typename PsnWV<TV>::type (&bb)[2 * NU + 2][4],
+                                 Feeder& fd, int par, typename PsnWV<TV>::type (&eprev)[2], typename PsnWV<TV>::type (&enext)[2], wd& dot,
+                                 const typename PsnWV<TV>::type (&rdA)[4], const typename PsnWV<TV>::type (&mk)[4], const PsnLevel& lv,
                                  const wd& bsc, const TV* eg, TV* ug, const wi& col0,
                                  const wb (&mp)[2], const wb (&so)[2], const wi& cj, const wb (&mc)[2], bool want_dot) {
     constexpr int NS = 2 * NU, W = NS + 2;
-    const wd zero = w_bcast(0.0);
-    wd rdB[4];
+    typedef typename PsnWV<TV>::type WV;
+    const WV zero = w_bcastT<TV>(0.0);
+    const WV q25 = w_bcastT<TV>(0.25);
+    const wd zerod = w_bcast(0.0);
+    WV rdB[4];
     if (!FAST) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) rdB[e] = mk[e] * w_sel((col0 + e) == last, w_bcast(lv.rd2), w_bcast(lv.rd1));
+        for (int e = 0; e < 4; ++e) rdB[e] = mk[e] * w_sel((col0 + e) == last, w_bcastT<TV>(lv.rd2), w_bcastT<TV>(lv.rd1));
     } else {
 #pragma unroll
         for (int e = 0; e < 4; ++e) rdB[e] = zero;
@@ -655,19 +687,21 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
         const int k0 = tt;
         // ---- new row: rhs and pre-smoothed iterate, then the prolongated correction on the red nodes
         {
-            wd rowv[2][4];
-            fd.template fetch<FAST>(w, tt, tc, par, rowv);
+            typename Feeder::V0 r0[4];
+            typename Feeder::V1 r1[4];
+            fd.template fetch<FAST>(w, tt, tc, par, r0, r1);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                bb[k0][e] = SCALE ? rowv[0][e] * bsc : rowv[0][e];
-                val[k0][e] = rowv[1][e];
+                if constexpr (SCALE) bb[k0][e] = w_cvt<TV>(r0[e] * bsc);
+                else bb[k0][e] = w_cvt<TV>(r0[e]);
+                val[k0][e] = w_cvt<TV>(r1[e]);
             }
         }
         if (FAST || tc <= last) {
             if (P == 0) {  // even row 2I, red = even columns: mean of coarse (I-1,J-1), (I-1,J), (I,J-1), (I,J)
                 const int I = tc >> 1;
                 // coarse row I was requested two fine rows ago (enext); request row I+1 now
-                const wd enew[2] = {enext[0], enext[1]};
+                const WV enew[2] = {enext[0], enext[1]};
                 enext[0] = enext[1] = zero;
                 if (FAST || I + 1 < nc) {
                     const TV* erow = eg + (long long)(I + 1) * nc;
@@ -675,10 +709,10 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
                     enext[1] = w_ld1(erow, cj + 1, mc[1]);
                     if (I + 9 < nc) w_prefetch_l2(eg + (long long)(I + 9) * nc, cj, mc[0]);
                 }
-                const wd s0 = eprev[0] + enew[0], s1 = eprev[1] + enew[1];   // column sums J = cj, cj+1
-                const wd sl = w_up_raw(s1);                                     // column J = cj-1
-                val[k0][0] = mk[0] * (val[k0][0] + 0.25 * (sl + s0));
-                val[k0][2] = mk[2] * (val[k0][2] + 0.25 * (s0 + s1));
+                const WV s0 = eprev[0] + enew[0], s1 = eprev[1] + enew[1];   // column sums J = cj, cj+1
+                const WV sl = w_up_raw(s1);                                     // column J = cj-1
+                val[k0][0] = mk[0] * (val[k0][0] + q25 * (sl + s0));
+                val[k0][2] = mk[2] * (val[k0][2] + q25 * (s0 + s1));
                 eprev[0] = enew[0];
                 eprev[1] = enew[1];
             } else {       // odd row 2I+1, red = odd columns: coincide with coarse (I, J)
@@ -696,10 +730,10 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
             if (FAST || (r >= ts && r <= last)) {
                 const int ks = (tt - s + 2 * W) % W, ku = (tt - s - 1 + 2 * W) % W, kd = (tt - s + 1 + 2 * W) % W;
                 const bool lastrow = !FAST && r == last;
-                const wd upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
-                const wd dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
-                const wd sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
-                const wd sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
+                const WV upv = (P == 0) ? w_up_raw(val[ks][3]) : zero;
+                const WV dnv = (P == 1) ? w_down_raw(val[ks][0]) : zero;
+                const WV sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upv, dnv);
+                const WV sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upv, dnv);
                 val[ks][P] = (bb[ks][P] + sa) * (lastrow ? rdB[P] : rdA[P]);
                 val[ks][P + 2] = (bb[ks][P + 2] + sb) * (lastrow ? rdB[P + 2] : rdA[P + 2]);
             }
@@ -711,8 +745,8 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
                 const int ko = (tt - NS + 2 * W) % W;
                 w_stq(ug + (long long)ro * n, col0, so[0], so[1], val[ko]);
                 if (want_dot)
-                    dot = dot + w_sel(so[0], val[ko][0] * bb[ko][0] + val[ko][1] * bb[ko][1], zero) +
-                          w_sel(so[1], val[ko][2] * bb[ko][2] + val[ko][3] * bb[ko][3], zero);
+                    dot = dot + w_sel(so[0], w_cvt<double>(val[ko][0]) * w_cvt<double>(bb[ko][0]) + w_cvt<double>(val[ko][1]) * w_cvt<double>(bb[ko][1]), zerod) +
+                          w_sel(so[1], w_cvt<double>(val[ko][2]) * w_cvt<double>(bb[ko][2]) + w_cvt<double>(val[ko][3]) * w_cvt<double>(bb[ko][3]), zerod);
             }
         }
     }
@@ -739,15 +773,16 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const wb so[2] = {mp[0] && (col0 >= a0) && (col0 < a1), mp[1] && (col2 >= a0) && (col2 < a1)};
     const wi cj = w_lane(w) * 2 + (c0 >> 1);
     const wb mc[2] = {(cj >= 0) && (cj < nc), (cj + 1 >= 0) && (cj + 1 < nc)};
-    const wd zero = w_bcast(0.0);
-    wd rdA[4], mk[4];
+    typedef typename PsnWV<TV>::type WV;
+    const WV zero = w_bcastT<TV>(0.0);
+    WV rdA[4], mk[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const wi ce = col0 + e;
         const wb in = (e < 2) ? mp[0] : mp[1];
         const wb lc_ = ce == last;
-        rdA[e] = w_sel(in, w_sel(lc_, w_bcast(lv.rd1), w_bcast(lv.rd0)), zero);
-        mk[e] = w_sel(in, w_bcast(1.0), zero);
+        rdA[e] = w_sel(in, w_sel(lc_, w_bcastT<TV>(lv.rd1), w_bcastT<TV>(lv.rd0)), zero);
+        mk[e] = w_sel(in, w_bcastT<TV>(1.0), zero);
     }
 
     const int ts = psn_imax(i0 - NS, 0);
@@ -760,7 +795,7 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const double bs = (SCALE && a.state) ? psn_vscale(a.state[b].rr) : 1.0;
     const wd bsc = w_bcast(bs);
 
-    wd val[W][4], bb[W][4], eprev[2], enext[2];
+    WV val[W][4], bb[W][4], eprev[2], enext[2];
 #pragma unroll
     for (int k = 0; k < W; ++k)
 #pragma unroll
@@ -773,7 +808,7 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     fd.prime(w, ts);
     // coarse correction rows: eprev = row ts/2 - 1 (zero above the grid), enext = row ts/2
     eprev[0] = eprev[1] = enext[0] = enext[1] = zero;
-    wd dot = zero;
+    wd dot = w_bcast(0.0);
     {
         const int Ip = (ts >> 1) - 1;
         if (Ip >= 0 && Ip < nc) {
@@ -792,10 +827,10 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
                           (t - NS >= i0) && (t + W - 1 - NS < i1);
         const int par = ((t - ts) / W) & 1;
         if (fast)
-            psn_strip_post_chunk<NU, true, SCALE>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
+            psn_strip_post_chunk<NU, true, SCALE, TV>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
                                                   bsc, eg, ug, col0, mp, so, cj, mc, want_dot);
         else
-            psn_strip_post_chunk<NU, false, SCALE>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
+            psn_strip_post_chunk<NU, false, SCALE, TV>(w, t, ts, tload, tend, last, n, nc, i0, i1, val, bb, fd, par, eprev, enext, dot, rdA, mk, lv,
                                                    bsc, eg, ug, col0, mp, so, cj, mc, want_dot);
     }
     if (want_dot) {
@@ -870,12 +905,14 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
             const int tc = t + tt;
             if (tc > tend) break;
             const int k0 = tt % 3, k1 = (tt + 2) % 3, k2 = (tt + 1) % 3;   // rows tc, tc-1, tc-2
-            wd rowv[2][4];
-            fd.template fetch<false>(w, tt, tc, par, rowv);
+            typename Feeder::V0 r0[4];
+            typename Feeder::V1 r1[4];
+            fd.template fetch<false>(w, tt, tc, par, r0, r1);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const wd zv = F32 ? rowv[0][e] * zinv : rowv[0][e];
-                pn[k0][e] = fresh ? zv : zv + beta * rowv[1][e];
+                wd zv = w_cvt<double>(r0[e]);
+                if constexpr (F32 != 0) zv = zv * zinv;
+                pn[k0][e] = fresh ? zv : zv + beta * r1[e];
             }
             if (tc >= i0 && tc < i1) {
                 double* rowp = pg + (long long)tc * n;
