@@ -287,12 +287,24 @@ def solve_from_wavenumbers(n: int, k1, k2, *, theta=None, out=None, chunks: Opti
     chunks = max(1, min(int(chunks), B)) if B else 1
     bounds = [(B * c) // chunks for c in range(chunks + 1)]
 
-    def sines(c):
-        lo, hi = bounds[c], bounds[c + 1]
+    def sines_range(lo, hi):
         w1 = (k1[lo:hi] * 2 * np.pi) if kfirst else (2 * np.pi * k1[lo:hi])
         w2 = (k2[lo:hi] * 2 * np.pi) if kfirst else (2 * np.pi * k2[lo:hi])
         np.sin(w1[:, None] * x[None, :], out=sx[lo:hi])
         np.sin(w2[:, None] * x[None, :], out=sy[lo:hi])
+
+    def sines(c):
+        lo, hi = bounds[c], bounds[c + 1]
+        work = (hi - lo) * n
+        nt = 1 if work < (1 << 16) else min(8, os.cpu_count() or 1, max(1, (hi - lo) // 8))
+        if nt <= 1:
+            sines_range(lo, hi)
+            return
+        # numpy's sin releases the GIL: split the rows over a few threads (elementwise, so the values do not
+        # depend on the split)
+        cuts = [lo + ((hi - lo) * t) // nt for t in range(nt + 1)]
+        with ThreadPoolExecutor(max_workers=nt) as tp:
+            list(tp.map(lambda t: sines_range(cuts[t], cuts[t + 1]), range(nt)))
 
     def view(a, lo, hi):
         return None if a is None else a[lo:hi]

@@ -389,7 +389,9 @@ struct Slot {
     cudaEvent_t staging_free = nullptr;   // recorded after the last copy of the chunk that used the staging arena
 };
 
-#define PSN_NCHUNK_STREAMS 6
+// few streams on purpose: a process has CUDA_DEVICE_MAX_CONNECTIONS (default 8) hardware queues, streams beyond that
+// share a queue and serialise falsely (seen as solves waiting for another chunk's H2D copy)
+#define PSN_NCHUNK_STREAMS 4
 
 struct ProfRec {
     const char* name;
@@ -397,10 +399,10 @@ struct ProfRec {
 };
 
 struct Context {
-    // Host-buffer pipeline: chunk c runs on chunk_stream[c % 6], created with DEcreasing priority, so that of two
+    // Host-buffer pipeline: chunk c runs on chunk_stream[c % 4], created with DEcreasing priority, so that of two
     // overlapping chunks the earlier one wins the SMs (it finishes, and its result copy starts, as early as it
     // would alone) while the later one fills the gaps.
-    cudaStream_t chunk_stream[PSN_NCHUNK_STREAMS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t chunk_stream[PSN_NCHUNK_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
     bool ready = false;
     int device = -1;
     int sm_count = 0;
@@ -1270,7 +1272,6 @@ int psn_init(int device) {
     g.smem_optin = prop.sharedMemPerBlockOptin;
     for (int k = 0; k < 2; ++k) CU_TRY(cudaEventCreateWithFlags(&g.ws_free[k], cudaEventDisableTiming));
     for (int i = 0; i < PSN_NSLOTS; ++i) {
-        CU_TRY(cudaStreamCreateWithFlags(&g.slots[i].stream, cudaStreamNonBlocking));
         CU_TRY(cudaEventCreateWithFlags(&g.slots[i].staging_free, cudaEventDisableTiming));
         for (int k = 0; k < 4; ++k) CU_TRY(cudaEventCreateWithFlags(&g.slots[i].ev[k], cudaEventDisableTiming));
     }
