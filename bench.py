@@ -24,10 +24,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-
-# more hardware work queues than the default 8, so that the library's chunk streams never share one with the
-# framework's own streams (shared queues serialise unrelated streams); must be set before CUDA initialises
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import threading
