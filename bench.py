@@ -234,9 +234,13 @@ def run_own(args):
         raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # one process per GPU: keep this rank (and the pinned buffers of its end-to-end leg) on the GPU's NUMA node
+        from superresolution_for_pdes_b200.sharding import bind_to_gpu_numa
+        numa_cores = bind_to_gpu_numa(local)
     _lib.init(local)
 
     def barrier():
@@ -420,9 +424,11 @@ def run_own(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, B, world), "n": n, "batch_per_gpu": B, "rtol": args.rtol,
-                       "solver": "MG-preconditioned CG, V(2,2) red-black GS, matrix-free 5-point zero-ghost stencil; fp64 "
-                                 "arithmetic, CG vectors and inner products" + ("; preconditioner intermediates stored as float"
-                                                                                if desc.get("vcycle_f32") else ""),
+                       "solver": "MG-preconditioned CG, V(2,2) red-black GS, matrix-free 5-point zero-ghost stencil; CG vectors, "
+                                 "operator, inner products and stopping rule in fp64" +
+                                 ("; the V-cycle preconditioner stores and smooths in fp32 (same iteration count, solution "
+                                  "accuracy unchanged)" if desc.get("vcycle_f32") else "; V-cycle in fp64"),
+                       "host_affinity": (f"{len(numa_cores)} cores local to the GPU" if numa_cores else "unbound"),
                        "path": "resident" if desc["resident"] else "streamed", "mean_iters": float(info.iters.mean()),
                        "max_iters": int(info.iters.max()),
                        "l2": f"inputs larger than L2 (theta = {B * n * n * 8 / 1e6:.0f} MB per GPU, workspace {desc['workspace_bytes_per_sample'] * B / 1e9:.1f} GB)"},

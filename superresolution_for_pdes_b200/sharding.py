@@ -28,6 +28,35 @@ def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(total, lo + per)
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[list]:
+    """Pin the calling process to the CPU cores that are local to GPU `device_index` (NVML's ideal affinity), so that
+    the pinned staging buffers it allocates afterwards and its copy threads sit on that GPU's NUMA node.  With one
+    process per GPU on a two-socket host this keeps the 3+ GB/step of host<->device traffic per GPU off the
+    inter-socket link.  Returns the core list, or None when NVML / the cpuset does not allow it (never raises)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = [c for c in cores if c in allowed]
+        if not cores or len(cores) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:
+        return None
+
+
 def _dist():
     import torch.distributed as dist
     return dist
