@@ -46,6 +46,15 @@ static int psn_fail(int code, const char* fmt, ...) {
     } while (0)
 
 // ----------------------------------------------------------------------------- kernels
+// Programmatic dependent launch: every kernel of the streamed solve waits here for the grid launched before it on the
+// stream (full completion + memory flush) and immediately allows the NEXT grid to be launched, so that the next
+// kernel's CTAs are already resident (waiting at this instruction) while this kernel's last CTAs drain.  Launched
+// without the attribute (option "pdl" = 0, or the profiler's event pairs in between) both instructions are no-ops.
+__device__ __forceinline__ void psn_pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 template <int T, int XPT>
 __global__ void __launch_bounds__(T) psn_smem_solve_kernel(const __grid_constant__ PsnPlan plan,
                                                            const __grid_constant__ PsnSolveArgs a) {
@@ -71,6 +80,7 @@ __global__ void __launch_bounds__(PsnBlockGeom<BX>::NTPAD, 1) psn_block_solve_ke
 
 __global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_pre_kernel(const __grid_constant__ PsnPlan plan,
                                                                         const __grid_constant__ PsnTileArgs a) {
+    psn_pdl_enter();
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, PSN_TILE_THREADS, red, 0};
@@ -79,6 +89,7 @@ __global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_pre_kernel(const __
 
 __global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_post_kernel(const __grid_constant__ PsnPlan plan,
                                                                          const __grid_constant__ PsnTileArgs a) {
+    psn_pdl_enter();
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, PSN_TILE_THREADS, red, 0};
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(PSN_TILE_THREADS) psn_tile_post_kernel(const _
 template <int NU, bool POST, bool TMA, class TB, class TV>
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, TMA ? (sizeof(TV) == 4 ? PSN_STRIP_MINB_F32 : PSN_STRIP_MINB_TMA) : PSN_STRIP_MINB)
 psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ PsnStripArgs a, long long ntasks) {
+    psn_pdl_enter();
     extern __shared__ __align__(128) unsigned char strip_smem[];
     const int warp = threadIdx.x >> 5;
     const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
@@ -126,6 +138,7 @@ psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ P
 template <bool TMA, class TZ>
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
 psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
+    psn_pdl_enter();
     extern __shared__ __align__(128) unsigned char strip_smem[];
     const int warp = threadIdx.x >> 5;
     const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
@@ -149,6 +162,7 @@ template <class TV>
 __global__ void __launch_bounds__(PSN_COARSE_THREADS) psn_coarse_vcycle_kernel(const __grid_constant__ PsnPlan plan, int l0,
                                                                                const TV* bg, TV* ug,
                                                                                const PsnSampleState* state) {
+    psn_pdl_enter();
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, PSN_COARSE_THREADS, red, 0};
@@ -156,34 +170,41 @@ __global__ void __launch_bounds__(PSN_COARSE_THREADS) psn_coarse_vcycle_kernel(c
 }
 
 __global__ void __launch_bounds__(PSN_CG_THREADS) psn_prologue_kernel(const __grid_constant__ PsnCgArgs a) {
+    psn_pdl_enter();
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, PSN_CG_THREADS, red, 0};
     psn_prologue_body(ctx, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x);
 }
 __global__ void __launch_bounds__(PSN_CG_THREADS) psn_dir_apply_kernel(const __grid_constant__ PsnCgArgs a) {
+    psn_pdl_enter();
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, PSN_CG_THREADS, red, 0};
     psn_dir_apply_body(ctx, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x);
 }
 __global__ void __launch_bounds__(PSN_CG_THREADS) psn_update_kernel(const __grid_constant__ PsnCgArgs a) {
+    psn_pdl_enter();
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, PSN_CG_THREADS, red, 0};
     psn_update_body(ctx, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x);
 }
 __global__ void __launch_bounds__(PSN_CG_THREADS) psn_true_residual_kernel(const __grid_constant__ PsnCgArgs a) {
+    psn_pdl_enter();
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, PSN_CG_THREADS, red, 0};
     psn_true_residual_body(ctx, a, (long long)blockIdx.z, (int)blockIdx.y, (int)blockIdx.x);
 }
 __global__ void psn_state_init_kernel(const __grid_constant__ PsnCgArgs a, long long B) {
+    psn_pdl_enter();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) psn_state_init(a, b);
 }
 __global__ void psn_state_after_update_kernel(const __grid_constant__ PsnCgArgs a, long long B) {
+    psn_pdl_enter();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) psn_state_after_update(a, b);
 }
 __global__ void psn_state_after_check_kernel(const __grid_constant__ PsnCgArgs a, long long B, int* counter) {
+    psn_pdl_enter();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int active = 0;
     if (b < B) active = psn_state_after_check(a, b);
@@ -193,13 +214,16 @@ __global__ void psn_state_after_check_kernel(const __grid_constant__ PsnCgArgs a
 // The convergence counter goes to the host through mapped pinned memory, not through a D2H copy: a copy would
 // queue behind the multi-hundred-MB result copies of the previous chunk on the same copy engine and stall the solve.
 __global__ void psn_publish_counter_kernel(const int* counter, int* host_slot) {
+    psn_pdl_enter();
     *reinterpret_cast<volatile int*>(host_slot) = *counter;
     __threadfence_system();
 }
 __global__ void psn_zero_ints_kernel(int* p, int n) {
+    psn_pdl_enter();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0;
 }
 __global__ void psn_finalize_kernel(const PsnSampleState* state, long long B, int32_t* iters, double* relres, int32_t* status) {
+    psn_pdl_enter();
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const PsnSampleState st = state[b];
@@ -210,6 +234,7 @@ __global__ void psn_finalize_kernel(const PsnSampleState* state, long long B, in
 // Sub-domain epilogue of the STREAMED path (the resident kernel fuses it): window extract + stride-2
 // downsample of u, f, theta for one sample per blockIdx.y  (src/enhanced_data_generation.py:141-148)
 __global__ void psn_window_kernel(const __grid_constant__ PsnSolveArgs a, int n, const double* u) {
+    psn_pdl_enter();
     const long long b = blockIdx.y;
     const int s = a.sub, sc = (s + 1) >> 1;
     const int x0 = a.start_x[b], y0 = a.start_y[b];
@@ -420,6 +445,7 @@ struct Context {
     int serialize_solves = 0;
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
+    int pdl = 1;           // programmatic dependent launch between the kernels of the streamed solve
     int band0 = 0;         // rows per warp task on level 0 (0 = automatic)
     int band_target = 8;   // largest number of bands per column the band split considers (choose_bands)
     int dir_band = 64;     // rows per warp task of the direction kernel (1 halo row per band: short bands balance better); 0: as level 0
@@ -613,18 +639,35 @@ struct CudaBackend {
         if (e != cudaSuccess && err == cudaSuccess) err = e;
     }
     dim3 cg_grid(const PsnCgArgs& a, long long B) { return dim3(a.ntx, a.nty, (unsigned)B); }
+    // kernel launch with the programmatic-stream-serialization attribute (see psn_pdl_enter)
+    template <class... KA, class... A>
+    void launch(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, A&&... args) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = (g.pdl && !g.profiling) ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
     void zero_counters(int* c, int cnt) {
-        psn_zero_ints_kernel<<<1, 128, 0, s>>>(c, cnt);
+        launch(psn_zero_ints_kernel, dim3(1), dim3(128), 0, c, cnt);
         chk();
     }
     void prologue(const PsnCgArgs& a, long long B) {
         ProfScope p("prologue", s);
-        psn_prologue_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        launch(psn_prologue_kernel, dim3(cg_grid(a, B)), dim3(PSN_CG_THREADS), 0, a);
         chk();
     }
     void state_init(const PsnCgArgs& a, long long B) {
         ProfScope p("state", s);
-        psn_state_init_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B);
+        launch(psn_state_init_kernel, dim3((unsigned)((B + 127) / 128)), dim3(128), 0, a, B);
         chk();
     }
     template <int NU, bool POST, bool TMA, class TB, class TV>
@@ -640,7 +683,7 @@ struct CudaBackend {
                 attr_done = true;
             }
         }
-        psn_strip_kernel<NU, POST, TMA, TB, TV><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(plan, a, ntasks);
+        launch(psn_strip_kernel<NU, POST, TMA, TB, TV>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, plan, a, ntasks);
     }
     template <int NU, bool POST>
     void strip_launch_nu(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool tma, bool f32) {
@@ -667,7 +710,7 @@ struct CudaBackend {
             const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
             ProfScope p(t.level == 0 ? "tile_pre_l0" : "tile_pre_coarse", s);
             const size_t smem = (size_t)psn_tile_pre_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
-            psn_tile_pre_kernel<<<dim3(t.ntx, t.nty, (unsigned)B), PSN_TILE_THREADS, smem, s>>>(plan, t);
+            launch(psn_tile_pre_kernel, dim3(dim3(t.ntx, t.nty, (unsigned)B)), dim3(PSN_TILE_THREADS), smem, plan, t);
         }
         chk();
     }
@@ -679,7 +722,7 @@ struct CudaBackend {
             const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
             ProfScope p(t.level == 0 ? "tile_post_l0" : "tile_post_coarse", s);
             const size_t smem = (size_t)psn_tile_post_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
-            psn_tile_post_kernel<<<dim3(t.ntx, t.nty, (unsigned)B), PSN_TILE_THREADS, smem, s>>>(plan, t);
+            launch(psn_tile_post_kernel, dim3(dim3(t.ntx, t.nty, (unsigned)B)), dim3(PSN_TILE_THREADS), smem, plan, t);
         }
         chk();
     }
@@ -688,10 +731,10 @@ struct CudaBackend {
         const int l0 = cfg.ls;
         const size_t smem = ((size_t)2 * plan.lv[l0].size + psn_pool_doubles(plan, l0)) * sizeof(double);
         if (cfg.mode == 2 && cfg.vf32)
-            psn_coarse_vcycle_kernel<float><<<(unsigned)B, PSN_COARSE_THREADS, smem, s>>>(plan, l0, reinterpret_cast<const float*>(bg),
+            launch(psn_coarse_vcycle_kernel<float>, dim3((unsigned)B), dim3(PSN_COARSE_THREADS), smem, plan, l0, reinterpret_cast<const float*>(bg),
                                                                                          reinterpret_cast<float*>(ug), st);
         else
-            psn_coarse_vcycle_kernel<double><<<(unsigned)B, PSN_COARSE_THREADS, smem, s>>>(plan, l0, bg, ug, st);
+            launch(psn_coarse_vcycle_kernel<double>, dim3((unsigned)B), dim3(PSN_COARSE_THREADS), smem, plan, l0, bg, ug, st);
         chk();
     }
     void dir_apply(const PsnCgArgs& a, long long B) {
@@ -706,7 +749,7 @@ struct CudaBackend {
                     cudaFuncSetAttribute(psn_dir_strip_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     attr_done = true;
                 }
-                psn_dir_strip_kernel<true, float><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(a, ntasks);
+                launch(psn_dir_strip_kernel<true, float>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
             } else if (a.dir_mode == 2) {
                 const size_t smem = (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<2, double, double>::smem_bytes();
                 static bool attr_done = false;
@@ -714,37 +757,37 @@ struct CudaBackend {
                     cudaFuncSetAttribute(psn_dir_strip_kernel<true, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     attr_done = true;
                 }
-                psn_dir_strip_kernel<true, double><<<grid, PSN_STRIP_WARPS * 32, smem, s>>>(a, ntasks);
+                launch(psn_dir_strip_kernel<true, double>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
             } else {
-                psn_dir_strip_kernel<false, double><<<grid, PSN_STRIP_WARPS * 32, 0, s>>>(a, ntasks);
+                launch(psn_dir_strip_kernel<false, double>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), 0, a, ntasks);
             }
         } else {
-            psn_dir_apply_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+            launch(psn_dir_apply_kernel, dim3(cg_grid(a, B)), dim3(PSN_CG_THREADS), 0, a);
         }
         chk();
     }
     void update(const PsnCgArgs& a, long long B) {
         ProfScope p("update_norm", s);
-        psn_update_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        launch(psn_update_kernel, dim3(cg_grid(a, B)), dim3(PSN_CG_THREADS), 0, a);
         chk();
     }
     void true_residual(const PsnCgArgs& a, long long B) {
         ProfScope p("true_residual", s);
-        psn_true_residual_kernel<<<cg_grid(a, B), PSN_CG_THREADS, 0, s>>>(a);
+        launch(psn_true_residual_kernel, dim3(cg_grid(a, B)), dim3(PSN_CG_THREADS), 0, a);
         chk();
     }
     void state_after_update(const PsnCgArgs& a, long long B) {
         ProfScope p("state", s);
-        psn_state_after_update_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B);
+        launch(psn_state_after_update_kernel, dim3((unsigned)((B + 127) / 128)), dim3(128), 0, a, B);
         chk();
     }
     void state_after_check(const PsnCgArgs& a, long long B, int* counter) {
         ProfScope p("state", s);
-        psn_state_after_check_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a, B, counter);
+        launch(psn_state_after_check_kernel, dim3((unsigned)((B + 127) / 128)), dim3(128), 0, a, B, counter);
         chk();
     }
     void fetch_counter_async(const int* c, int it) {
-        psn_publish_counter_kernel<<<1, 1, 0, s>>>(c, slot->d_counters_map + it);
+        launch(psn_publish_counter_kernel, dim3(1), dim3(1), 0, c, slot->d_counters_map + it);
         chk();
         cudaError_t e = cudaEventRecord(slot->ev[it & 3], s);
         if (e != cudaSuccess && err == cudaSuccess) err = e;
@@ -1514,6 +1557,9 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;
+    } else if (!strcmp(name, "pdl")) {
+        if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "pdl must be 0 or 1");
+        g.pdl = (int)value;
     } else if (!strcmp(name, "host_edge_div")) {
         if (value < 1 || value > 64) return psn_fail(PSN_ERR_INVALID, "host_edge_div must be in 1..64");
         g.host_edge_div = (int)value;

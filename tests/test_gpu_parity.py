@@ -120,6 +120,31 @@ def test_float_stored_vcycle_is_scale_invariant(gpu_lib):
         assert O.rel_l2(us / scale, u) <= 1e-10
 
 
+@pytest.mark.parametrize("nu", [1, 3])
+@pytest.mark.parametrize("n,B", [(160, 300), (320, 5)])
+def test_other_sweep_counts_on_the_streamed_path(gpu_lib, nu, n, B):
+    """V(1,1) and V(3,3) cycles instantiate different strip geometries (halo widths, ring depths, float quads);
+    large and small batches exercise different band splits.  Same 1e-10 bar against the reference operator."""
+    rs = np.random.RandomState(10 * n + nu)
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    k = rs.uniform(0.5, 12.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    try:
+        gpu_lib.set_option("nu", nu)
+        u, info = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+        gpu_lib.set_option("vcycle_f32", 0)
+        u64, info64 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    finally:
+        gpu_lib.set_option("nu", 2)
+        gpu_lib.set_option("vcycle_f32", 1)
+    assert (info.status <= 1).all() and (info64.status <= 1).all()
+    assert (info.iters <= info64.iters + 1).all() and info.iters.max() <= (18 if nu == 1 else 9)
+    assert O.rel_l2(u, u64) <= 1e-11
+    for b in (0, B - 1):
+        assert O.rel_l2(u[b], O.solve_poisson(np.outer(sy[b], sx[b]), theta[b], n)) <= TOL
+
+
 def test_generate_dataset_matches_reference_fixture(gpu_lib):
     from superresolution_for_pdes_b200 import PoissonSolver
     gold = np.load(os.path.join(GOLDEN, "dataset_standard_seed0.npz"))
