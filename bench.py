@@ -350,7 +350,11 @@ def run_own(args):
     sample_iters = float(info.iters.sum())
     desc = _lib.describe(n)
     global KERNEL_BYTES
-    KERNEL_BYTES = KERNEL_BYTES_F32 if desc.get("vcycle_f32") else KERNEL_BYTES_F64
+    KERNEL_BYTES = {k: dict(v) for k, v in (KERNEL_BYTES_F32 if desc.get("vcycle_f32") else KERNEL_BYTES_F64).items()}
+    if desc.get("update_strip"):
+        # q = A p is recomputed by the update kernel from a 3-row window of p and never stored
+        KERNEL_BYTES["dir_apply_dot"]["own"] -= 8.0     # no q write
+        KERNEL_BYTES["update_norm"]["own"] = 40.0       # read p, x, r; write x, r
     roof = None
     kernels = {}
     if prof:
@@ -427,7 +431,8 @@ def run_own(args):
                        "solver": "MG-preconditioned CG, V(2,2) red-black GS, matrix-free 5-point zero-ghost stencil; CG vectors, "
                                  "operator, inner products and stopping rule in fp64" +
                                  ("; the V-cycle preconditioner stores and smooths in fp32 (same iteration count, solution "
-                                  "accuracy unchanged)" if desc.get("vcycle_f32") else "; V-cycle in fp64"),
+                                  "accuracy unchanged)" if desc.get("vcycle_f32") else "; V-cycle in fp64") +
+                                 ("; q = A p recomputed in the update kernel, never stored" if desc.get("update_strip") else ""),
                        "host_affinity": (f"{len(numa_cores)} cores local to the GPU" if numa_cores else "unbound"),
                        "path": "resident" if desc["resident"] else "streamed", "mean_iters": float(info.iters.mean()),
                        "max_iters": int(info.iters.max()),

@@ -158,6 +158,42 @@ psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     }
 }
 
+__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
+psn_update_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
+    psn_pdl_enter();
+    extern __shared__ __align__(128) unsigned char strip_smem[];
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
+    if (task >= ntasks) return;
+    const int per = a.upd_nstrips * a.upd_nbands;
+    const long long b = task / per;
+    const int rem = (int)(task - b * per);
+    const int band = rem / a.upd_nstrips, strip = rem - band * a.upd_nstrips;
+    const PsnWarp w{(int)(threadIdx.x & 31)};
+    typedef PsnTmaFeeder<2, double, double, double> Feeder;
+    Feeder fd;
+    fd.attach(strip_smem + (size_t)warp * Feeder::smem_bytes());
+    psn_update_strip_body(w, a, b, band, strip, fd);
+}
+
+__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
+psn_true_residual_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
+    psn_pdl_enter();
+    extern __shared__ __align__(128) unsigned char strip_smem[];
+    const int warp = threadIdx.x >> 5;
+    const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
+    if (task >= ntasks) return;
+    const int per = a.upd_nstrips * a.upd_nbands;
+    const long long b = task / per;
+    const int rem = (int)(task - b * per);
+    const int band = rem / a.upd_nstrips, strip = rem - band * a.upd_nstrips;
+    const PsnWarp w{(int)(threadIdx.x & 31)};
+    typedef PsnTmaFeeder<2, double, double> Feeder;
+    Feeder fd;
+    fd.attach(strip_smem + (size_t)warp * Feeder::smem_bytes());
+    psn_true_residual_strip_body(w, a, b, band, strip, fd);
+}
+
 template <class TV>
 __global__ void __launch_bounds__(PSN_COARSE_THREADS) psn_coarse_vcycle_kernel(const __grid_constant__ PsnPlan plan, int l0,
                                                                                const TV* bg, TV* ug,
@@ -445,6 +481,8 @@ struct Context {
     int serialize_solves = 0;
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
+    int upd_strip = 1;     // mode 2: strip update kernel that recomputes q = At p (q is never written to HBM)
+    int upd_band = 64;     // rows per warp task of the strip update kernel (0: twice the direction kernel's)
     int pdl = 1;           // programmatic dependent launch between the kernels of the streamed solve
     int band0 = 0;         // rows per warp task on level 0 (0 = automatic)
     int band_target = 8;   // largest number of bands per column the band split considers (choose_bands)
@@ -768,11 +806,39 @@ struct CudaBackend {
     }
     void update(const PsnCgArgs& a, long long B) {
         ProfScope p("update_norm", s);
+        if (a.upd_mode == 2) {
+            typedef PsnTmaFeeder<2, double, double, double> Feeder;
+            const long long ntasks = B * a.upd_nstrips * a.upd_nbands;
+            const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
+            const size_t smem = (size_t)PSN_STRIP_WARPS * Feeder::smem_bytes();
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(psn_update_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_done = true;
+            }
+            launch(psn_update_strip_kernel, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+            chk();
+            return;
+        }
         launch(psn_update_kernel, dim3(cg_grid(a, B)), dim3(PSN_CG_THREADS), 0, a);
         chk();
     }
     void true_residual(const PsnCgArgs& a, long long B) {
         ProfScope p("true_residual", s);
+        if (a.chk_mode == 2) {
+            typedef PsnTmaFeeder<2, double, double> Feeder;
+            const long long ntasks = B * a.upd_nstrips * a.upd_nbands;
+            const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
+            const size_t smem = (size_t)PSN_STRIP_WARPS * Feeder::smem_bytes();
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaFuncSetAttribute(psn_true_residual_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_done = true;
+            }
+            launch(psn_true_residual_strip_kernel, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+            chk();
+            return;
+        }
         launch(psn_true_residual_kernel, dim3(cg_grid(a, B)), dim3(PSN_CG_THREADS), 0, a);
         chk();
     }
@@ -883,6 +949,8 @@ void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
     }
     if (g.band0 >= 16 && cfg->ls >= 1) cfg->band[0] = (g.band0 + 1) & ~1;   // experiment knob
     cfg->dir_band = g.dir_band >= 16 ? ((g.dir_band + 1) & ~1) : cfg->band[0];
+    cfg->upd_band = g.upd_band >= 16 ? ((g.upd_band + 1) & ~1) : 0;
+    cfg->upd_strip = g.upd_strip;
 }
 
 size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) {
@@ -893,7 +961,7 @@ size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) 
         b += (l < cfg.ls ? 3 : 2) * m;
     }
     const int gx = (plan.n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (plan.n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
-    b += ((size_t)psn_rz_max(plan, cfg) + (size_t)psn_pq_max(plan.n) + 2 * (size_t)gx * gy) * sizeof(double) + sizeof(PsnSampleState);
+    b += ((size_t)psn_rz_max(plan, cfg) + 2 * (size_t)psn_pq_max(plan.n) + 2 * (size_t)gx * gy) * sizeof(double) + sizeof(PsnSampleState);
     return b + 4096 / 16;
 }
 
@@ -922,9 +990,10 @@ int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, lon
     ws->part_a = arena_take<double>(ar, (size_t)Bc * gx * gy);
     ws->part_pq = arena_take<double>(ar, (size_t)Bc * psn_pq_max(plan.n));
     ws->part_b = arena_take<double>(ar, (size_t)Bc * gx * gy);
+    ws->part_u = arena_take<double>(ar, (size_t)Bc * psn_pq_max(plan.n));
     ws->state = arena_take<PsnSampleState>(ar, Bc);
     ws->counters = arena_take<int>(ar, max_iter + 8);
-    ok = ok && ws->part_rz && ws->part_a && ws->part_pq && ws->part_b && ws->state && ws->counters;
+    ok = ok && ws->part_rz && ws->part_a && ws->part_pq && ws->part_b && ws->part_u && ws->state && ws->counters;
     return ok ? PSN_OK : psn_fail(PSN_ERR_NOMEM, "workspace arena exhausted");
 }
 
@@ -1557,6 +1626,12 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;
+    } else if (!strcmp(name, "upd_strip")) {
+        if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "upd_strip must be 0 or 1");
+        g.upd_strip = (int)value;
+    } else if (!strcmp(name, "upd_band")) {
+        if (value < 0 || value > 65536) return psn_fail(PSN_ERR_INVALID, "upd_band must be 0 (automatic) or >= 16");
+        g.upd_band = (int)value;
     } else if (!strcmp(name, "pdl")) {
         if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "pdl must be 0 or 1");
         g.pdl = (int)value;
@@ -1653,7 +1728,7 @@ int psn_describe(int n, int64_t* info) {
         sc.ls = stream_ls(plan); sc.TH = sc.TW = g.tile; sc.mode = g.vcycle_mode;
         if (sc.ls >= 1 && !psn_strip_ok(plan, sc.ls)) sc.mode = 0;
         sc.vf32 = (sc.mode == 2 && g.vcycle_f32 && sc.ls >= 1 && psn_vf32_ok(plan, sc.ls)) ? 1 : 0;
-        info[7] = sc.vf32;
+        info[7] = sc.vf32 | ((sc.mode == 2 && g.upd_strip && (plan.n & 1) == 0) ? 2 : 0);
         info[0] = 0;
         info[2] = sc.ls;
         info[3] = PSN_TILE_THREADS;

@@ -764,6 +764,10 @@ struct PsnCgArgs {
     int dir_mode;            // 0: 2-D tile kernel, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     int dir_band, dir_nstrips, dir_nbands;   // strip decomposition of the direction kernel
     int vf32;                // z is stored as float, scaled by psn_vscale(||r||^2) (PsnStreamCfg::vf32)
+    int upd_mode;            // 0: 2-D tile update that reads q; 2: strip update that recomputes q from p (q is never stored)
+    int upd_band, upd_nstrips, upd_nbands;   // strip decomposition of the update kernel
+    int chk_mode;            // 0: 2-D tile true-residual kernel; 2: strip form (sine-factor forcing + theta on the solve grid)
+    double* part_u;          // [B, upd_nstrips*upd_nbands] ||r||^2 partials of the strip update / strip true-residual kernels
     double* part_b;          // [B, ntx*nty]   ||r||^2 partials
     PsnSampleState* state;   // [B]
     double rtol;
@@ -927,8 +931,9 @@ PSN_FN void psn_state_after_update(const PsnCgArgs& a, long long b) {
     PsnSampleState st = a.state[b];
     if (st.phase != PSN_PHASE_ITER) return;
     double rr = 0.0;
-    const double* pb = a.part_b + b * (long long)(a.ntx * a.nty);
-    for (int k = 0; k < a.ntx * a.nty; ++k) rr += pb[k];
+    const int cnt = a.upd_mode ? a.upd_nstrips * a.upd_nbands : a.ntx * a.nty;
+    const double* pb = a.upd_mode ? a.part_u + b * (long long)cnt : a.part_b + b * (long long)cnt;
+    for (int k = 0; k < cnt; ++k) rr += pb[k];
     st.rr = rr;
     st.rz_old = st.rz;
     st.restart = 0;
@@ -947,8 +952,9 @@ PSN_FN int psn_state_after_check(const PsnCgArgs& a, long long b) {
     PsnSampleState st = a.state[b];
     if (st.phase == PSN_PHASE_CHECK) {
         double rt = 0.0;
-        const double* pb = a.part_b + b * (long long)(a.ntx * a.nty);
-        for (int k = 0; k < a.ntx * a.nty; ++k) rt += pb[k];
+        const int cnt = a.chk_mode ? a.upd_nstrips * a.upd_nbands : a.ntx * a.nty;
+        const double* pb = a.chk_mode ? a.part_u + b * (long long)cnt : a.part_b + b * (long long)cnt;
+        for (int k = 0; k < cnt; ++k) rt += pb[k];
         st.rr = rt;
         const double tol2 = a.rtol * a.rtol * st.bb;
         if (rt <= tol2) {

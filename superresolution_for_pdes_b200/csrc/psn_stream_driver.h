@@ -18,6 +18,8 @@ struct PsnStreamCfg {
                   //               2 = warp strips fed by TMA bulk copies through a shared-memory ring
     int band[PSN_MAX_LEVELS];  // mode 1: output rows per warp task on each streamed level (even)
     int dir_band; // rows per warp task of the direction kernel (0: band[0])
+    int upd_band; // rows per warp task of the strip update kernel (0: 2 * dir_band)
+    int upd_strip; // mode 2 only: the update kernel recomputes q = At p in strips and q is never stored
     int vf32;     // mode 2 only: V-cycle intermediates (iterates, restricted residuals, z) are STORED as float; all
                   // arithmetic, the CG vectors x r p q and every inner product stay fp64.  The preconditioner only has
                   // to be an approximate inverse, so CG converges in the same number of iterations (tests), while the
@@ -77,6 +79,7 @@ struct PsnStreamWs {
     double* part_a;
     double* part_pq;
     double* part_b;
+    double* part_u;              // ||r||^2 partials of the strip update kernel
     PsnSampleState* state;
     int* counters;               // [max_iter + 8] active-sample count per outer iteration
 };
@@ -138,6 +141,12 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.dir_nstrips = (n + psn_dir_use(cg.vf32) - 1) / psn_dir_use(cg.vf32);
     cg.dir_nbands = psn_band_count(n, cg.dir_band);
     cg.npq = cg.dir_mode ? cg.dir_nstrips * cg.dir_nbands : cg.ntx * cg.nty;
+    cg.upd_mode = (cg.dir_mode == 2 && cfg.upd_strip) ? 2 : 0;
+    cg.upd_band = cfg.upd_band >= 16 ? cfg.upd_band : 2 * cg.dir_band;
+    cg.upd_nstrips = (n + PSN_DIR_USE - 1) / PSN_DIR_USE;
+    cg.upd_nbands = psn_band_count(n, cg.upd_band);
+    cg.part_u = ws.part_u;
+    cg.chk_mode = (cg.upd_mode == 2 && rhs.sx && rhs.theta && rhs.step == 1 && rhs.mn == n) ? 2 : 0;
     cg.part_b = ws.part_b;
     cg.state = ws.state;
     cg.rtol = rtol;

@@ -22,6 +22,7 @@ struct PsnWarp {
 PSN_FN wd w_bcast(double s) { return s; }
 PSN_FN wi w_lane(const PsnWarp& w) { return w.lane; }
 PSN_FN wd w_sel(wb c, wd a, wd b) { return c ? a : b; }
+PSN_FN wd w_div(wd a, wd b) { return a / b; }
 // value of the previous / next lane; the edge lane receives 0
 PSN_FN wd w_up(const PsnWarp& w, wd v) {
     const wd r = __shfl_up_sync(0xffffffffu, v, 1);
@@ -191,6 +192,7 @@ inline wb operator>=(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] >= 
 inline wb operator<(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] < b; return r; }
 inline wb operator==(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] == b; return r; }
 inline wb operator&&(const wb& a, const wb& b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] && b.v[l_]; return r; }
+template <class S> inline wvt<S> w_div(const wvt<S>& a, const wvt<S>& b) { wvt<S> r; PSN_W_FOR r.v[l_] = a.v[l_] / b.v[l_]; return r; }
 template <class S> inline wvt<S> w_sel(const wb& c, const wvt<S>& a, const wvt<S>& b) { wvt<S> r; PSN_W_FOR r.v[l_] = c.v[l_] ? a.v[l_] : b.v[l_]; return r; }
 inline wd w_up(const PsnWarp&, const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 0 ? 0.0 : v.v[l_ - 1]; return r; }
 inline wd w_down(const PsnWarp&, const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 31 ? 0.0 : v.v[l_ + 1]; return r; }
@@ -392,20 +394,25 @@ struct PsnElemOr<void> {
     static constexpr int narr = 0;
 };
 
-// T0 / T1: element types of the one or two streamed arrays (T1 = void: one array)
-template <int NU, class T0, class T1 = void>
+// T0 / T1 / T2: element types of the one to three streamed arrays (void: absent)
+template <int NU, class T0, class T1 = void, class T2 = void>
 struct PsnTmaFeeder {
     typedef typename PsnElemOr<T1>::type U1;
+    typedef typename PsnElemOr<T2>::type U2;
     typedef typename PsnWV<T0>::type V0;   // register type the rows are delivered in: the array's own precision
     typedef typename PsnWV<U1>::type V1;
-    static constexpr int NARR = 1 + PsnElemOr<T1>::narr;
+    typedef typename PsnWV<U2>::type V2;
+    static constexpr int NARR = 1 + PsnElemOr<T1>::narr + PsnElemOr<T2>::narr;
     static constexpr int W = 2 * NU + 2, D = W - 1;
-    static constexpr int RING_BYTES = W * PSN_STRIP_COLS * ((int)sizeof(T0) + PsnElemOr<T1>::bytes);
+    static constexpr int ROW_BYTES = (int)sizeof(T0) + PsnElemOr<T1>::bytes + PsnElemOr<T2>::bytes;
+    static constexpr int RING_BYTES = W * PSN_STRIP_COLS * ROW_BYTES;
     T0* ring0;                   // [W][PSN_STRIP_COLS], shared memory of this warp
     U1* ring1;
+    U2* ring2;
     unsigned long long* bar;     // [W]
     const T0* base0;
     const U1* base1;
+    const U2* base2;
     int n, tload, ts;
     int cA, cB, c0;              // in-domain column range [cA, cB) of the strip, strip origin
 #if defined(__CUDACC__)
@@ -415,40 +422,69 @@ struct PsnTmaFeeder {
     PSN_FN void attach(unsigned char* mem) {
         ring0 = reinterpret_cast<T0*>(mem);
         ring1 = reinterpret_cast<U1*>(mem + (size_t)W * PSN_STRIP_COLS * sizeof(T0));
+        ring2 = reinterpret_cast<U2*>(mem + (size_t)W * PSN_STRIP_COLS * (sizeof(T0) + PsnElemOr<T1>::bytes));
         bar = reinterpret_cast<unsigned long long*>(mem + RING_BYTES);
         base1 = nullptr;
+        base2 = nullptr;
     }
     PSN_FN void set_base0(const T0* p) { base0 = p; }
     PSN_FN void set_base1(const U1* p) { base1 = p; }
+    PSN_FN void set_base2(const U2* p) { base2 = p; }
     PSN_FN void issue(const PsnWarp& w, int row, int slot) {
         const unsigned cnt = (unsigned)(cB - cA);
-        w_bar_expect(w, bar + slot, cnt * (unsigned)(sizeof(T0) + PsnElemOr<T1>::bytes));
+        w_bar_expect(w, bar + slot, cnt * (unsigned)ROW_BYTES);
         w_bulk_g2s(w, ring0 + slot * PSN_STRIP_COLS + (cA - c0), base0 + (long long)row * n + cA, cnt * (unsigned)sizeof(T0), bar + slot);
-        if (NARR == 2)
+        if (NARR >= 2)
             w_bulk_g2s(w, ring1 + slot * PSN_STRIP_COLS + (cA - c0), base1 + (long long)row * n + cA, cnt * (unsigned)sizeof(U1), bar + slot);
+        if (NARR >= 3)
+            w_bulk_g2s(w, ring2 + slot * PSN_STRIP_COLS + (cA - c0), base2 + (long long)row * n + cA, cnt * (unsigned)sizeof(U2), bar + slot);
     }
     PSN_FN void prime(const PsnWarp& w, int ts_) {
         ts = ts_;
         w_zero_smem(w, ring0, W * PSN_STRIP_COLS);   // out-of-domain columns stay zero
-        if (NARR == 2) w_zero_smem(w, ring1, W * PSN_STRIP_COLS);
+        if (NARR >= 2) w_zero_smem(w, ring1, W * PSN_STRIP_COLS);
+        if (NARR >= 3) w_zero_smem(w, ring2, W * PSN_STRIP_COLS);
         w_bar_init(w, bar, W);
         for (int k = 0; k < D; ++k)
             if (ts + k <= tload) issue(w, ts + k, k);
     }
+    // refill the slot of the previous row, then wait for row tc; returns false (rows read as zero) beyond tload
     template <bool FAST>
-    PSN_FN void fetch(const PsnWarp& w, int tt, int tc, int par, V0 (&o0)[4], V1 (&o1)[4]) {
+    PSN_FN bool advance(const PsnWarp& w, int tt, int tc, int par) {
         // every lane has finished reading the slot of row tc-1 (previous time step): refill it with row tc+D
         w_sync(w);
         if (FAST || tc + D <= tload) issue(w, tc + D, (tt + W - 1) % W);
         if (FAST || tc <= tload) {
             w_bar_wait(bar + tt, (unsigned)par);
+            return true;
+        }
+        return false;
+    }
+    template <bool FAST>
+    PSN_FN void fetch(const PsnWarp& w, int tt, int tc, int par, V0 (&o0)[4], V1 (&o1)[4]) {
+        if (advance<FAST>(w, tt, tc, par)) {
             w_lds4(w, ring0 + tt * PSN_STRIP_COLS, o0);
-            if (NARR == 2) w_lds4(w, ring1 + tt * PSN_STRIP_COLS, o1);
+            if (NARR >= 2) w_lds4(w, ring1 + tt * PSN_STRIP_COLS, o1);
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 o0[e] = w_bcastT<T0>(0.0);
-                if (NARR == 2) o1[e] = w_bcastT<U1>(0.0);
+                if (NARR >= 2) o1[e] = w_bcastT<U1>(0.0);
+            }
+        }
+    }
+    template <bool FAST>
+    PSN_FN void fetch3(const PsnWarp& w, int tt, int tc, int par, V0 (&o0)[4], V1 (&o1)[4], V2 (&o2)[4]) {
+        if (advance<FAST>(w, tt, tc, par)) {
+            w_lds4(w, ring0 + tt * PSN_STRIP_COLS, o0);
+            w_lds4(w, ring1 + tt * PSN_STRIP_COLS, o1);
+            w_lds4(w, ring2 + tt * PSN_STRIP_COLS, o2);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                o0[e] = w_bcastT<T0>(0.0);
+                o1[e] = w_bcastT<U1>(0.0);
+                o2[e] = w_bcastT<U2>(0.0);
             }
         }
     }
@@ -470,8 +506,8 @@ PSN_FN void psn_feeder_geom(PsnRegFeeder<NU, NARR>& fd, const wi& col0, const wb
     fd.mp[0] = mp[0];
     fd.mp[1] = mp[1];
 }
-template <int NU, class T0, class T1>
-PSN_FN void psn_feeder_geom(PsnTmaFeeder<NU, T0, T1>& fd, const wi&, const wb (&)[2], int c0, int n) {
+template <int NU, class T0, class T1, class T2>
+PSN_FN void psn_feeder_geom(PsnTmaFeeder<NU, T0, T1, T2>& fd, const wi&, const wb (&)[2], int c0, int n) {
     fd.c0 = c0;
     fd.cA = psn_imax(c0, 0);
     fd.cB = psn_imin(c0 + PSN_STRIP_COLS, n);
@@ -928,9 +964,11 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
                 q[1] = 4.0 * pn[k1][1] - ((pn[k0][1] + pn[k2][1]) + (pn[k1][0] + pn[k1][2]));
                 q[2] = 4.0 * pn[k1][2] - ((pn[k0][2] + pn[k2][2]) + (pn[k1][1] + pn[k1][3]));
                 q[3] = 4.0 * pn[k1][3] - ((pn[k0][3] + pn[k2][3]) + (pn[k1][2] + dnv));
-                double* rowq = qg + (long long)r * n;
-                w_stp(rowq, col0, so[0], q[0], q[1]);
-                w_stp(rowq, col2, so[1], q[2], q[3]);
+                if (a.upd_mode == 0) {   // the strip update kernel recomputes q = At p from p instead of reading it back
+                    double* rowq = qg + (long long)r * n;
+                    w_stp(rowq, col0, so[0], q[0], q[1]);
+                    w_stp(rowq, col2, so[1], q[2], q[3]);
+                }
                 dot = dot + w_sel(so[0], pn[k1][0] * q[0] + pn[k1][1] * q[1], zero) + w_sel(so[1], pn[k1][2] * q[2] + pn[k1][3] * q[3], zero);
             }
         }
@@ -940,4 +978,182 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
         a.part_pq[b * (long long)a.npq + (long long)band * a.dir_nstrips + strip] = s;
         if (band == 0 && strip == 0) a.state[b].rz = rz;
     }
+}
+
+
+// ----------------------------------------------------------------------------- CG update, strip form
+// x += alpha p;  r -= alpha q with q = At p RECOMPUTED from a 3-row window of p (identical expression to the direction
+// kernel, so r is bit-identical to the stored-q variant);  partial ||r||^2.  Not storing q saves its 8-byte write in
+// the direction kernel and its 8-byte read here: 76 -> 60 bytes per node and iteration for the two kernels together.
+// One warp per 128-column strip (2 halo columns for the stencil), p / x / r rows through a 3-array TMA ring.
+template <class Feeder>
+PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b, int band, int strip, Feeder& fd) {
+    const PsnSampleState st = a.state[b];
+    if (st.phase != PSN_PHASE_ITER) return;
+    constexpr int W = Feeder::W;
+    static_assert(W % 3 == 0, "the 3-row window rotates inside one ring period");
+    const double pq = psn_warp_sum_partials(w, a.part_pq + b * (long long)a.npq, a.npq);
+    const wd alpha = w_bcast((pq > 0.0) ? st.rz / pq : 0.0);
+    const int n = a.n, last = n - 1;
+    const int a0 = strip * PSN_DIR_USE, a1 = psn_imin(a0 + PSN_DIR_USE, n);
+    const int c0 = a0 - 2;
+    const int i0 = band * a.upd_band, i1 = psn_imin(i0 + a.upd_band, n);
+    const wi col0 = w_lane(w) * 4 + c0;
+    const wi col2 = col0 + 2;
+    const wb mp[2] = {(col0 >= 0) && (col0 < n), (col2 >= 0) && (col2 < n)};
+    const wb so[2] = {mp[0] && (col0 >= a0) && (col0 < a1), mp[1] && (col2 >= a0) && (col2 < a1)};
+    const long long base = b * (long long)n * n;
+    const wd zero = w_bcast(0.0);
+
+    const int ts = psn_imax(i0 - 1, 0);
+    const int tload = psn_imin(i1, last);
+    const int tend = i1;   // row r is finished at time r + 1; row n reads as zero
+    fd.set_base0(a.p_new + base);
+    fd.set_base1(a.x + base);
+    fd.set_base2(a.r + base);
+    fd.n = n;
+    fd.tload = tload;
+    psn_feeder_geom(fd, col0, mp, c0, n);
+    fd.prime(w, ts);
+
+    wd pn[3][4], xp[4], rp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        xp[e] = rp[e] = zero;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pn[k][e] = zero;
+    }
+    wd acc = zero;
+    double* xg = a.x + base;
+    double* rg = a.r + base;
+
+    for (int t = ts; t <= tend; t += W) {
+        const int par = ((t - ts) / W) & 1;
+#pragma unroll
+        for (int tt = 0; tt < W; ++tt) {
+            const int tc = t + tt;
+            if (tc > tend) break;
+            const int k0 = tt % 3, k1 = (tt + 2) % 3, k2 = (tt + 1) % 3;   // rows tc, tc-1, tc-2
+            wd xc[4], rc[4];
+            fd.template fetch3<false>(w, tt, tc, par, pn[k0], xc, rc);
+            const int r = tc - 1;
+            if (r >= i0 && r < i1) {
+                const wd upv = w_up_raw(pn[k1][3]);
+                const wd dnv = w_down_raw(pn[k1][0]);
+                wd q[4];
+                q[0] = 4.0 * pn[k1][0] - ((pn[k0][0] + pn[k2][0]) + (upv + pn[k1][1]));
+                q[1] = 4.0 * pn[k1][1] - ((pn[k0][1] + pn[k2][1]) + (pn[k1][0] + pn[k1][2]));
+                q[2] = 4.0 * pn[k1][2] - ((pn[k0][2] + pn[k2][2]) + (pn[k1][1] + pn[k1][3]));
+                q[3] = 4.0 * pn[k1][3] - ((pn[k0][3] + pn[k2][3]) + (pn[k1][2] + dnv));
+                wd xn[4], rn[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    xn[e] = xp[e] + alpha * pn[k1][e];
+                    rn[e] = rp[e] - alpha * q[e];
+                }
+                double* rowx = xg + (long long)r * n;
+                double* rowr = rg + (long long)r * n;
+                w_stp(rowx, col0, so[0], xn[0], xn[1]);
+                w_stp(rowx, col2, so[1], xn[2], xn[3]);
+                w_stp(rowr, col0, so[0], rn[0], rn[1]);
+                w_stp(rowr, col2, so[1], rn[2], rn[3]);
+                acc = acc + w_sel(so[0], rn[0] * rn[0] + rn[1] * rn[1], zero) + w_sel(so[1], rn[2] * rn[2] + rn[3] * rn[3], zero);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                xp[e] = xc[e];
+                rp[e] = rc[e];
+            }
+        }
+    }
+    const double s = w_sum(acc);
+    if (w_lane0(w)) {
+        a.part_u[b * (long long)(a.upd_nstrips * a.upd_nbands) + (long long)band * a.upd_nstrips + strip] = s;
+        if (band == 0 && strip == 0) a.state[b].pq = pq;
+    }
+}
+
+
+// ----------------------------------------------------------------------------- true residual, strip form
+// Samples in PSN_PHASE_CHECK: r = bt - At x with bt = -(sy_i sx_j / theta_ij) h^2 (the same operations as psn_rhs, so
+// r is bit-identical to the 2-D tile kernel); partial ||r||^2.  Only for the product's standard call form: sine
+// factors + theta on the solve grid itself (no master-field stride); other forcings keep the tile kernel.
+template <class Feeder>
+PSN_FN void psn_true_residual_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b, int band, int strip, Feeder& fd) {
+    if (a.state[b].phase != PSN_PHASE_CHECK) return;
+    constexpr int W = Feeder::W;
+    static_assert(W % 3 == 0, "the 3-row window rotates inside one ring period");
+    const int n = a.n, last = n - 1;
+    const int a0 = strip * PSN_DIR_USE, a1 = psn_imin(a0 + PSN_DIR_USE, n);
+    const int c0 = a0 - 2;
+    const int i0 = band * a.upd_band, i1 = psn_imin(i0 + a.upd_band, n);
+    const wi col0 = w_lane(w) * 4 + c0;
+    const wi col2 = col0 + 2;
+    const wb mp[2] = {(col0 >= 0) && (col0 < n), (col2 >= 0) && (col2 < n)};
+    const wb so[2] = {mp[0] && (col0 >= a0) && (col0 < a1), mp[1] && (col2 >= a0) && (col2 < a1)};
+    const long long base = b * (long long)n * n;
+    const wd zero = w_bcast(0.0);
+    const wd h2 = w_bcast(a.h2);
+    wd sxv[4];
+    w_ldp(a.rhs.sx + b * (long long)n, col0, mp[0], sxv[0], sxv[1]);
+    w_ldp(a.rhs.sx + b * (long long)n, col2, mp[1], sxv[2], sxv[3]);
+    const double* syp = a.rhs.sy + b * (long long)n;
+
+    const int ts = psn_imax(i0 - 1, 0);
+    const int tload = psn_imin(i1, last);
+    const int tend = i1;
+    fd.set_base0(a.x + base);
+    fd.set_base1(a.rhs.theta + base);
+    fd.n = n;
+    fd.tload = tload;
+    psn_feeder_geom(fd, col0, mp, c0, n);
+    fd.prime(w, ts);
+
+    wd xw[3][4], thp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        thp[e] = w_bcast(1.0);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) xw[k][e] = zero;
+    }
+    wd acc = zero;
+    double* rg = a.r + base;
+
+    for (int t = ts; t <= tend; t += W) {
+        const int par = ((t - ts) / W) & 1;
+#pragma unroll
+        for (int tt = 0; tt < W; ++tt) {
+            const int tc = t + tt;
+            if (tc > tend) break;
+            const int k0 = tt % 3, k1 = (tt + 2) % 3, k2 = (tt + 1) % 3;   // rows tc, tc-1, tc-2
+            wd thc[4];
+            fd.template fetch<false>(w, tt, tc, par, xw[k0], thc);
+            const int r = tc - 1;
+            if (r >= i0 && r < i1) {
+                const wd upv = w_up_raw(xw[k1][3]);
+                const wd dnv = w_down_raw(xw[k1][0]);
+                wd ax[4];
+                ax[0] = 4.0 * xw[k1][0] - ((upv + xw[k1][1]) + (xw[k2][0] + xw[k0][0]));
+                ax[1] = 4.0 * xw[k1][1] - ((xw[k1][0] + xw[k1][2]) + (xw[k2][1] + xw[k0][1]));
+                ax[2] = 4.0 * xw[k1][2] - ((xw[k1][1] + xw[k1][3]) + (xw[k2][2] + xw[k0][2]));
+                ax[3] = 4.0 * xw[k1][3] - ((xw[k1][2] + dnv) + (xw[k2][3] + xw[k0][3]));
+                const wd syr = w_bcast(syp[r]);
+                wd rv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    // out-of-domain lanes divide 0 by 1 (thp is 1 there: the ring's un-copied columns are zero, see below)
+                    const wd f = w_div(syr * sxv[e], thp[e]);
+                    rv[e] = (zero - (f * h2)) - ax[e];
+                }
+                double* rowr = rg + (long long)r * n;
+                w_stp(rowr, col0, so[0], rv[0], rv[1]);
+                w_stp(rowr, col2, so[1], rv[2], rv[3]);
+                acc = acc + w_sel(so[0], rv[0] * rv[0] + rv[1] * rv[1], zero) + w_sel(so[1], rv[2] * rv[2] + rv[3] * rv[3], zero);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) thp[e] = w_sel((e < 2) ? mp[0] : mp[1], thc[e], w_bcast(1.0));
+        }
+    }
+    const double s = w_sum(acc);
+    if (w_lane0(w)) a.part_u[b * (long long)(a.upd_nstrips * a.upd_nbands) + (long long)band * a.upd_nstrips + strip] = s;
 }

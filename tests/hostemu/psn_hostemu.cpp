@@ -118,12 +118,38 @@ struct HostBackend {
                 for (int tx = 0; tx < a.ntx; ++tx) psn_dir_apply_body(ctx, a, b, ty, tx);
     }
     void update(const PsnCgArgs& a, long long B) {
+        if (a.upd_mode == 2) {
+            typedef PsnTmaFeeder<2, double, double, double> Feeder;
+            PsnWarp w;
+            std::vector<unsigned char> ring(Feeder::smem_bytes() + 256);
+            for (long long b = 0; b < B; ++b)
+                for (int band = 0; band < a.upd_nbands; ++band)
+                    for (int strip = 0; strip < a.upd_nstrips; ++strip) {
+                        std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
+                        Feeder fd; fd.attach(ring.data());
+                        psn_update_strip_body(w, a, b, band, strip, fd);
+                    }
+            return;
+        }
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
             for (int ty = 0; ty < a.nty; ++ty)
                 for (int tx = 0; tx < a.ntx; ++tx) psn_update_body(ctx, a, b, ty, tx);
     }
     void true_residual(const PsnCgArgs& a, long long B) {
+        if (a.chk_mode == 2) {
+            typedef PsnTmaFeeder<2, double, double> Feeder;
+            PsnWarp w;
+            std::vector<unsigned char> ring(Feeder::smem_bytes() + 256);
+            for (long long b = 0; b < B; ++b)
+                for (int band = 0; band < a.upd_nbands; ++band)
+                    for (int strip = 0; strip < a.upd_nstrips; ++strip) {
+                        std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
+                        Feeder fd; fd.attach(ring.data());
+                        psn_true_residual_strip_body(w, a, b, band, strip, fd);
+                    }
+            return;
+        }
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
             for (int ty = 0; ty < a.nty; ++ty)
@@ -191,6 +217,8 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? (mode == 3 ? 2 : mode) : 0;
     cfg.vf32 = (mode == 3 && cfg.mode == 2 && psn_vf32_ok(plan, ls)) ? 1 : 0;
     cfg.dir_band = 0;
+    cfg.upd_band = 0;
+    cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
     if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
@@ -210,6 +238,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     ws.part_a = alloc((size_t)B * gx * gy);
     ws.part_pq = alloc((size_t)B * psn_pq_max(n));
     ws.part_b = alloc((size_t)B * gx * gy);
+    ws.part_u = alloc((size_t)B * psn_pq_max(n));
     std::vector<PsnSampleState> st(B);
     ws.state = st.data();
     std::vector<int> counters(max_iter + 8);
@@ -252,6 +281,8 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? (mode == 3 ? 2 : mode) : 0;
     cfg.vf32 = (mode == 3 && cfg.mode == 2 && psn_vf32_ok(plan, ls)) ? 1 : 0;
     cfg.dir_band = 0;
+    cfg.upd_band = 0;
+    cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
     if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     std::vector<std::vector<double>> keep;

@@ -94,7 +94,8 @@ def test_tile_and_strip_vcycles_agree(gpu_lib, n, B):
         gpu_lib.set_option("vcycle_f32", 1)
     assert (i0.status <= 1).all() and (i1.status <= 1).all() and (i2.status <= 1).all()
     assert O.rel_l2(u1, u0) <= 1e-12
-    assert np.array_equal(u1, u2)     # register-fed and TMA-fed strips do identical arithmetic
+    assert O.rel_l2(u1, u2) <= 1e-13  # register-fed and TMA-fed strips do identical V-cycle arithmetic (the TMA mode's
+    #                                   strip update kernel sums its partial dot products in another order)
     assert O.rel_l2(u1[0], O.solve_poisson(np.outer(sy[0], sx[0]), theta[0], n)) <= TOL
     # default configuration: V-cycle intermediates stored as float where every streamed level is a multiple of 4
     # (160, 320: yes; 200 -> 100 -> 50: no, stays fp64).  Same iteration counts, same accuracy bar.
