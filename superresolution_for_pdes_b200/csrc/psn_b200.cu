@@ -135,7 +135,7 @@ psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ P
     }
 }
 
-template <bool TMA, class TZ>
+template <bool TMA, class TZ, class TP>
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
 psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     psn_pdl_enter();
@@ -149,15 +149,16 @@ psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     const int band = rem / a.dir_nstrips, strip = rem - band * a.dir_nstrips;
     const PsnWarp w{(int)(threadIdx.x & 31)};
     if constexpr (TMA) {
-        PsnTmaFeeder<2, TZ, double> fd;
-        fd.attach(strip_smem + (size_t)warp * PsnTmaFeeder<2, TZ, double>::smem_bytes());
-        psn_dir_strip_body<TZ>(w, a, b, band, strip, fd);
+        PsnTmaFeeder<2, TZ, TP> fd;
+        fd.attach(strip_smem + (size_t)warp * PsnTmaFeeder<2, TZ, TP>::smem_bytes());
+        psn_dir_strip_body<TZ, TP>(w, a, b, band, strip, fd);
     } else {
         PsnRegFeeder<2, 2> fd;
-        psn_dir_strip_body<TZ>(w, a, b, band, strip, fd);
+        psn_dir_strip_body<TZ, TP>(w, a, b, band, strip, fd);
     }
 }
 
+template <class TP>
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
 psn_update_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     psn_pdl_enter();
@@ -170,10 +171,10 @@ psn_update_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     const int rem = (int)(task - b * per);
     const int band = rem / a.upd_nstrips, strip = rem - band * a.upd_nstrips;
     const PsnWarp w{(int)(threadIdx.x & 31)};
-    typedef PsnTmaFeeder<2, double, double, double> Feeder;
+    typedef PsnTmaFeeder<2, TP, double, double> Feeder;
     Feeder fd;
     fd.attach(strip_smem + (size_t)warp * Feeder::smem_bytes());
-    psn_update_strip_body(w, a, b, band, strip, fd);
+    psn_update_strip_body<TP>(w, a, b, band, strip, fd);
 }
 
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
@@ -481,6 +482,7 @@ struct Context {
     int serialize_solves = 0;
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
+    int p_f32 = 1;         // with vcycle_f32 and upd_strip: the search direction is stored as (scaled) float too
     int upd_strip = 1;     // mode 2: strip update kernel that recomputes q = At p (q is never written to HBM)
     int upd_band = 64;     // rows per warp task of the strip update kernel (0: twice the direction kernel's)
     int pdl = 1;           // programmatic dependent launch between the kernels of the streamed solve
@@ -775,29 +777,40 @@ struct CudaBackend {
             launch(psn_coarse_vcycle_kernel<double>, dim3((unsigned)B), dim3(PSN_COARSE_THREADS), smem, plan, l0, bg, ug, st);
         chk();
     }
+    template <bool TMA, class TZ, class TP>
+    void dir_launch(const PsnCgArgs& a, unsigned grid, long long ntasks) {
+        const size_t smem = (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<2, TZ, TP>::smem_bytes();
+        static bool attr_done = false;   // one flag per template instantiation
+        if (!attr_done) {
+            cudaFuncSetAttribute(psn_dir_strip_kernel<TMA, TZ, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        launch(psn_dir_strip_kernel<TMA, TZ, TP>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+    }
+    template <class TP>
+    void update_launch(const PsnCgArgs& a, unsigned grid, long long ntasks) {
+        typedef PsnTmaFeeder<2, TP, double, double> Feeder;
+        const size_t smem = (size_t)PSN_STRIP_WARPS * Feeder::smem_bytes();
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(psn_update_strip_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        launch(psn_update_strip_kernel<TP>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+    }
     void dir_apply(const PsnCgArgs& a, long long B) {
         ProfScope p("dir_apply_dot", s);
         if (a.dir_mode >= 1) {
             const long long ntasks = B * a.dir_nstrips * a.dir_nbands;
             const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
-            if (a.dir_mode == 2 && a.vf32) {
-                const size_t smem = (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<2, float, double>::smem_bytes();
-                static bool attr_done = false;
-                if (!attr_done) {
-                    cudaFuncSetAttribute(psn_dir_strip_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    attr_done = true;
-                }
-                launch(psn_dir_strip_kernel<true, float>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+            if (a.dir_mode == 2 && a.vf32 && a.pf32) {
+                dir_launch<true, float, float>(a, grid, ntasks);
+            } else if (a.dir_mode == 2 && a.vf32) {
+                dir_launch<true, float, double>(a, grid, ntasks);
             } else if (a.dir_mode == 2) {
-                const size_t smem = (size_t)PSN_STRIP_WARPS * PsnTmaFeeder<2, double, double>::smem_bytes();
-                static bool attr_done = false;
-                if (!attr_done) {
-                    cudaFuncSetAttribute(psn_dir_strip_kernel<true, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    attr_done = true;
-                }
-                launch(psn_dir_strip_kernel<true, double>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+                dir_launch<true, double, double>(a, grid, ntasks);
             } else {
-                launch(psn_dir_strip_kernel<false, double>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), 0, a, ntasks);
+                launch(psn_dir_strip_kernel<false, double, double>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), 0, a, ntasks);
             }
         } else {
             launch(psn_dir_apply_kernel, dim3(cg_grid(a, B)), dim3(PSN_CG_THREADS), 0, a);
@@ -807,16 +820,10 @@ struct CudaBackend {
     void update(const PsnCgArgs& a, long long B) {
         ProfScope p("update_norm", s);
         if (a.upd_mode == 2) {
-            typedef PsnTmaFeeder<2, double, double, double> Feeder;
             const long long ntasks = B * a.upd_nstrips * a.upd_nbands;
             const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
-            const size_t smem = (size_t)PSN_STRIP_WARPS * Feeder::smem_bytes();
-            static bool attr_done = false;
-            if (!attr_done) {
-                cudaFuncSetAttribute(psn_update_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_done = true;
-            }
-            launch(psn_update_strip_kernel, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+            if (a.pf32) update_launch<float>(a, grid, ntasks);
+            else update_launch<double>(a, grid, ntasks);
             chk();
             return;
         }
@@ -951,6 +958,7 @@ void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
     cfg->dir_band = g.dir_band >= 16 ? ((g.dir_band + 1) & ~1) : cfg->band[0];
     cfg->upd_band = g.upd_band >= 16 ? ((g.upd_band + 1) & ~1) : 0;
     cfg->upd_strip = g.upd_strip;
+    cfg->pf32 = g.p_f32;
 }
 
 size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) {
@@ -1626,6 +1634,9 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;
+    } else if (!strcmp(name, "p_f32")) {
+        if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "p_f32 must be 0 or 1");
+        g.p_f32 = (int)value;
     } else if (!strcmp(name, "upd_strip")) {
         if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "upd_strip must be 0 or 1");
         g.upd_strip = (int)value;
@@ -1729,6 +1740,7 @@ int psn_describe(int n, int64_t* info) {
         if (sc.ls >= 1 && !psn_strip_ok(plan, sc.ls)) sc.mode = 0;
         sc.vf32 = (sc.mode == 2 && g.vcycle_f32 && sc.ls >= 1 && psn_vf32_ok(plan, sc.ls)) ? 1 : 0;
         info[7] = sc.vf32 | ((sc.mode == 2 && g.upd_strip && (plan.n & 1) == 0) ? 2 : 0);
+        if ((info[7] & 3) == 3 && g.p_f32) info[7] |= 4;
         info[0] = 0;
         info[2] = sc.ls;
         info[3] = PSN_TILE_THREADS;

@@ -69,6 +69,7 @@ struct PsnSampleState {
     double pq;         // <p, A p>
     double rr;         // ||r||^2 (recursive, or true after a check)
     double prev_true;  // true ||r||^2 at the previous check
+    double rr_prev;    // ||r||^2 one iteration earlier (scale of the float-stored previous search direction)
     int32_t iters;
     int32_t status;
     int32_t phase;
@@ -766,6 +767,7 @@ struct PsnCgArgs {
     int vf32;                // z is stored as float, scaled by psn_vscale(||r||^2) (PsnStreamCfg::vf32)
     int upd_mode;            // 0: 2-D tile update that reads q; 2: strip update that recomputes q from p (q is never stored)
     int upd_band, upd_nstrips, upd_nbands;   // strip decomposition of the update kernel
+    int pf32;                // the search direction is stored as float, scaled by psn_vscale(||r||^2) (needs vf32 and upd_mode 2)
     int chk_mode;            // 0: 2-D tile true-residual kernel; 2: strip form (sine-factor forcing + theta on the solve grid)
     double* part_u;          // [B, upd_nstrips*upd_nbands] ||r||^2 partials of the strip update / strip true-residual kernels
     double* part_b;          // [B, ntx*nty]   ||r||^2 partials
@@ -911,6 +913,7 @@ PSN_FN void psn_state_init(const PsnCgArgs& a, long long b) {
     st.rz = 0.0;
     st.pq = 0.0;
     st.rr = bb;
+    st.rr_prev = bb;
     st.prev_true = 0.0;
     st.iters = 0;
     st.status = PSN_ST_MAXITER;
@@ -934,6 +937,7 @@ PSN_FN void psn_state_after_update(const PsnCgArgs& a, long long b) {
     const int cnt = a.upd_mode ? a.upd_nstrips * a.upd_nbands : a.ntx * a.nty;
     const double* pb = a.upd_mode ? a.part_u + b * (long long)cnt : a.part_b + b * (long long)cnt;
     for (int k = 0; k < cnt; ++k) rr += pb[k];
+    st.rr_prev = st.rr;
     st.rr = rr;
     st.rz_old = st.rz;
     st.restart = 0;

@@ -20,6 +20,7 @@ struct PsnStreamCfg {
     int dir_band; // rows per warp task of the direction kernel (0: band[0])
     int upd_band; // rows per warp task of the strip update kernel (0: 2 * dir_band)
     int upd_strip; // mode 2 only: the update kernel recomputes q = At p in strips and q is never stored
+    int pf32;      // with vf32 and upd_strip: the search direction p is stored as (scaled) float as well
     int vf32;     // mode 2 only: V-cycle intermediates (iterates, restricted residuals, z) are STORED as float; all
                   // arithmetic, the CG vectors x r p q and every inner product stay fp64.  The preconditioner only has
                   // to be an approximate inverse, so CG converges in the same number of iterations (tests), while the
@@ -143,7 +144,8 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.npq = cg.dir_mode ? cg.dir_nstrips * cg.dir_nbands : cg.ntx * cg.nty;
     cg.upd_mode = (cg.dir_mode == 2 && cfg.upd_strip) ? 2 : 0;
     cg.upd_band = cfg.upd_band >= 16 ? cfg.upd_band : 2 * cg.dir_band;
-    cg.upd_nstrips = (n + PSN_DIR_USE - 1) / PSN_DIR_USE;
+    cg.pf32 = (cg.upd_mode == 2 && cg.vf32 && cfg.pf32) ? 1 : 0;
+    cg.upd_nstrips = (n + psn_dir_use(cg.pf32) - 1) / psn_dir_use(cg.pf32);
     cg.upd_nbands = psn_band_count(n, cg.upd_band);
     cg.part_u = ws.part_u;
     cg.chk_mode = (cg.upd_mode == 2 && rhs.sx && rhs.theta && rhs.step == 1 && rhs.mn == n) ? 2 : 0;

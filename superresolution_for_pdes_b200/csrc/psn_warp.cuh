@@ -893,7 +893,11 @@ PSN_FN double psn_warp_sum_partials(const PsnWarp& w, const double* part, int co
 }
 
 // TZ: storage type of z (float: the value read is s z with s = psn_vscale(||r||^2), undone here)
-template <class TZ, class Feeder>
+// TP: storage type of the search direction.  float (needs TZ = float and the strip update kernel): p is kept as the
+//     float s_k p_k with s_k = psn_vscale(||r_k||^2); CG stays exact for the ROUNDED direction because q = At p, <p,q>,
+//     x += alpha p and r -= alpha q are all formed from that same rounded p in fp64 (rounding p perturbs the search
+//     direction like the float-stored preconditioner does, not the solution: same iteration counts, tests).
+template <class TZ, class TP, class Feeder>
 PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b, int band, int strip, Feeder& fd) {
     const PsnSampleState st = a.state[b];
     if (st.phase != PSN_PHASE_ITER) return;
@@ -904,9 +908,14 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
     const wd beta = w_bcast(fresh ? 0.0 : rz / st.rz_old);
     const int n = a.n, last = n - 1;
     constexpr int F32 = sizeof(TZ) == 4 ? 1 : 0;
+    constexpr bool PF32 = sizeof(TP) == 4;
+    static_assert(!PF32 || F32, "a float search direction needs the float-stored (scaled) z");
     const int a0 = strip * psn_dir_use(F32), a1 = psn_imin(a0 + psn_dir_use(F32), n);
     const int c0 = a0 - psn_dir_hl(F32);
-    const wd zinv = w_bcast(F32 ? 1.0 / psn_vscale(st.rr) : 1.0);
+    const double sk = F32 ? psn_vscale(st.rr) : 1.0;
+    const wd zinv = w_bcast(1.0 / sk);
+    // scaled domain: s_k p_k = s_k z_k + beta (s_k / s_{k-1}) (s_{k-1} p_{k-1})   (powers of two: exact)
+    const wd beta_s = w_bcast((fresh || !PF32) ? 0.0 : (rz / st.rz_old) * (sk / psn_vscale(st.rr_prev)));
     const int i0 = band * a.dir_band, i1 = psn_imin(i0 + a.dir_band, n);
     const wi col0 = w_lane(w) * 4 + c0;
     const wi col2 = col0 + 2;
@@ -919,7 +928,7 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
     const int tload = psn_imin(i1, last);
     const int tend = i1;   // q(row r) is formed at time r + 1; row n reads as zero
     fd.set_base0(reinterpret_cast<const TZ*>(a.z) + base);
-    fd.set_base1(a.p_old + base);
+    fd.set_base1(reinterpret_cast<const TP*>(a.p_old) + base);
     fd.n = n;
     fd.tload = tload;
     psn_feeder_geom(fd, col0, mp, c0, n);
@@ -931,7 +940,7 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
 #pragma unroll
         for (int e = 0; e < 4; ++e) pn[k][e] = zero;
     wd dot = zero;
-    double* pg = a.p_new + base;
+    TP* pg = reinterpret_cast<TP*>(a.p_new) + base;
     double* qg = a.q + base;
 
     for (int t = ts; t <= tend; t += W) {
@@ -945,15 +954,27 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
             typename Feeder::V1 r1[4];
             fd.template fetch<false>(w, tt, tc, par, r0, r1);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                wd zv = w_cvt<double>(r0[e]);
-                if constexpr (F32 != 0) zv = zv * zinv;
-                pn[k0][e] = fresh ? zv : zv + beta * r1[e];
-            }
-            if (tc >= i0 && tc < i1) {
-                double* rowp = pg + (long long)tc * n;
-                w_stp(rowp, col0, so[0], pn[k0][0], pn[k0][1]);
-                w_stp(rowp, col2, so[1], pn[k0][2], pn[k0][3]);
+            if constexpr (PF32) {
+                typename PsnWV<TP>::type pr[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const wd zv = w_cvt<double>(r0[e]);
+                    pr[e] = w_cvt<TP>(fresh ? zv : zv + beta_s * w_cvt<double>(r1[e]));
+                    pn[k0][e] = w_cvt<double>(pr[e]);   // everything below sees the rounded direction
+                }
+                if (tc >= i0 && tc < i1) w_stq(pg + (long long)tc * n, col0, so[0], so[1], pr);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    wd zv = w_cvt<double>(r0[e]);
+                    if constexpr (F32 != 0) zv = zv * zinv;
+                    pn[k0][e] = fresh ? zv : zv + beta * w_cvt<double>(r1[e]);
+                }
+                if (tc >= i0 && tc < i1) {
+                    TP* rowp = pg + (long long)tc * n;
+                    w_stp(rowp, col0, so[0], pn[k0][0], pn[k0][1]);
+                    w_stp(rowp, col2, so[1], pn[k0][2], pn[k0][3]);
+                }
             }
             const int r = tc - 1;
             if (r >= i0 && r < i1) {
@@ -973,7 +994,8 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
             }
         }
     }
-    const double s = w_sum(dot);
+    // with a float direction p and q carry the scale s_k: <p,q> = <s p, s q> / s^2
+    const double s = PF32 ? w_sum(dot) * ((1.0 / sk) * (1.0 / sk)) : w_sum(dot);
     if (w_lane0(w)) {
         a.part_pq[b * (long long)a.npq + (long long)band * a.dir_nstrips + strip] = s;
         if (band == 0 && strip == 0) a.state[b].rz = rz;
@@ -986,17 +1008,20 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
 // kernel, so r is bit-identical to the stored-q variant);  partial ||r||^2.  Not storing q saves its 8-byte write in
 // the direction kernel and its 8-byte read here: 76 -> 60 bytes per node and iteration for the two kernels together.
 // One warp per 128-column strip (2 halo columns for the stencil), p / x / r rows through a 3-array TMA ring.
-template <class Feeder>
+// TP: storage type of p (float: s_k p_k, see psn_dir_strip_body; x and r are always fp64)
+template <class TP, class Feeder>
 PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b, int band, int strip, Feeder& fd) {
     const PsnSampleState st = a.state[b];
     if (st.phase != PSN_PHASE_ITER) return;
     constexpr int W = Feeder::W;
     static_assert(W % 3 == 0, "the 3-row window rotates inside one ring period");
+    constexpr int PF32 = sizeof(TP) == 4 ? 1 : 0;
     const double pq = psn_warp_sum_partials(w, a.part_pq + b * (long long)a.npq, a.npq);
-    const wd alpha = w_bcast((pq > 0.0) ? st.rz / pq : 0.0);
+    // with a float direction the window holds s_k p_k and s_k q_k: fold 1 / s_k into alpha (power of two, exact)
+    const wd alpha = w_bcast(((pq > 0.0) ? st.rz / pq : 0.0) * (PF32 ? 1.0 / psn_vscale(st.rr) : 1.0));
     const int n = a.n, last = n - 1;
-    const int a0 = strip * PSN_DIR_USE, a1 = psn_imin(a0 + PSN_DIR_USE, n);
-    const int c0 = a0 - 2;
+    const int a0 = strip * psn_dir_use(PF32), a1 = psn_imin(a0 + psn_dir_use(PF32), n);
+    const int c0 = a0 - psn_dir_hl(PF32);
     const int i0 = band * a.upd_band, i1 = psn_imin(i0 + a.upd_band, n);
     const wi col0 = w_lane(w) * 4 + c0;
     const wi col2 = col0 + 2;
@@ -1008,7 +1033,7 @@ PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long lon
     const int ts = psn_imax(i0 - 1, 0);
     const int tload = psn_imin(i1, last);
     const int tend = i1;   // row r is finished at time r + 1; row n reads as zero
-    fd.set_base0(a.p_new + base);
+    fd.set_base0(reinterpret_cast<const TP*>(a.p_new) + base);
     fd.set_base1(a.x + base);
     fd.set_base2(a.r + base);
     fd.n = n;
@@ -1035,7 +1060,10 @@ PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long lon
             if (tc > tend) break;
             const int k0 = tt % 3, k1 = (tt + 2) % 3, k2 = (tt + 1) % 3;   // rows tc, tc-1, tc-2
             wd xc[4], rc[4];
-            fd.template fetch3<false>(w, tt, tc, par, pn[k0], xc, rc);
+            typename Feeder::V0 pr[4];
+            fd.template fetch3<false>(w, tt, tc, par, pr, xc, rc);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pn[k0][e] = w_cvt<double>(pr[e]);
             const int r = tc - 1;
             if (r >= i0 && r < i1) {
                 const wd upv = w_up_raw(pn[k1][3]);
@@ -1084,8 +1112,9 @@ PSN_FN void psn_true_residual_strip_body(const PsnWarp& w, const PsnCgArgs& a, l
     constexpr int W = Feeder::W;
     static_assert(W % 3 == 0, "the 3-row window rotates inside one ring period");
     const int n = a.n, last = n - 1;
-    const int a0 = strip * PSN_DIR_USE, a1 = psn_imin(a0 + PSN_DIR_USE, n);
-    const int c0 = a0 - 2;
+    // same strip decomposition as the update kernel (its partial-sum slots are reused)
+    const int a0 = strip * psn_dir_use(a.pf32), a1 = psn_imin(a0 + psn_dir_use(a.pf32), n);
+    const int c0 = a0 - psn_dir_hl(a.pf32);
     const int i0 = band * a.upd_band, i1 = psn_imin(i0 + a.upd_band, n);
     const wi col0 = w_lane(w) * 4 + c0;
     const wi col2 = col0 + 2;

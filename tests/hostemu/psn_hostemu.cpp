@@ -106,9 +106,10 @@ struct HostBackend {
                 for (int band = 0; band < a.dir_nbands; ++band)
                     for (int strip = 0; strip < a.dir_nstrips; ++strip) {
                         std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
-                        if (a.dir_mode == 2 && a.vf32) { PsnTmaFeeder<2, float, double> fd; fd.attach(ring.data()); psn_dir_strip_body<float>(w, a, b, band, strip, fd); }
-                        else if (a.dir_mode == 2) { PsnTmaFeeder<2, double, double> fd; fd.attach(ring.data()); psn_dir_strip_body<double>(w, a, b, band, strip, fd); }
-                        else { PsnRegFeeder<2, 2> fd; psn_dir_strip_body<double>(w, a, b, band, strip, fd); }
+                        if (a.dir_mode == 2 && a.vf32 && a.pf32) { PsnTmaFeeder<2, float, float> fd; fd.attach(ring.data()); psn_dir_strip_body<float, float>(w, a, b, band, strip, fd); }
+                        else if (a.dir_mode == 2 && a.vf32) { PsnTmaFeeder<2, float, double> fd; fd.attach(ring.data()); psn_dir_strip_body<float, double>(w, a, b, band, strip, fd); }
+                        else if (a.dir_mode == 2) { PsnTmaFeeder<2, double, double> fd; fd.attach(ring.data()); psn_dir_strip_body<double, double>(w, a, b, band, strip, fd); }
+                        else { PsnRegFeeder<2, 2> fd; psn_dir_strip_body<double, double>(w, a, b, band, strip, fd); }
                     }
             return;
         }
@@ -126,8 +127,8 @@ struct HostBackend {
                 for (int band = 0; band < a.upd_nbands; ++band)
                     for (int strip = 0; strip < a.upd_nstrips; ++strip) {
                         std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
-                        Feeder fd; fd.attach(ring.data());
-                        psn_update_strip_body(w, a, b, band, strip, fd);
+                        if (a.pf32) { PsnTmaFeeder<2, float, double, double> fd; fd.attach(ring.data()); psn_update_strip_body<float>(w, a, b, band, strip, fd); }
+                        else { Feeder fd; fd.attach(ring.data()); psn_update_strip_body<double>(w, a, b, band, strip, fd); }
                     }
             return;
         }
@@ -219,6 +220,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     cfg.dir_band = 0;
     cfg.upd_band = 0;
     cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
+    cfg.pf32 = cfg.vf32;
     if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
@@ -283,6 +285,7 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     cfg.dir_band = 0;
     cfg.upd_band = 0;
     cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
+    cfg.pf32 = cfg.vf32;
     if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     std::vector<std::vector<double>> keep;
