@@ -355,6 +355,10 @@ def run_own(args):
         # q = A p is recomputed by the update kernel from a 3-row window of p and never stored
         KERNEL_BYTES["dir_apply_dot"]["own"] -= 8.0     # no q write
         KERNEL_BYTES["update_norm"]["own"] = 40.0       # read p, x, r; write x, r
+    if desc.get("p_f32"):
+        # the search direction is stored as scaled float
+        KERNEL_BYTES["dir_apply_dot"]["own"] -= 8.0     # read p 4, write p 4 instead of 8 + 8
+        KERNEL_BYTES["update_norm"]["own"] -= 4.0       # read p 4
     roof = None
     kernels = {}
     if prof:
@@ -432,7 +436,8 @@ def run_own(args):
                                  "operator, inner products and stopping rule in fp64" +
                                  ("; the V-cycle preconditioner stores and smooths in fp32 (same iteration count, solution "
                                   "accuracy unchanged)" if desc.get("vcycle_f32") else "; V-cycle in fp64") +
-                                 ("; q = A p recomputed in the update kernel, never stored" if desc.get("update_strip") else ""),
+                                 ("; q = A p recomputed in the update kernel, never stored" if desc.get("update_strip") else "") +
+                                 ("; search direction stored as scaled float (x, r, q, all dots fp64)" if desc.get("p_f32") else ""),
                        "host_affinity": (f"{len(numa_cores)} cores local to the GPU" if numa_cores else "unbound"),
                        "path": "resident" if desc["resident"] else "streamed", "mean_iters": float(info.iters.mean()),
                        "max_iters": int(info.iters.max()),

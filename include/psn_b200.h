@@ -170,7 +170,9 @@ int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const dou
  * (default 1: with vcycle_mode 2 and grid sizes divisible by 4 on every streamed level, the preconditioner's
  * intermediate arrays are stored as float; x, r, p, q, every inner product and all arithmetic stay fp64, so the
  * accuracy of the solution is unchanged), "upd_strip" (default 1: with vcycle_mode 2 the CG update kernel recomputes
- * q = A p from p instead of reading it back, q is never written to HBM), "pdl" (default 1: programmatic dependent
+ * q = A p from p instead of reading it back, q is never written to HBM), "p_f32" (default 1: with vcycle_f32 and
+ * upd_strip the search direction is stored as a power-of-two-scaled float; q, <p,q>, x and r are formed in fp64 from
+ * that same rounded direction, so the recurrences stay exact), "pdl" (default 1: programmatic dependent
  * launch between the kernels of a solve), "coarse_max_n", "host_chunks", "host_edge_div", "dir_band", "upd_band",
  * "band_target", "res_block", "serialize_solves" (pipeline / decomposition tuning, see psn_b200.cu). */
 int psn_set_option(const char* name, int64_t value);
@@ -187,7 +189,8 @@ int psn_profile_end(void);
  * {resident(1)/streamed(0), levels, first shared-memory level, threads per CTA,
  *  dynamic shared memory bytes of the dominant kernel, tile edge, workspace bytes per sample,
  *  bit 0: the V-cycle intermediates of this size are stored as float (option "vcycle_f32", streamed path),
- *  bit 1: the CG update recomputes q = A p in strips instead of storing it (option "upd_strip")}. */
+ *  bit 1: the CG update recomputes q = A p in strips instead of storing it (option "upd_strip"),
+ *  bit 2: the search direction p is stored as scaled float (option "p_f32"; x, r, q and every dot stay fp64)}. */
 int psn_describe(int n, int64_t* info);
 
 #ifdef __cplusplus

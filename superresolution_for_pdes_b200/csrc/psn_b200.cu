@@ -489,9 +489,9 @@ struct Context {
     int band0 = 0;         // rows per warp task on level 0 (0 = automatic)
     int band_target = 8;   // largest number of bands per column the band split considers (choose_bands)
     int dir_band = 64;     // rows per warp task of the direction kernel (1 halo row per band: short bands balance better); 0: as level 0
-    int host_edge_div = 4; // first / last chunk of the host pipeline = regular chunk / host_edge_div
+    int host_edge_div = 2; // first / last chunk of the host pipeline = regular chunk / host_edge_div
     int vcycle_f32 = 1;    // streamed path: store V-cycle intermediates as float where the grid sizes allow (PsnStreamCfg::vf32)
-    int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 5 streamed / 8 resident)
+    int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 6 streamed / 8 resident)
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     bool attrs_set = false;
     bool profiling = false;
@@ -1078,7 +1078,7 @@ int solve_internal(const Problem& P) {
         if (cap > 65535 && !resident) cap = 65535;   // gridDim.z
         if (any_host) {
             // at least ~8 chunks so that copies overlap the solve, but keep chunks large enough to fill the GPU
-            const int hc = g.host_chunks > 0 ? g.host_chunks : (resident ? 8 : 5);
+            const int hc = g.host_chunks > 0 ? g.host_chunks : (resident ? 8 : 6);
             long long want = (P.B + hc - 1) / hc;
             const long long floor_ = resident ? 4ll * g.sm_count : 64;
             if (want < floor_) want = floor_;

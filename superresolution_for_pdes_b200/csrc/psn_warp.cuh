@@ -953,7 +953,6 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
             typename Feeder::V0 r0[4];
             typename Feeder::V1 r1[4];
             fd.template fetch<false>(w, tt, tc, par, r0, r1);
-#pragma unroll
             if constexpr (PF32) {
                 typename PsnWV<TP>::type pr[4];
 #pragma unroll
