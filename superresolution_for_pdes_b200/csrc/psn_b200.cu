@@ -158,7 +158,13 @@ psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     }
 }
 
-template <class TP>
+__global__ void __launch_bounds__(256) psn_flush_x_kernel(const __grid_constant__ PsnCgArgs a) {
+    psn_pdl_enter();
+    PsnDevCtx ctx{(int)threadIdx.x, 256, nullptr, 0};
+    psn_flush_body(ctx, a, (long long)blockIdx.y, (int)blockIdx.x, (int)gridDim.x);
+}
+
+template <class TP, bool XDEFER>
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
 psn_update_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     psn_pdl_enter();
@@ -171,10 +177,10 @@ psn_update_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     const int rem = (int)(task - b * per);
     const int band = rem / a.upd_nstrips, strip = rem - band * a.upd_nstrips;
     const PsnWarp w{(int)(threadIdx.x & 31)};
-    typedef PsnTmaFeeder<2, TP, double, double> Feeder;
+    typedef typename PsnUpdateFeederSel<TP, XDEFER>::type Feeder;
     Feeder fd;
     fd.attach(strip_smem + (size_t)warp * Feeder::smem_bytes());
-    psn_update_strip_body<TP>(w, a, b, band, strip, fd);
+    psn_update_strip_body<TP, XDEFER>(w, a, b, band, strip, fd);
 }
 
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
@@ -482,6 +488,7 @@ struct Context {
     int serialize_solves = 0;
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
+    int x_defer = 1;       // with p_f32: x is accumulated from the ring of stored directions when a sample is checked
     int p_f32 = 1;         // with vcycle_f32 and upd_strip: the search direction is stored as (scaled) float too
     int upd_strip = 1;     // mode 2: strip update kernel that recomputes q = At p (q is never written to HBM)
     int upd_band = 64;     // rows per warp task of the strip update kernel (0: twice the direction kernel's)
@@ -787,16 +794,21 @@ struct CudaBackend {
         }
         launch(psn_dir_strip_kernel<TMA, TZ, TP>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
     }
-    template <class TP>
+    template <class TP, bool XDEFER>
     void update_launch(const PsnCgArgs& a, unsigned grid, long long ntasks) {
-        typedef PsnTmaFeeder<2, TP, double, double> Feeder;
+        typedef typename PsnUpdateFeederSel<TP, XDEFER>::type Feeder;
         const size_t smem = (size_t)PSN_STRIP_WARPS * Feeder::smem_bytes();
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(psn_update_strip_kernel<TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(psn_update_strip_kernel<TP, XDEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_done = true;
         }
-        launch(psn_update_strip_kernel<TP>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+        launch(psn_update_strip_kernel<TP, XDEFER>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
+    }
+    void flush_x(const PsnCgArgs& a, long long B) {
+        ProfScope p("flush_x", s);
+        launch(psn_flush_x_kernel, dim3(PSN_FLUSH_BLOCKS, (unsigned)B), dim3(256), 0, a);
+        chk();
     }
     void dir_apply(const PsnCgArgs& a, long long B) {
         ProfScope p("dir_apply_dot", s);
@@ -822,8 +834,9 @@ struct CudaBackend {
         if (a.upd_mode == 2) {
             const long long ntasks = B * a.upd_nstrips * a.upd_nbands;
             const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
-            if (a.pf32) update_launch<float>(a, grid, ntasks);
-            else update_launch<double>(a, grid, ntasks);
+            if (a.pf32 && a.xdefer) update_launch<float, true>(a, grid, ntasks);
+            else if (a.pf32) update_launch<float, false>(a, grid, ntasks);
+            else update_launch<double, false>(a, grid, ntasks);
             chk();
             return;
         }
@@ -958,12 +971,14 @@ void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
     cfg->dir_band = g.dir_band >= 16 ? ((g.dir_band + 1) & ~1) : cfg->band[0];
     cfg->upd_band = g.upd_band >= 16 ? ((g.upd_band + 1) & ~1) : 0;
     cfg->upd_strip = g.upd_strip;
-    cfg->pf32 = g.p_f32;
+    cfg->pf32 = (cfg->vf32 && g.upd_strip && g.p_f32) ? 1 : 0;
+    cfg->xdefer = (cfg->pf32 && g.x_defer) ? 1 : 0;
 }
 
 size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     const size_t nn = (size_t)plan.n * plan.n;
     size_t b = 5 * nn * sizeof(double);
+    if (cfg.xdefer) b += (size_t)PSN_PEND_K * nn * sizeof(float) - 2 * nn * sizeof(double) + sizeof(PsnPend);
     for (int l = 1; l <= cfg.ls; ++l) {
         const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n * sizeof(double);
         b += (l < cfg.ls ? 3 : 2) * m;
@@ -980,9 +995,17 @@ int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, lon
     ws->r = arena_take<double>(ar, Bc * nn);
     ws->q = arena_take<double>(ar, Bc * nn);
     ws->z = arena_take<double>(ar, Bc * nn);
-    ws->p[0] = arena_take<double>(ar, Bc * nn);
-    ws->p[1] = arena_take<double>(ar, Bc * nn);
-    bool ok = ws->r && ws->q && ws->z && ws->p[0] && ws->p[1];
+    bool ok = true;
+    if (cfg.xdefer) {   // the ring of float directions replaces the fp64 ping-pong pair
+        ws->pring = arena_take<float>(ar, (size_t)PSN_PEND_K * Bc * nn);
+        ws->pend = arena_take<PsnPend>(ar, Bc);
+        ok = ws->pring && ws->pend;
+    } else {
+        ws->p[0] = arena_take<double>(ar, Bc * nn);
+        ws->p[1] = arena_take<double>(ar, Bc * nn);
+        ok = ws->p[0] && ws->p[1];
+    }
+    ok = ok && ws->r && ws->q && ws->z;
     for (int l = 1; l <= cfg.ls && ok; ++l) {
         const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n;
         ws->bl[l] = arena_take<double>(ar, Bc * m);
@@ -1037,6 +1060,9 @@ int solve_internal(const Problem& P) {
         scfg.ls = stream_ls(plan);
         if (scfg.ls >= 1 && !psn_strip_ok(plan, scfg.ls)) scfg.mode = 0;   // odd level sizes: shared-memory tile kernels
         scfg.vf32 = (scfg.mode == 2 && g.vcycle_f32 && scfg.ls >= 1 && psn_vf32_ok(plan, scfg.ls)) ? 1 : 0;
+        scfg.upd_strip = g.upd_strip;
+        scfg.pf32 = (scfg.vf32 && g.upd_strip && g.p_f32) ? 1 : 0;
+        scfg.xdefer = (scfg.pf32 && g.x_defer) ? 1 : 0;
         if (scfg.ls < 1) return psn_fail(PSN_ERR_UNSUPPORTED, "no shared-memory coarse level for n=%d", P.n);
     }
 
@@ -1634,6 +1660,9 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;
+    } else if (!strcmp(name, "x_defer")) {
+        if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "x_defer must be 0 or 1");
+        g.x_defer = (int)value;
     } else if (!strcmp(name, "p_f32")) {
         if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "p_f32 must be 0 or 1");
         g.p_f32 = (int)value;
@@ -1741,6 +1770,8 @@ int psn_describe(int n, int64_t* info) {
         sc.vf32 = (sc.mode == 2 && g.vcycle_f32 && sc.ls >= 1 && psn_vf32_ok(plan, sc.ls)) ? 1 : 0;
         info[7] = sc.vf32 | ((sc.mode == 2 && g.upd_strip && (plan.n & 1) == 0) ? 2 : 0);
         if ((info[7] & 3) == 3 && g.p_f32) info[7] |= 4;
+        if ((info[7] & 4) && g.x_defer) info[7] |= 8;
+        sc.upd_strip = g.upd_strip; sc.pf32 = (info[7] & 4) ? 1 : 0; sc.xdefer = (info[7] & 8) ? 1 : 0;
         info[0] = 0;
         info[2] = sc.ls;
         info[3] = PSN_TILE_THREADS;

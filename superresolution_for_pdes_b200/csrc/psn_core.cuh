@@ -78,6 +78,18 @@ struct PsnSampleState {
     int32_t pad;
 };
 
+// Deferred solution update (PsnCgArgs::xdefer): x is only needed when a sample is checked or finished, and the
+// float-stored search directions of the last PSN_PEND_K outer iterations are still in their ring slots, so instead of
+// x += alpha p every iteration (read + write of x: 16 of 83 bytes per node) the step lengths are recorded here and
+// x (+)= sum_j a_j p_j is formed in one pass when the sample leaves the iteration (or the ring is full).
+#define PSN_PEND_K 12
+struct PsnPend {
+    int32_t lo, hi;    // pending outer iterations [lo, hi): direction j lives in ring slot j % PSN_PEND_K
+    int32_t xinit;     // x holds a value (0: the first flush writes instead of accumulating)
+    int32_t pad;
+    double a[PSN_PEND_K];   // alpha_j / s_j (the stored direction is s_j p_j)
+};
+
 struct PsnPatch {
     int oi, oj;  // global coordinates of patch element [0][0]
     int pitch;
@@ -768,6 +780,11 @@ struct PsnCgArgs {
     int upd_mode;            // 0: 2-D tile update that reads q; 2: strip update that recomputes q from p (q is never stored)
     int upd_band, upd_nstrips, upd_nbands;   // strip decomposition of the update kernel
     int pf32;                // the search direction is stored as float, scaled by psn_vscale(||r||^2) (needs vf32 and upd_mode 2)
+    int xdefer;              // needs pf32: x is not touched by the update kernel; see PsnPend
+    int it;                  // outer iteration index of this launch (ring slot of p_new = it % PSN_PEND_K)
+    const float* pring;      // [PSN_PEND_K][B, n, n] ring of float search directions (xdefer)
+    long long ring_stride;   // floats between two ring slots
+    PsnPend* pend;           // [B]
     int chk_mode;            // 0: 2-D tile true-residual kernel; 2: strip form (sine-factor forcing + theta on the solve grid)
     double* part_u;          // [B, upd_nstrips*upd_nbands] ||r||^2 partials of the strip update / strip true-residual kernels
     double* part_b;          // [B, ntx*nty]   ||r||^2 partials
@@ -808,7 +825,7 @@ PSN_FN void psn_prologue_body(Ctx& ctx, const PsnCgArgs& a, long long b, int ty,
     PSN_GT_LOOP(ctx, a, ty, tx, {
         const double v = psn_rhs(a.rhs, b, i, j, a.h2);
         a.r[base + (long long)i * a.n + j] = v;
-        a.x[base + (long long)i * a.n + j] = 0.0;
+        if (!a.xdefer) a.x[base + (long long)i * a.n + j] = 0.0;   // xdefer: the first flush writes x
         acc += v * v;
     })
     const double s = ctx.block_sum(acc);
@@ -927,6 +944,43 @@ PSN_FN void psn_state_init(const PsnCgArgs& a, long long b) {
         st.rr = 0.0;
     }
     a.state[b] = st;
+    if (a.xdefer) {
+        PsnPend pd;
+        pd.lo = pd.hi = 0;
+        pd.xinit = 0;
+        pd.pad = 0;
+        for (int k = 0; k < PSN_PEND_K; ++k) pd.a[k] = 0.0;
+        a.pend[b] = pd;
+    }
+}
+
+// does the flush pass act on this sample now?  (evaluated identically by the flush kernel and, afterwards, by
+// psn_state_after_check, which retires the pending range)
+PSN_FN bool psn_flush_due(const PsnSampleState& st, const PsnPend& pd) {
+    const bool leaving = st.phase != PSN_PHASE_ITER;
+    const bool full = pd.hi - pd.lo >= PSN_PEND_K;
+    return (leaving || full) && (pd.hi > pd.lo || !pd.xinit);
+}
+
+// x (+)= sum over the pending directions; block `blk` of `nblk` per sample, grid-stride over the sample's nodes
+#define PSN_FLUSH_BLOCKS 20
+template <class Ctx>
+PSN_FN void psn_flush_body(Ctx& ctx, const PsnCgArgs& a, long long b, int blk, int nblk) {
+    const PsnSampleState st = a.state[b];
+    const PsnPend pd = a.pend[b];
+    if (!psn_flush_due(st, pd)) return;
+    const long long nn = (long long)a.n * a.n;
+    const float* ring = a.pring + b * nn;
+    const double* av = a.pend[b].a;   // read through the cache (uniform per sample), not a register-indexed copy
+    double* x = a.x + b * nn;
+    for (long long c = (long long)blk * ctx.nthreads + ctx.tid; c < nn; c += (long long)nblk * ctx.nthreads) {
+        double acc = pd.xinit ? x[c] : 0.0;
+        for (int k = pd.lo; k < pd.hi; ++k) {
+            const int slot = k % PSN_PEND_K;
+            acc += av[slot] * (double)ring[(long long)slot * a.ring_stride + c];
+        }
+        x[c] = acc;
+    }
 }
 
 // after update: bookkeeping + convergence test on the recursive residual
@@ -954,6 +1008,13 @@ PSN_FN void psn_state_after_update(const PsnCgArgs& a, long long b) {
 // after the true-residual pass; returns 1 if the sample keeps iterating
 PSN_FN int psn_state_after_check(const PsnCgArgs& a, long long b) {
     PsnSampleState st = a.state[b];
+    if (a.xdefer) {
+        PsnPend pd = a.pend[b];
+        if (psn_flush_due(st, pd)) {   // the flush kernel that ran just before has put these directions into x
+            a.pend[b].lo = pd.hi;
+            a.pend[b].xinit = 1;
+        }
+    }
     if (st.phase == PSN_PHASE_CHECK) {
         double rt = 0.0;
         const int cnt = a.chk_mode ? a.upd_nstrips * a.upd_nbands : a.ntx * a.nty;

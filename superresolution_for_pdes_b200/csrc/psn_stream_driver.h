@@ -21,6 +21,7 @@ struct PsnStreamCfg {
     int upd_band; // rows per warp task of the strip update kernel (0: 2 * dir_band)
     int upd_strip; // mode 2 only: the update kernel recomputes q = At p in strips and q is never stored
     int pf32;      // with vf32 and upd_strip: the search direction p is stored as (scaled) float as well
+    int xdefer;    // with pf32: x is accumulated from the ring of stored directions when a sample is checked (PsnPend)
     int vf32;     // mode 2 only: V-cycle intermediates (iterates, restricted residuals, z) are STORED as float; all
                   // arithmetic, the CG vectors x r p q and every inner product stay fp64.  The preconditioner only has
                   // to be an approximate inverse, so CG converges in the same number of iterations (tests), while the
@@ -81,6 +82,8 @@ struct PsnStreamWs {
     double* part_pq;
     double* part_b;
     double* part_u;              // ||r||^2 partials of the strip update kernel
+    float* pring;                // xdefer: ring of PSN_PEND_K float search directions, [K][cap, n, n]
+    PsnPend* pend;               // xdefer: [cap]
     PsnSampleState* state;
     int* counters;               // [max_iter + 8] active-sample count per outer iteration
 };
@@ -148,6 +151,11 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.upd_nstrips = (n + psn_dir_use(cg.pf32) - 1) / psn_dir_use(cg.pf32);
     cg.upd_nbands = psn_band_count(n, cg.upd_band);
     cg.part_u = ws.part_u;
+    cg.xdefer = (cg.pf32 && cfg.xdefer && ws.pring && ws.pend) ? 1 : 0;
+    cg.pring = ws.pring;
+    cg.ring_stride = ws.cap * (long long)n * n;
+    cg.pend = ws.pend;
+    cg.it = start_it;
     cg.chk_mode = (cg.upd_mode == 2 && rhs.sx && rhs.theta && rhs.step == 1 && rhs.mn == n) ? 2 : 0;
     cg.part_b = ws.part_b;
     cg.state = ws.state;
@@ -190,11 +198,18 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
             bk.leg_post(plan, cfg, g, B);
         }
         // ---- CG update
-        cg.p_old = ws.p[it & 1];
-        cg.p_new = ws.p[(it & 1) ^ 1];
+        cg.it = it;
+        if (cg.xdefer) {   // the directions of the last PSN_PEND_K iterations stay in their ring slots until x has absorbed them
+            cg.p_old = reinterpret_cast<double*>(ws.pring + (long long)((it + PSN_PEND_K - 1) % PSN_PEND_K) * cg.ring_stride);
+            cg.p_new = reinterpret_cast<double*>(ws.pring + (long long)(it % PSN_PEND_K) * cg.ring_stride);
+        } else {
+            cg.p_old = ws.p[it & 1];
+            cg.p_new = ws.p[(it & 1) ^ 1];
+        }
         bk.dir_apply(cg, B);
         bk.update(cg, B);
         bk.state_after_update(cg, B);
+        if (cg.xdefer) bk.flush_x(cg, B);
         bk.true_residual(cg, B);
         bk.state_after_check(cg, B, ws.counters + it);
         bk.fetch_counter_async(ws.counters + it, it);

@@ -1007,8 +1007,19 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
 // kernel, so r is bit-identical to the stored-q variant);  partial ||r||^2.  Not storing q saves its 8-byte write in
 // the direction kernel and its 8-byte read here: 76 -> 60 bytes per node and iteration for the two kernels together.
 // One warp per 128-column strip (2 halo columns for the stencil), p / x / r rows through a 3-array TMA ring.
+// feeder of the strip update kernel: p, x, r -- or p, r when x is deferred
+template <class TP, bool XDEFER>
+struct PsnUpdateFeederSel {
+    typedef PsnTmaFeeder<2, TP, double, double> type;
+};
+template <class TP>
+struct PsnUpdateFeederSel<TP, true> {
+    typedef PsnTmaFeeder<2, TP, double> type;
+};
+
 // TP: storage type of p (float: s_k p_k, see psn_dir_strip_body; x and r are always fp64)
-template <class TP, class Feeder>
+// XDEFER: x is not touched; the step length is recorded in PsnPend instead (feeder streams p and r only)
+template <class TP, bool XDEFER, class Feeder>
 PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b, int band, int strip, Feeder& fd) {
     const PsnSampleState st = a.state[b];
     if (st.phase != PSN_PHASE_ITER) return;
@@ -1033,8 +1044,12 @@ PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long lon
     const int tload = psn_imin(i1, last);
     const int tend = i1;   // row r is finished at time r + 1; row n reads as zero
     fd.set_base0(reinterpret_cast<const TP*>(a.p_new) + base);
-    fd.set_base1(a.x + base);
-    fd.set_base2(a.r + base);
+    if constexpr (XDEFER) {
+        fd.set_base1(a.r + base);
+    } else {
+        fd.set_base1(a.x + base);
+        fd.set_base2(a.r + base);
+    }
     fd.n = n;
     fd.tload = tload;
     psn_feeder_geom(fd, col0, mp, c0, n);
@@ -1060,7 +1075,8 @@ PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long lon
             const int k0 = tt % 3, k1 = (tt + 2) % 3, k2 = (tt + 1) % 3;   // rows tc, tc-1, tc-2
             wd xc[4], rc[4];
             typename Feeder::V0 pr[4];
-            fd.template fetch3<false>(w, tt, tc, par, pr, xc, rc);
+            if constexpr (XDEFER) fd.template fetch<false>(w, tt, tc, par, pr, rc);
+            else fd.template fetch3<false>(w, tt, tc, par, pr, xc, rc);
 #pragma unroll
             for (int e = 0; e < 4; ++e) pn[k0][e] = w_cvt<double>(pr[e]);
             const int r = tc - 1;
@@ -1072,23 +1088,25 @@ PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long lon
                 q[1] = 4.0 * pn[k1][1] - ((pn[k0][1] + pn[k2][1]) + (pn[k1][0] + pn[k1][2]));
                 q[2] = 4.0 * pn[k1][2] - ((pn[k0][2] + pn[k2][2]) + (pn[k1][1] + pn[k1][3]));
                 q[3] = 4.0 * pn[k1][3] - ((pn[k0][3] + pn[k2][3]) + (pn[k1][2] + dnv));
-                wd xn[4], rn[4];
+                wd rn[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    xn[e] = xp[e] + alpha * pn[k1][e];
-                    rn[e] = rp[e] - alpha * q[e];
+                for (int e = 0; e < 4; ++e) rn[e] = rp[e] - alpha * q[e];
+                if constexpr (!XDEFER) {
+                    wd xn[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) xn[e] = xp[e] + alpha * pn[k1][e];
+                    double* rowx = xg + (long long)r * n;
+                    w_stp(rowx, col0, so[0], xn[0], xn[1]);
+                    w_stp(rowx, col2, so[1], xn[2], xn[3]);
                 }
-                double* rowx = xg + (long long)r * n;
                 double* rowr = rg + (long long)r * n;
-                w_stp(rowx, col0, so[0], xn[0], xn[1]);
-                w_stp(rowx, col2, so[1], xn[2], xn[3]);
                 w_stp(rowr, col0, so[0], rn[0], rn[1]);
                 w_stp(rowr, col2, so[1], rn[2], rn[3]);
                 acc = acc + w_sel(so[0], rn[0] * rn[0] + rn[1] * rn[1], zero) + w_sel(so[1], rn[2] * rn[2] + rn[3] * rn[3], zero);
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                xp[e] = xc[e];
+                if constexpr (!XDEFER) xp[e] = xc[e];
                 rp[e] = rc[e];
             }
         }
@@ -1096,7 +1114,16 @@ PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long lon
     const double s = w_sum(acc);
     if (w_lane0(w)) {
         a.part_u[b * (long long)(a.upd_nstrips * a.upd_nbands) + (long long)band * a.upd_nstrips + strip] = s;
-        if (band == 0 && strip == 0) a.state[b].pq = pq;
+        if (band == 0 && strip == 0) {
+            a.state[b].pq = pq;
+            if constexpr (XDEFER) {
+                // record the step: x will receive (alpha / s_k) * (s_k p_k) when this sample is flushed
+                PsnPend* pd = a.pend + b;
+                if (pd->lo == pd->hi) pd->lo = a.it;
+                pd->a[a.it % PSN_PEND_K] = ((pq > 0.0) ? st.rz / pq : 0.0) * (1.0 / psn_vscale(st.rr));
+                pd->hi = a.it + 1;
+            }
+        }
     }
 }
 

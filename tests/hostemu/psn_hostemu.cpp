@@ -127,8 +127,9 @@ struct HostBackend {
                 for (int band = 0; band < a.upd_nbands; ++band)
                     for (int strip = 0; strip < a.upd_nstrips; ++strip) {
                         std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
-                        if (a.pf32) { PsnTmaFeeder<2, float, double, double> fd; fd.attach(ring.data()); psn_update_strip_body<float>(w, a, b, band, strip, fd); }
-                        else { Feeder fd; fd.attach(ring.data()); psn_update_strip_body<double>(w, a, b, band, strip, fd); }
+                        if (a.pf32 && a.xdefer) { PsnTmaFeeder<2, float, double> fd; fd.attach(ring.data()); psn_update_strip_body<float, true>(w, a, b, band, strip, fd); }
+                        else if (a.pf32) { PsnTmaFeeder<2, float, double, double> fd; fd.attach(ring.data()); psn_update_strip_body<float, false>(w, a, b, band, strip, fd); }
+                        else { Feeder fd; fd.attach(ring.data()); psn_update_strip_body<double, false>(w, a, b, band, strip, fd); }
                     }
             return;
         }
@@ -136,6 +137,11 @@ struct HostBackend {
         for (long long b = 0; b < B; ++b)
             for (int ty = 0; ty < a.nty; ++ty)
                 for (int tx = 0; tx < a.ntx; ++tx) psn_update_body(ctx, a, b, ty, tx);
+    }
+    void flush_x(const PsnCgArgs& a, long long B) {
+        PsnHostCtx ctx;
+        for (long long b = 0; b < B; ++b)
+            for (int blk = 0; blk < 3; ++blk) psn_flush_body(ctx, a, b, blk, 3);
     }
     void true_residual(const PsnCgArgs& a, long long B) {
         if (a.chk_mode == 2) {
@@ -221,6 +227,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     cfg.upd_band = 0;
     cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
     cfg.pf32 = cfg.vf32;
+    cfg.xdefer = cfg.pf32;
     if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
@@ -241,6 +248,13 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     ws.part_pq = alloc((size_t)B * psn_pq_max(n));
     ws.part_b = alloc((size_t)B * gx * gy);
     ws.part_u = alloc((size_t)B * psn_pq_max(n));
+    std::vector<float> pring;
+    std::vector<PsnPend> pend(B);
+    if (cfg.xdefer) {
+        pring.assign((size_t)PSN_PEND_K * B * nn, std::nanf(""));
+        ws.pring = pring.data();
+        ws.pend = pend.data();
+    }
     std::vector<PsnSampleState> st(B);
     ws.state = st.data();
     std::vector<int> counters(max_iter + 8);
@@ -286,6 +300,7 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     cfg.upd_band = 0;
     cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
     cfg.pf32 = cfg.vf32;
+    cfg.xdefer = cfg.pf32;
     if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     std::vector<std::vector<double>> keep;

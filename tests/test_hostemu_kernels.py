@@ -274,3 +274,19 @@ def test_strip_update_and_strip_true_residual_kernels(he, n, ls, band):
         f = np.outer(sy[b], sx[b])
         assert O.rel_l2(u2[b], O.solve_poisson(f, theta[b], n)) <= 1e-10
         assert O.residual_rel(u2[b], f, theta[b]) <= 1e-11        # the reported convergence is the true residual's
+
+
+def test_deferred_solution_update_restart_and_full_ring(he):
+    """Mode 3 accumulates x from the ring of stored float directions only when a sample is checked.  (a) a failed
+    check (rtol below the fp64 floor) restarts from the flushed x and ends with status 1; (b) V(1,1) needs more outer
+    iterations than the ring has slots (12), so the ring-full flush runs mid-solve."""
+    n = 160
+    f, theta = kat_inputs(n, 0, 0)
+    u, it, rr, st = run_stream(he, n, theta[None], f[None], 64, 64, 1, rtol=1e-14, mode=3, band=64)
+    assert st[0] == 1 and it[0] < 30
+    assert O.rel_l2(u[0], O.solve_poisson(f, theta, n)) <= 1e-10
+    fb, thb = batch_inputs(n, 1)
+    u1, it1, _, st1 = run_stream(he, n, thb, fb, 64, 64, 2, mode=3, band=48, nu=1, rtol=1e-13)
+    assert (st1 <= 1).all() and it1.max() > 12
+    for b in range(3):
+        assert O.rel_l2(u1[b], O.solve_poisson(fb[b], thb[b], n)) <= 1e-10
