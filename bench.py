@@ -359,6 +359,9 @@ def run_own(args):
         # the search direction is stored as scaled float
         KERNEL_BYTES["dir_apply_dot"]["own"] -= 8.0     # read p 4, write p 4 instead of 8 + 8
         KERNEL_BYTES["update_norm"]["own"] -= 4.0       # read p 4
+    if desc.get("x_defer"):
+        # x is formed from the ring of stored directions when a sample is checked (flush_x, 44 B/node once per solve)
+        KERNEL_BYTES["update_norm"]["own"] -= 16.0      # no x read / write
     roof = None
     kernels = {}
     if prof:
@@ -437,7 +440,8 @@ def run_own(args):
                                  ("; the V-cycle preconditioner stores and smooths in fp32 (same iteration count, solution "
                                   "accuracy unchanged)" if desc.get("vcycle_f32") else "; V-cycle in fp64") +
                                  ("; q = A p recomputed in the update kernel, never stored" if desc.get("update_strip") else "") +
-                                 ("; search direction stored as scaled float (x, r, q, all dots fp64)" if desc.get("p_f32") else ""),
+                                 ("; search direction stored as scaled float (x, r, q, all dots fp64)" if desc.get("p_f32") else "") +
+                                 ("; x accumulated from the stored directions at check time" if desc.get("x_defer") else ""),
                        "host_affinity": (f"{len(numa_cores)} cores local to the GPU" if numa_cores else "unbound"),
                        "path": "resident" if desc["resident"] else "streamed", "mean_iters": float(info.iters.mean()),
                        "max_iters": int(info.iters.max()),

@@ -172,7 +172,9 @@ int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const dou
  * accuracy of the solution is unchanged), "upd_strip" (default 1: with vcycle_mode 2 the CG update kernel recomputes
  * q = A p from p instead of reading it back, q is never written to HBM), "p_f32" (default 1: with vcycle_f32 and
  * upd_strip the search direction is stored as a power-of-two-scaled float; q, <p,q>, x and r are formed in fp64 from
- * that same rounded direction, so the recurrences stay exact), "pdl" (default 1: programmatic dependent
+ * that same rounded direction, so the recurrences stay exact), "x_defer" (default 1: with p_f32 the last 12 directions
+ * stay in a ring and x = sum alpha_k p_k is formed in one fp64 pass when a sample is checked or the ring is full,
+ * instead of a read-modify-write of x every iteration), "pdl" (default 1: programmatic dependent
  * launch between the kernels of a solve), "coarse_max_n", "host_chunks", "host_edge_div", "dir_band", "upd_band",
  * "band_target", "res_block", "serialize_solves" (pipeline / decomposition tuning, see psn_b200.cu). */
 int psn_set_option(const char* name, int64_t value);
@@ -190,7 +192,8 @@ int psn_profile_end(void);
  *  dynamic shared memory bytes of the dominant kernel, tile edge, workspace bytes per sample,
  *  bit 0: the V-cycle intermediates of this size are stored as float (option "vcycle_f32", streamed path),
  *  bit 1: the CG update recomputes q = A p in strips instead of storing it (option "upd_strip"),
- *  bit 2: the search direction p is stored as scaled float (option "p_f32"; x, r, q and every dot stay fp64)}. */
+ *  bit 2: the search direction p is stored as scaled float (option "p_f32"; x, r, q and every dot stay fp64),
+ *  bit 3: x is accumulated from the ring of stored directions when a sample is checked (option "x_defer")}. */
 int psn_describe(int n, int64_t* info);
 
 #ifdef __cplusplus

@@ -137,7 +137,8 @@ def describe(n: int) -> dict:
     return {"resident": bool(info[0]), "levels": int(info[1]), "first_smem_level": int(info[2]),
             "threads": int(info[3]), "smem_bytes": int(info[4]), "tile": int(info[5]),
             "workspace_bytes_per_sample": int(info[6]), "vcycle_f32": bool(info[7] & 1),
-            "update_strip": bool(info[7] & 2), "p_f32": bool(info[7] & 4)}
+            "update_strip": bool(info[7] & 2), "p_f32": bool(info[7] & 4),
+            "x_defer": bool(info[7] & 8)}
 
 
 def profile_begin() -> None:

@@ -5,11 +5,12 @@
 // backend (tests/hostemu, TEST ONLY) loops over the blocks on the CPU.  The driver never
 // synchronises with the device inside an iteration: alpha/beta live in per-sample device state,
 // converged samples are masked out per CTA, and the number of still-active samples is read
-// back with a lag of PSN_COUNTER_LAG iterations.
+// back with a lag of PSN_COUNTER_LAG iteration(s): the host waits for the counter of iteration it-1 after it has
+// enqueued iteration it, so the device always has a full iteration of work queued.
 #pragma once
 #include "psn_warp.cuh"
 
-#define PSN_COUNTER_LAG 2
+#define PSN_COUNTER_LAG 1
 
 struct PsnStreamCfg {
     int ls;       // first level handled by the shared-memory coarse kernel (levels 0..ls-1 are streamed)
