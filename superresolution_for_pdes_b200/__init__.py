@@ -8,7 +8,7 @@ Device side: ``libpsn_b200.so`` (hand-written sm_100a CUDA behind a C ABI, inclu
 There is no CPU fallback.
 """
 from . import _lib
-from ._lib import PsnError
+from ._lib import PsnError, describe, set_option
 from .data_generation import PoissonSolver
 from .dataset_tensors import PDEDataset
 from .enhanced_data_generation import EnhancedPoissonSolver
@@ -16,4 +16,5 @@ from .resolution_comparison import (bilinear_multi_level_upscale, cubic_multi_le
                                     solve_multi_resolution_batch, split_into_subdomains, stitch_subdomains)
 
 __all__ = ["PoissonSolver", "EnhancedPoissonSolver", "PDEDataset", "solve_multi_resolution",
-           "solve_multi_resolution_batch", "PsnError", "_lib"]
+           "solve_multi_resolution_batch", "bilinear_multi_level_upscale", "cubic_multi_level_upscale",
+           "split_into_subdomains", "stitch_subdomains", "set_option", "describe", "PsnError", "_lib"]
