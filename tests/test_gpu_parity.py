@@ -397,3 +397,43 @@ def test_upscale_cascades_match_reference_semantics(gpu_lib, mode):
     # the tiling helpers of the evaluation scripts round-trip
     parts = P.split_into_subdomains(u40, 10)
     assert np.array_equal(P.stitch_subdomains(parts), u40)
+
+
+def test_streamed_edge_cases_and_speculative_pipeline(gpu_lib):
+    """Large-grid (streamed, float-stored, deferred-x) path through HOST buffers in several pipeline chunks:
+    (a) the first chunk is easy, later chunks need more outer iterations than the count the pipeline speculates with,
+        so the deferred convergence check has to resume them;  (b) zero right-hand sides and a singular theta inside
+        a batch;  (c) max_iter smaller than the iterations needed: status 2, finite partial solutions."""
+    n, B = 176, 300
+    rs = np.random.RandomState(11)
+    x = np.linspace(0, 1, n)
+    # high wave numbers converge in 10 outer iterations on this grid, smooth low ones need 11-12
+    k = np.concatenate([rs.uniform(9.0, 12.0, size=(80, 2)), rs.uniform(0.5, 1.5, size=(B - 80, 2))])
+    theta = np.concatenate([rs.uniform(0.5, 2.0, size=(80, n, n)), np.ones((B - 80, n, n))])
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    sy[7] = 0.0                                   # zero forcing inside the batch
+    theta[150, 5, 9] = 0.0                        # singular sample
+    u, info = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    assert (u[7] == 0).all() and info.status[7] == 0 and info.iters[7] == 0
+    assert info.status[150] >= 2
+    good = np.ones(B, bool); good[150] = False
+    assert (info.status[good] <= 1).all() and np.isfinite(u[good]).all()
+    assert info.iters[good].max() > info.iters[:80].max()          # later chunks did need more iterations
+    for b in (0, 79, 80, 200, B - 1):
+        assert O.rel_l2(u[b], O.solve_poisson(np.outer(sy[b], sx[b]), theta[b], n)) <= TOL
+    # the same batch through device buffers in one chunk: another band split of the strip kernels (it depends on the
+    # chunk size), hence another summation order of the dot products -- same answers to round-off, iteration counts
+    # of borderline samples may move by one
+    import torch
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ud = torch.empty((B, n, n), dtype=torch.float64, device="cuda")
+    _, info_d = gpu_lib.solve_batch(n, B, theta=d(theta), sin_x=d(sx), sin_y=d(sy), out=ud)
+    torch.cuda.synchronize()
+    info_d = info_d.to_host()
+    assert np.abs(info_d.iters[good] - info.iters[good]).max() <= 1
+    assert O.rel_l2(ud.cpu().numpy()[good], u[good]) <= 1e-11
+    # (c)
+    u3, info3 = gpu_lib.solve_batch(n, 90, theta=theta[80:170], sin_x=sx[80:170], sin_y=sy[80:170], max_iter=4)
+    g3 = np.ones(90, bool); g3[70] = False
+    assert (info3.status[g3] == 2).all() and (info3.iters[g3] == 4).all() and np.isfinite(u3[g3]).all()
+    assert (info3.relres[g3] > 1e-9).all() and (info3.relres[g3] < 1e-2).all()
