@@ -170,6 +170,17 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     }
 
     const int max_outer = max_iter + 4;  // every check/restart costs at most one extra outer pass
+    // The check block (x flush, true residual, state transition, counter) is four launches that do nothing until the
+    // first sample converges.  It is skipped for the first outer iterations: a sample that converges earlier simply
+    // waits in PSN_PHASE_CHECK (nothing touches it) until the first check.  Never later than PSN_PEND_K - 2, so that a
+    // full direction ring is always flushed in time.
+    int check_from = start_it;
+    if (start_it == 0) {
+        check_from = fixed_iters > 0 ? fixed_iters - 4 : 3;
+        if (check_from > PSN_PEND_K - 2) check_from = PSN_PEND_K - 2;
+        if (check_from > max_iter - 1) check_from = max_iter - 1;   // samples that stop at max_iter are checked at once
+        if (check_from < 0) check_from = 0;
+    }
     int it = start_it;
     for (; it < max_outer; ++it) {
         // ---- z = M^{-1} r : one V(nu,nu) cycle
@@ -210,16 +221,18 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
         bk.dir_apply(cg, B);
         bk.update(cg, B);
         bk.state_after_update(cg, B);
-        if (cg.xdefer) bk.flush_x(cg, B);
-        bk.true_residual(cg, B);
-        bk.state_after_check(cg, B, ws.counters + it);
-        bk.fetch_counter_async(ws.counters + it, it);
+        if (it >= check_from) {
+            if (cg.xdefer) bk.flush_x(cg, B);
+            bk.true_residual(cg, B);
+            bk.state_after_check(cg, B, ws.counters + it);
+            bk.fetch_counter_async(ws.counters + it, it);
+        }
         if (fixed_iters > 0) {
             if (it + 1 >= start_it + fixed_iters) {
                 ++it;
                 break;
             }
-        } else if (it >= PSN_COUNTER_LAG && bk.wait_counter(it - PSN_COUNTER_LAG) == 0) {
+        } else if (it - PSN_COUNTER_LAG >= check_from && bk.wait_counter(it - PSN_COUNTER_LAG) == 0) {
             ++it;
             break;
         }
