@@ -105,6 +105,15 @@ PSN_FN void w_bulk_g2s(const PsnWarp& w, void* dst, const void* src, unsigned by
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(psn_smem_addr(dst)), "l"(src), "r"(bytes), "r"(psn_smem_addr(bar)) : "memory");
 }
+// the same two operations for a caller that is already inside `if (w_lane0(w))` (one divergent region per row
+// instead of one per instruction)
+PSN_FN void w_bar_expect_l0(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(psn_smem_addr(bar)), "r"(bytes) : "memory");
+}
+PSN_FN void w_bulk_g2s_l0(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(psn_smem_addr(dst)), "l"(src), "r"(bytes), "r"(psn_smem_addr(bar)) : "memory");
+}
 PSN_FN void w_bar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned a = psn_smem_addr(bar);
     unsigned done = 0;
@@ -230,6 +239,8 @@ inline void w_sync(const PsnWarp&) {}
 inline void w_bar_expect(const PsnWarp&, unsigned long long*, unsigned) {}
 inline void w_bulk_g2s(const PsnWarp&, void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
 inline void w_bar_wait(unsigned long long*, unsigned) {}
+inline void w_bar_expect_l0(unsigned long long*, unsigned) {}
+inline void w_bulk_g2s_l0(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
 inline void w_lds4(const PsnWarp&, const double* row, wd (&out)[4]) {
     PSN_W_FOR for (int e = 0; e < 4; ++e) out[e].v[l_] = row[4 * l_ + e];
 }
@@ -431,13 +442,15 @@ struct PsnTmaFeeder {
     PSN_FN void set_base1(const U1* p) { base1 = p; }
     PSN_FN void set_base2(const U2* p) { base2 = p; }
     PSN_FN void issue(const PsnWarp& w, int row, int slot) {
-        const unsigned cnt = (unsigned)(cB - cA);
-        w_bar_expect(w, bar + slot, cnt * (unsigned)ROW_BYTES);
-        w_bulk_g2s(w, ring0 + slot * PSN_STRIP_COLS + (cA - c0), base0 + (long long)row * n + cA, cnt * (unsigned)sizeof(T0), bar + slot);
-        if (NARR >= 2)
-            w_bulk_g2s(w, ring1 + slot * PSN_STRIP_COLS + (cA - c0), base1 + (long long)row * n + cA, cnt * (unsigned)sizeof(U1), bar + slot);
-        if (NARR >= 3)
-            w_bulk_g2s(w, ring2 + slot * PSN_STRIP_COLS + (cA - c0), base2 + (long long)row * n + cA, cnt * (unsigned)sizeof(U2), bar + slot);
+        if (w_lane0(w)) {
+            const unsigned cnt = (unsigned)(cB - cA);
+            const long long off = (long long)row * n + cA;
+            const int so = slot * PSN_STRIP_COLS + (cA - c0);
+            w_bar_expect_l0(bar + slot, cnt * (unsigned)ROW_BYTES);
+            w_bulk_g2s_l0(ring0 + so, base0 + off, cnt * (unsigned)sizeof(T0), bar + slot);
+            if (NARR >= 2) w_bulk_g2s_l0(ring1 + so, base1 + off, cnt * (unsigned)sizeof(U1), bar + slot);
+            if (NARR >= 3) w_bulk_g2s_l0(ring2 + so, base2 + off, cnt * (unsigned)sizeof(U2), bar + slot);
+        }
     }
     PSN_FN void prime(const PsnWarp& w, int ts_) {
         ts = ts_;
@@ -698,7 +711,7 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
 template <int NU, bool FAST, bool SCALE, class TV, class Feeder>
 PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc, int i0, int i1,
                                  typename PsnWV<TV>::type (&val)[2 * NU + 2][4], typename PsnWV<TV>::type (&bb)[2 * NU + 2][4],
-                                 Feeder& fd, int par, typename PsnWV<TV>::type (&eprev)[2], typename PsnWV<TV>::type (&enext)[2], wd& dot,
+                                 Feeder& fd, int par, typename PsnWV<TV>::type (&eprev)[2], typename PsnWV<TV>::type (&enext)[4], wd& dot,
                                  const typename PsnWV<TV>::type (&rdA)[4], const typename PsnWV<TV>::type (&mk)[4], const PsnLevel& lv,
                                  const wd& bsc, const TV* eg, TV* ug, const wi& col0,
                                  const wb (&mp)[2], const wb (&so)[2], const wi& cj, const wb (&mc)[2], bool want_dot) {
@@ -736,14 +749,17 @@ PSN_FN void psn_strip_post_chunk(const PsnWarp& w, int t, int ts, int tload, int
         if (FAST || tc <= last) {
             if (P == 0) {  // even row 2I, red = even columns: mean of coarse (I-1,J-1), (I-1,J), (I,J-1), (I,J)
                 const int I = tc >> 1;
-                // coarse row I was requested two fine rows ago (enext); request row I+1 now
+                // coarse row I was requested four fine rows ago (two-deep queue enext[0..1] = row I, enext[2..3] =
+                // row I+1); request row I+2 now
                 const WV enew[2] = {enext[0], enext[1]};
-                enext[0] = enext[1] = zero;
-                if (FAST || I + 1 < nc) {
-                    const TV* erow = eg + (long long)(I + 1) * nc;
-                    enext[0] = w_ld1(erow, cj, mc[0]);
-                    enext[1] = w_ld1(erow, cj + 1, mc[1]);
-                    if (I + 9 < nc) w_prefetch_l2(eg + (long long)(I + 9) * nc, cj, mc[0]);
+                enext[0] = enext[2];
+                enext[1] = enext[3];
+                enext[2] = enext[3] = zero;
+                if (FAST || I + 2 < nc) {
+                    const TV* erow = eg + (long long)(I + 2) * nc;
+                    enext[2] = w_ld1(erow, cj, mc[0]);
+                    enext[3] = w_ld1(erow, cj + 1, mc[1]);
+                    if (I + 10 < nc) w_prefetch_l2(eg + (long long)(I + 10) * nc, cj, mc[0]);
                 }
                 const WV s0 = eprev[0] + enew[0], s1 = eprev[1] + enew[1];   // column sums J = cj, cj+1
                 const WV sl = w_up_raw(s1);                                     // column J = cj-1
@@ -831,7 +847,7 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const double bs = (SCALE && a.state) ? psn_vscale(a.state[b].rr) : 1.0;
     const wd bsc = w_bcast(bs);
 
-    WV val[W][4], bb[W][4], eprev[2], enext[2];
+    WV val[W][4], bb[W][4], eprev[2], enext[4];
 #pragma unroll
     for (int k = 0; k < W; ++k)
 #pragma unroll
@@ -842,8 +858,8 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     fd.tload = tload;
     psn_feeder_geom(fd, col0, mp, c0, n);
     fd.prime(w, ts);
-    // coarse correction rows: eprev = row ts/2 - 1 (zero above the grid), enext = row ts/2
-    eprev[0] = eprev[1] = enext[0] = enext[1] = zero;
+    // coarse correction rows: eprev = row ts/2 - 1 (zero above the grid), enext = rows ts/2 and ts/2 + 1
+    eprev[0] = eprev[1] = enext[0] = enext[1] = enext[2] = enext[3] = zero;
     wd dot = w_bcast(0.0);
     {
         const int Ip = (ts >> 1) - 1;
@@ -855,11 +871,15 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
             enext[0] = w_ld1(eg + (long long)(Ip + 1) * nc, cj, mc[0]);
             enext[1] = w_ld1(eg + (long long)(Ip + 1) * nc, cj + 1, mc[1]);
         }
+        if (Ip + 2 < nc) {
+            enext[2] = w_ld1(eg + (long long)(Ip + 2) * nc, cj, mc[0]);
+            enext[3] = w_ld1(eg + (long long)(Ip + 2) * nc, cj + 1, mc[1]);
+        }
     }
     const bool want_dot = a.part != nullptr;
 
     for (int t = ts; t <= tend; t += W) {
-        const bool fast = (t - NS - 1 >= ts) && (t + W - 1 + (W - 1) <= tload) && (t + W - 1 < last) && (((t + W - 1) >> 1) + 1 < nc) &&
+        const bool fast = (t - NS - 1 >= ts) && (t + W - 1 + (W - 1) <= tload) && (t + W - 1 < last) && (((t + W - 1) >> 1) + 2 < nc) &&
                           (t - NS >= i0) && (t + W - 1 - NS < i1);
         const int par = ((t - ts) / W) & 1;
         if (fast)
