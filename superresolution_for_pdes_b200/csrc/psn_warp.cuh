@@ -424,6 +424,9 @@ struct PsnTmaFeeder {
     const T0* base0;
     const U1* base1;
     const U2* base2;
+    const T0* nx0;               // source of the next row to be issued (rows are issued strictly in order, so the
+    const U1* nx1;               // address advances by one row pitch per issue instead of being recomputed)
+    const U2* nx2;
     int n, tload, ts;
     int cA, cB, c0;              // in-domain column range [cA, cB) of the strip, strip origin
 #if defined(__CUDACC__)
@@ -441,19 +444,24 @@ struct PsnTmaFeeder {
     PSN_FN void set_base0(const T0* p) { base0 = p; }
     PSN_FN void set_base1(const U1* p) { base1 = p; }
     PSN_FN void set_base2(const U2* p) { base2 = p; }
-    PSN_FN void issue(const PsnWarp& w, int row, int slot) {
+    PSN_FN void issue(const PsnWarp& w, int /*row: always the successor of the previously issued row*/, int slot) {
         if (w_lane0(w)) {
             const unsigned cnt = (unsigned)(cB - cA);
-            const long long off = (long long)row * n + cA;
             const int so = slot * PSN_STRIP_COLS + (cA - c0);
             w_bar_expect_l0(bar + slot, cnt * (unsigned)ROW_BYTES);
-            w_bulk_g2s_l0(ring0 + so, base0 + off, cnt * (unsigned)sizeof(T0), bar + slot);
-            if (NARR >= 2) w_bulk_g2s_l0(ring1 + so, base1 + off, cnt * (unsigned)sizeof(U1), bar + slot);
-            if (NARR >= 3) w_bulk_g2s_l0(ring2 + so, base2 + off, cnt * (unsigned)sizeof(U2), bar + slot);
+            w_bulk_g2s_l0(ring0 + so, nx0, cnt * (unsigned)sizeof(T0), bar + slot);
+            if (NARR >= 2) w_bulk_g2s_l0(ring1 + so, nx1, cnt * (unsigned)sizeof(U1), bar + slot);
+            if (NARR >= 3) w_bulk_g2s_l0(ring2 + so, nx2, cnt * (unsigned)sizeof(U2), bar + slot);
         }
+        nx0 += n;
+        if (NARR >= 2) nx1 += n;
+        if (NARR >= 3) nx2 += n;
     }
     PSN_FN void prime(const PsnWarp& w, int ts_) {
         ts = ts_;
+        nx0 = base0 + (long long)ts * n + cA;
+        nx1 = (NARR >= 2) ? base1 + (long long)ts * n + cA : nullptr;
+        nx2 = (NARR >= 3) ? base2 + (long long)ts * n + cA : nullptr;
         w_zero_smem(w, ring0, W * PSN_STRIP_COLS);   // out-of-domain columns stay zero
         if (NARR >= 2) w_zero_smem(w, ring1, W * PSN_STRIP_COLS);
         if (NARR >= 3) w_zero_smem(w, ring2, W * PSN_STRIP_COLS);
