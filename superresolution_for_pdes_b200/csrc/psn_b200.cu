@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, TMA ? (sizeof(TV) == 4 ?
 psn_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ PsnStripArgs a, long long ntasks) {
     psn_pdl_enter();
     extern __shared__ __align__(128) unsigned char strip_smem[];
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0 so that the compiler treats the warp index (and the task, strip, band and every TMA
+    // address derived from it) as warp-uniform: uniform registers for UBLKCP operands instead of an election loop
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
     if (task >= ntasks) return;
     const int per = a.nstrips * a.nbands;
@@ -140,7 +142,9 @@ __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
 psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     psn_pdl_enter();
     extern __shared__ __align__(128) unsigned char strip_smem[];
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0 so that the compiler treats the warp index (and the task, strip, band and every TMA
+    // address derived from it) as warp-uniform: uniform registers for UBLKCP operands instead of an election loop
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
     if (task >= ntasks) return;
     const int per = a.dir_nstrips * a.dir_nbands;
@@ -169,7 +173,9 @@ __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
 psn_update_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     psn_pdl_enter();
     extern __shared__ __align__(128) unsigned char strip_smem[];
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0 so that the compiler treats the warp index (and the task, strip, band and every TMA
+    // address derived from it) as warp-uniform: uniform registers for UBLKCP operands instead of an election loop
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
     if (task >= ntasks) return;
     const int per = a.upd_nstrips * a.upd_nbands;
@@ -187,7 +193,9 @@ __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, 3)
 psn_true_residual_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     psn_pdl_enter();
     extern __shared__ __align__(128) unsigned char strip_smem[];
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0 so that the compiler treats the warp index (and the task, strip, band and every TMA
+    // address derived from it) as warp-uniform: uniform registers for UBLKCP operands instead of an election loop
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
     if (task >= ntasks) return;
     const int per = a.upd_nstrips * a.upd_nbands;
