@@ -22,7 +22,7 @@ struct PsnWarp {
 PSN_FN wd w_bcast(double s) { return s; }
 PSN_FN wi w_lane(const PsnWarp& w) { return w.lane; }
 PSN_FN wd w_sel(wb c, wd a, wd b) { return c ? a : b; }
-PSN_FN wd w_div(wd a, wd b) { return a / b; }
+PSN_FN wd w_rcp(wd a) { return 1.0 / a; }
 // value of the previous / next lane; the edge lane receives 0
 PSN_FN wd w_up(const PsnWarp& w, wd v) {
     const wd r = __shfl_up_sync(0xffffffffu, v, 1);
@@ -201,7 +201,7 @@ inline wb operator>=(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] >= 
 inline wb operator<(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] < b; return r; }
 inline wb operator==(const wi& a, int b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] == b; return r; }
 inline wb operator&&(const wb& a, const wb& b) { wb r; PSN_W_FOR r.v[l_] = a.v[l_] && b.v[l_]; return r; }
-template <class S> inline wvt<S> w_div(const wvt<S>& a, const wvt<S>& b) { wvt<S> r; PSN_W_FOR r.v[l_] = a.v[l_] / b.v[l_]; return r; }
+template <class S> inline wvt<S> w_rcp(const wvt<S>& a) { wvt<S> r; PSN_W_FOR r.v[l_] = (S)1 / a.v[l_]; return r; }
 template <class S> inline wvt<S> w_sel(const wb& c, const wvt<S>& a, const wvt<S>& b) { wvt<S> r; PSN_W_FOR r.v[l_] = c.v[l_] ? a.v[l_] : b.v[l_]; return r; }
 inline wd w_up(const PsnWarp&, const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 0 ? 0.0 : v.v[l_ - 1]; return r; }
 inline wd w_down(const PsnWarp&, const wd& v) { wd r; PSN_W_FOR r.v[l_] = l_ == 31 ? 0.0 : v.v[l_ + 1]; return r; }
@@ -1224,8 +1224,8 @@ PSN_FN void psn_true_residual_strip_body(const PsnWarp& w, const PsnCgArgs& a, l
                 wd rv[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    // out-of-domain lanes divide 0 by 1 (thp is 1 there: the ring's un-copied columns are zero, see below)
-                    const wd f = w_div(syr * sxv[e], thp[e]);
+                    // out-of-domain lanes multiply 0 by 1 / 1 (thp is 1 there: the ring's un-copied columns are zero, see below)
+                    const wd f = (syr * sxv[e]) * w_rcp(thp[e]);   // same expression as psn_rhs
                     rv[e] = (zero - (f * h2)) - ax[e];
                 }
                 double* rowr = rg + (long long)r * n;
