@@ -18,6 +18,10 @@ What is restated, with the reference lines each function follows
 * ``combine_datasets``            src/enhanced_data_generation.py:167-191
 * ``solve_multi_resolution``      src/resolution_comparison.py:13-78 and the timed
                                   variant src/resolution_comparison_statistical.py:25-96
+* ``solve_large_scale``           src/subdomain_upscaling.py:11-60
+* ``solve_multi_level``           src/subdomain_upscaling.py:276-330
+* ``generate_test_data``          src/compare_test_cases.py:12-79 (without the ``np.savez``)
+* ``generate_out_of_sample_data`` src/test_out_of_sample.py:13-35 (without the ``np.savez``)
 
 Third-party arithmetic: the reference's solve is ``scipy.sparse.linalg.spsolve``
 (SciPy's vendored SuperLU ``gssv``, COLAMD ordering; UMFPACK branch inactive because
@@ -224,3 +228,57 @@ def solve_multi_resolution(n_coarse: int = 40, resolutions: Sequence[int] = (80,
         if timed:
             data["solve_times"][res] = time.time() - t0
     return data
+
+
+# --------------------------------------------------------------------------- evaluation-script callers
+def solve_large_scale(n_coarse: int = 80, n_fine: int = 160) -> dict:
+    """src/subdomain_upscaling.py:11-60.  RNG order: k1, k2 ~ U(5, 8), then the theta block on the
+    fine grid; f and theta of the coarse solve are the ``[::2, ::2]`` gathers of the fine fields."""
+    k1 = np.random.uniform(5.0, 8.0)
+    k2 = np.random.uniform(5.0, 8.0)
+    f_fine = forcing_term_kfirst(k1, k2, n_fine)
+    theta_fine = np.random.uniform(0.5, 2.0, size=(n_fine, n_fine))
+    f_coarse, theta_coarse = f_fine[::2, ::2], theta_fine[::2, ::2]
+    return {"u_fine": solve_poisson(f_fine, theta_fine, n_fine),
+            "u_coarse": solve_poisson(f_coarse, theta_coarse, n_coarse),
+            "f_fine": f_fine, "f_coarse": f_coarse, "theta_fine": theta_fine, "theta_coarse": theta_coarse,
+            "k1": k1, "k2": k2}
+
+
+def solve_multi_level(n_coarse: int = 40, n_mid: int = 80, n_fine: int = 160) -> dict:
+    """src/subdomain_upscaling.py:276-330: three solves on f / theta gathered twice by ``[::2, ::2]``."""
+    k1 = np.random.uniform(5.0, 8.0)
+    k2 = np.random.uniform(5.0, 8.0)
+    f_fine = forcing_term_kfirst(k1, k2, n_fine)
+    f_mid = f_fine[::2, ::2]
+    f_coarse = f_mid[::2, ::2]
+    theta_fine = np.random.uniform(0.5, 2.0, size=(n_fine, n_fine))
+    theta_mid = theta_fine[::2, ::2]
+    theta_coarse = theta_mid[::2, ::2]
+    return {"u_fine": solve_poisson(f_fine, theta_fine, n_fine), "u_mid": solve_poisson(f_mid, theta_mid, n_mid),
+            "u_coarse": solve_poisson(f_coarse, theta_coarse, n_coarse),
+            "f_fine": f_fine, "f_mid": f_mid, "f_coarse": f_coarse,
+            "theta_fine": theta_fine, "theta_mid": theta_mid, "theta_coarse": theta_coarse, "k1": k1, "k2": k2}
+
+
+def generate_test_data(k_range: Tuple[float, float], n_samples: int = 10, constant_theta: bool = True) -> dict:
+    """src/compare_test_cases.py:12-79 minus the file write.  The standard dataset is drawn first (all k);
+    with ``constant_theta=False`` one 40x40 theta block per sample follows in the RNG stream, the coarse
+    theta is its ``[::2, ::2]`` gather, and f_coarse stays the forcing evaluated ON the coarse grid."""
+    ds = generate_dataset(n_samples, k_range)
+    n_c, n_f = ds["u_coarse"].shape[1], ds["u_fine"].shape[1]
+    for i in range(n_samples):
+        if constant_theta:
+            th_f, th_c = np.ones((n_f, n_f)), np.ones((n_c, n_c))
+        else:
+            th_f = np.random.uniform(0.5, 2.0, size=(n_f, n_f))
+            th_c = th_f[::2, ::2]
+        ds["theta_fine"][i], ds["theta_coarse"][i] = th_f, th_c
+        ds["u_fine"][i] = solve_poisson(ds["f_fine"][i], th_f, n_f)
+        ds["u_coarse"][i] = solve_poisson(ds["f_coarse"][i], th_c, n_c)
+    return ds
+
+
+def generate_out_of_sample_data(n_samples: int = 10) -> dict:
+    """src/test_out_of_sample.py:13-35 minus the file write: the standard generator with k ~ U(5, 8)."""
+    return generate_dataset(n_samples, (5.0, 8.0))

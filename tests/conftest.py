@@ -42,3 +42,27 @@ def gpu_lib():
         pytest.fail("gpu test selected but no CUDA device is visible")
     _lib.init(0)
     return _lib
+
+
+def _rel_l2(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
+
+
+def check_caller_dict(d, gold, prefix, tol_u):
+    """Compare one caller's returned dict with the reference fixture (tests/golden/make_golden_callers.py)."""
+    for k, v in d.items():
+        v = np.asarray(v)
+        key = f"{prefix}_{k}"
+        is_u = k.startswith("u_")
+        if key in gold.files:
+            assert v.shape == gold[key].shape, key
+            if is_u:
+                assert _rel_l2(v, gold[key]) <= tol_u, key
+            else:
+                assert np.array_equal(v, gold[key]), key
+        else:  # 160x160 field: norm / sum (+ [::2, ::2] samples of u)
+            if is_u:
+                assert _rel_l2(v[::2, ::2], gold[key + "_s2"]) <= tol_u, key
+                assert abs(np.linalg.norm(v) - gold[key + "_norm"]) <= tol_u * gold[key + "_norm"], key
+            else:
+                assert v.sum() == gold[key + "_sum"] and np.linalg.norm(v) == gold[key + "_norm"], key

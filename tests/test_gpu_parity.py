@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, KAT_K, kat_inputs, kat_sub
+from conftest import GOLDEN, KAT_K, check_caller_dict, kat_inputs, kat_sub
 from oracle import poisson_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -437,3 +437,37 @@ def test_streamed_edge_cases_and_speculative_pipeline(gpu_lib):
     g3 = np.ones(90, bool); g3[70] = False
     assert (info3.status[g3] == 2).all() and (info3.iters[g3] == 4).all() and np.isfinite(u3[g3]).all()
     assert (info3.relres[g3] > 1e-9).all() and (info3.relres[g3] < 1e-2).all()
+
+
+@pytest.mark.gpu
+def test_evaluation_script_callers_match_reference_fixture(gpu_lib, tmp_path, monkeypatch):
+    """Row a10: solve_large_scale / solve_multi_level (src/subdomain_upscaling.py), generate_test_data
+    (src/compare_test_cases.py, both theta modes) and generate_out_of_sample_data (src/test_out_of_sample.py)
+    through the shims, against the live reference's outputs on the same seeds (k, f, theta bit-exact, u <= 1e-10)."""
+    import superresolution_for_pdes_b200 as pkg
+    gold = np.load(os.path.join(GOLDEN, "callers_seed5.npz"))
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(5)
+    check_caller_dict(pkg.solve_large_scale(20, 40), gold, "large_small", TOL)
+    np.random.seed(5)
+    d = pkg.solve_large_scale()
+    check_caller_dict(d, gold, "large", TOL)
+    assert np.array_equal(d["f_coarse"], d["f_fine"][::2, ::2]) and np.array_equal(d["theta_coarse"], d["theta_fine"][::2, ::2])
+    np.random.seed(5)
+    check_caller_dict(pkg.solve_multi_level(), gold, "level", TOL)
+    with pytest.raises(ValueError):
+        pkg.solve_large_scale(60, 160)
+    for name, const in (("test_const", True), ("test_rand", False)):
+        np.random.seed(6)
+        d = pkg.generate_test_data((1.0, 6.0), 3, name, const)
+        check_caller_dict(d, gold, name, TOL)
+        saved = np.load(tmp_path / "data" / f"{name}_dataset.npz")
+        assert set(saved.files) == set(d) and all(np.array_equal(saved[k], d[k]) for k in d)
+    np.random.seed(7)
+    d = pkg.generate_out_of_sample_data(3)
+    check_caller_dict(d, gold, "oos", TOL)
+    assert (tmp_path / "data" / "out_of_sample_dataset.npz").exists()
+    state = np.random.get_state()[1].copy()
+    np.random.seed(7)
+    O.generate_out_of_sample_data(3)
+    assert np.array_equal(state, np.random.get_state()[1])      # same RNG consumption as the reference

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, kat_inputs, kat_sub
+from conftest import GOLDEN, check_caller_dict, kat_inputs, kat_sub
 from oracle import poisson_oracle as O
 
 
@@ -100,3 +100,19 @@ def test_upscale_oracle_against_golden():
     assert uo.multi_level_upscale(data, 40, "bilinear").shape == (40, 40)
     parts = uo.split_into_subdomains(u40, 10)
     assert len(parts) == 4 and len(parts[0]) == 4 and np.array_equal(uo.stitch_subdomains(parts), u40)
+
+
+def test_oracle_callers_against_golden():
+    """Row a10: evaluation-script callers restated in the oracle reproduce the live reference's outputs."""
+    gold = np.load(os.path.join(GOLDEN, "callers_seed5.npz"))
+    np.random.seed(5)
+    check_caller_dict(O.solve_large_scale(20, 40), gold, "large_small", 1e-13)
+    np.random.seed(5)
+    check_caller_dict(O.solve_large_scale(80, 160), gold, "large", 1e-13)
+    np.random.seed(5)
+    check_caller_dict(O.solve_multi_level(40, 80, 160), gold, "level", 1e-13)
+    for name, const in (("test_const", True), ("test_rand", False)):
+        np.random.seed(6)
+        check_caller_dict(O.generate_test_data((1.0, 6.0), 3, const), gold, name, 1e-13)
+    np.random.seed(7)
+    check_caller_dict(O.generate_out_of_sample_data(3), gold, "oos", 1e-13)
