@@ -9,7 +9,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT
+from conftest import GOLDEN, ROOT, check_caller_dict
 from oracle import poisson_oracle as O
 import superresolution_for_pdes_b200 as pkg
 from superresolution_for_pdes_b200 import _lib
@@ -106,7 +106,8 @@ def oracle_backend(monkeypatch):
     import superresolution_for_pdes_b200.data_generation as dg
     import superresolution_for_pdes_b200.enhanced_data_generation as eg
     import superresolution_for_pdes_b200.resolution_comparison as rc
-    for mod in (dg, eg, rc):
+    import superresolution_for_pdes_b200.subdomain_upscaling as su
+    for mod in (dg, eg, rc, su):
         monkeypatch.setattr(mod._lib, "solve_batch", bk.solve_batch)   # solve_from_wavenumbers calls this per chunk
         monkeypatch.setattr(mod._lib, "subdomain_batch", bk.subdomain_batch)
         monkeypatch.setattr(mod._lib, "multires", bk.multires)
@@ -177,6 +178,44 @@ def test_host_logic_multires(oracle_backend):
     r0 = O.solve_multi_resolution(40, [80])
     r1 = O.solve_multi_resolution(40, [80])
     assert O.rel_l2(b["u"][80][0], r0["u"][80]) <= 1e-13 and O.rel_l2(b["u"][40][1], r1["u"][40]) <= 1e-13
+
+
+def test_host_logic_evaluation_script_callers(oracle_backend, tmp_path, monkeypatch):
+    """Row a10 on the CPU tier: RNG order, gathers, dict keys, file writes and signatures of the
+    src/subdomain_upscaling.py / src/compare_test_cases.py / src/test_out_of_sample.py generators."""
+    gold = np.load(os.path.join(GOLDEN, "callers_seed5.npz"))
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(5)
+    check_caller_dict(pkg.solve_large_scale(20, 40), gold, "large_small", 1e-13)
+    np.random.seed(5)
+    d = pkg.solve_multi_level()
+    check_caller_dict(d, gold, "level", 1e-13)
+    assert list(d) == ["u_fine", "u_mid", "u_coarse", "f_fine", "f_mid", "f_coarse",
+                       "theta_fine", "theta_mid", "theta_coarse", "k1", "k2"]
+    assert d["f_coarse"].base is not None and np.array_equal(d["theta_coarse"], d["theta_fine"][::4, ::4])
+    with pytest.raises(ValueError, match="halve"):
+        pkg.solve_multi_level(40, 80, 200)
+    for name, const in (("test_const", True), ("test_rand", False)):
+        np.random.seed(6)
+        d = pkg.generate_test_data((1.0, 6.0), 3, name, const)
+        check_caller_dict(d, gold, name, 1e-13)
+        saved = np.load(tmp_path / "data" / f"{name}_dataset.npz")
+        assert saved.files == list(d) and all(np.array_equal(saved[k], d[k]) for k in d)
+        nxt = np.random.uniform()
+        np.random.seed(6)
+        O.generate_test_data((1.0, 6.0), 3, const)
+        assert nxt == np.random.uniform()          # stream left where the reference leaves it
+    np.random.seed(7)
+    check_caller_dict(pkg.generate_out_of_sample_data(3, save=False), gold, "oos", 1e-13)
+    assert not (tmp_path / "data" / "out_of_sample_dataset.npz").exists()
+    ls = inspect.signature(pkg.solve_large_scale).parameters
+    assert ls["n_coarse"].default == 80 and ls["n_fine"].default == 160
+    ml = inspect.signature(pkg.solve_multi_level).parameters
+    assert (ml["n_coarse"].default, ml["n_mid"].default, ml["n_fine"].default) == (40, 80, 160)
+    td = inspect.signature(pkg.generate_test_data).parameters
+    assert list(td)[:4] == ["k_range", "n_samples", "label", "constant_theta"] and td["n_samples"].default == 10
+    assert td["label"].default == "test" and td["constant_theta"].default is True
+    assert inspect.signature(pkg.generate_out_of_sample_data).parameters["n_samples"].default == 10
 
 
 def test_unconverged_solutions_are_never_returned_silently():
