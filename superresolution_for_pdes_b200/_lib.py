@@ -264,11 +264,14 @@ def multires(n_finest: int, resolutions: Sequence[int], batch: int, theta_finest
 
 
 def solve_from_wavenumbers(n: int, k1, k2, *, theta=None, out=None, chunks: Optional[int] = None, kfirst: bool = False,
-                           rtol: float = 2.5e-13, max_iter: int = 100):
+                           rtol: float = 2.5e-13, max_iter: int = 100, sines_out=None):
     """Host-side convenience used by the dataset shims and by bench.py's end-to-end leg: evaluates the 2n sine
     factors per sample with numpy (operand order of the reference, so f is bit-identical) for chunk c+1 on a
     helper thread WHILE chunk c is inside the C call (both release the GIL), then solves.  theta / out are host
-    arrays [B, n, n] (theta may be None).  Returns (u, SolveInfo, sin_x, sin_y)."""
+    arrays [B, n, n] (theta may be None).  ``sines_out=(sin_x, sin_y)``: caller-owned float64 [B, n] arrays to
+    evaluate the sines into -- a caller whose theta / out are page-locked passes page-locked ones here, so that
+    every copy of the call is asynchronous and the library takes its deep upload pipeline.
+    Returns (u, SolveInfo, sin_x, sin_y)."""
     from concurrent.futures import ThreadPoolExecutor
 
     k1 = np.ascontiguousarray(k1, dtype=np.float64).reshape(-1)
@@ -277,8 +280,14 @@ def solve_from_wavenumbers(n: int, k1, k2, *, theta=None, out=None, chunks: Opti
     x = np.linspace(0, 1, n)
     if out is None:
         out = np.empty((B, n, n), dtype=np.float64)
-    sx = np.empty((B, n), dtype=np.float64)
-    sy = np.empty((B, n), dtype=np.float64)
+    if sines_out is not None:
+        sx, sy = sines_out
+        for a_ in (sx, sy):
+            if a_.shape != (B, n) or a_.dtype != np.float64 or not a_.flags.c_contiguous:
+                raise ValueError(f"sines_out arrays must be C-contiguous float64 of shape {(B, n)}")
+    else:
+        sx = np.empty((B, n), dtype=np.float64)
+        sy = np.empty((B, n), dtype=np.float64)
     iters = np.zeros(B, dtype=np.int32)
     relres = np.zeros(B, dtype=np.float64)
     status = np.zeros(B, dtype=np.int32)

@@ -447,7 +447,7 @@ struct PlanEntry {
     double* d_inv;
 };
 
-#define PSN_NSLOTS 3
+#define PSN_NSLOTS 6   // staging slots that exist; Context::host_slots of them are used
 
 struct Arena {
     char* base = nullptr;
@@ -463,6 +463,7 @@ struct Slot {
     int h_counters_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t staging_free = nullptr;   // recorded after the last copy of the chunk that used the staging arena
+    cudaEvent_t h2d_done = nullptr;       // recorded on the upload stream after the chunk's last H2D copy
 };
 
 // few streams on purpose: a process has CUDA_DEVICE_MAX_CONNECTIONS (default 8) hardware queues, streams beyond that
@@ -479,6 +480,7 @@ struct Context {
     // overlapping chunks the earlier one wins the SMs (it finishes, and its result copy starts, as early as it
     // would alone) while the later one fills the gaps.
     cudaStream_t chunk_stream[PSN_NCHUNK_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t h2d_stream = nullptr;   // uploads of all chunks, in chunk order (host_h2d_stream)
     bool ready = false;
     int device = -1;
     int sm_count = 0;
@@ -507,6 +509,9 @@ struct Context {
     int host_edge_div = 2; // first / last chunk of the host pipeline = regular chunk / host_edge_div
     int vcycle_f32 = 1;    // streamed path: store V-cycle intermediates as float where the grid sizes allow (PsnStreamCfg::vf32)
     int host_chunks = 0;   // target number of pipeline chunks when staging host buffers (0: 6 streamed / 8 resident)
+    int host_slots = 5;    // staging slots in use (3..PSN_NSLOTS): chunk c's upload waits for chunk c - host_slots to leave its slot
+    int host_prefetch = 3; // uploads enqueued this many chunks ahead of the solve being enqueued (<= host_slots - 2, <= 3)
+    int host_h2d_stream = 1;  // 1: uploads go through their own stream instead of the chunk's solve stream
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     bool attrs_set = false;
     bool profiling = false;
@@ -546,6 +551,17 @@ MemKind classify(const void* p) {
         return MEM_HOST;
     }
     return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? MEM_DEVICE : MEM_HOST;
+}
+
+// pageable host memory: cudaMemcpyAsync to / from it holds the calling thread until the copy has run
+bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
 }
 
 int ensure_init() {
@@ -1082,6 +1098,14 @@ int solve_internal(const Problem& P) {
     const MemKind kinds[] = {k_theta, k_f, k_sx, k_sy, k_k1, k_k2, k_u, k_it, k_rr, k_st, k_x0, k_y0, k_uf, k_ff, k_tf, k_uc, k_fc, k_tc};
     bool any_host = false;
     for (MemKind k : kinds) any_host = any_host || (k == MEM_HOST);
+    // The deep upload pipeline (host_slots / host_prefetch / host_h2d_stream) enqueues the copies of several chunks before
+    // the solve of the current one; a copy from or to pageable memory would hold the host inside that enqueue until the
+    // copies queued in front of it have run, so callers with pageable buffers keep the shallow 3-slot pipeline.
+    // (iters / relres / status of host callers go through the pinned bounce buffer.)
+    const void* bulk[] = {P.theta, P.f, P.sx, P.sy, P.k1, P.k2, P.u, P.start_x, P.start_y,
+                          P.u_fine, P.f_fine, P.th_fine, P.u_coarse, P.f_coarse, P.th_coarse};
+    bool deep = any_host;
+    for (const void* q : bulk) deep = deep && !is_pageable(q);
 
     const size_t nn = (size_t)P.n * P.n, mm = (size_t)P.mn * P.mn;
     const int sc = (P.sub + 1) / 2;
@@ -1120,7 +1144,7 @@ int solve_internal(const Problem& P) {
         }
         if (Bc > cap) Bc = cap;
     }
-    const int nslots = any_host ? PSN_NSLOTS : 1;
+    const int nslots = any_host ? (deep ? g.host_slots : 3) : 1;
     if (any_host) CU_TRY(cudaStreamSynchronize(P.stream));
     Trace trace;
     if (any_host) trace.begin(g.chunk_stream[0]);  // device inputs may still be in flight on the caller's stream
@@ -1219,7 +1243,9 @@ int solve_internal(const Problem& P) {
         cx.slot = &g.slots[c % nslots];
         cx.s = any_host ? g.chunk_stream[c % PSN_NCHUNK_STREAMS] : P.stream;
         const long long b0 = cx.b0, bc = cx.bc;
-        cudaStream_t s = cx.s;
+        const cudaStream_t solve_s = cx.s;
+        // uploads either ride the chunk's own stream or a dedicated upload stream (FIFO over chunks) that the solve waits for
+        cudaStream_t s = (deep && g.host_h2d_stream) ? g.h2d_stream : solve_s;
         if (c < nslots) {
             rc2 = arena_reserve(cx.slot->arena, pad256(stage_ps * Bc) + 64 * 256 + (size_t)Bc * 64);
             if (rc2) return rc2;
@@ -1265,6 +1291,10 @@ int solve_internal(const Problem& P) {
             }
         }
         trace.mark("h2d_end", c, s);
+        if (s != solve_s) {
+            CU_TRY(cudaEventRecord(cx.slot->h2d_done, s));
+            CU_TRY(cudaStreamWaitEvent(solve_s, cx.slot->h2d_done, 0));
+        }
         return PSN_OK;
     };
 
@@ -1380,15 +1410,26 @@ int solve_internal(const Problem& P) {
         return PSN_OK;
     };
 
-    ChunkCtx cur, nxt;
-    if ((rc = prepare(0, cur))) return rc;
+    // Uploads run `ahead` chunks in front of the solve being enqueued.  Chunk c + ahead reuses the staging slot of chunk
+    // c + ahead - nslots, whose last copy is enqueued by run() or, for a resumed straggler, by resolve() two iterations
+    // later: ahead <= nslots - 2 keeps every staging_free record ahead (in host order) of the wait that needs it.  Without
+    // the upload stream the copy rides the solve stream of chunk c + ahead, which chunk c + ahead - PSN_NCHUNK_STREAMS
+    // used: ahead < PSN_NCHUNK_STREAMS keeps it out of the way of a solve that is yet to be enqueued.
+    int ahead = 1;
+    if (deep) {
+        ahead = g.host_prefetch;
+        if (ahead > nslots - 2) ahead = nslots - 2;
+        if (ahead > PSN_NCHUNK_STREAMS - 1) ahead = PSN_NCHUNK_STREAMS - 1;
+        if (ahead < 1) ahead = 1;
+    }
+    ChunkCtx ring[PSN_NCHUNK_STREAMS];   // chunks c .. c + ahead
+    long long prepared = 0;
     for (long long c = 0; c < nchunks; ++c) {
-        const bool more = c + 1 < nchunks;
         // chunk c-2 used the workspace (and chunk c+1 reuses the staging slot) that are about to be recycled
         if (nws == 2 && (rc = resolve((int)(c & 1)))) return rc;
-        if (more && (rc = prepare(c + 1, nxt))) return rc;
-        if ((rc = run(c, cur))) return rc;
-        if (more) cur = nxt;
+        for (; prepared <= c + ahead && prepared < nchunks; ++prepared)
+            if ((rc = prepare(prepared, ring[prepared % PSN_NCHUNK_STREAMS]))) return rc;
+        if ((rc = run(c, ring[c % PSN_NCHUNK_STREAMS]))) return rc;
     }
     if (nws == 2) {
         if ((rc = resolve(0))) return rc;
@@ -1396,6 +1437,7 @@ int solve_internal(const Problem& P) {
     }
     if (any_host) {
         for (int i = 0; i < PSN_NCHUNK_STREAMS; ++i) CU_TRY(cudaStreamSynchronize(g.chunk_stream[i]));
+        CU_TRY(cudaStreamSynchronize(g.h2d_stream));
         if (hb_it && k_it == MEM_HOST) memcpy(P.iters, hb_it, (size_t)P.B * 4);
         if (hb_rr && k_rr == MEM_HOST) memcpy(P.relres, hb_rr, (size_t)P.B * 8);
         if (hb_st && k_st == MEM_HOST) memcpy(P.status, hb_st, (size_t)P.B * 4);
@@ -1439,6 +1481,7 @@ int psn_init(int device) {
     for (int k = 0; k < 2; ++k) CU_TRY(cudaEventCreateWithFlags(&g.ws_free[k], cudaEventDisableTiming));
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         CU_TRY(cudaEventCreateWithFlags(&g.slots[i].staging_free, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&g.slots[i].h2d_done, cudaEventDisableTiming));
         for (int k = 0; k < 4; ++k) CU_TRY(cudaEventCreateWithFlags(&g.slots[i].ev[k], cudaEventDisableTiming));
     }
     {
@@ -1449,6 +1492,7 @@ int psn_init(int device) {
             if (pr > prio_lo) pr = prio_lo;
             CU_TRY(cudaStreamCreateWithPriority(&g.chunk_stream[i], cudaStreamNonBlocking, pr));
         }
+        CU_TRY(cudaStreamCreateWithPriority(&g.h2d_stream, cudaStreamNonBlocking, prio_hi));
     }
     const char* env = getenv("PSN_WS_BYTES");
     if (env) g.ws_bytes = atoll(env);
@@ -1473,6 +1517,8 @@ void psn_shutdown(void) {
         if (g.chunk_stream[i]) cudaStreamDestroy(g.chunk_stream[i]);
         g.chunk_stream[i] = nullptr;
     }
+    if (g.h2d_stream) cudaStreamDestroy(g.h2d_stream);
+    g.h2d_stream = nullptr;
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         Slot& s = g.slots[i];
         if (s.arena.base) cudaFree(s.arena.base);
@@ -1482,6 +1528,7 @@ void psn_shutdown(void) {
             if (s.ev[k]) cudaEventDestroy(s.ev[k]);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.staging_free) cudaEventDestroy(s.staging_free);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         s = Slot();
     }
     for (auto& r : g.prof) {
@@ -1698,6 +1745,14 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "vcycle_f32")) {
         if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "vcycle_f32 must be 0 or 1");
         g.vcycle_f32 = (int)value;
+    } else if (!strcmp(name, "host_slots")) {
+        if (value < 3 || value > PSN_NSLOTS) return psn_fail(PSN_ERR_INVALID, "host_slots must be in 3..%d", PSN_NSLOTS);
+        g.host_slots = (int)value;
+    } else if (!strcmp(name, "host_prefetch")) {
+        if (value < 1 || value > PSN_NCHUNK_STREAMS - 1) return psn_fail(PSN_ERR_INVALID, "host_prefetch must be in 1..%d", PSN_NCHUNK_STREAMS - 1);
+        g.host_prefetch = (int)value;
+    } else if (!strcmp(name, "host_h2d_stream")) {
+        g.host_h2d_stream = value ? 1 : 0;
     } else if (!strcmp(name, "host_chunks")) {
         if (value < 0 || value > 1024) return psn_fail(PSN_ERR_INVALID, "host_chunks must be in 0..1024");
         g.host_chunks = (int)value;
