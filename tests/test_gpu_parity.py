@@ -440,6 +440,44 @@ def test_streamed_edge_cases_and_speculative_pipeline(gpu_lib):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,B", [(176, 300), (80, 5000)])
+def test_page_locked_callers_take_the_deep_upload_pipeline(gpu_lib, n, B):
+    """Host-buffer calls with page-locked theta / sines / u use 5 staging slots with the uploads running 3 chunks ahead
+    on their own stream; pageable callers keep the 3-slot pipeline.  Same chunking, same kernels: the results must be
+    bit-identical, for every slot / prefetch / upload-stream setting, including chunks that the speculative enqueue
+    has to resume (streamed case: later chunks need more outer iterations than the first)."""
+    import torch
+    rs = np.random.RandomState(21)
+    x = np.linspace(0, 1, n)
+    k = np.concatenate([rs.uniform(9.0, 12.0, size=(B // 4, 2)), rs.uniform(0.5, 1.5, size=(B - B // 4, 2))])
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    theta[B // 4:B // 2] = 1.0
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    u_ref, info_ref = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)           # pageable numpy buffers
+    assert (info_ref.status <= 1).all()
+    for b in (0, B // 3, B - 1):
+        assert O.rel_l2(u_ref[b], O.solve_poisson(np.outer(sy[b], sx[b]), theta[b], n)) <= TOL
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    th_p, sx_p, sy_p = pin(theta), pin(sx), pin(sy)
+    try:
+        for slots, ahead, own_stream in ((5, 3, 1), (6, 3, 1), (6, 2, 0), (4, 3, 1), (3, 1, 1)):
+            gpu_lib.set_option("host_slots", slots)
+            gpu_lib.set_option("host_prefetch", ahead)
+            gpu_lib.set_option("host_h2d_stream", own_stream)
+            u_p = torch.full((B, n, n), float("nan"), dtype=torch.float64).pin_memory()
+            for _ in range(2):   # the second call reuses staging slots that the first one left behind
+                _, info = gpu_lib.solve_batch(n, B, theta=th_p, sin_x=sx_p, sin_y=sy_p, out=u_p)
+            assert np.array_equal(u_p.numpy(), u_ref), (slots, ahead, own_stream)
+            assert np.array_equal(info.iters, info_ref.iters) and np.array_equal(info.status, info_ref.status)
+    finally:
+        gpu_lib.set_option("host_slots", 5)
+        gpu_lib.set_option("host_prefetch", 3)
+        gpu_lib.set_option("host_h2d_stream", 1)
+    with pytest.raises(gpu_lib.PsnError):
+        gpu_lib.set_option("host_slots", 7)
+
+
+@pytest.mark.gpu
 def test_evaluation_script_callers_match_reference_fixture(gpu_lib, tmp_path, monkeypatch):
     """Row a10: solve_large_scale / solve_multi_level (src/subdomain_upscaling.py), generate_test_data
     (src/compare_test_cases.py, both theta modes) and generate_out_of_sample_data (src/test_out_of_sample.py)
