@@ -175,7 +175,8 @@ int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const dou
  * that same rounded direction, so the recurrences stay exact), "x_defer" (default 1: with p_f32 the last 12 directions
  * stay in a ring and x = sum alpha_k p_k is formed in one fp64 pass when a sample is checked or the ring is full,
  * instead of a read-modify-write of x every iteration), "pdl" (default 1: programmatic dependent
- * launch between the kernels of a solve), "host_slots" (default 5, 3..6: staging slots of the host-buffer pipeline),
+ * launch between the kernels of a solve), the host-buffer pipeline of resident grids with page-locked buffers:
+ * "host_slots" (default 5, 3..6: staging slots),
  * "host_prefetch" (default 3, 1..3: uploads are enqueued this many chunks ahead of the solve being enqueued),
  * "host_h2d_stream" (default 1: uploads of all chunks go through one dedicated stream, in chunk order),
  * "coarse_max_n", "host_chunks", "host_edge_div", "dir_band", "upd_band",

@@ -1102,9 +1102,12 @@ int solve_internal(const Problem& P) {
     // the solve of the current one; a copy from or to pageable memory would hold the host inside that enqueue until the
     // copies queued in front of it have run, so callers with pageable buffers keep the shallow 3-slot pipeline.
     // (iters / relres / status of host callers go through the pinned bounce buffer.)
+    // Resident grids only: the streamed sizes are bound by the PCIe link at any depth on one GPU (640^2: 44.4 ms per 3.36 GB
+    // either way), and with two ranks sharing the host fabric the uploads running ahead took bandwidth from the result
+    // copies on the critical path (640^2 at 2 GPUs: 18.1k -> 14.3k solves/s end to end), while 80^2 gained at 1 and 2 GPUs.
     const void* bulk[] = {P.theta, P.f, P.sx, P.sy, P.k1, P.k2, P.u, P.start_x, P.start_y,
                           P.u_fine, P.f_fine, P.th_fine, P.u_coarse, P.f_coarse, P.th_coarse};
-    bool deep = any_host;
+    bool deep = any_host && resident;
     for (const void* q : bulk) deep = deep && !is_pageable(q);
 
     const size_t nn = (size_t)P.n * P.n, mm = (size_t)P.mn * P.mn;

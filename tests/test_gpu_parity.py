@@ -442,10 +442,11 @@ def test_streamed_edge_cases_and_speculative_pipeline(gpu_lib):
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,B", [(176, 300), (80, 5000)])
 def test_page_locked_callers_take_the_deep_upload_pipeline(gpu_lib, n, B):
-    """Host-buffer calls with page-locked theta / sines / u use 5 staging slots with the uploads running 3 chunks ahead
-    on their own stream; pageable callers keep the 3-slot pipeline.  Same chunking, same kernels: the results must be
-    bit-identical, for every slot / prefetch / upload-stream setting, including chunks that the speculative enqueue
-    has to resume (streamed case: later chunks need more outer iterations than the first)."""
+    """Host-buffer calls on resident grids with page-locked theta / sines / u use 5 staging slots with the uploads running
+    3 chunks ahead on their own stream; pageable callers and streamed grids keep the 3-slot pipeline.  Same chunking, same
+    kernels: the results must be bit-identical for every slot / prefetch / upload-stream setting and for page-locked
+    vs pageable buffers, including chunks that the speculative enqueue has to resume (streamed case: later chunks need
+    more outer iterations than the first)."""
     import torch
     rs = np.random.RandomState(21)
     x = np.linspace(0, 1, n)
