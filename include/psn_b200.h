@@ -11,7 +11,9 @@
  *  - all arrays are float64 (int32 where stated), C-contiguous, row index = y, column = x;
  *  - every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer on the
  *    library's device; the library detects which (cudaPointerGetAttributes) and stages host
- *    data through its own device buffers in overlapped chunks;
+ *    data through its own device buffers in overlapped chunks; DEVICE arrays must be 16-byte aligned (they are
+ *    accessed in place with 128-bit loads / stores and bulk copies; PSN_ERR_INVALID otherwise), host arrays
+ *    need only their natural alignment;
  *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  When every
  *    data pointer is a device pointer the call only ENQUEUES work on `stream` and returns
  *    without synchronising, except for small D2H reads of convergence counters on the
@@ -29,10 +31,12 @@
  *
  * status[] values per sample:
  *   0 PSN_ST_CONVERGED   true relative residual <= rtol
- *   1 PSN_ST_FP64_FLOOR  residual stagnated at the fp64 round-off floor above rtol (as accurate as
- *                        a backward-stable direct solve; happens for very smooth f on large grids)
+ *   1 PSN_ST_FP64_FLOOR  residual stagnated at the fp64 round-off floor above rtol but below 1e-10 (as accurate
+ *                        as a backward-stable direct solve; happens for very smooth f on large grids)
  *   2 PSN_ST_MAXITER     max_iter reached without convergence
  *   3 PSN_ST_BREAKDOWN   non-finite / non-SPD data (e.g. theta == 0, NaN input)
+ *   4 PSN_ST_STAGNATED   a restart from the true residual did not reduce it 4x and it is above 1e-10:
+ *                        not converged (callers must treat 2, 3 and 4 as failures)
  */
 #ifndef PSN_B200_H
 #define PSN_B200_H
@@ -163,7 +167,9 @@ int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine,
  */
 int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const double* u_in, float* out, void* stream);
 
-/* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg, default 2), "tile" (interior
+/* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg, default 2), "coarsest_max" (0 = automatic: 10 for grids
+ * of 32 x 32 and more, 6 below; else 2..10: largest level n x n that is solved with the precomputed dense inverse instead
+ * of being smoothed), "tile" (interior
  * tile edge of the streamed kernels, default 64), "ws_bytes" (workspace budget per pipeline slot),
  * "smem_max_n" (largest n solved fully in shared memory; 0 = as large as fits), "vcycle_mode" (streamed V-cycle
  * legs: 0 shared-memory tiles, 1 register-fed warp strips, 2 TMA-fed warp strips = default), "vcycle_f32"

@@ -2,7 +2,7 @@
 
 There is NO CPU fallback: if the CUDA library has not been built, or no CUDA device is
 present, every compute call raises.  Build with ``python -c "import __graft_entry__ as g; g.build()"``
-(or ``make -C superresolution_for_pdes_b200/csrc``).
+-- the single nvcc command it runs is printed, so the library can also be rebuilt by hand).
 """
 from __future__ import annotations
 
@@ -18,7 +18,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PSN_B200_LIB") or os.path.join(_HERE, "libpsn_b200.so")
 
 PSN_OK = 0
-STATUS_CONVERGED, STATUS_FP64_FLOOR, STATUS_MAXITER, STATUS_BREAKDOWN = 0, 1, 2, 3
+STATUS_CONVERGED, STATUS_FP64_FLOOR, STATUS_MAXITER, STATUS_BREAKDOWN, STATUS_STAGNATED = 0, 1, 2, 3, 4
+# a sample that ends at the fp64 round-off floor (status 1) is only accepted below this relative true residual
+# (PSN_FLOOR_CEIL of the library; checked again here so that no entry point returns a stagnated sample silently)
+FLOOR_RELRES_CEILING = 1e-10
 
 EXPORTED_SYMBOLS = (
     "psn_version", "psn_get_device_count", "psn_init", "psn_shutdown", "psn_last_error",
@@ -115,6 +118,35 @@ def _f64(a, shape=None, name="array"):
     return arr
 
 
+_TORCH_NAMES = {"float64": "torch.float64", "float32": "torch.float32", "int32": "torch.int32"}
+
+
+def _out(a, shape, dtype: str, name: str):
+    """Validate a caller-supplied OUTPUT buffer before its raw address crosses the C ABI: the library writes
+    prod(shape) elements of `dtype` through it, so a wrong dtype, a non-contiguous view or a short array would
+    corrupt host or device memory.  numpy arrays and torch tensors (host or CUDA) are accepted."""
+    shape = tuple(int(v) for v in shape)
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.dtype(dtype):
+            raise ValueError(f"{name}: expected dtype {dtype}, got {a.dtype}")
+        if not a.flags.c_contiguous:
+            raise ValueError(f"{name}: output array must be C-contiguous")
+        if not a.flags.writeable:
+            raise ValueError(f"{name}: output array is read-only")
+        if tuple(a.shape) != shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {tuple(a.shape)}")
+        return a
+    if hasattr(a, "data_ptr"):
+        if str(a.dtype) != _TORCH_NAMES[dtype]:
+            raise ValueError(f"{name}: expected dtype {_TORCH_NAMES[dtype]}, got {a.dtype}")
+        if not a.is_contiguous():
+            raise ValueError(f"{name}: output tensor must be contiguous")
+        if tuple(a.shape) != shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {tuple(a.shape)}")
+        return a
+    raise TypeError(f"{name}: unsupported buffer type {type(a)!r}")
+
+
 def device_count() -> int:
     return int(load().psn_get_device_count())
 
@@ -169,10 +201,18 @@ class SolveInfo:
         cv = lambda a: a.cpu().numpy() if hasattr(a, "cpu") else a
         return SolveInfo(cv(self.iters), cv(self.relres), cv(self.status))
 
+    def accepted(self) -> np.ndarray:
+        """Per-sample bool: converged, or at the fp64 round-off floor with a relative true residual below
+        FLOOR_RELRES_CEILING."""
+        if hasattr(self.status, "cpu"):
+            return self.to_host().accepted()
+        status = np.asarray(self.status)
+        return (status == STATUS_CONVERGED) | ((status == STATUS_FP64_FLOOR) & (np.asarray(self.relres) <= FLOOR_RELRES_CEILING))
+
     def raise_if_failed(self, what: str = "solve") -> None:
         if hasattr(self.status, "cpu"):
             return self.to_host().raise_if_failed(what)
-        bad = np.flatnonzero(np.asarray(self.status) >= STATUS_MAXITER)
+        bad = np.flatnonzero(~self.accepted())
         if bad.size:
             i = int(bad[0])
             raise PsnError(
@@ -196,6 +236,8 @@ def solve_batch(n: int, batch: int, *, theta=None, f=None, sin_x=None, sin_y=Non
     k2 = _f64(k2, (batch,), "k2")
     if out is None:
         out = np.empty((batch, n, n), dtype=np.float64)
+    else:
+        out = _out(out, (batch, n, n), "float64", "out")
     if hasattr(out, "is_cuda") and out.is_cuda:
         # device-resident call: keep the per-sample record on the device too, so that the call
         # only enqueues work on `stream` (no host pointer -> no staging, no synchronisation)
@@ -280,6 +322,8 @@ def solve_from_wavenumbers(n: int, k1, k2, *, theta=None, out=None, chunks: Opti
     x = np.linspace(0, 1, n)
     if out is None:
         out = np.empty((B, n, n), dtype=np.float64)
+    else:
+        out = _out(out, (B, n, n), "float64", "out")
     if sines_out is not None:
         sx, sy = sines_out
         for a_ in (sx, sy):
@@ -349,10 +393,8 @@ def dataset_tensors(u_coarse, u_fine, f_fine, theta_fine, *, x=None, y=None, str
     u_fine = _f64(u_fine, (N, nf, nf), "u_fine")
     f_fine = _f64(f_fine, (N, nf, nf), "f_fine")
     theta_fine = _f64(theta_fine, (N, nf, nf), "theta_fine")
-    if x is None:
-        x = np.empty((N, 3, nf, nf), dtype=np.float32)
-    if y is None:
-        y = np.empty((N, 1, nf, nf), dtype=np.float32)
+    x = np.empty((N, 3, nf, nf), dtype=np.float32) if x is None else _out(x, (N, 3, nf, nf), "float32", "x")
+    y = np.empty((N, 1, nf, nf), dtype=np.float32) if y is None else _out(y, (N, 1, nf, nf), "float32", "y")
     stats = np.zeros(8, dtype=np.float64)
     rc = lib.psn_dataset_tensors(N, nc, nf, _ptr(u_coarse), _ptr(u_fine), _ptr(f_fine), _ptr(theta_fine), _ptr(x), _ptr(y),
                                  _ptr(stats), ctypes.c_void_p(stream))
@@ -367,8 +409,7 @@ def upscale_cascade(u, levels: int, mode: str = "bilinear", out=None, stream: in
     B, n = int(u.shape[0]), int(u.shape[-1])
     u = _f64(u, (B, n, n), "u")
     m = n << levels
-    if out is None:
-        out = np.empty((B, m, m), dtype=np.float32)
+    out = np.empty((B, m, m), dtype=np.float32) if out is None else _out(out, (B, m, m), "float32", "out")
     rc = lib.psn_upscale_cascade({"bilinear": 0, "bicubic": 1}[mode], n, int(levels), B, _ptr(u), _ptr(out), ctypes.c_void_p(stream))
     _check(rc)
     return out

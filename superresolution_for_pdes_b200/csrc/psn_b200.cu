@@ -14,6 +14,7 @@
 #include <string.h>
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <chrono>
 #include <vector>
@@ -489,8 +490,9 @@ struct Context {
     cudaEvent_t ws_free[2] = {nullptr, nullptr};   // recorded after the last kernel that touches streamed workspace k
     char* h_info = nullptr;          // pinned bounce buffer for iters / relres / status of host callers
     size_t h_info_cap = 0;   // recorded after the last kernel that touches the shared streamed workspace
-    std::map<long long, PlanEntry> plans;  // key = n * 16 + nu
+    std::map<long long, PlanEntry> plans;  // key = (n * 16 + nu) * 64 + coarsest_max
     int nu = 2;
+    int coarsest_max = 0;   // largest level solved with the dense inverse (option "coarsest_max"; 0: psn_default_coarsest(n))
     int tile = 64;
     long long ws_bytes = 16ll << 30;
     int smem_max_n = 0;
@@ -513,12 +515,33 @@ struct Context {
     int host_prefetch = 3; // uploads enqueued this many chunks ahead of the solve being enqueued (<= host_slots - 2, <= 3)
     int host_h2d_stream = 1;  // 1: uploads go through their own stream instead of the chunk's solve stream
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
+    // Every call shares the staging arenas, the streamed workspaces and the plan cache.  Host threads are serialised by
+    // g_mu; on the device, a call on a different stream than the previous one first waits for that call's last
+    // operation (device-pointer calls return without synchronising, so their kernels may still be in flight).
+    Arena master[2];                       // psn_multires: device copies of host master fields (theta, sine factors)
+    cudaEvent_t master_done[2] = {nullptr, nullptr};
+    cudaEvent_t last_call = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
     bool attrs_set = false;
     bool profiling = false;
     std::vector<ProfRec> prof;
 };
 
 Context g;
+std::recursive_mutex g_mu;   // recursive: entry points call each other (ensure_init -> psn_init)
+
+// order a call on stream `s` after the previous call's device work
+int call_begin(cudaStream_t s) {
+    if (g.have_last && g.last_stream != s) CU_TRY(cudaStreamWaitEvent(s, g.last_call, 0));
+    return PSN_OK;
+}
+int call_end(cudaStream_t s) {
+    CU_TRY(cudaEventRecord(g.last_call, s));
+    g.last_stream = s;
+    g.have_last = true;
+    return PSN_OK;
+}
 
 int arena_reserve(Arena& a, size_t bytes) {
     if (bytes > a.cap) {
@@ -570,11 +593,11 @@ int ensure_init() {
 }
 
 int get_plan(int n, PlanEntry** out) {
-    const long long key = (long long)n * 16 + g.nu;
+    const long long key = ((long long)n * 16 + g.nu) * 64 + g.coarsest_max;
     auto it = g.plans.find(key);
     if (it == g.plans.end()) {
         PlanEntry e;
-        psn_plan_levels(&e.plan, n, g.nu);
+        psn_plan_levels(&e.plan, n, g.nu, g.coarsest_max);
         std::vector<double> inv = psn_coarse_inverse(e.plan);
         e.d_inv = nullptr;
         CU_TRY(cudaMalloc(&e.d_inv, inv.size() * sizeof(double)));
@@ -1052,7 +1075,17 @@ int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, lon
     return ok ? PSN_OK : psn_fail(PSN_ERR_NOMEM, "workspace arena exhausted");
 }
 
+int solve_impl(const Problem& P);
 int solve_internal(const Problem& P) {
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (P.B <= 0 || P.n < 2) return solve_impl(P);   // argument errors / empty batch: no device work
+    if ((rc = call_begin(P.stream))) return rc;
+    if ((rc = solve_impl(P))) return rc;
+    return call_end(P.stream);
+}
+
+int solve_impl(const Problem& P) {
     int rc = ensure_init();
     if (rc) return rc;
     if (P.n < 2) return psn_fail(PSN_ERR_INVALID, "n must be >= 2 (got %d)", P.n);
@@ -1098,6 +1131,15 @@ int solve_internal(const Problem& P) {
     const MemKind kinds[] = {k_theta, k_f, k_sx, k_sy, k_k1, k_k2, k_u, k_it, k_rr, k_st, k_x0, k_y0, k_uf, k_ff, k_tf, k_uc, k_fc, k_tc};
     bool any_host = false;
     for (MemKind k : kinds) any_host = any_host || (k == MEM_HOST);
+    {
+        // Caller-owned DEVICE arrays are read and written in place with 128-bit accesses and bulk (TMA) copies:
+        // they must be 16-byte aligned (host arrays are staged through the library's own aligned buffers).
+        const struct { const void* p; MemKind k; const char* name; } dev_arrays[] = {
+            {P.theta, k_theta, "theta"}, {P.f, k_f, "f"}, {P.sx, k_sx, "sin_x"}, {P.sy, k_sy, "sin_y"}, {P.u, k_u, "u"}};
+        for (const auto& d : dev_arrays)
+            if (d.k == MEM_DEVICE && (reinterpret_cast<uintptr_t>(d.p) & 15) != 0)
+                return psn_fail(PSN_ERR_INVALID, "device array %s (%p) is not 16-byte aligned", d.name, d.p);
+    }
     // The deep upload pipeline (host_slots / host_prefetch / host_h2d_stream) enqueues the copies of several chunks before
     // the solve of the current one; a copy from or to pageable memory would hold the host inside that enqueue until the
     // copies queued in front of it have run, so callers with pageable buffers keep the shallow 3-slot pipeline.
@@ -1468,6 +1510,7 @@ int psn_get_device_count(void) {
 const char* psn_last_error(void) { return g_err; }
 
 int psn_init(int device) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     int count = psn_get_device_count();
     if (count <= 0) return psn_fail(PSN_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
     if (device >= count) return psn_fail(PSN_ERR_INVALID, "device %d out of range (%d devices)", device, count);
@@ -1482,6 +1525,9 @@ int psn_init(int device) {
     g.sm_count = prop.multiProcessorCount;
     g.smem_optin = prop.sharedMemPerBlockOptin;
     for (int k = 0; k < 2; ++k) CU_TRY(cudaEventCreateWithFlags(&g.ws_free[k], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&g.last_call, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) CU_TRY(cudaEventCreateWithFlags(&g.master_done[k], cudaEventDisableTiming));
+    g.have_last = false;
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         CU_TRY(cudaEventCreateWithFlags(&g.slots[i].staging_free, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&g.slots[i].h2d_done, cudaEventDisableTiming));
@@ -1505,6 +1551,7 @@ int psn_init(int device) {
 }
 
 void psn_shutdown(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (!g.ready) return;
     cudaDeviceSynchronize();
     for (auto& kv : g.plans) cudaFree(kv.second.d_inv);
@@ -1513,6 +1560,15 @@ void psn_shutdown(void) {
         if (g.ws_free[k]) cudaEventDestroy(g.ws_free[k]);
         g.ws_free[k] = nullptr;
     }
+    if (g.last_call) cudaEventDestroy(g.last_call);
+    g.last_call = nullptr;
+    for (int k = 0; k < 2; ++k) {
+        if (g.master_done[k]) cudaEventDestroy(g.master_done[k]);
+        g.master_done[k] = nullptr;
+        if (g.master[k].base) cudaFree(g.master[k].base);
+        g.master[k] = Arena();
+    }
+    g.have_last = false;
     if (g.h_info) cudaFreeHost(g.h_info);
     g.h_info = nullptr;
     g.h_info_cap = 0;
@@ -1546,6 +1602,7 @@ void psn_shutdown(void) {
 int psn_solve_batch(int n, int64_t batch, const double* theta, const double* f, const double* sin_x, const double* sin_y,
                     const double* k1, const double* k2, int master_n, int step, int operator_mode, double rtol, int max_iter,
                     double* u, int32_t* iters, double* relres, int32_t* status, void* stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     g_err[0] = 0;
     if (operator_mode != PSN_OPERATOR_REFERENCE)
         return psn_fail(PSN_ERR_UNSUPPORTED, "operator_mode %d not implemented (only the reference operator diag(theta) L u = f)", operator_mode);
@@ -1561,6 +1618,7 @@ int psn_subdomain_batch(int n_super, int n_fine, int64_t batch, const double* si
                         const int32_t* start_x, const int32_t* start_y, double rtol, int max_iter,
                         double* u_fine, double* f_fine, double* theta_fine, double* u_coarse, double* f_coarse, double* theta_coarse,
                         int32_t* iters, double* relres, int32_t* status, void* stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     g_err[0] = 0;
     if (n_fine < 1 || n_fine > n_super) return psn_fail(PSN_ERR_INVALID, "need 1 <= n_fine <= n_super");
     if (!sin_x || !sin_y) return psn_fail(PSN_ERR_INVALID, "sin_x / sin_y are required");
@@ -1578,30 +1636,78 @@ int psn_subdomain_batch(int n_super, int n_fine, int64_t batch, const double* si
 int psn_multires(int n_finest, const int32_t* resolutions, int n_res, int64_t batch, const double* theta_finest,
                  const double* sin_x, const double* sin_y, double rtol, int max_iter, double* const* u_out,
                  int32_t* iters, double* relres, int32_t* status, void* stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     g_err[0] = 0;
     if (!resolutions || n_res < 1 || !u_out || !sin_x || !sin_y) return psn_fail(PSN_ERR_INVALID, "resolutions, u_out, sin_x, sin_y are required");
     for (int k = 0; k < n_res; ++k) {
         const int r = resolutions[k];
         if (r < 2 || r > n_finest || n_finest % r != 0) return psn_fail(PSN_ERR_INVALID, "resolution %d does not divide n_finest=%d", r, n_finest);
     }
-    for (int k = 0; k < n_res; ++k) {
-        Problem P;
-        memset(&P, 0, sizeof(P));
-        P.n = resolutions[k]; P.B = batch; P.theta = theta_finest; P.sx = sin_x; P.sy = sin_y;
-        P.mn = n_finest; P.step = n_finest / resolutions[k]; P.rtol = rtol; P.max_iter = max_iter;
-        P.u = u_out[k];
-        P.iters = iters ? iters + (size_t)k * batch : nullptr;
-        P.relres = relres ? relres + (size_t)k * batch : nullptr;
-        P.status = status ? status + (size_t)k * batch : nullptr;
-        P.stream = (cudaStream_t)stream;
-        int rc = solve_internal(P);
-        if (rc) return rc;
+    int rc = ensure_init();
+    if (rc) return rc;
+    if (batch < 0) return psn_fail(PSN_ERR_INVALID, "batch must be >= 0");
+    if (batch == 0) return PSN_OK;
+    auto solve_range = [&](const double* th, const double* sx, const double* sy, long long b0, long long bc) -> int {
+        for (int k = 0; k < n_res; ++k) {
+            Problem P;
+            memset(&P, 0, sizeof(P));
+            const size_t rr = (size_t)resolutions[k] * resolutions[k];
+            P.n = resolutions[k]; P.B = bc; P.theta = th; P.sx = sx; P.sy = sy;
+            P.mn = n_finest; P.step = n_finest / resolutions[k]; P.rtol = rtol; P.max_iter = max_iter;
+            P.u = u_out[k] + (size_t)b0 * rr;
+            P.iters = iters ? iters + (size_t)k * batch + b0 : nullptr;
+            P.relres = relres ? relres + (size_t)k * batch + b0 : nullptr;
+            P.status = status ? status + (size_t)k * batch + b0 : nullptr;
+            P.stream = (cudaStream_t)stream;
+            int rc2 = solve_internal(P);
+            if (rc2) return rc2;
+        }
+        return PSN_OK;
+    };
+    const MemKind k_th = classify(theta_finest), k_sx = classify(sin_x), k_sy = classify(sin_y);
+    if (k_th != MEM_HOST && k_sx != MEM_HOST && k_sy != MEM_HOST) return solve_range(theta_finest, sin_x, sin_y, 0, batch);
+
+    // Host master fields: every resolution reads the SAME theta / sine factors through a stride gather, so they are
+    // uploaded once per chunk of examples (two alternating device buffers: the upload of chunk c+1 runs on the upload
+    // stream while the resolutions of chunk c are solved) instead of once per resolution.
+    const size_t mm = (size_t)n_finest * n_finest;
+    const size_t per = (k_th == MEM_HOST ? mm * 8 : 0) + 2 * pad256((size_t)n_finest * 8) + 64;
+    long long Bm = (long long)((4ull << 30) / per);
+    if (Bm < 1) Bm = 1;
+    if (Bm > batch) Bm = batch;
+    const long long nchunks = (batch + Bm - 1) / Bm;
+    const double *d_th[2] = {nullptr, nullptr}, *d_sx[2] = {nullptr, nullptr}, *d_sy[2] = {nullptr, nullptr};
+    auto upload = [&](long long c) -> int {
+        const int k = (int)(c & 1);
+        const long long b0 = c * Bm, bc = std::min<long long>(Bm, batch - b0);
+        Arena& ar = g.master[k];
+        int rc2 = arena_reserve(ar, per * (size_t)Bm + 4 * 256);
+        if (rc2) return rc2;
+        if ((rc2 = stage_in(ar, g.h2d_stream, theta_finest, k_th, b0 * (long long)mm, (size_t)bc * mm, &d_th[k]))) return rc2;
+        if ((rc2 = stage_in(ar, g.h2d_stream, sin_x, k_sx, b0 * (long long)n_finest, (size_t)bc * n_finest, &d_sx[k]))) return rc2;
+        if ((rc2 = stage_in(ar, g.h2d_stream, sin_y, k_sy, b0 * (long long)n_finest, (size_t)bc * n_finest, &d_sy[k]))) return rc2;
+        CU_TRY(cudaEventRecord(g.master_done[k], g.h2d_stream));
+        return PSN_OK;
+    };
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));   // device inputs of the caller may still be in flight
+    if ((rc = call_begin(g.h2d_stream))) return rc;
+    if ((rc = upload(0))) return rc;
+    for (long long c = 0; c < nchunks; ++c) {
+        // buffer (c+1)&1 was last read by the solves of chunk c-1: complete for host outputs (those calls return
+        // synchronised), possibly still in flight on the caller's stream when every output is a device array
+        if (c >= 1 && c + 1 < nchunks) CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+        if (c + 1 < nchunks && (rc = upload(c + 1))) return rc;
+        CU_TRY(cudaEventSynchronize(g.master_done[c & 1]));
+        const long long b0 = c * Bm, bc = std::min<long long>(Bm, batch - b0);
+        if ((rc = solve_range(d_th[c & 1], d_sx[c & 1], d_sy[c & 1], b0, bc))) return rc;
     }
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));   // all-device outputs: the master buffers must outlive the solves
     return PSN_OK;
 }
 
 int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine, const double* u_coarse, const double* u_fine,
                         const double* f_fine, const double* theta_fine, float* x, float* y, double* stats, void* stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     g_err[0] = 0;
     int rc = ensure_init();
     if (rc) return rc;
@@ -1609,6 +1715,7 @@ int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine, const doubl
     if (!u_coarse || !u_fine || !f_fine || !theta_fine || !x || !y) return psn_fail(PSN_ERR_INVALID, "NULL array");
     if (n_samples == 0) return PSN_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = call_begin(s))) return rc;
     const size_t cc = (size_t)n_samples * n_coarse * n_coarse, cf = (size_t)n_samples * n_fine * n_fine;
     const MemKind k_uc = classify(u_coarse), k_uf = classify(u_fine), k_ff = classify(f_fine), k_th = classify(theta_fine),
                   k_x = classify(x), k_y = classify(y), k_s = classify(stats);
@@ -1651,10 +1758,11 @@ int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine, const doubl
     bool any_host = false;
     for (MemKind k : kinds) any_host = any_host || (k == MEM_HOST);
     if (any_host) CU_TRY(cudaStreamSynchronize(s));
-    return PSN_OK;
+    return call_end(s);
 }
 
 int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const double* u_in, float* out, void* stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     g_err[0] = 0;
     int rc = ensure_init();
     if (rc) return rc;
@@ -1662,6 +1770,7 @@ int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const dou
     if (!u_in || !out) return psn_fail(PSN_ERR_INVALID, "NULL array");
     if (batch == 0) return PSN_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = call_begin(s))) return rc;
     const long long n_out = (long long)n_in << levels;
     const size_t c_in = (size_t)batch * n_in * n_in, c_out = (size_t)batch * n_out * n_out;
     const MemKind k_in = classify(u_in), k_out = classify(out);
@@ -1691,15 +1800,19 @@ int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const dou
         CU_TRY(cudaMemcpyAsync(out, cur, c_out * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     if (k_in == MEM_HOST || k_out == MEM_HOST) CU_TRY(cudaStreamSynchronize(s));
-    return PSN_OK;
+    return call_end(s);
 }
 
 int psn_set_option(const char* name, int64_t value) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     g_err[0] = 0;
     if (!name) return psn_fail(PSN_ERR_INVALID, "option name is NULL");
     if (!strcmp(name, "nu")) {
         if (value < 1 || value > 3) return psn_fail(PSN_ERR_INVALID, "nu must be in 1..3");
         g.nu = (int)value;
+    } else if (!strcmp(name, "coarsest_max")) {
+        if (value != 0 && (value < 2 || value > PSN_COARSEST_MAX)) return psn_fail(PSN_ERR_INVALID, "coarsest_max must be 0 (automatic) or in 2..%d", PSN_COARSEST_MAX);
+        g.coarsest_max = (int)value;
     } else if (!strcmp(name, "tile")) {
         if (value < 8 || value > 96 || (value & 1)) return psn_fail(PSN_ERR_INVALID, "tile must be even, in 8..96");
         g.tile = (int)value;
@@ -1769,6 +1882,7 @@ int psn_set_option(const char* name, int64_t value) {
 }
 
 int psn_profile_begin(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     int rc = ensure_init();
     if (rc) return rc;
     for (auto& r : g.prof) {
@@ -1781,6 +1895,7 @@ int psn_profile_begin(void) {
 }
 
 int psn_profile_read(char* buf, int64_t buf_bytes) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     if (cudaDeviceSynchronize() != cudaSuccess) return psn_fail(PSN_ERR_CUDA, "device synchronize failed");
     std::map<std::string, std::pair<long long, double>> agg;
     for (auto& r : g.prof) {
@@ -1808,15 +1923,17 @@ int psn_profile_read(char* buf, int64_t buf_bytes) {
 }
 
 int psn_profile_end(void) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     g.profiling = false;
     return PSN_OK;
 }
 
 int psn_describe(int n, int64_t* info) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
     g_err[0] = 0;
     if (!info || n < 2) return psn_fail(PSN_ERR_INVALID, "bad arguments");
     PsnPlan plan;
-    psn_plan_levels(&plan, n, g.nu);
+    psn_plan_levels(&plan, n, g.nu, g.coarsest_max);
     if (!g.ready) g.smem_optin = 232448;  // sm_100 opt-in limit; lets the CPU-only tier query the layout
     const ResidentCfg rc = resident_cfg(plan);
     memset(info, 0, 8 * sizeof(int64_t));

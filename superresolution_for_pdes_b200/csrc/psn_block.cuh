@@ -693,7 +693,7 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
                 const double rt = S.tsum(acc);
                 rr_final = rt;
                 if (rt <= tol2) { status = PSN_ST_CONVERGED; break; }
-                if (nrestart >= 1 && rt > prev_true * 0.0625) { status = PSN_ST_FP64_FLOOR; break; }
+                if (nrestart >= 1 && rt > prev_true * 0.0625) { status = psn_stagnation_status(rt, bb, a.rtol); break; }
                 if (it >= a.max_iter) { status = PSN_ST_MAXITER; break; }
                 prev_true = rt;
                 ++nrestart;

@@ -29,7 +29,7 @@ def test_layout_queries_need_no_gpu():
     d80, d640, d20 = _lib.describe(80), _lib.describe(640), _lib.describe(20)
     assert d80["resident"] and d80["smem_bytes"] <= 227 * 1024 and d80["threads"] == 512
     assert d20["resident"] and d20["threads"] == 128
-    assert not d640["resident"] and d640["first_smem_level"] == 4 and d640["levels"] == 8   # 640,320,160,80 streamed; 40^2 down in shared memory
+    assert not d640["resident"] and d640["first_smem_level"] == 4 and d640["levels"] == 7   # 640,320,160,80 streamed; 40^2, 20^2 in shared memory, 10^2 = dense inverse
 
 
 @pytest.mark.skipif(_lib.device_count() > 0, reason="a GPU is present")
@@ -223,3 +223,52 @@ def test_unconverged_solutions_are_never_returned_silently():
     with pytest.raises(_lib.PsnError, match="did not converge"):
         info.raise_if_failed("x")
     _lib.SolveInfo(np.array([9]), np.array([1e-13]), np.array([1])).raise_if_failed("x")   # fp64 floor is accepted
+
+
+def test_output_buffers_are_validated_before_the_abi():
+    """A caller-supplied output goes to the C ABI as a raw address: wrong dtype / shape / layout must raise before
+    the library could write past it (no GPU needed: validation precedes the call)."""
+    n, B = 16, 3
+    th = np.ones((B, n, n))
+    f = np.zeros((B, n, n))
+    bad_outs = [np.empty((B, n, n), dtype=np.float32), np.empty((B, n, n + 1)), np.empty((B, n, 2 * n))[:, :, ::2],
+                np.empty((B - 1, n, n))]
+    ro = np.empty((B, n, n))
+    ro.setflags(write=False)
+    for out in bad_outs + [ro]:
+        with pytest.raises(ValueError):
+            _lib.solve_batch(n, B, theta=th, f=f, out=out)
+        with pytest.raises(ValueError):
+            _lib.solve_from_wavenumbers(n, np.ones(B), np.ones(B), theta=th, out=out)
+    with pytest.raises(TypeError):
+        _lib.solve_batch(n, B, theta=th, f=f, out=[0.0] * (B * n * n))
+    uc, uf = np.zeros((B, 8, 8)), np.zeros((B, n, n))
+    with pytest.raises(ValueError):
+        _lib.dataset_tensors(uc, uf, uf, uf, x=np.empty((B, 3, n, n), dtype=np.float64))
+    with pytest.raises(ValueError):
+        _lib.dataset_tensors(uc, uf, uf, uf, y=np.empty((B, n, n), dtype=np.float32))
+    with pytest.raises(ValueError):
+        _lib.upscale_cascade(uf, 1, out=np.empty((B, 2 * n, 2 * n), dtype=np.float64))
+    try:
+        import torch
+    except ImportError:
+        return
+    with pytest.raises(ValueError):
+        _lib.solve_batch(n, B, theta=th, f=f, out=torch.empty((B, n, n), dtype=torch.float32))
+    with pytest.raises(ValueError):
+        _lib.solve_batch(n, B, theta=th, f=f, out=torch.empty((B, n, 2 * n), dtype=torch.float64)[:, :, ::2])
+
+
+def test_floor_status_is_only_accepted_below_the_residual_ceiling():
+    """Status 1 (fp64 round-off floor) with a relative true residual above the ceiling, and status 4 (stagnated),
+    are failures: no entry point may hand such a sample back silently."""
+    st = np.array([0, 1, 1, 1, 2, 3, 4], dtype=np.int32)
+    rr = np.array([1e-13, 3e-12, 5e-10, np.nan, 1e-3, np.nan, 1e-7])
+    info = _lib.SolveInfo(np.zeros(7, dtype=np.int32), rr, st)
+    assert info.accepted().tolist() == [True, True, False, False, False, False, False]
+    with pytest.raises(_lib.PsnError, match="5 of 7"):
+        info.raise_if_failed()
+    _lib.SolveInfo(np.zeros(2, dtype=np.int32), rr[:2], st[:2]).raise_if_failed()
+    assert _lib.FLOOR_RELRES_CEILING == 1e-10 and _lib.STATUS_STAGNATED == 4
+    core = open(os.path.join(ROOT, "superresolution_for_pdes_b200", "csrc", "psn_core.cuh")).read()
+    assert "#define PSN_FLOOR_CEIL 1e-10" in core and "PSN_ST_STAGNATED = 4" in core

@@ -79,10 +79,14 @@ def test_plan_hierarchy():
     ns = (ctypes.c_int * 12)()
     g = (ctypes.c_double * 12)()
     L = he.hostemu_plan(ctypes.c_int(640), ctypes.c_int(2), ns, g, None)
-    assert list(ns)[:L] == [640, 320, 160, 80, 40, 20, 10, 5]
-    assert list(g)[:L] == [0, 1, 3, 7, 15, 31, 63, 127]          # gam' = 2 gam + 1 on even levels
+    assert list(ns)[:L] == [640, 320, 160, 80, 40, 20, 10]         # 10 x 10 = the dense-inverse level (PSN_COARSEST_MAX)
+    assert list(g)[:L] == [0, 1, 3, 7, 15, 31, 63]               # gam' = 2 gam + 1 on even levels
     L = he.hostemu_plan(ctypes.c_int(37), ctypes.c_int(2), ns, g, None)
-    assert list(ns)[:L] == [37, 18, 9, 4] and list(g)[:L] == [0, 0, 1, 0.5]
+    assert list(ns)[:L] == [37, 18, 9] and list(g)[:L] == [0, 0, 1]
+    L = he.hostemu_plan(ctypes.c_int(20), ctypes.c_int(2), ns, g, None)
+    assert list(ns)[:L] == [20, 10, 5]                             # grids below 32 x 32 keep the 6 x 6 dense-inverse limit
+    L = he.hostemu_plan(ctypes.c_int(45), ctypes.c_int(2), ns, g, None)
+    assert list(ns)[:L] == [45, 22, 11, 5] and list(g)[:L] == [0, 0, 1, 0.5]   # gam' = gam / 2 on odd levels
 
 
 @pytest.mark.parametrize("n", [5, 6, 7, 9, 13, 20, 37, 40, 75, 80, 86])
