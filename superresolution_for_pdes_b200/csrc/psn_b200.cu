@@ -65,14 +65,29 @@ __global__ void __launch_bounds__(T) psn_smem_solve_kernel(const __grid_constant
     psn_smem_solve_body<XPT>(ctx, plan, a, (long long)blockIdx.x, smem);
 }
 
-// register-blocked resident solver (n = 4*BX): one CTA per sample, 4x4 nodes per thread in registers
+// register-blocked resident solver (n = 4*BX): one CTA per SM, persistent over the samples b = blockIdx.x, + gridDim.x, ...;
+// 4x4 nodes per thread in registers.  inv_doubles > 0: the dense inverse of the coarsest level is copied into shared
+// memory once per CTA (behind the solver's arrays) -- read through L2 it was the top stall of the kernel
+// (long scoreboard 3.2 of 11 stall cycles per issue).
+// (128 registers: the register file is split per scheduler, 16 K each, and one scheduler holds 4 of the 13 warps --
+//  __maxnreg__(152) compiles but cannot be launched)
 template <int BX>
 __global__ void __launch_bounds__(PsnBlockGeom<BX>::NTPAD, 1) psn_block_solve_kernel(const __grid_constant__ PsnPlan plan,
-                                                                                     const __grid_constant__ PsnSolveArgs a) {
+                                                                                     const __grid_constant__ PsnSolveArgs a,
+                                                                                     long long B, int inv_doubles) {
     extern __shared__ __align__(16) double smem[];
     __shared__ double red[64];
     PsnDevCtx ctx{(int)threadIdx.x, PsnBlockGeom<BX>::NTPAD, red, 0};
-    psn_block_solve_body<BX>(ctx, plan, a, (long long)blockIdx.x, smem);
+    double* inv_s = nullptr;
+    if (inv_doubles > 0) {
+        inv_s = smem + psn_block_smem_doubles<BX>(plan);
+        for (int i = threadIdx.x; i < inv_doubles; i += PsnBlockGeom<BX>::NTPAD) inv_s[i] = __ldg(plan.coarse_inv + i);
+        __syncthreads();
+    }
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) {
+        psn_block_solve_body<BX>(ctx, plan, a, b, smem, inv_s);
+        __syncthreads();   // the next sample re-initialises the shared arrays
+    }
 }
 
 #define PSN_TILE_THREADS 256
@@ -500,6 +515,9 @@ struct Context {
     int serialize_solves = 0;
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
+    int res_persist = 1;   // register-blocked resident kernel: one persistent CTA per SM loops over the samples
+    int res_waves = 1;     // persistent CTAs per SM (the kernel holds 1 CTA per SM: more only queue up)
+    int inv_smem = 1;      // persistent kernel: keep the coarsest-level inverse in shared memory when it fits
     int x_defer = 1;       // with p_f32: x is accumulated from the ring of stored directions when a sample is checked
     int p_f32 = 1;         // with vcycle_f32 and upd_strip: the search direction is stored as (scaled) float too
     int upd_strip = 1;     // mode 2: strip update kernel that recomputes q = At p (q is never written to HBM)
@@ -1354,8 +1372,12 @@ int solve_impl(const Problem& P) {
                 ProfScope pr("smem_solve", s);
                 const unsigned grid = (unsigned)bc;
                 if (g.res_block && plan.n == 80) {
-                    const size_t bsm = (size_t)psn_block_smem_doubles<20>(plan) * sizeof(double);
-                    psn_block_solve_kernel<20><<<grid, PsnBlockGeom<20>::NTPAD, bsm, s>>>(plan, a);
+                    size_t bsm = (size_t)psn_block_smem_doubles<20>(plan) * sizeof(double);
+                    int invd = psn_coarse_inv_doubles(plan);
+                    if (!g.inv_smem || bsm + (size_t)invd * sizeof(double) + 1024 > g.smem_optin) invd = 0;
+                    bsm += (size_t)invd * sizeof(double);
+                    const unsigned pgrid = (unsigned)std::min<long long>(bc, (long long)g.sm_count * (g.res_waves > 0 ? g.res_waves : 1));
+                    psn_block_solve_kernel<20><<<g.res_persist ? pgrid : grid, PsnBlockGeom<20>::NTPAD, bsm, s>>>(plan, a, bc, invd);
                 } else {
 #define PSN_RES_LAUNCH(T_, X_) \
     if (rcfg.T == T_ && rcfg.XPT == X_) psn_smem_solve_kernel<T_, X_><<<grid, T_, rcfg.smem, s>>>(plan, a)
@@ -1828,6 +1850,10 @@ int psn_set_option(const char* name, int64_t value) {
         g.serialize_solves = value ? 1 : 0;
     } else if (!strcmp(name, "res_block")) {
         g.res_block = value ? 1 : 0;
+    } else if (!strcmp(name, "res_persist")) {
+        g.res_persist = value ? 1 : 0;
+    } else if (!strcmp(name, "inv_smem")) {
+        g.inv_smem = value ? 1 : 0;
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;

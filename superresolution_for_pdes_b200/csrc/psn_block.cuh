@@ -77,6 +77,11 @@ template <int BX>
 PSN_HDFN int psn_block_smem_doubles(const PsnPlan& plan) {
     return PsnBlockGeom<BX>::XS + PsnBlockGeom<BX>::ES + psn_pool_doubles(plan, 0);
 }
+// doubles of the dense coarsest-level inverse, kept behind the arrays above by the persistent kernel when it fits
+PSN_HDFN int psn_coarse_inv_doubles(const PsnPlan& plan) {
+    const int N = plan.lv[plan.nlev - 1].n * plan.lv[plan.nlev - 1].n;
+    return N * N;
+}
 
 template <int BX, class Ctx>
 struct PsnBlockSolver {
@@ -89,6 +94,7 @@ struct PsnBlockSolver {
     PsnShF64 edge;   // [4][4][NTPAD]
     double z[PSN_BK_TS][16], r[PSN_BK_TS][16], p[PSN_BK_TS][16];
 
+    const double* inv_s = nullptr;   // shared-memory copy of the coarsest-level inverse (or null)
     PSN_FN PsnBlockSolver(Ctx& c, double* smem) : ctx(c), xs(smem), edge(smem + G::XS) {}   // (explicit PsnShF64 ctors)
 
     // element t of edge buffer (side, slot)
@@ -255,7 +261,7 @@ struct PsnBlockSolver {
             half_sweep(1, false);
         }
         residual_restrict(l1, b1);
-        psn_vcycle_smem(ctx, plan, 1, b1, u1, pool + 2 * l1.size);
+        psn_vcycle_smem(ctx, plan, 1, b1, u1, pool + 2 * l1.size, inv_s);
         prolong(l1, u1);
         for (int s = 0; s < nu; ++s) {
             half_sweep(1, false);
@@ -468,7 +474,7 @@ struct PsnBlockSolver {
         ctx.sync();
         // ---------------- levels >= 3 in shared memory (all warps; running them on a single warp with
         // __syncwarp instead of CTA barriers was measured 7 % slower)
-        psn_vcycle_smem(ctx, plan, 3, b3, u3, pool4);
+        psn_vcycle_smem(ctx, plan, 3, b3, u3, pool4, inv_s);
         // ---------------- level 2 up
         PSN_BK_FOR(ctx, NT) {
             if (t_ < NT) {
@@ -555,10 +561,12 @@ struct PsnBlockSolver {
 
 // Whole solve of sample b.  smem: dynamic shared memory (psn_block_smem_doubles doubles).
 template <int BX, class Ctx>
-PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveArgs& a, long long b, double* smem) {
+PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveArgs& a, long long b, double* smem,
+                                 const double* inv_s = nullptr) {
     typedef PsnBlockGeom<BX> G;
     constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
     PsnBlockSolver<BX, Ctx> S(ctx, smem);
+    S.inv_s = inv_s;
     double* pool = smem + G::XS + G::ES;
     const int pool_n = psn_pool_doubles(plan, 0);
     for (int idx = ctx.tid; idx < pool_n; idx += ctx.nthreads) pool[idx] = 0.0;   // ghost rings of the coarse levels

@@ -358,25 +358,31 @@ __device__ __forceinline__ double psn_group_sum(Ctx&, double v, int G) {
 #endif
 
 // Coarsest level: u = inv * b (dense, N = nc*nc <= 100), both in shared level layout.  The N dot products are
-// spread over the CTA: G = 2^k adjacent lanes share one output (interleaved grid rows, fixed-order partial sums, one
-// xor-butterfly), so a 100 x 100 solve is 20-30 independent loads + FMAs per thread instead of 100 dependent ones.
+// spread over the CTA: G = 2^k adjacent lanes share one output (interleaved k, fixed-order partial sums, one
+// xor-butterfly), so a 100 x 100 solve is 25 independent loads + FMAs per thread instead of 100 dependent ones.
+// inv_s: a copy of the inverse in shared memory (persistent resident kernel), or null: read it through L2.
 template <class Ctx>
-PSN_FN void psn_coarsest(Ctx& ctx, const PsnPlan& plan, const double* b, double* u) {
+PSN_FN void psn_coarsest(Ctx& ctx, const PsnPlan& plan, const double* b, double* u, const double* inv_s = nullptr) {
     const PsnLevel& lv = plan.lv[plan.nlev - 1];
     const int nc = lv.n, N = nc * nc, pitch = lv.pitch;
-    // G lanes per output, each taking the grid rows ki = g, g + G, ... of the dot product
     int G = 1;
-    while (2 * G * N <= ctx.nthreads && 2 * G <= nc && G < 32) G *= 2;   // CTA sizes are multiples of 32 and G | 32: no group straddles a warp
+    while (2 * G * N <= ctx.nthreads && G < 32) G *= 2;   // CTA sizes are multiples of 32 and G | 32: no group straddles a warp
     const int g = ctx.tid & (G - 1);
     const int per = ctx.nthreads >= G ? ctx.nthreads / G : 1;   // outputs per pass
     for (int base = 0; base < N; base += per) {                 // same trip count for every thread (the butterfly is warp-wide)
         const int t = base + ctx.tid / G;
         double acc = 0.0;
         if (t < N) {
-            for (int ki = g; ki < nc; ki += G) {
-                const double* ir = plan.coarse_inv + (size_t)(ki * nc) * N + t;
-                const double* br = b + (ki + 1) * pitch + 1;
-                for (int kj = 0; kj < nc; ++kj) acc += psn_ldg(ir + (size_t)kj * N) * br[kj];
+            if (inv_s) {
+                for (int k = g; k < N; k += G) {
+                    const int ki = (int)psn_fdiv((unsigned)k, lv.nmagic);
+                    acc += inv_s[k * N + t] * b[k + 2 * ki + pitch + 1];   // (ki+1)*pitch + kj+1
+                }
+            } else {
+                for (int k = g; k < N; k += G) {
+                    const int ki = (int)psn_fdiv((unsigned)k, lv.nmagic);
+                    acc += psn_ldg(plan.coarse_inv + (size_t)k * N + t) * b[k + 2 * ki + pitch + 1];
+                }
             }
         }
         acc = psn_group_sum(ctx, acc, G);
@@ -396,7 +402,8 @@ PSN_FN int psn_pool_off(const PsnPlan& plan, int l) { return (l >= 1 && l < plan
 // pool: storage for levels l0+1.. (rhs then solution per level), zero-initialised once.
 // Ends with a sync; u0 then holds M^{-1} b0.
 template <class Ctx>
-PSN_FN void psn_vcycle_smem(Ctx& ctx, const PsnPlan& plan, int l0, const double* b0, double* u0, double* pool) {
+PSN_FN void psn_vcycle_smem(Ctx& ctx, const PsnPlan& plan, int l0, const double* b0, double* u0, double* pool,
+                            const double* inv_s = nullptr) {
     const int L = plan.nlev;
     const int nu = plan.nu;
     const int base = psn_pool_off(plan, l0 + 1);
@@ -427,7 +434,7 @@ PSN_FN void psn_vcycle_smem(Ctx& ctx, const PsnPlan& plan, int l0, const double*
         const int off = psn_pool_off(plan, l) - base;
         const double* bl = (l == l0) ? b0 : pool + off;
         double* ul = (l == l0) ? u0 : pool + off + plan.lv[l].size;
-        psn_coarsest(ctx, plan, bl, ul);
+        psn_coarsest(ctx, plan, bl, ul, inv_s);
         ctx.sync();
     }
     for (int l = L - 2; l >= l0; --l) {
