@@ -167,6 +167,30 @@ int psn_dataset_tensors(int64_t n_samples, int n_coarse, int n_fine,
  */
 int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const double* u_in, float* out, void* stream);
 
+/* The theta fields of the evaluation-script callers, produced on the device bit-identically to numpy's legacy global
+ * RNG (MT19937).
+ *
+ * Replaces the host draws  k1 = np.random.uniform(*k_range); k2 = np.random.uniform(*k_range);
+ * theta = np.random.uniform(0.5, 2.0, (n, n))  of solve_multi_resolution (src/resolution_comparison.py:27-28,42), of
+ * solve_large_scale / solve_multi_level (src/subdomain_upscaling.py:19-20,31 and :284-285,299) and the theta block of
+ * generate_test_data (src/compare_test_cases.py:39), for `n_blocks` consecutive examples at once.
+ *
+ *   key [624] uint32, pos in 0..624: the generator state, np.random.get_state()[1:3]  (host)
+ *   the stream is consumed as n_blocks x (skip + count) doubles: per block first `skip` raw doubles d in [0, 1)
+ *   (returned in `skipped` [n_blocks, skip], may be NULL: the caller forms low + (high - low) * d for the wave
+ *   numbers exactly like numpy), then `count` values low + (high - low) * d written to out [n_blocks, count];
+ *   out / skipped: host or device.  key_out [624] / pos_out (host, may be NULL): the state after the call, to be
+ *   handed back with np.random.set_state.  A state with pos == 0 (only reachable through set_state) needs
+ *   skip + count >= 312.  The values are those of numpy's x86-64 builds (multiply, then add: no FMA contraction).
+ */
+int psn_mt19937_uniform_blocks(const uint32_t* key, int pos, int64_t n_blocks, int64_t skip, int64_t count,
+                               double low, double high, double* out, double* skipped,
+                               uint32_t* key_out, int* pos_out, void* stream);
+
+/* Host-only companion (no device work): the generator state after `n_words` more 32-bit outputs, by the same
+ * jump-ahead polynomials the device path uses (one double = 2 words).  Used by the tests and to skip draws. */
+int psn_mt19937_jump_host(const uint32_t* key, int pos, int64_t n_words, uint32_t* key_out, int* pos_out);
+
 /* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg, default 2), "coarsest_max" (0 = automatic: 10 for grids
  * of 32 x 32 and more, 6 below; else 2..10: largest level n x n that is solved with the precomputed dense inverse instead
  * of being smoothed), "tile" (interior

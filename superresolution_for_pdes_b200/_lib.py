@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = (
     "psn_version", "psn_get_device_count", "psn_init", "psn_shutdown", "psn_last_error",
     "psn_solve_batch", "psn_subdomain_batch", "psn_multires", "psn_set_option",
     "psn_profile_begin", "psn_profile_read", "psn_profile_end", "psn_describe", "psn_dataset_tensors", "psn_upscale_cascade",
+    "psn_mt19937_uniform_blocks", "psn_mt19937_jump_host",
 )
 
 
@@ -77,6 +78,11 @@ def load() -> ctypes.CDLL:
     lib.psn_dataset_tensors.restype = ctypes.c_int
     lib.psn_upscale_cascade.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64, _c_dp, _c_dp, ctypes.c_void_p]
     lib.psn_upscale_cascade.restype = ctypes.c_int
+    lib.psn_mt19937_uniform_blocks.argtypes = [_c_dp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_double,
+                                               ctypes.c_double, _c_dp, _c_dp, _c_dp, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]
+    lib.psn_mt19937_uniform_blocks.restype = ctypes.c_int
+    lib.psn_mt19937_jump_host.argtypes = [_c_dp, ctypes.c_int, ctypes.c_int64, _c_dp, ctypes.POINTER(ctypes.c_int)]
+    lib.psn_mt19937_jump_host.restype = ctypes.c_int
     lib.psn_describe.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
     lib.psn_describe.restype = ctypes.c_int
     _lib = lib
@@ -412,4 +418,85 @@ def upscale_cascade(u, levels: int, mode: str = "bilinear", out=None, stream: in
     out = np.empty((B, m, m), dtype=np.float32) if out is None else _out(out, (B, m, m), "float32", "out")
     rc = lib.psn_upscale_cascade({"bilinear": 0, "bicubic": 1}[mode], n, int(levels), B, _ptr(u), _ptr(out), ctypes.c_void_p(stream))
     _check(rc)
+    return out
+
+
+# --------------------------------------------------------------------------- numpy's legacy global RNG on the device
+def _legacy_state(random_state=None):
+    st = (random_state or np.random).get_state()
+    if st[0] != "MT19937":
+        raise ValueError(f"legacy MT19937 state expected, got {st[0]}")
+    return st
+
+
+def mt19937_jump(n_words: int, random_state=None) -> None:
+    """Advance numpy's legacy generator (the global one, or a RandomState) by `n_words` 32-bit outputs -- one double is
+    two words -- with the library's jump-ahead polynomials (host only)."""
+    lib = load()
+    st = _legacy_state(random_state)
+    key = np.ascontiguousarray(st[1], dtype=np.uint32)
+    key_out = np.empty(624, dtype=np.uint32)
+    pos_out = ctypes.c_int(0)
+    _check(lib.psn_mt19937_jump_host(_ptr(key), int(st[2]), int(n_words), _ptr(key_out), ctypes.byref(pos_out)))
+    (random_state or np.random).set_state((st[0], key_out, int(pos_out.value), 0, 0.0))
+
+
+def mt19937_uniform_blocks(n_blocks: int, skip: int, count: int, low: float, high: float, *, out=None, random_state=None,
+                           stream: int = 0):
+    """Device-side replay of ``for b in range(n_blocks): [np.random.random_sample() for _ in range(skip)];
+    np.random.uniform(low, high, count)`` on numpy's legacy generator (global, or `random_state`), whose state is advanced
+    exactly as the host loop would.  `out`: float64 [n_blocks, count] numpy array or torch CUDA tensor (default: a new
+    numpy array).  Returns (out, skipped) with skipped [n_blocks, skip] the raw doubles in [0, 1) (numpy)."""
+    lib = load()
+    st = _legacy_state(random_state)
+    if st[3] != 0 and skip + count > 0:
+        pass   # a cached Gaussian is unaffected by uniform draws; it is carried over below
+    key = np.ascontiguousarray(st[1], dtype=np.uint32)
+    out = np.empty((n_blocks, count), dtype=np.float64) if out is None else _out(out, (n_blocks, count), "float64", "out")
+    skipped = np.empty((n_blocks, skip), dtype=np.float64)
+    key_out = np.empty(624, dtype=np.uint32)
+    pos_out = ctypes.c_int(0)
+    rc = lib.psn_mt19937_uniform_blocks(_ptr(key), int(st[2]), int(n_blocks), int(skip), int(count), float(low), float(high),
+                                        _ptr(out), _ptr(skipped), _ptr(key_out), ctypes.byref(pos_out), ctypes.c_void_p(stream))
+    _check(rc)
+    (random_state or np.random).set_state((st[0], key_out, int(pos_out.value), st[3], st[4]))
+    return out, skipped
+
+
+_MT_SPLIT = 1 << 15   # doubles per block when one long draw is split over CTAs
+
+
+def reshaped(a, shape):
+    """C-order reshape of a numpy array or a contiguous torch tensor (no copy)."""
+    return a.reshape(shape) if isinstance(a, np.ndarray) else a.view(*shape)
+
+
+def to_host(a) -> np.ndarray:
+    return a if isinstance(a, np.ndarray) else a.cpu().numpy()
+
+
+def device_empty_f64(shape):
+    """float64 CUDA tensor on the library's device (torch is the allocator here, nothing more)."""
+    import torch
+    return torch.empty(tuple(int(v) for v in shape), dtype=torch.float64, device="cuda")
+
+
+def mt19937_uniform(shape, low: float, high: float, *, out=None, random_state=None, stream: int = 0):
+    """``np.random.uniform(low, high, shape)`` of the legacy generator, produced on the device (bit-identical values,
+    generator state advanced as numpy would).  One long draw is cut into blocks of 32,768 doubles, one CTA each.
+    `out`: float64 array / CUDA tensor with prod(shape) elements, C-contiguous (default: new numpy array of `shape`)."""
+    shape = tuple(int(v) for v in (shape if hasattr(shape, "__len__") else (shape,)))
+    total = int(np.prod(shape)) if len(shape) else 1
+    if out is None:
+        out = np.empty(shape, dtype=np.float64)
+    flat = reshaped(out, (-1,))
+    if flat.shape[0] != total:
+        raise ValueError(f"out: expected {total} elements, got {flat.shape[0]}")
+    nb, rem = divmod(total, _MT_SPLIT)
+    if nb:
+        head = flat[:nb * _MT_SPLIT]
+        mt19937_uniform_blocks(nb, 0, _MT_SPLIT, low, high, out=reshaped(head, (nb, _MT_SPLIT)), random_state=random_state, stream=stream)
+    if rem:
+        tail = flat[nb * _MT_SPLIT:]
+        mt19937_uniform_blocks(1, 0, rem, low, high, out=reshaped(tail, (1, rem)), random_state=random_state, stream=stream)
     return out

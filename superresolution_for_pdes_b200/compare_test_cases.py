@@ -9,6 +9,7 @@ from typing import Tuple
 
 import numpy as np
 
+from . import _lib
 from .data_generation import PoissonSolver
 
 
@@ -26,7 +27,8 @@ def generate_test_data(k_range: Tuple[float, float], n_samples: int = 10, label:
         dataset['theta_fine'] = np.ones_like(dataset['theta_fine'])
         dataset['theta_coarse'] = np.ones_like(dataset['theta_coarse'])
     else:
-        theta_fine = np.random.uniform(0.5, 2.0, size=(n_samples, solver.n_fine, solver.n_fine))
+        # one draw of n_samples * n_fine^2 doubles from the global legacy generator, replayed on the device
+        theta_fine = _lib.mt19937_uniform((n_samples, solver.n_fine, solver.n_fine), 0.5, 2.0)
         theta_coarse = np.ascontiguousarray(theta_fine[:, ::2, ::2])
         dataset['theta_fine'] = theta_fine
         dataset['theta_coarse'] = theta_coarse

@@ -22,6 +22,7 @@
 #include "../../include/psn_b200.h"
 #include "psn_stream_driver.h"
 #include "psn_block.cuh"
+#include "psn_mt19937.cuh"
 
 #define PSN_VERSION 100
 
@@ -536,6 +537,7 @@ struct Context {
     // Every call shares the staging arenas, the streamed workspaces and the plan cache.  Host threads are serialised by
     // g_mu; on the device, a call on a different stream than the previous one first waits for that call's last
     // operation (device-pointer calls return without synchronising, so their kernels may still be in flight).
+    Arena mt_arena;                        // psn_mt19937_uniform_blocks: jumped states, polynomials, staging
     Arena master[2];                       // psn_multires: device copies of host master fields (theta, sine factors)
     cudaEvent_t master_done[2] = {nullptr, nullptr};
     cudaEvent_t last_call = nullptr;
@@ -1584,6 +1586,8 @@ void psn_shutdown(void) {
     }
     if (g.last_call) cudaEventDestroy(g.last_call);
     g.last_call = nullptr;
+    if (g.mt_arena.base) cudaFree(g.mt_arena.base);
+    g.mt_arena = Arena();
     for (int k = 0; k < 2; ++k) {
         if (g.master_done[k]) cudaEventDestroy(g.master_done[k]);
         g.master_done[k] = nullptr;
@@ -1822,6 +1826,110 @@ int psn_upscale_cascade(int mode, int n_in, int levels, int64_t batch, const dou
         CU_TRY(cudaMemcpyAsync(out, cur, c_out * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     if (k_in == MEM_HOST || k_out == MEM_HOST) CU_TRY(cudaStreamSynchronize(s));
+    return call_end(s);
+}
+
+int psn_mt19937_jump_host(const uint32_t* key, int pos, int64_t n_words, uint32_t* key_out, int* pos_out) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    g_err[0] = 0;
+    if (!key || !key_out || !pos_out || pos < 0 || pos > psn_mt::N || n_words < 0) return psn_fail(PSN_ERR_INVALID, "bad arguments");
+    if (!psn_mt::chi_ok()) return psn_fail(PSN_ERR_UNSUPPORTED, "characteristic polynomial of MT19937 could not be derived");
+    if (n_words == 0) {
+        memcpy(key_out, key, psn_mt::N * sizeof(uint32_t));
+        *pos_out = pos;
+        return PSN_OK;
+    }
+    // keep pos (the window moves by n_words); pos == 0: move the window by n_words - 624 and report pos = 624, so that the
+    // undetermined low bits of the jumped window's first word are never output
+    int64_t shift = n_words;
+    int pos2 = pos;
+    if (pos == 0) {
+        if (n_words < psn_mt::N) return psn_fail(PSN_ERR_UNSUPPORTED, "a state with pos == 0 can only jump by >= 624 words");
+        shift = n_words - psn_mt::N;
+        pos2 = psn_mt::N;
+    }
+    psn_mt::host_apply(psn_mt::jump_poly((uint64_t)shift, 0), key, key_out);
+    *pos_out = pos2;
+    return PSN_OK;
+}
+
+int psn_mt19937_uniform_blocks(const uint32_t* key, int pos, int64_t n_blocks, int64_t skip, int64_t count, double low, double high,
+                               double* out, double* skipped, uint32_t* key_out, int* pos_out, void* stream) {
+    std::lock_guard<std::recursive_mutex> lk(g_mu);
+    g_err[0] = 0;
+    int rc = ensure_init();
+    if (rc) return rc;
+    using namespace psn_mt;
+    if (!key || pos < 0 || pos > N || n_blocks < 0 || skip < 0 || count < 0) return psn_fail(PSN_ERR_INVALID, "bad arguments");
+    if (n_blocks > 0 && count > 0 && !out) return psn_fail(PSN_ERR_INVALID, "out is NULL");
+    if (classify(key) == MEM_DEVICE || classify(key_out) == MEM_DEVICE || classify(pos_out) == MEM_DEVICE)
+        return psn_fail(PSN_ERR_INVALID, "key / key_out / pos_out must be host arrays");
+    const int64_t J = 2 * (skip + count);   // words per block
+    if (n_blocks == 0 || J == 0) {
+        if (key_out) memcpy(key_out, key, N * sizeof(uint32_t));
+        if (pos_out) *pos_out = pos;
+        return PSN_OK;
+    }
+    if (n_blocks > (1ll << 31) / 2 || J > (1ll << 40)) return psn_fail(PSN_ERR_INVALID, "stream too long");
+    if (!chi_ok()) return psn_fail(PSN_ERR_UNSUPPORTED, "characteristic polynomial of MT19937 could not be derived");
+    // state index b = the state block b starts from; index n_blocks = the state after the call.  pos > 0: every state
+    // keeps pos and state b = t^(bJ) state 0.  pos == 0: states b >= 1 are windows 624 words further back with
+    // pos = 624 (see psn_mt19937_jump_host), state 1 = t^(J - 624) state 0.
+    const int first = (pos == 0) ? 1 : 0;
+    if (pos == 0 && J < N) return psn_fail(PSN_ERR_UNSUPPORTED, "a state with pos == 0 needs blocks of >= 312 doubles");
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = call_begin(s))) return rc;
+    const MemKind k_out = classify(out), k_sk = classify(skipped);
+    const long long nstates = n_blocks + 1;
+    int rounds = 0;
+    for (long long have = 1; have < nstates - first; have *= 2) ++rounds;
+    size_t need = pad256((size_t)nstates * N * 4) + pad256((size_t)(rounds + 1) * CHUNKS * 4) + 8 * 256;
+    if (k_out == MEM_HOST) need += pad256((size_t)n_blocks * count * 8);
+    if (k_sk == MEM_HOST) need += pad256((size_t)n_blocks * skip * 8);
+    Arena& ar = g.mt_arena;
+    if ((rc = arena_reserve(ar, need))) return rc;
+    uint32_t* d_states = arena_take<uint32_t>(ar, (size_t)nstates * N);
+    uint32_t* d_polys = arena_take<uint32_t>(ar, (size_t)(rounds + 1) * CHUNKS);
+    double* d_out = (k_out == MEM_HOST) ? arena_take<double>(ar, (size_t)n_blocks * count) : out;
+    double* d_sk = (k_sk == MEM_HOST) ? arena_take<double>(ar, (size_t)n_blocks * skip) : skipped;
+    if (!d_states || !d_polys || (k_out == MEM_HOST && !d_out) || (k_sk == MEM_HOST && !d_sk)) return psn_fail(PSN_ERR_NOMEM, "arena exhausted");
+    CU_TRY(cudaMemcpyAsync(d_states, key, N * 4, cudaMemcpyHostToDevice, s));
+    // polynomials: [0 .. rounds) = t^(J 2^k); [rounds] = t^(J - 624) (pos == 0 only)
+    std::vector<uint32_t> h_polys((size_t)(rounds + 1) * CHUNKS, 0u);
+    for (int k = 0; k < rounds; ++k) to_chunks(jump_poly((uint64_t)J, k), h_polys.data() + (size_t)k * CHUNKS);
+    if (first) to_chunks(jump_poly((uint64_t)(J - N), 0), h_polys.data() + (size_t)rounds * CHUNKS);
+    CU_TRY(cudaMemcpyAsync(d_polys, h_polys.data(), h_polys.size() * 4, cudaMemcpyHostToDevice, s));
+    CU_TRY(cudaStreamSynchronize(s));   // h_polys and key are host temporaries
+    if (first) {
+        ProfScope pr("mt_jump", s);
+        psn_mt_jump_kernel<<<1, PSN_MT_THREADS, 0, s>>>(d_states, 0, 1, d_polys + (size_t)rounds * CHUNKS);
+    }
+    {
+        int k = 0;
+        for (long long have = 1; have < nstates - first; have *= 2, ++k) {
+            const long long cnt = std::min<long long>(have, nstates - first - have);
+            ProfScope pr("mt_jump", s);
+            psn_mt_jump_kernel<<<(unsigned)cnt, PSN_MT_THREADS, 0, s>>>(d_states, first, first + have, d_polys + (size_t)k * CHUNKS);
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    {
+        ProfScope pr("mt_uniform", s);
+        if (first) {
+            psn_mt_uniform_kernel<<<1, PSN_MT_GEN_THREADS, 0, s>>>(d_states, 0, skip, count, low, high - low, d_out, d_sk);
+            if (n_blocks > 1)
+                psn_mt_uniform_kernel<<<(unsigned)(n_blocks - 1), PSN_MT_GEN_THREADS, 0, s>>>(d_states + N, N, skip, count, low, high - low,
+                                                                                           d_out + count, d_sk ? d_sk + skip : nullptr);
+        } else {
+            psn_mt_uniform_kernel<<<(unsigned)n_blocks, PSN_MT_GEN_THREADS, 0, s>>>(d_states, pos, skip, count, low, high - low, d_out, d_sk);
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    if (k_out == MEM_HOST) CU_TRY(cudaMemcpyAsync(out, d_out, (size_t)n_blocks * count * 8, cudaMemcpyDeviceToHost, s));
+    if (k_sk == MEM_HOST) CU_TRY(cudaMemcpyAsync(skipped, d_sk, (size_t)n_blocks * skip * 8, cudaMemcpyDeviceToHost, s));
+    if (key_out) CU_TRY(cudaMemcpyAsync(key_out, d_states + (size_t)n_blocks * N, N * 4, cudaMemcpyDeviceToHost, s));
+    if (pos_out) *pos_out = first ? N : pos;
+    if (k_out == MEM_HOST || k_sk == MEM_HOST || key_out) CU_TRY(cudaStreamSynchronize(s));
     return call_end(s);
 }
 

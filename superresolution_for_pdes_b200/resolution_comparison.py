@@ -21,20 +21,47 @@ def _sines_kfirst(k1: np.ndarray, k2: np.ndarray, x: np.ndarray):
     return np.sin((k1 * 2 * np.pi) * x[None, :]), np.sin((k2 * 2 * np.pi) * x[None, :])
 
 
-def solve_multi_resolution(n_coarse: int = 40, resolutions: List[int] = [80, 160, 320, 640], *,
+def draw_examples(n_examples: int, n_finest: int, k_range: Tuple[float, float], *, device_rng: bool = True, theta_on_host: bool = True):
+    """The RNG part of ``n_examples`` consecutive chains: per example k1, k2 ~ U(*k_range) and the master field
+    theta ~ U(0.5, 2.0) on the finest grid, from numpy's GLOBAL legacy generator in the reference's order
+    (src/resolution_comparison.py:27-28,42; src/subdomain_upscaling.py:19-20,31).  With ``device_rng`` the
+    Mersenne-Twister stream is replayed on the GPU (``psn_mt19937_uniform_blocks``: bit-identical values, global state
+    advanced as numpy would) and theta stays a CUDA tensor for the solve -- the 2 ms per 640 x 640 field of host RNG and
+    its PCIe upload disappear.  Returns (k1 [E], k2 [E], theta for the solver, theta as a host array or None)."""
+    lo, hi = float(k_range[0]), float(k_range[1])
+    nn = n_finest * n_finest
+    if device_rng:
+        theta_dev = _lib.device_empty_f64((n_examples, nn))
+        _, raw = _lib.mt19937_uniform_blocks(n_examples, 2, nn, 0.5, 2.0, out=theta_dev)
+        k1 = lo + (hi - lo) * raw[:, 0]        # numpy's random_uniform: lower + range * d (separate multiply and add)
+        k2 = lo + (hi - lo) * raw[:, 1]
+        theta_dev = _lib.reshaped(theta_dev, (n_examples, n_finest, n_finest))
+        theta_host = _lib.to_host(theta_dev) if theta_on_host else None
+        return k1, k2, theta_dev, theta_host
+    k1 = np.empty(n_examples)
+    k2 = np.empty(n_examples)
+    theta = np.empty((n_examples, n_finest, n_finest))
+    for e in range(n_examples):
+        k1[e] = np.random.uniform(lo, hi)
+        k2[e] = np.random.uniform(lo, hi)
+        theta[e] = np.random.uniform(0.5, 2.0, size=(n_finest, n_finest))
+    return k1, k2, theta, theta
+
+
+def solve_multi_resolution(n_coarse: int = 40, resolutions: List[int] = [80, 160, 320, 640], *, device_rng: bool = True,
                            k_range: Tuple[float, float] = (10.0, 11.0), timed: bool = False,
                            rtol: float = DEFAULT_RTOL, max_iter: int = DEFAULT_MAX_ITER, verbose: bool = False):
     """src/resolution_comparison.py:13-78.  RNG order: k1, k2, then the theta block.
     ``timed=True`` adds ``solve_times`` (per-resolution wall seconds) like
     src/resolution_comparison_statistical.py:75-90, which uses ``k_range=(8.0, 12.0)``."""
     resolutions = list(resolutions)
-    k1 = np.random.uniform(*k_range)
-    k2 = np.random.uniform(*k_range)
     n_finest = max(resolutions)
+    k1a, k2a, theta_solver, theta_host = draw_examples(1, n_finest, k_range, device_rng=device_rng)
+    k1, k2 = float(k1a[0]), float(k2a[0])
     x = np.linspace(0, 1, n_finest)
-    sx, sy = _sines_kfirst(np.array([k1]), np.array([k2]), x)
+    sx, sy = _sines_kfirst(k1a, k2a, x)
     f_finest = sy[0][:, None] * sx[0][None, :]
-    theta_finest = np.random.uniform(0.5, 2.0, size=(n_finest, n_finest))
+    theta_finest = theta_host[0]
 
     data = {'k1': k1, 'k2': k2, 'f': {}, 'theta': {}, 'u': {}}
     if timed:
@@ -53,12 +80,12 @@ def solve_multi_resolution(n_coarse: int = 40, resolutions: List[int] = [80, 160
     if timed:
         for res in all_res:
             t0 = time.time()
-            us, info = _lib.multires(n_finest, [res], 1, theta_finest[None], sx, sy, rtol=rtol, max_iter=max_iter)
+            us, info = _lib.multires(n_finest, [res], 1, theta_solver, sx, sy, rtol=rtol, max_iter=max_iter)
             data['solve_times'][res] = time.time() - t0
             info.raise_if_failed(f"solve_multi_resolution ({res}x{res})")
             data['u'][res] = us[res][0]
     else:
-        us, info = _lib.multires(n_finest, all_res, 1, theta_finest[None], sx, sy, rtol=rtol, max_iter=max_iter)
+        us, info = _lib.multires(n_finest, all_res, 1, theta_solver, sx, sy, rtol=rtol, max_iter=max_iter)
         info.raise_if_failed("solve_multi_resolution")
         for res in all_res:
             data['u'][res] = us[res][0]
@@ -70,24 +97,20 @@ def solve_multi_resolution(n_coarse: int = 40, resolutions: List[int] = [80, 160
 
 def solve_multi_resolution_batch(n_examples: int, n_coarse: int = 40, resolutions: Sequence[int] = (80, 160, 320, 640), *,
                                  k_range: Tuple[float, float] = (10.0, 11.0), rtol: float = DEFAULT_RTOL,
-                                 max_iter: int = DEFAULT_MAX_ITER):
+                                 max_iter: int = DEFAULT_MAX_ITER, device_rng: bool = True, theta_on_host: bool = True):
     """New: ``n_examples`` independent multi-resolution chains in one call per resolution.  The RNG is
-    consumed exactly as ``n_examples`` consecutive calls of ``solve_multi_resolution`` would."""
+    consumed exactly as ``n_examples`` consecutive calls of ``solve_multi_resolution`` would (see ``draw_examples``);
+    ``theta_on_host=False`` leaves the master fields on the device (``theta_finest`` is then a CUDA tensor)."""
     resolutions = list(resolutions)
     n_finest = max(resolutions)
-    k1 = np.empty(n_examples)
-    k2 = np.empty(n_examples)
-    theta = np.empty((n_examples, n_finest, n_finest))
-    for e in range(n_examples):
-        k1[e] = np.random.uniform(*k_range)
-        k2[e] = np.random.uniform(*k_range)
-        theta[e] = np.random.uniform(0.5, 2.0, size=(n_finest, n_finest))
+    k1, k2, theta_solver, theta_host = draw_examples(n_examples, n_finest, k_range, device_rng=device_rng, theta_on_host=theta_on_host)
     x = np.linspace(0, 1, n_finest)
     sx, sy = _sines_kfirst(k1, k2, x)
     all_res = [n_coarse] + resolutions
-    us, info = _lib.multires(n_finest, all_res, n_examples, theta, sx, sy, rtol=rtol, max_iter=max_iter)
+    us, info = _lib.multires(n_finest, all_res, n_examples, theta_solver, sx, sy, rtol=rtol, max_iter=max_iter)
     info.raise_if_failed("solve_multi_resolution_batch")
-    return {'k1': k1, 'k2': k2, 'theta_finest': theta, 'sin_x': sx, 'sin_y': sy, 'u': us, 'info': info}
+    return {'k1': k1, 'k2': k2, 'theta_finest': theta_host if theta_host is not None else theta_solver, 'sin_x': sx, 'sin_y': sy,
+            'u': us, 'info': info}
 
 
 # --------------------------------------------------------------------------- interpolation baselines (row f4)

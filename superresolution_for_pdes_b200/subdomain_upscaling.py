@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 from .data_generation import DEFAULT_MAX_ITER, DEFAULT_RTOL
-from .resolution_comparison import _sines_kfirst
+from .resolution_comparison import _sines_kfirst, draw_examples
 
 
 def _chain(sizes, rtol, max_iter, what):
@@ -20,16 +20,16 @@ def _chain(sizes, rtol, max_iter, what):
     for a, b in zip(sizes, sizes[1:]):
         if a != 2 * b:
             raise ValueError(f"{what}: grid sizes must halve ({a} -> {b}); the reference gathers [::2, ::2]")
-    k1 = np.random.uniform(5.0, 8.0)
-    k2 = np.random.uniform(5.0, 8.0)
+    k1a, k2a, theta_solver, theta_host = draw_examples(1, n_fine, (5.0, 8.0))   # RNG replayed on the device
+    k1, k2 = float(k1a[0]), float(k2a[0])
     x = np.linspace(0, 1, n_fine)
-    sx, sy = _sines_kfirst(np.array([k1]), np.array([k2]), x)
+    sx, sy = _sines_kfirst(k1a, k2a, x)
     f = [sy[0][:, None] * sx[0][None, :]]
-    theta = [np.random.uniform(0.5, 2.0, size=(n_fine, n_fine))]
+    theta = [theta_host[0]]
     for _ in sizes[1:]:
         f.append(f[-1][::2, ::2])
         theta.append(theta[-1][::2, ::2])
-    us, info = _lib.multires(n_fine, list(sizes), 1, theta[0][None], sx, sy, rtol=rtol, max_iter=max_iter)
+    us, info = _lib.multires(n_fine, list(sizes), 1, theta_solver, sx, sy, rtol=rtol, max_iter=max_iter)
     info.raise_if_failed(what)
     return k1, k2, f, theta, [us[n][0] for n in sizes]
 

@@ -17,7 +17,7 @@ from superresolution_for_pdes_b200 import _lib
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "psn_b200.h")).read()
-    declared = sorted(set(re.findall(r"\b(psn_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(psn_[a-z0-9_]+)\s*\(", hdr)))
     assert set(declared) == set(_lib.EXPORTED_SYMBOLS)
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
@@ -100,6 +100,17 @@ class _OracleBackend:
         return outs, _lib.SolveInfo(z, z.astype(float), z.copy())
 
 
+    def mt19937_uniform_blocks(self, n_blocks, skip, count, low, high, *, out=None, random_state=None, stream=0):
+        """TEST ONLY: the host loop that psn_mt19937_uniform_blocks replays on the device."""
+        rs = random_state or np.random
+        out = np.empty((n_blocks, count)) if out is None else out
+        skipped = np.empty((n_blocks, skip))
+        for b in range(n_blocks):
+            skipped[b] = rs.random_sample(skip)
+            out[b] = rs.uniform(low, high, count)
+        return out, skipped
+
+
 @pytest.fixture
 def oracle_backend(monkeypatch):
     bk = _OracleBackend()
@@ -111,6 +122,8 @@ def oracle_backend(monkeypatch):
         monkeypatch.setattr(mod._lib, "solve_batch", bk.solve_batch)   # solve_from_wavenumbers calls this per chunk
         monkeypatch.setattr(mod._lib, "subdomain_batch", bk.subdomain_batch)
         monkeypatch.setattr(mod._lib, "multires", bk.multires)
+        monkeypatch.setattr(mod._lib, "mt19937_uniform_blocks", bk.mt19937_uniform_blocks)
+        monkeypatch.setattr(mod._lib, "device_empty_f64", lambda shape: np.empty(shape))
     return bk
 
 
@@ -272,3 +285,36 @@ def test_floor_status_is_only_accepted_below_the_residual_ceiling():
     assert _lib.FLOOR_RELRES_CEILING == 1e-10 and _lib.STATUS_STAGNATED == 4
     core = open(os.path.join(ROOT, "superresolution_for_pdes_b200", "csrc", "psn_core.cuh")).read()
     assert "#define PSN_FLOOR_CEIL 1e-10" in core and "PSN_ST_STAGNATED = 4" in core
+
+
+@pytest.mark.parametrize("seed,pre,n_words", [(0, 3, 2), (1, 3, 623), (2, 0, 624), (3, 7, 1000), (4, 1, 819204), (5, 311, 2 * 819204 + 1)])
+def test_mt19937_jump_polynomials_match_numpy(seed, pre, n_words):
+    """Host logic of the device RNG path: the characteristic polynomial (Berlekamp-Massey), t^J mod chi and g(F) s.
+    Jumping numpy's legacy generator by J words must land exactly where drawing J words lands."""
+    rs = np.random.RandomState(seed)
+    rs.random_sample(pre)                       # pos = 2 * pre (624 for a fresh seed)
+    ref = np.random.RandomState()
+    ref.set_state(rs.get_state())
+    ref.bytes(4 * n_words)                      # one 32-bit output per 4 bytes
+    _lib.mt19937_jump(n_words, rs)
+    assert np.array_equal(rs.random_sample(700), ref.random_sample(700))   # > 624 words: crosses a regeneration
+    assert rs.uniform(0.5, 2.0) == ref.uniform(0.5, 2.0)
+
+
+def test_mt19937_jump_from_pos_zero_and_bad_arguments():
+    rs = np.random.RandomState(8)
+    st = rs.get_state()
+    rs.set_state((st[0], st[1], 0, 0, 0.0))     # pos == 0 is only reachable through set_state
+    ref = np.random.RandomState()
+    ref.set_state(rs.get_state())
+    _lib.mt19937_jump(5000, rs)
+    ref.bytes(20000)
+    assert rs.get_state()[2] == 624 and np.array_equal(rs.random_sample(700), ref.random_sample(700))
+    rs.set_state((st[0], st[1], 0, 0, 0.0))
+    with pytest.raises(_lib.PsnError, match="624"):
+        _lib.mt19937_jump(100, rs)
+    with pytest.raises(ValueError, match="MT19937"):
+        class _Fake:
+            def get_state(self):
+                return ("PCG64", None, 0, 0, 0.0)
+        _lib.mt19937_jump(10, _Fake())

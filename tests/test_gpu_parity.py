@@ -591,3 +591,79 @@ def test_multires_uploads_the_master_field_once(gpu_lib):
     for r in res[:2]:
         st = N // r
         assert O.rel_l2(us1[r][1], O.solve_poisson(np.outer(sy[1], sx[1])[::st, ::st], np.ones((r, r)), r)) <= TOL
+
+
+def _host_blocks(rs, n_blocks, skip, count, low, high):
+    out = np.empty((n_blocks, count))
+    sk = np.empty((n_blocks, skip))
+    for b in range(n_blocks):
+        sk[b] = rs.random_sample(skip)
+        out[b] = rs.uniform(low, high, count)
+    return out, sk
+
+
+@pytest.mark.parametrize("pre,n_blocks,skip,count", [(0, 1, 0, 10), (3, 5, 2, 1600), (311, 7, 1, 313), (312, 3, 0, 624),
+                                                      (100, 64, 2, 25600), (5, 33, 3, 6401), (17, 4, 2, 409600), (9, 300, 0, 1)])
+def test_mt19937_device_stream_is_bit_identical_to_numpy(gpu_lib, pre, n_blocks, skip, count):
+    """psn_mt19937_uniform_blocks replays numpy's legacy generator on the device: every value, the raw skipped doubles
+    and the generator state afterwards are identical to the host loop (all block / word alignments: odd offsets make
+    every double straddle a regeneration boundary)."""
+    import torch
+    rs = np.random.RandomState(1234 + pre)
+    rs.random_sample(pre)
+    ref = np.random.RandomState()
+    ref.set_state(rs.get_state())
+    if pre % 2 == 1:          # odd word offset: consume a single 32-bit word on both
+        rs.bytes(4)
+        ref.bytes(4)
+    want, want_sk = _host_blocks(ref, n_blocks, skip, count, 0.5, 2.0)
+    got, got_sk = gpu_lib.mt19937_uniform_blocks(n_blocks, skip, count, 0.5, 2.0, random_state=rs)
+    assert np.array_equal(got, want) and np.array_equal(got_sk, want_sk)
+    assert np.array_equal(rs.random_sample(700), ref.random_sample(700))        # state handed back to numpy
+    # device-resident output
+    dev = torch.empty((n_blocks, count), dtype=torch.float64, device="cuda")
+    rs2 = np.random.RandomState(77)
+    ref2 = np.random.RandomState(77)
+    gpu_lib.mt19937_uniform_blocks(n_blocks, skip, count, -1.0, 3.0, out=dev, random_state=rs2)
+    want2, _ = _host_blocks(ref2, n_blocks, skip, count, -1.0, 3.0)
+    assert np.array_equal(dev.cpu().numpy(), want2) and rs2.uniform() == ref2.uniform()
+
+
+def test_mt19937_device_stream_from_pos_zero_and_long_draws(gpu_lib):
+    rs = np.random.RandomState(8)
+    st = rs.get_state()
+    rs.set_state((st[0], st[1], 0, 0, 0.0))
+    ref = np.random.RandomState()
+    ref.set_state(rs.get_state())
+    want, want_sk = _host_blocks(ref, 6, 2, 1000, 0.5, 2.0)
+    got, got_sk = gpu_lib.mt19937_uniform_blocks(6, 2, 1000, 0.5, 2.0, random_state=rs)
+    assert np.array_equal(got, want) and np.array_equal(got_sk, want_sk)
+    assert np.array_equal(rs.random_sample(700), ref.random_sample(700))
+    # one long draw, cut into 32,768-double blocks + remainder, on the GLOBAL generator
+    np.random.seed(99)
+    a = gpu_lib.mt19937_uniform((37, 80, 80), 0.5, 2.0)
+    nxt = np.random.uniform()
+    np.random.seed(99)
+    b = np.random.uniform(0.5, 2.0, (37, 80, 80))
+    assert np.array_equal(a, b) and nxt == np.random.uniform()
+
+
+def test_multires_batch_with_device_rng_matches_host_rng(gpu_lib):
+    """solve_multi_resolution_batch draws k1, k2 and the master theta fields on the device: same values, same
+    solutions and same global generator state as the host-RNG path (the reference's own order of draws)."""
+    from superresolution_for_pdes_b200 import solve_multi_resolution_batch
+    np.random.seed(31)
+    d = solve_multi_resolution_batch(5, 40, [80, 160, 320], k_range=(8.0, 12.0))
+    nxt = np.random.uniform()
+    np.random.seed(31)
+    h = solve_multi_resolution_batch(5, 40, [80, 160, 320], k_range=(8.0, 12.0), device_rng=False)
+    assert nxt == np.random.uniform()
+    assert np.array_equal(d["k1"], h["k1"]) and np.array_equal(d["k2"], h["k2"])
+    assert np.array_equal(d["theta_finest"], h["theta_finest"])
+    for r in (40, 80, 160, 320):
+        assert np.array_equal(d["u"][r], h["u"][r]), r
+    np.random.seed(31)
+    ref = O.solve_multi_resolution(40, [80, 160, 320], k_lo=8.0, k_hi=12.0)       # oracle = the reference's own loop body
+    assert ref["k1"] == d["k1"][0] and ref["k2"] == d["k2"][0] and np.array_equal(ref["theta"][320], d["theta_finest"][0])
+    for r in (40, 80, 160, 320):
+        assert O.rel_l2(d["u"][r][0], ref["u"][r]) <= TOL
