@@ -1893,7 +1893,15 @@ int psn_mt19937_uniform_blocks(const uint32_t* key, int pos, int64_t n_blocks, i
     double* d_out = (k_out == MEM_HOST) ? arena_take<double>(ar, (size_t)n_blocks * count) : out;
     double* d_sk = (k_sk == MEM_HOST) ? arena_take<double>(ar, (size_t)n_blocks * skip) : skipped;
     if (!d_states || !d_polys || (k_out == MEM_HOST && !d_out) || (k_sk == MEM_HOST && !d_sk)) return psn_fail(PSN_ERR_NOMEM, "arena exhausted");
+    CU_TRY(cudaMemsetAsync(d_states, 0, (size_t)nstates * N * 4, s));   // the jump kernel accumulates with atomicXor
     CU_TRY(cudaMemcpyAsync(d_states, key, N * 4, cudaMemcpyHostToDevice, s));
+    {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CU_TRY(cudaFuncSetAttribute(psn_mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psn_mt_jump_smem()));
+            attr_done = true;
+        }
+    }
     // polynomials: [0 .. rounds) = t^(J 2^k); [rounds] = t^(J - 624) (pos == 0 only)
     std::vector<uint32_t> h_polys((size_t)(rounds + 1) * CHUNKS, 0u);
     for (int k = 0; k < rounds; ++k) to_chunks(jump_poly((uint64_t)J, k), h_polys.data() + (size_t)k * CHUNKS);
@@ -1902,14 +1910,15 @@ int psn_mt19937_uniform_blocks(const uint32_t* key, int pos, int64_t n_blocks, i
     CU_TRY(cudaStreamSynchronize(s));   // h_polys and key are host temporaries
     if (first) {
         ProfScope pr("mt_jump", s);
-        psn_mt_jump_kernel<<<1, PSN_MT_THREADS, 0, s>>>(d_states, 0, 1, d_polys + (size_t)rounds * CHUNKS);
+        psn_mt_jump_kernel<<<dim3(PSN_MT_SPLIT, 1), PSN_MT_THREADS, psn_mt_jump_smem(), s>>>(d_states, 0, 1, d_polys + (size_t)rounds * CHUNKS);
     }
     {
         int k = 0;
         for (long long have = 1; have < nstates - first; have *= 2, ++k) {
             const long long cnt = std::min<long long>(have, nstates - first - have);
             ProfScope pr("mt_jump", s);
-            psn_mt_jump_kernel<<<(unsigned)cnt, PSN_MT_THREADS, 0, s>>>(d_states, first, first + have, d_polys + (size_t)k * CHUNKS);
+            psn_mt_jump_kernel<<<dim3(PSN_MT_SPLIT, (unsigned)cnt), PSN_MT_THREADS, psn_mt_jump_smem(), s>>>(d_states, first, first + have,
+                                                                                                           d_polys + (size_t)k * CHUNKS);
         }
     }
     CU_TRY(cudaGetLastError());

@@ -12,8 +12,9 @@
 //   * the stream is split into independent blocks (one per example) by JUMP-AHEAD: the state after J more words is
 //     g(F) s with g(t) = t^J mod chi(t), F the one-word transition and chi its characteristic polynomial (degree
 //     19937).  chi is obtained once per process with Berlekamp-Massey from the generator's own output, g by
-//     square-and-multiply on the host (cached per J); g(F) s is evaluated on the device by Horner in 32-bit chunks:
-//     (v(F) s)[j] = XOR of the source words x[j + i] over the set bits i of v, so no table of shifted states is needed;
+//     square-and-multiply on the host (cached per J); g(F) s is evaluated on the device as a binary convolution:
+//     (g(F) s)[j] = XOR of x[i + j] over the set bits i of g, x the source state's own output sequence extended by
+//     ~20,000 words in shared memory -- no dependent steps, so 16 CTAs share one jump;
 //   * block b's state is reached in ceil(log2 B) rounds of doubling (round k: states 2^k .. 2^(k+1)-1 from states
 //     0 .. 2^k-1 with the polynomial of J * 2^k), every round one launch with one CTA per state;
 //   * one CTA per block then regenerates ("twists") its state in shared memory -- three barrier-separated phases of
@@ -208,63 +209,47 @@ inline void host_apply(const Poly& g, const uint32_t* s, uint32_t* out) {
 #if defined(__CUDACC__)
 // ----------------------------------------------------------------------------- device kernels
 #define PSN_MT_THREADS 640   // 20 warps: one thread per state word (624 active)
+#define PSN_MT_SPLIT 16      // CTAs that share one jump (each takes 39 of the 624 polynomial chunks)
+#define PSN_MT_SEQ (psn_mt::N + 88 * 227)   // extended source sequence x[0 .. 20599] (x[19936 + 623] is the last one used)
 
-// states[dst0 + c] = g(F) states[src0 + c] for c = blockIdx.x; states are [*, 624] words, g as 624 32-bit chunks
+// states[dst0 + c] ^= (part of g)(F) states[src0 + c] for c = blockIdx.y; the destination states must be zero before
+// the launch.  g(F) s = sum_i g_i F^i s and (F^i s)[j] = x[i + j]: with the source sequence extended to
+// x[0 .. 19936 + 623] in shared memory (88 barrier-separated rounds of 227 independent words) output word j is the XOR of
+// x[i + j] over the set bits i of g -- no dependent steps, so PSN_MT_SPLIT CTAs take disjoint bit ranges of g and
+// combine with atomicXor.  (A Horner formulation with one CTA per jump took 0.6 ms per doubling round, 6 ms for 512
+// blocks; this one is bound by the ~10^4 shared-memory loads per thread of a single round.)
 __global__ void __launch_bounds__(PSN_MT_THREADS) psn_mt_jump_kernel(uint32_t* states, long long src0, long long dst0,
                                                                      const uint32_t* __restrict__ gchunks) {
     using namespace psn_mt;
-    __shared__ uint32_t X[N + QB];   // source sequence x[0 .. 624 + 31]
-    __shared__ uint32_t A[N];        // accumulator window, circular: logical j lives at (head + j) % 624
-    __shared__ uint32_t G[CHUNKS];
+    extern __shared__ uint32_t mt_smem[];
+    uint32_t* X = mt_smem;               // [PSN_MT_SEQ]
+    uint32_t* G = mt_smem + PSN_MT_SEQ;  // [CHUNKS / PSN_MT_SPLIT]
     const int t = threadIdx.x;
-    const uint32_t* src = states + (src0 + blockIdx.x) * (long long)N;
-    if (t < N) {
-        X[t] = src[t];
-        A[t] = 0u;
-        G[t] = gchunks[t];
-    }
+    constexpr int CPB = CHUNKS / PSN_MT_SPLIT;
+    const int c0 = blockIdx.x * CPB;
+    const uint32_t* src = states + (src0 + blockIdx.y) * (long long)N;
+    if (t < N) X[t] = src[t];
+    if (t < CPB) G[t] = gchunks[c0 + t];
     __syncthreads();
-    if (t < QB) X[N + t] = twist(X[t], X[t + 1], X[t + M]);   // x[624 + t], t < 32 < 227: independent of each other
-    __syncthreads();
-    int head = 0;
-    int top = CHUNKS - 1;
-    while (top > 0 && G[top] == 0u) --top;   // uniform across the CTA
-    for (int c = top; c >= 0; --c) {
-        // acc = F^32 acc : the 32 oldest words are replaced by the 32 next ones (mutually independent)
-        if (t < QB) {
-            int i0 = head + t, i1 = head + t + 1, im = head + t + M;
-            i0 -= (i0 >= N) ? N : 0;
-            i1 -= (i1 >= N) ? N : 0;
-            im -= (im >= N) ? N : 0;
-            const uint32_t nw = twist(A[i0], A[i1], A[im]);
-            __syncwarp();            // lane t+1 overwrites the word lane t has just read as its second operand
-            A[i0] = nw;
-        }
-        head += QB;
-        head -= (head >= N) ? N : 0;
-        __syncthreads();
-        // acc ^= v(F) s,  (v(F) s)[j] = XOR_{i in v} x[j + i]
-        uint32_t v = G[c];
-        if (t < N && v) {
-            uint32_t a = 0u;
-            while (v) {
-                const int i = __ffs(v) - 1;
-                v &= v - 1;
-                a ^= X[t + i];
-            }
-            int p = head + t;
-            p -= (p >= N) ? N : 0;
-            A[p] ^= a;
-        }
+    // only the part of the sequence this CTA reads: x[32 c0 .. 32 (c0 + CPB) + 623]
+    const int need = 32 * (c0 + CPB) + N;
+    for (int base = N; base < need; base += 227) {
+        if (t < 227) X[base + t] = twist(X[base + t - N], X[base + t - N + 1], X[base + t - 227]);
         __syncthreads();
     }
-    uint32_t* dst = states + (dst0 + blockIdx.x) * (long long)N;
     if (t < N) {
-        int p = head + t;
-        p -= (p >= N) ? N : 0;
-        dst[t] = A[p];
+        uint32_t a = 0u;
+        for (int c = 0; c < CPB; ++c) {
+            uint32_t v = G[c];          // uniform
+            const uint32_t* xp = X + 32 * (c0 + c) + t;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if ((v >> i) & 1u) a ^= xp[i];
+        }
+        if (a) atomicXor(states + (dst0 + blockIdx.y) * (long long)N + t, a);
     }
 }
+inline size_t psn_mt_jump_smem() { return (size_t)(PSN_MT_SEQ + psn_mt::CHUNKS / PSN_MT_SPLIT) * sizeof(uint32_t); }
 
 // One CTA per block of the stream: emits `skip` raw doubles in [0, 1) followed by `count` doubles low + range * d,
 // starting at word `pos` of its state.
