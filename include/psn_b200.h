@@ -204,7 +204,8 @@ int psn_mt19937_jump_host(const uint32_t* key, int pos, int64_t n_words, uint32_
  * upd_strip the search direction is stored as a power-of-two-scaled float; q, <p,q>, x and r are formed in fp64 from
  * that same rounded direction, so the recurrences stay exact), "x_defer" (default 1: with p_f32 the last 12 directions
  * stay in a ring and x = sum alpha_k p_k is formed in one fp64 pass when a sample is checked or the ring is full,
- * instead of a read-modify-write of x every iteration), "pdl" (default 1: programmatic dependent
+ * instead of a read-modify-write of x every iteration), "fuse_upd" (default 1: with x_defer the CG update of iteration k and the
+ * level-0 down-leg of iteration k+1 are one kernel; the residual is double-buffered and not re-read), "pdl" (default 1: programmatic dependent
  * launch between the kernels of a solve), the host-buffer pipeline of resident grids with page-locked buffers:
  * "host_slots" (default 5, 3..6: staging slots),
  * "host_prefetch" (default 3, 1..3: uploads are enqueued this many chunks ahead of the solve being enqueued),
@@ -227,7 +228,8 @@ int psn_profile_end(void);
  *  bit 0: the V-cycle intermediates of this size are stored as float (option "vcycle_f32", streamed path),
  *  bit 1: the CG update recomputes q = A p in strips instead of storing it (option "upd_strip"),
  *  bit 2: the search direction p is stored as scaled float (option "p_f32"; x, r, q and every dot stay fp64),
- *  bit 3: x is accumulated from the ring of stored directions when a sample is checked (option "x_defer")}. */
+ *  bit 3: x is accumulated from the ring of stored directions when a sample is checked (option "x_defer"),
+ *  bit 4: the CG update is fused with the level-0 down-leg of the next V-cycle (option "fuse_upd")}. */
 int psn_describe(int n, int64_t* info);
 
 #ifdef __cplusplus

@@ -204,7 +204,7 @@ def describe(n: int) -> dict:
             "threads": int(info[3]), "smem_bytes": int(info[4]), "tile": int(info[5]),
             "workspace_bytes_per_sample": int(info[6]), "vcycle_f32": bool(info[7] & 1),
             "update_strip": bool(info[7] & 2), "p_f32": bool(info[7] & 4),
-            "x_defer": bool(info[7] & 8)}
+            "x_defer": bool(info[7] & 8), "fused_update": bool(info[7] & 16)}
 
 
 def profile_begin() -> None:

@@ -179,6 +179,30 @@ psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
     }
 }
 
+// CG update of iteration k fused with the level-0 down-leg of iteration k+1 (psn_strip_upre_body)
+#ifndef PSN_UPRE_MINB
+#define PSN_UPRE_MINB 3
+#endif
+template <int NU>
+__global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, PSN_UPRE_MINB)
+psn_upre_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ PsnStripArgs a, const __grid_constant__ PsnCgArgs cg,
+                      long long ntasks) {
+    psn_pdl_enter();
+    extern __shared__ __align__(128) unsigned char strip_smem[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const long long task = (long long)blockIdx.x * PSN_STRIP_WARPS + warp;
+    if (task >= ntasks) return;
+    const int per = a.nstrips * a.nbands;
+    const long long b = task / per;
+    const int rem = (int)(task - b * per);
+    const int band = rem / a.nstrips, strip = rem - band * a.nstrips;
+    const PsnWarp w{(int)(threadIdx.x & 31)};
+    typedef PsnTmaFeeder<NU, double, float> Feeder;
+    Feeder fd;
+    fd.attach(strip_smem + (size_t)warp * Feeder::smem_bytes());
+    psn_strip_upre_body<NU>(w, plan, a, cg, b, band, strip, fd);
+}
+
 __global__ void __launch_bounds__(256) psn_flush_x_kernel(const __grid_constant__ PsnCgArgs a) {
     psn_pdl_enter();
     PsnDevCtx ctx{(int)threadIdx.x, 256, nullptr, 0};
@@ -510,7 +534,7 @@ struct Context {
     int nu = 2;
     int coarsest_max = 0;   // largest level solved with the dense inverse (option "coarsest_max"; 0: psn_default_coarsest(n))
     int tile = 64;
-    long long ws_bytes = 16ll << 30;
+    long long ws_bytes = 24ll << 30;
     int smem_max_n = 0;
     int coarse_max_n = 40; // largest level handed to the shared-memory coarse V-cycle kernel (0: as large as fits)
     int serialize_solves = 0;
@@ -519,6 +543,7 @@ struct Context {
     int res_persist = 1;   // register-blocked resident kernel: one persistent CTA per SM loops over the samples
     int res_waves = 1;     // persistent CTAs per SM (the kernel holds 1 CTA per SM: more only queue up)
     int inv_smem = 1;      // persistent kernel: keep the coarsest-level inverse in shared memory when it fits
+    int fuse_upd = 1;      // with x_defer: CG update fused with the level-0 down-leg of the next V-cycle (PsnStreamCfg::fuse)
     int x_defer = 1;       // with p_f32: x is accumulated from the ring of stored directions when a sample is checked
     int p_f32 = 1;         // with vcycle_f32 and upd_strip: the search direction is stored as (scaled) float too
     int upd_strip = 1;     // mode 2: strip update kernel that recomputes q = At p (q is never written to HBM)
@@ -872,6 +897,26 @@ struct CudaBackend {
         }
         launch(psn_update_strip_kernel<TP, XDEFER>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
     }
+    template <int NU>
+    void fused_launch(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
+        typedef PsnTmaFeeder<NU, double, float> Feeder;
+        const long long ntasks = B * a.nstrips * a.nbands;
+        const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
+        const size_t smem = (size_t)PSN_STRIP_WARPS * Feeder::smem_bytes();
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(psn_upre_strip_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_done = true;
+        }
+        launch(psn_upre_strip_kernel<NU>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, plan, a, cg, ntasks);
+    }
+    void fused_update(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
+        ProfScope p("update_pre_l0", s);
+        if (plan.nu == 1) fused_launch<1>(plan, a, cg, B);
+        else if (plan.nu == 2) fused_launch<2>(plan, a, cg, B);
+        else fused_launch<3>(plan, a, cg, B);
+        chk();
+    }
     void flush_x(const PsnCgArgs& a, long long B) {
         ProfScope p("flush_x", s);
         launch(psn_flush_x_kernel, dim3(PSN_FLUSH_BLOCKS, (unsigned)B), dim3(256), 0, a);
@@ -1040,18 +1085,21 @@ void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
     cfg->upd_strip = g.upd_strip;
     cfg->pf32 = (cfg->vf32 && g.upd_strip && g.p_f32) ? 1 : 0;
     cfg->xdefer = (cfg->pf32 && g.x_defer) ? 1 : 0;
+    cfg->fuse = (cfg->xdefer && g.fuse_upd) ? 1 : 0;
 }
 
 size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     const size_t nn = (size_t)plan.n * plan.n;
     size_t b = 5 * nn * sizeof(double);
     if (cfg.xdefer) b += (size_t)PSN_PEND_K * nn * sizeof(float) - 2 * nn * sizeof(double) + sizeof(PsnPend);
+    if (cfg.fuse) b += nn * sizeof(double);   // second residual buffer
     for (int l = 1; l <= cfg.ls; ++l) {
         const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n * sizeof(double);
         b += (l < cfg.ls ? 3 : 2) * m;
     }
     const int gx = (plan.n + PSN_GT_COLS - 1) / PSN_GT_COLS, gy = (plan.n + PSN_GT_ROWS - 1) / PSN_GT_ROWS;
-    b += ((size_t)psn_rz_max(plan, cfg) + 2 * (size_t)psn_pq_max(plan.n) + 2 * (size_t)gx * gy) * sizeof(double) + sizeof(PsnSampleState);
+    b += ((size_t)psn_rz_max(plan, cfg) + (size_t)psn_pq_max(plan.n) + (size_t)psn_pu_max(plan.n, plan.nu) + 2 * (size_t)gx * gy) * sizeof(double) +
+         sizeof(PsnSampleState);
     return b + 4096 / 16;
 }
 
@@ -1073,6 +1121,10 @@ int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, lon
         ok = ws->p[0] && ws->p[1];
     }
     ok = ok && ws->r && ws->q && ws->z;
+    if (cfg.fuse) {
+        ws->r2 = arena_take<double>(ar, Bc * nn);
+        ok = ok && ws->r2;
+    }
     for (int l = 1; l <= cfg.ls && ok; ++l) {
         const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n;
         ws->bl[l] = arena_take<double>(ar, Bc * m);
@@ -1088,7 +1140,7 @@ int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, lon
     ws->part_a = arena_take<double>(ar, (size_t)Bc * gx * gy);
     ws->part_pq = arena_take<double>(ar, (size_t)Bc * psn_pq_max(plan.n));
     ws->part_b = arena_take<double>(ar, (size_t)Bc * gx * gy);
-    ws->part_u = arena_take<double>(ar, (size_t)Bc * psn_pq_max(plan.n));
+    ws->part_u = arena_take<double>(ar, (size_t)Bc * psn_pu_max(plan.n, plan.nu));
     ws->state = arena_take<PsnSampleState>(ar, Bc);
     ws->counters = arena_take<int>(ar, max_iter + 8);
     ok = ok && ws->part_rz && ws->part_a && ws->part_pq && ws->part_b && ws->part_u && ws->state && ws->counters;
@@ -1140,6 +1192,7 @@ int solve_impl(const Problem& P) {
         scfg.upd_strip = g.upd_strip;
         scfg.pf32 = (scfg.vf32 && g.upd_strip && g.p_f32) ? 1 : 0;
         scfg.xdefer = (scfg.pf32 && g.x_defer) ? 1 : 0;
+        scfg.fuse = (scfg.xdefer && g.fuse_upd) ? 1 : 0;
         if (scfg.ls < 1) return psn_fail(PSN_ERR_UNSUPPORTED, "no shared-memory coarse level for n=%d", P.n);
     }
 
@@ -1974,6 +2027,9 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "res_threads")) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;
+    } else if (!strcmp(name, "fuse_upd")) {
+        if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "fuse_upd must be 0 or 1");
+        g.fuse_upd = (int)value;
     } else if (!strcmp(name, "x_defer")) {
         if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "x_defer must be 0 or 1");
         g.x_defer = (int)value;
@@ -2097,7 +2153,8 @@ int psn_describe(int n, int64_t* info) {
         info[7] = sc.vf32 | ((sc.mode == 2 && g.upd_strip && (plan.n & 1) == 0) ? 2 : 0);
         if ((info[7] & 3) == 3 && g.p_f32) info[7] |= 4;
         if ((info[7] & 4) && g.x_defer) info[7] |= 8;
-        sc.upd_strip = g.upd_strip; sc.pf32 = (info[7] & 4) ? 1 : 0; sc.xdefer = (info[7] & 8) ? 1 : 0;
+        if ((info[7] & 8) && g.fuse_upd) info[7] |= 16;
+        sc.upd_strip = g.upd_strip; sc.pf32 = (info[7] & 4) ? 1 : 0; sc.xdefer = (info[7] & 8) ? 1 : 0; sc.fuse = (info[7] & 16) ? 1 : 0;
         info[0] = 0;
         info[2] = sc.ls;
         info[3] = PSN_TILE_THREADS;

@@ -830,6 +830,10 @@ struct PsnCgArgs {
     const float* pring;      // [PSN_PEND_K][B, n, n] ring of float search directions (xdefer)
     long long ring_stride;   // floats between two ring slots
     PsnPend* pend;           // [B]
+    int fused;               // the CG update runs inside the level-0 down-leg of the next V-cycle (psn_strip_upre_body):
+                             // r -> r_out double buffer, ||r||^2 partials indexed by the down-leg's tasks (fu_nparts)
+    double* r_out;           // fused: [B, n, n] residual written by this iteration's update
+    int fu_nparts;           // fused: partials per sample in part_u
     int chk_mode;            // 0: 2-D tile true-residual kernel; 2: strip form (sine-factor forcing + theta on the solve grid)
     double* part_u;          // [B, upd_nstrips*upd_nbands] ||r||^2 partials of the strip update / strip true-residual kernels
     double* part_b;          // [B, ntx*nty]   ||r||^2 partials
@@ -1070,8 +1074,8 @@ PSN_FN void psn_state_after_update(const PsnCgArgs& a, long long b) {
     PsnSampleState st = a.state[b];
     if (st.phase != PSN_PHASE_ITER) return;
     double rr = 0.0;
-    const int cnt = a.upd_mode ? a.upd_nstrips * a.upd_nbands : a.ntx * a.nty;
-    const double* pb = a.upd_mode ? a.part_u + b * (long long)cnt : a.part_b + b * (long long)cnt;
+    const int cnt = a.fused ? a.fu_nparts : (a.upd_mode ? a.upd_nstrips * a.upd_nbands : a.ntx * a.nty);
+    const double* pb = (a.upd_mode || a.fused) ? a.part_u + b * (long long)cnt : a.part_b + b * (long long)cnt;
     for (int k = 0; k < cnt; ++k) rr += pb[k];
     st.rr_prev = st.rr;
     st.rr = rr;

@@ -23,6 +23,8 @@ struct PsnStreamCfg {
     int upd_strip; // mode 2 only: the update kernel recomputes q = At p in strips and q is never stored
     int pf32;      // with vf32 and upd_strip: the search direction p is stored as (scaled) float as well
     int xdefer;    // with pf32: x is accumulated from the ring of stored directions when a sample is checked (PsnPend)
+    int fuse;      // with xdefer: the CG update of iteration k and the level-0 down-leg of iteration k+1 are ONE strip kernel
+                   // (psn_strip_upre_body): r is not re-read, 33 -> 25 bytes per node and iteration for the two
     int vf32;     // mode 2 only: V-cycle intermediates (iterates, restricted residuals, z) are STORED as float; all
                   // arithmetic, the CG vectors x r p q and every inner product stay fp64.  The preconditioner only has
                   // to be an approximate inverse, so CG converges in the same number of iterations (tests), while the
@@ -39,6 +41,8 @@ struct PsnLegArgs {
     const double* ec;   // up-leg: coarse correction in
     double* part;       // up-leg on level 0: partial <b,u> per task
     const PsnSampleState* state;
+    int fused = 0;        // fused schedule (see PsnStreamCfg::fuse): V-cycle scale from rr_prev
+    int only_restart = 0; // down-leg on level 0, fused schedule: only samples whose residual was rebuilt
 };
 
 // the warp-strip kernels use 128-bit pair accesses: every streamed level must have an even size
@@ -61,6 +65,13 @@ static inline int psn_pq_max(int n) {
     const int tiles = ((n + PSN_GT_COLS - 1) / PSN_GT_COLS) * ((n + PSN_GT_ROWS - 1) / PSN_GT_ROWS);
     return strips > tiles ? strips : tiles;
 }
+// upper bound of the ||r||^2 partial count per sample: the strip update / true-residual kernels (as <p,q>), or the fused
+// update + down-leg kernel (112-column strips for nu = 2, bands of >= 16 rows)
+static inline int psn_pu_max(int n, int nu) {
+    const int fused = psn_strip_count(n, psn_fused_use(nu)) * psn_band_count(n, 16);
+    const int pq = psn_pq_max(n);
+    return fused > pq ? fused : pq;
+}
 // number of <r,z> partials per sample produced by the level-0 up-leg
 static inline int psn_rz_count(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     const int n = plan.n;
@@ -72,6 +83,8 @@ static inline int psn_rz_count(const PsnPlan& plan, const PsnStreamCfg& cfg) {
 struct PsnStreamWs {
     long long cap;               // samples this workspace was sized for
     double* r;                   // level 0: residual (= rhs of the V-cycle)
+    double* r2;                  // fused schedule: second residual buffer (the update writes r[cur ^ 1])
+    int rcur;                    // fused schedule: buffer that holds the current residual
     double* q;                   // level 0: A p  (doubles as the pre-smoothed iterate)
     double* z;                   // level 0: preconditioned residual
     double* p[2];                // level 0: search direction, ping-pong
@@ -111,8 +124,10 @@ static inline PsnStripArgs psn_leg_to_strip(const PsnPlan& plan, const PsnStream
     a.nstrips = psn_strip_count(n, post ? psn_strip_use_post(plan.nu, cfg.vf32) : psn_strip_use_pre(plan.nu, cfg.vf32));
     a.nbands = psn_band_count(n, a.band);
     a.b = g.b; a.uin = g.uin; a.uout = g.uout; a.bc = g.bc; a.ec = g.ec; a.part = g.part; a.state = g.state;
+    a.fused = g.fused; a.only_restart = g.only_restart;
     return a;
 }
+static inline bool psn_fuse_ok(const PsnStreamCfg& cfg) { return cfg.mode == 2 && cfg.vf32 && cfg.upd_strip && cfg.pf32 && cfg.xdefer && cfg.fuse; }
 
 // x: [B, n, n] device array that receives the solution.
 // start_it == 0: fresh solve (prologue + state init); > 0: resume an earlier call at that outer iteration.
@@ -158,6 +173,23 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.pend = ws.pend;
     cg.it = start_it;
     cg.chk_mode = (cg.upd_mode == 2 && rhs.sx && rhs.theta && rhs.step == 1 && rhs.mn == n) ? 2 : 0;
+    const int fuse = (psn_fuse_ok(cfg) && cg.xdefer && ws.r2) ? 1 : 0;
+    PsnStripArgs fa;                      // fused update + down-leg: level-0 strip task geometry
+    memset(&fa, 0, sizeof(fa));
+    fa.level = 0;
+    fa.band = cfg.band[0];
+    fa.nstrips = psn_strip_count(n, psn_fused_use(plan.nu));
+    fa.nbands = psn_band_count(n, fa.band);
+    fa.uout = ws.q;
+    fa.bc = ws.bl[1];
+    fa.state = ws.state;
+    fa.fused = 1;
+    cg.fused = fuse;
+    cg.fu_nparts = fa.nstrips * fa.nbands;
+    cg.r_out = nullptr;
+    double* rbuf[2] = {ws.r, fuse ? ws.r2 : ws.r};
+    if (start_it == 0) ws.rcur = 0;
+    cg.r = rbuf[ws.rcur];
     cg.part_b = ws.part_b;
     cg.state = ws.state;
     cg.rtol = rtol;
@@ -182,12 +214,16 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
         if (check_from < 0) check_from = 0;
     }
     int it = start_it;
+    bool rebuilt = true;   // fused schedule: some samples may carry a residual that no fused kernel has smoothed yet
     for (; it < max_outer; ++it) {
         // ---- z = M^{-1} r : one V(nu,nu) cycle
         for (int l = 0; l < cfg.ls; ++l) {
+            if (l == 0 && fuse && !rebuilt) continue;   // done by the previous iteration's fused update kernel
             PsnLegArgs g;
             g.level = l;
-            g.b = (l == 0) ? ws.r : ws.bl[l];
+            g.fused = fuse;
+            g.only_restart = (l == 0 && fuse) ? 1 : 0;
+            g.b = (l == 0) ? rbuf[ws.rcur] : ws.bl[l];
             g.uin = nullptr;
             g.uout = (l == 0) ? ws.q : ws.ua[l];
             g.bc = ws.bl[l + 1];
@@ -200,7 +236,8 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
         for (int l = cfg.ls - 1; l >= 0; --l) {
             PsnLegArgs g;
             g.level = l;
-            g.b = (l == 0) ? ws.r : ws.bl[l];
+            g.fused = fuse;
+            g.b = (l == 0) ? rbuf[ws.rcur] : ws.bl[l];
             g.uin = (l == 0) ? ws.q : ws.ua[l];
             g.uout = (l == 0) ? ws.z : ws.ub[l];
             g.bc = nullptr;
@@ -219,8 +256,17 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
             cg.p_new = ws.p[(it & 1) ^ 1];
         }
         bk.dir_apply(cg, B);
-        bk.update(cg, B);
+        if (fuse) {
+            cg.r = rbuf[ws.rcur];
+            cg.r_out = rbuf[ws.rcur ^ 1];
+            bk.fused_update(plan, fa, cg, B);
+            ws.rcur ^= 1;
+            cg.r = rbuf[ws.rcur];          // flush / true residual / the next up-leg work on the new residual
+        } else {
+            bk.update(cg, B);
+        }
         bk.state_after_update(cg, B);
+        rebuilt = it >= check_from;        // the check block below may restart samples from a recomputed residual
         if (it >= check_from) {
             if (cg.xdefer) bk.flush_x(cg, B);
             bk.true_residual(cg, B);

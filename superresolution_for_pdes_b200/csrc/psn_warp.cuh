@@ -300,6 +300,8 @@ struct PsnStripArgs {
     const void* ec;      // post: [B, nc, nc] in
     double* part;        // post, level 0: [B, nstrips*nbands] partial <b,u>
     const PsnSampleState* state;
+    int fused;           // the CG update is fused with the level-0 down-leg (psn_strip_upre_body): see psn_vcycle_scale
+    int only_restart;    // pre, level 0, fused schedule: only samples whose residual was rebuilt (prologue / true residual)
 };
 
 // useful (output) columns per strip: pre needs 2NU halo columns left and 2NU+1 right; post needs
@@ -325,6 +327,15 @@ PSN_HDFN double psn_vscale(double rr) {
     int e = 0;
     frexp(rr, &e);
     return ldexp(1.0, -(e / 2));
+}
+
+// Scale of the float-stored V-cycle of a sample's CURRENT outer iteration (a power of two near 1 / ||r||).  Unfused: from
+// the residual norm itself.  Fused schedule: the down-leg of iteration k+1 runs inside the update kernel of iteration k,
+// before ||r_{k+1}|| exists, so it scales with ||r_k|| -- which the later kernels of iteration k+1 find in rr_prev.  (The
+// scale only positions the data in the float exponent range; a residual that is 30x smaller than its scale assumes
+// loses nothing.)  Samples whose residual was rebuilt (restart) were smoothed by the plain kernel with their own norm.
+PSN_FN double psn_vcycle_scale(const PsnSampleState& st, int fused) {
+    return psn_vscale((fused && !st.restart) ? st.rr_prev : st.rr);
 }
 
 // horizontal neighbour sum of offset e (static) in a row held as v[0..3]
@@ -428,6 +439,7 @@ struct PsnTmaFeeder {
     const U1* nx1;               // address advances by one row pitch per issue instead of being recomputed)
     const U2* nx2;
     int n, tload, ts;
+    int rows1_max;               // array 1 is only copied for rows <= rows1_max (fused update + down-leg: its rows run one ahead)
     int cA, cB, c0;              // in-domain column range [cA, cB) of the strip, strip origin
 #if defined(__CUDACC__)
     __host__ __device__
@@ -440,17 +452,19 @@ struct PsnTmaFeeder {
         bar = reinterpret_cast<unsigned long long*>(mem + RING_BYTES);
         base1 = nullptr;
         base2 = nullptr;
+        rows1_max = 0x7fffffff;
     }
     PSN_FN void set_base0(const T0* p) { base0 = p; }
     PSN_FN void set_base1(const U1* p) { base1 = p; }
     PSN_FN void set_base2(const U2* p) { base2 = p; }
-    PSN_FN void issue(const PsnWarp& w, int /*row: always the successor of the previously issued row*/, int slot) {
+    PSN_FN void issue(const PsnWarp& w, int row /*always the successor of the previously issued row*/, int slot) {
         if (w_lane0(w)) {
             const unsigned cnt = (unsigned)(cB - cA);
             const int so = slot * PSN_STRIP_COLS + (cA - c0);
-            w_bar_expect_l0(bar + slot, cnt * (unsigned)ROW_BYTES);
+            const bool a1 = NARR >= 2 && row <= rows1_max;
+            w_bar_expect_l0(bar + slot, cnt * (unsigned)(ROW_BYTES - (a1 ? 0 : PsnElemOr<T1>::bytes)));
             w_bulk_g2s_l0(ring0 + so, nx0, cnt * (unsigned)sizeof(T0), bar + slot);
-            if (NARR >= 2) w_bulk_g2s_l0(ring1 + so, nx1, cnt * (unsigned)sizeof(U1), bar + slot);
+            if (a1) w_bulk_g2s_l0(ring1 + so, nx1, cnt * (unsigned)sizeof(U1), bar + slot);
             if (NARR >= 3) w_bulk_g2s_l0(ring2 + so, nx2, cnt * (unsigned)sizeof(U2), bar + slot);
         }
         nx0 += n;
@@ -648,6 +662,7 @@ PSN_FN void psn_strip_pre_chunk(const PsnWarp& w, int t, int ts, int tload, int 
 template <int NU, class TB, class TV, class Feeder>
 PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, long long b, int band, int strip, Feeder& fd) {
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
+    if (a.state && a.only_restart && !a.state[b].restart) return;
     constexpr int NS = 2 * NU, W = NS + 2;
     constexpr int F32 = sizeof(TV) == 4 ? 1 : 0;
     constexpr bool SCALE = F32 && sizeof(TB) == 8;
@@ -852,7 +867,7 @@ PSN_FN void psn_strip_post_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const TV* uig = reinterpret_cast<const TV*>(a.uin) + b * (long long)n * n;
     const TV* eg = reinterpret_cast<const TV*>(a.ec) + b * (long long)nc * nc;
     TV* ug = reinterpret_cast<TV*>(a.uout) + b * (long long)n * n;
-    const double bs = (SCALE && a.state) ? psn_vscale(a.state[b].rr) : 1.0;
+    const double bs = (SCALE && a.state) ? psn_vcycle_scale(a.state[b], a.fused) : 1.0;
     const wd bsc = w_bcast(bs);
 
     WV val[W][4], bb[W][4], eprev[2], enext[4];
@@ -940,8 +955,10 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
     static_assert(!PF32 || F32, "a float search direction needs the float-stored (scaled) z");
     const int a0 = strip * psn_dir_use(F32), a1 = psn_imin(a0 + psn_dir_use(F32), n);
     const int c0 = a0 - psn_dir_hl(F32);
-    const double sk = F32 ? psn_vscale(st.rr) : 1.0;
-    const wd zinv = w_bcast(1.0 / sk);
+    const double sk = F32 ? psn_vscale(st.rr) : 1.0;                 // scale of the direction stored by THIS launch
+    const double sz = F32 ? psn_vcycle_scale(st, a.fused) : 1.0;     // scale z was computed and stored with (== sk unless fused)
+    const wd zinv = w_bcast(1.0 / sz);
+    const wd zr = w_bcast(sk / sz);                                  // power of two (1 when unfused): exact
     // scaled domain: s_k p_k = s_k z_k + beta (s_k / s_{k-1}) (s_{k-1} p_{k-1})   (powers of two: exact)
     const wd beta_s = w_bcast((fresh || !PF32) ? 0.0 : (rz / st.rz_old) * (sk / psn_vscale(st.rr_prev)));
     const int i0 = band * a.dir_band, i1 = psn_imin(i0 + a.dir_band, n);
@@ -985,7 +1002,7 @@ PSN_FN void psn_dir_strip_body(const PsnWarp& w, const PsnCgArgs& a, long long b
                 typename PsnWV<TP>::type pr[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const wd zv = w_cvt<double>(r0[e]);
+                    const wd zv = w_cvt<double>(r0[e]) * zr;
                     pr[e] = w_cvt<TP>(fresh ? zv : zv + beta_s * w_cvt<double>(r1[e]));
                     pn[k0][e] = w_cvt<double>(pr[e]);   // everything below sees the rounded direction
                 }
@@ -1155,6 +1172,271 @@ PSN_FN void psn_update_strip_body(const PsnWarp& w, const PsnCgArgs& a, long lon
     }
 }
 
+
+
+// ----------------------------------------------------------------------------- fused CG update + level-0 down-leg
+// The update kernel ends with r_{k+1} = r_k - alpha A p_k written to HBM and the down-leg of the next V-cycle starts by
+// reading it back: 8 of the 67 bytes per node and iteration.  Here one pass does both: the strip marches down with a
+// 3-row window of p_k (float ring slot, converted to fp64) one row AHEAD of the smoother's newest row, forms
+// q = At p, r_{k+1} (fp64, stored for the owned part), its partial ||r||^2, and hands the row -- scaled and rounded to
+// float exactly like the plain down-leg does on load -- to the temporally blocked sweeps.  r is double-buffered
+// (PsnCgArgs::r -> r_out): neighbouring tasks still read r_k in their halos.  One more halo column per side than the
+// plain strips (q at the strip edge needs p one column further out): 112 useful columns for nu = 2.
+// Level 0 of the float-stored configuration only (rhs fp64, iterate float, float search direction, deferred x).
+PSN_HDFN int psn_fused_hl(int nu) { return (2 * nu + 1 + 3) & ~3; }
+PSN_HDFN int psn_fused_use(int nu) { return (PSN_STRIP_COLS - psn_fused_hl(nu) - (2 * nu + 2)) & ~3; }
+
+struct PsnFusedRow {     // per-task constants and running state of the update part
+    wd alpha;            // alpha_k / s_k (the ring slot holds s_k p_k)
+    wd bsc;              // V-cycle scale of the NEXT iteration (psn_vcycle_scale as iteration k+1 will see it)
+    wd pm[4], pc[4];     // p rows tc-1, tc (fp64 copies of the float slot)
+    wd dot;              // partial ||r_{k+1}||^2 over the owned nodes
+    double* rout;        // r_{k+1} of this sample
+    wb ind[2];           // column pairs inside the domain
+};
+
+template <int NU, bool FAST, class Feeder>
+PSN_FN void psn_strip_upre_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc,
+                                 int i0, int i1, int I0, int I1, wf (&val)[2 * NU + 2][4], wf (&bb)[2 * NU + 2][4],
+                                 Feeder& fd, int par, wf (&acc)[2], const wf (&rdA)[4], const wf (&dA)[4], const wf (&mk)[4],
+                                 const PsnLevel& lv, PsnFusedRow& fr, float* ug, float* cg, const wi& col0, const wb (&so)[2],
+                                 const wi& cj, const wb (&sc)[2]) {
+    constexpr int NS = 2 * NU, W = NS + 2;
+    const wf zero = w_bcastT<float>(0.0);
+    const wf q25 = w_bcastT<float>(0.25);
+    const wd zerod = w_bcast(0.0);
+    wf rdB[4], dB[4];
+    if (!FAST) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const wb lc_ = (col0 + e) == last;
+            rdB[e] = mk[e] * w_sel(lc_, w_bcastT<float>(lv.rd2), w_bcastT<float>(lv.rd1));
+            dB[e] = w_sel(lc_, w_bcastT<float>(4.0 + 2.0 * lv.gam), w_bcastT<float>(4.0 + lv.gam));
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rdB[e] = dB[e] = zero;
+    }
+#pragma unroll
+    for (int tt = 0; tt < W; ++tt) {
+        const int tc = t + tt;
+        if (!FAST && tc > tend) break;
+        const int P = tt & 1;
+        const int k0 = tt;
+        // ---- new row: r_k(tc) and p_k(tc+1) from the feeder; q(tc), r_{k+1}(tc); first red half sweep from the zero guess
+        {
+            typename Feeder::V0 r0[4];
+            typename Feeder::V1 r1[4];
+            fd.template fetch<FAST>(w, tt, tc, par, r0, r1);
+            wd pn[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pn[e] = w_cvt<double>(r1[e]);
+            if (!FAST && tc + 1 > last) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pn[e] = zerod;          // row n of p: outside the grid (its copy was skipped)
+            }
+            const wd upv = w_up_raw(fr.pc[3]);
+            const wd dnv = w_down_raw(fr.pc[0]);
+            wd q[4], rn[4];
+            q[0] = 4.0 * fr.pc[0] - ((pn[0] + fr.pm[0]) + (upv + fr.pc[1]));
+            q[1] = 4.0 * fr.pc[1] - ((pn[1] + fr.pm[1]) + (fr.pc[0] + fr.pc[2]));
+            q[2] = 4.0 * fr.pc[2] - ((pn[2] + fr.pm[2]) + (fr.pc[1] + fr.pc[3]));
+            q[3] = 4.0 * fr.pc[3] - ((pn[3] + fr.pm[3]) + (fr.pc[2] + dnv));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                rn[e] = w_sel(fr.ind[e >> 1], r0[e] - fr.alpha * q[e], zerod);
+                fr.pm[e] = fr.pc[e];
+                fr.pc[e] = pn[e];
+            }
+            if (tc >= i0 && tc < i1) {
+                double* rowr = fr.rout + (long long)tc * n;
+                w_stp(rowr, col0, so[0], rn[0], rn[1]);
+                w_stp(rowr, col0 + 2, so[1], rn[2], rn[3]);
+                fr.dot = fr.dot + w_sel(so[0], rn[0] * rn[0] + rn[1] * rn[1], zerod) + w_sel(so[1], rn[2] * rn[2] + rn[3] * rn[3], zerod);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) bb[k0][e] = w_cvt<float>(rn[e] * fr.bsc);
+        }
+        if (FAST || tc <= last) {
+            const bool lastrow = !FAST && tc == last;
+            val[k0][P] = bb[k0][P] * (lastrow ? rdB[P] : rdA[P]);
+            val[k0][P + 2] = bb[k0][P + 2] * (lastrow ? rdB[P + 2] : rdA[P + 2]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) bb[k0][e] = zero;
+            val[k0][P] = val[k0][P + 2] = zero;
+        }
+        val[k0][1 - P] = val[k0][3 - P] = zero;
+        // ---- smoothing stages 1 .. NS-1 on rows tc-1 .. tc-NS+1
+#pragma unroll
+        for (int s = 1; s < NS; ++s) {
+            const int r = tc - s;
+            if (FAST || (r >= ts && r <= last)) {
+                const int ks = (tt - s + 2 * W) % W, ku = (tt - s - 1 + 2 * W) % W, kd = (tt - s + 1 + 2 * W) % W;
+                const bool lastrow = !FAST && r == last;
+                const wf upf = (P == 0) ? w_up_raw(val[ks][3]) : zero;
+                const wf dnf = (P == 1) ? w_down_raw(val[ks][0]) : zero;
+                const wf sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upf, dnf);
+                const wf sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upf, dnf);
+                val[ks][P] = (bb[ks][P] + sa) * (lastrow ? rdB[P] : rdA[P]);
+                val[ks][P + 2] = (bb[ks][P + 2] + sb) * (lastrow ? rdB[P + 2] : rdA[P + 2]);
+            }
+        }
+        // ---- residual on the red nodes of row tc-NS, accumulate the restriction
+        {
+            const int r = tc - NS;
+            wf ra = zero, rb = zero;
+            if (FAST || (r >= ts && r <= last)) {
+                const int ks = (tt - NS + 2 * W) % W, ku = (tt - NS - 1 + 2 * W) % W, kd = (tt - NS + 1 + 2 * W) % W;
+                const bool lastrow = !FAST && r == last;
+                const wf upf = (P == 0) ? w_up_raw(val[ks][3]) : zero;
+                const wf dnf = (P == 1) ? w_down_raw(val[ks][0]) : zero;
+                const wf sa = (val[ku][P] + val[kd][P]) + PSN_LR(val[ks], P, upf, dnf);
+                const wf sb = (val[ku][P + 2] + val[kd][P + 2]) + PSN_LR(val[ks], P + 2, upf, dnf);
+                ra = mk[P] * (bb[ks][P] - ((lastrow ? dB[P] : dA[P]) * val[ks][P] - sa));
+                rb = mk[P + 2] * (bb[ks][P + 2] - ((lastrow ? dB[P + 2] : dA[P + 2]) * val[ks][P + 2] - sb));
+            }
+            if (P == 0) {
+                const wf c0v = q25 * (ra + rb);
+                const wf c1v = q25 * (rb + w_down_raw(ra));
+                const int I = (r >> 1) - 1;
+                if (FAST || (r >= 2 && I >= I0 && I < I1)) {
+                    float* crow = cg + (long long)I * nc;
+                    w_st1(crow, cj, sc[0], acc[0] + c0v);
+                    w_st1(crow, cj + 1, sc[1], acc[1] + c1v);
+                }
+                acc[0] = c0v;
+                acc[1] = c1v;
+            } else {
+                acc[0] = acc[0] + ra;
+                acc[1] = acc[1] + rb;
+            }
+        }
+        // ---- row tc-NS+1 is final after its last black half sweep
+        {
+            const int ro = tc - (NS - 1);
+            if (FAST || (ro >= i0 && ro < i1)) {
+                const int ko = (tt - (NS - 1) + 2 * W) % W;
+                w_stq(ug + (long long)ro * n, col0, so[0], so[1], val[ko]);
+            }
+        }
+    }
+}
+
+// Feeder: PsnTmaFeeder<NU, double /* r_k */, float /* s_k p_k, rows offset by one */>
+template <int NU, class Feeder>
+PSN_FN void psn_strip_upre_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& g, long long b,
+                                int band, int strip, Feeder& fd) {
+    const PsnSampleState st = g.state[b];
+    if (st.phase != PSN_PHASE_ITER) return;
+    constexpr int NS = 2 * NU, W = NS + 2;
+    const int USE = psn_fused_use(NU);
+    const int HL = psn_fused_hl(NU);
+    const PsnLevel& lv = plan.lv[0];
+    const PsnLevel& lc = plan.lv[1];
+    const int n = lv.n, nc = lc.n, last = n - 1;
+    const int a0 = strip * USE, a1 = psn_imin(a0 + USE, n);
+    const int c0 = a0 - HL;
+    const int i0 = band * a.band, i1 = psn_imin(i0 + a.band, n);
+    const int I0 = i0 >> 1, I1 = psn_imin(i1 >> 1, nc);
+    const int J0 = a0 >> 1, J1 = psn_imin(a1 >> 1, nc);
+
+    const double pq = psn_warp_sum_partials(w, g.part_pq + b * (long long)g.npq, g.npq);
+    const double pscale = psn_vscale(st.rr);                       // scale of the stored direction s_k p_k
+    const double alpha = (pq > 0.0) ? st.rz / pq : 0.0;
+
+    const wi col0 = w_lane(w) * 4 + c0;
+    const wi col2 = col0 + 2;
+    const wb mp[2] = {(col0 >= 0) && (col0 < n), (col2 >= 0) && (col2 < n)};
+    const wb so[2] = {mp[0] && (col0 >= a0) && (col0 < a1), mp[1] && (col2 >= a0) && (col2 < a1)};
+    const wi cj = w_lane(w) * 2 + (c0 >> 1);
+    const wb sc[2] = {(cj >= J0) && (cj < J1), (cj + 1 >= J0) && (cj + 1 < J1)};
+    const wf zero = w_bcastT<float>(0.0);
+    const wd zerod = w_bcast(0.0);
+    wf rdA[4], dA[4], mk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const wi ce = col0 + e;
+        const wb in = (e < 2) ? mp[0] : mp[1];
+        const wb lc_ = ce == last;
+        rdA[e] = w_sel(in, w_sel(lc_, w_bcastT<float>(lv.rd1), w_bcastT<float>(lv.rd0)), zero);
+        dA[e] = w_sel(lc_, w_bcastT<float>(4.0 + lv.gam), w_bcastT<float>(4.0));
+        mk[e] = w_sel(in, w_bcastT<float>(1.0), zero);
+    }
+
+    const int ts = psn_imax(i0 - NS, 0);
+    const int tload = psn_imin(i1 + NS, last);
+    const int tend = i1 + NS;
+    const long long base = b * (long long)n * n;
+    const float* pg = reinterpret_cast<const float*>(g.p_new) + base;
+    float* ug = reinterpret_cast<float*>(a.uout) + base;
+    float* cgp = reinterpret_cast<float*>(a.bc) + b * (long long)nc * nc;
+
+    PsnFusedRow fr;
+    fr.alpha = w_bcast(alpha * (1.0 / pscale));
+    fr.bsc = w_bcast(pscale);              // = psn_vscale(||r_k||^2): what iteration k+1 finds in rr_prev
+    fr.dot = zerod;
+    fr.rout = g.r_out + base;
+    fr.ind[0] = mp[0];
+    fr.ind[1] = mp[1];
+    // p rows ts-1 and ts (the feeder delivers row tc+1 at time tc)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) fr.pm[e] = fr.pc[e] = zerod;
+    {
+        wf t0[4], t1[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t0[e] = t1[e] = zero;
+        if (ts >= 1) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) t0[e] = w_ld1(pg + (long long)(ts - 1) * n, col0 + e, (e < 2) ? mp[0] : mp[1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t1[e] = w_ld1(pg + (long long)ts * n, col0 + e, (e < 2) ? mp[0] : mp[1]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            fr.pm[e] = w_cvt<double>(t0[e]);
+            fr.pc[e] = w_cvt<double>(t1[e]);
+        }
+    }
+
+    wf val[W][4], bb[W][4], acc[2];
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) val[k][e] = bb[k][e] = zero;
+    fd.set_base0(g.r + base);
+    fd.set_base1(pg + n);                  // array 1 runs one row ahead
+    fd.rows1_max = last - 1;               // ... and has no row n
+    fd.n = n;
+    fd.tload = tload;
+    psn_feeder_geom(fd, col0, mp, c0, n);
+    fd.prime(w, ts);
+    acc[0] = acc[1] = zero;
+
+    for (int t = ts; t <= tend; t += W) {
+        const bool fast = (t - NS - 1 >= ts) && (t - NS >= 2) && (t + W - 1 + (W - 1) <= tload) && (t + W - 1 < last) &&
+                          (t - (NS - 1) >= i0) && (t + W - 1 - (NS - 1) < i1) &&
+                          (((t - NS) >> 1) - 1 >= I0) && (((t + W - 1 - NS) >> 1) - 1 < I1);
+        const int par = ((t - ts) / W) & 1;
+        if (fast)
+            psn_strip_upre_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv, fr,
+                                           ug, cgp, col0, so, cj, sc);
+        else
+            psn_strip_upre_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv, fr,
+                                            ug, cgp, col0, so, cj, sc);
+    }
+    const double sdot = w_sum(fr.dot);
+    if (w_lane0(w)) {
+        g.part_u[b * (long long)(a.nstrips * a.nbands) + (long long)band * a.nstrips + strip] = sdot;
+        if (band == 0 && strip == 0) {
+            g.state[b].pq = pq;
+            PsnPend* pd = g.pend + b;       // deferred x: record the step, x receives (alpha / s_k) (s_k p_k) at the next flush
+            if (pd->lo == pd->hi) pd->lo = g.it;
+            pd->a[g.it % PSN_PEND_K] = alpha * (1.0 / pscale);
+            pd->hi = g.it + 1;
+        }
+    }
+}
 
 // ----------------------------------------------------------------------------- true residual, strip form
 // Samples in PSN_PHASE_CHECK: r = bt - At x with bt = -(sy_i sx_j / theta_ij) h^2 (the same operations as psn_rhs, so

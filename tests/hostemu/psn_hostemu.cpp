@@ -13,6 +13,8 @@
 
 namespace {
 
+long long g_fused_launches = 0;   // how often the fused update + down-leg backend entry ran (asserted by the tests)
+
 struct HostPlan {
     PsnPlan plan;
     std::vector<double> inv;
@@ -138,6 +140,25 @@ struct HostBackend {
             for (int ty = 0; ty < a.nty; ++ty)
                 for (int tx = 0; tx < a.ntx; ++tx) psn_update_body(ctx, a, b, ty, tx);
     }
+    template <int NU>
+    void fused_t(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
+        typedef PsnTmaFeeder<NU, double, float> Feeder;
+        PsnWarp w;
+        std::vector<unsigned char> ring(Feeder::smem_bytes() + 256);
+        for (long long b = 0; b < B; ++b)
+            for (int band = 0; band < a.nbands; ++band)
+                for (int strip = 0; strip < a.nstrips; ++strip) {
+                    std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
+                    Feeder fd; fd.attach(ring.data());
+                    psn_strip_upre_body<NU>(w, plan, a, cg, b, band, strip, fd);
+                }
+    }
+    void fused_update(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
+        ++g_fused_launches;
+        if (plan.nu == 1) fused_t<1>(plan, a, cg, B);
+        else if (plan.nu == 2) fused_t<2>(plan, a, cg, B);
+        else fused_t<3>(plan, a, cg, B);
+    }
     void flush_x(const PsnCgArgs& a, long long B) {
         PsnHostCtx ctx;
         for (long long b = 0; b < B; ++b)
@@ -181,6 +202,8 @@ PsnRhs make_rhs(const double* theta, const double* f, const double* sx, const do
 
 extern "C" {
 
+long long hostemu_fused_launches(void) { return g_fused_launches; }
+
 // levels / gammas of the plan, for direct comparison with the numpy prototype
 int hostemu_plan(int n, int nu, int* ns, double* gams, double* inv_out) {
     HostPlan hp(n, nu);
@@ -220,15 +243,16 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
     PsnStreamCfg cfg;
-    // mode 3 = mode 2 (TMA-fed strips) with float storage of the V-cycle intermediates
-    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? (mode == 3 ? 2 : mode) : 0;
-    cfg.vf32 = (mode == 3 && cfg.mode == 2 && psn_vf32_ok(plan, ls)) ? 1 : 0;
+    // mode 3 = mode 2 (TMA-fed strips) with float storage of the V-cycle intermediates; mode 4 = mode 3 + fused update / down-leg
+    cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? (mode >= 3 ? 2 : mode) : 0;
+    cfg.vf32 = (mode >= 3 && cfg.mode == 2 && psn_vf32_ok(plan, ls)) ? 1 : 0;
     cfg.dir_band = 0;
     cfg.upd_band = 0;
     cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
     cfg.pf32 = cfg.vf32;
     cfg.xdefer = cfg.pf32;
-    if (mode == 3 && !cfg.vf32) return -2;
+    cfg.fuse = (mode == 4 && cfg.xdefer) ? 1 : 0;
+    if (mode >= 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
     memset(&ws, 0, sizeof(ws));
@@ -236,6 +260,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     auto alloc = [&](size_t cnt) { keep.emplace_back(cnt, std::nan("")); return keep.back().data(); };
     const size_t nn = (size_t)n * n;
     ws.cap = B;
+    if (cfg.fuse) ws.r2 = alloc(B * nn);
     ws.r = alloc(B * nn); ws.q = alloc(B * nn); ws.z = alloc(B * nn); ws.p[0] = alloc(B * nn); ws.p[1] = alloc(B * nn);
     for (int l = 1; l <= ls; ++l) {
         size_t m = (size_t)plan.lv[l].n * plan.lv[l].n;
@@ -247,7 +272,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     ws.part_a = alloc((size_t)B * gx * gy);
     ws.part_pq = alloc((size_t)B * psn_pq_max(n));
     ws.part_b = alloc((size_t)B * gx * gy);
-    ws.part_u = alloc((size_t)B * psn_pq_max(n));
+    ws.part_u = alloc((size_t)B * psn_pu_max(n, nu));
     std::vector<float> pring;
     std::vector<PsnPend> pend(B);
     if (cfg.xdefer) {
@@ -301,6 +326,7 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
     cfg.pf32 = cfg.vf32;
     cfg.xdefer = cfg.pf32;
+    cfg.fuse = 0;
     if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     std::vector<std::vector<double>> keep;

@@ -294,3 +294,52 @@ def test_deferred_solution_update_restart_and_full_ring(he):
     assert (st1 <= 1).all() and it1.max() > 12
     for b in range(3):
         assert O.rel_l2(u1[b], O.solve_poisson(fb[b], thb[b], n)) <= 1e-10
+
+
+@pytest.mark.parametrize("n,ls,band,nu", [(120, 2, 16, 2), (160, 2, 48, 2), (160, 1, 64, 2), (256, 2, 86, 2), (200, 1, 200, 2), (160, 2, 64, 1), (176, 1, 32, 3)])
+def test_fused_update_and_down_leg(he, n, ls, band, nu):
+    """Mode 4 = mode 3 with the CG update of iteration k and the level-0 down-leg of iteration k+1 in ONE strip kernel
+    (double-buffered residual, p window one row ahead, V-cycle scale taken from the previous residual norm).  Same
+    iteration counts as the unfused schedule, solutions equal to round-off, 1e-10 against the reference operator --
+    for band splits with halo re-computation, several strips (n > 112) and V(1,1) / V(3,3) windows."""
+    rs = np.random.RandomState(n + nu)
+    B = 3
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    k = rs.uniform(0.5, 12.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    he.hostemu_fused_launches.restype = ctypes.c_longlong
+    before = he.hostemu_fused_launches()
+    u4, it4, rr4, st4 = run_stream(he, n, theta, None, 64, 64, ls, mode=4, band=band, nu=nu, sx=sx, sy=sy)
+    assert he.hostemu_fused_launches() - before >= it4.max()        # one fused launch per outer iteration
+    u3, it3, rr3, st3 = run_stream(he, n, theta, None, 64, 64, ls, mode=3, band=band, nu=nu, sx=sx, sy=sy)
+    assert he.hostemu_fused_launches() - before < 2 * it4.max() + 8   # ... and none in the unfused mode
+    assert (st4 <= 1).all() and (st3 <= 1).all()
+    assert (np.abs(it4 - it3) <= 1).all() and it4.sum() <= it3.sum() + 1
+    assert O.rel_l2(u4, u3) <= 1e-11
+    for b in range(B):
+        f = np.outer(sy[b], sx[b])
+        assert O.rel_l2(u4[b], O.solve_poisson(f, theta[b], n)) <= 1e-10
+        assert O.residual_rel(u4[b], f, theta[b]) <= 1e-11
+
+
+def test_fused_update_restart_full_ring_and_scales(he):
+    """Fused schedule through its rare paths: (a) a failed check restarts from the recomputed residual (the plain
+    down-leg then runs for that sample only); (b) more outer iterations than ring slots; (c) data of extreme magnitude
+    (the V-cycle scale of iteration k+1 comes from ||r_k||)."""
+    n = 160
+    f, theta = kat_inputs(n, 0, 0)
+    u, it, rr, st = run_stream(he, n, theta[None], f[None], 64, 64, 1, rtol=1e-14, mode=4, band=64)
+    u3, it3, _, st3 = run_stream(he, n, theta[None], f[None], 64, 64, 1, rtol=1e-14, mode=3, band=64)
+    assert st[0] == 1 and it[0] < 30 and abs(int(it[0]) - int(it3[0])) <= 2
+    assert O.rel_l2(u[0], O.solve_poisson(f, theta, n)) <= 1e-10
+    fb, thb = batch_inputs(n, 1)
+    u1, it1, _, st1 = run_stream(he, n, thb, fb, 64, 64, 2, mode=4, band=48, nu=1, rtol=1e-13)
+    assert (st1 <= 1).all() and it1.max() > 12
+    for b in range(3):
+        assert O.rel_l2(u1[b], O.solve_poisson(fb[b], thb[b], n)) <= 1e-10
+    u2, it2, _, _ = run_stream(he, n, thb, fb, 64, 64, 2, mode=3, band=48)
+    for scale in (1e-30, 1e+30):
+        us, its, _, sts = run_stream(he, n, thb[:1], fb[:1] * scale, 64, 64, 2, mode=4, band=48)
+        assert (sts <= 1).all() and its[0] <= it2[0] + 1
+        assert O.rel_l2(us[0] / scale, u2[0]) <= 1e-10
