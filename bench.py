@@ -217,6 +217,9 @@ KERNEL_BYTES_F32 = {
     "strip_post_l0": {"own": 17.0, "survey": 66.0},    # read r (8), u_pre (4), coarse corr (4/4); write z (4)
     "dir_apply_dot": {"own": 28.0, "survey": 40.0},    # read z (4), p (8); write p, q (16)
     "update_norm": {"own": 48.0, "survey": 48.0},
+    # CG update of iteration k fused with the level-0 down-leg of iteration k+1 (describe()["fused_update"]):
+    # read p (4), r (8); write r (8, second buffer), u_pre (4), coarse rhs (4/4)
+    "update_pre_l0": {"own": 25.0, "survey": 114.0},
 }
 KERNEL_BYTES = KERNEL_BYTES_F64
 
@@ -383,14 +386,21 @@ def run_own(args):
         else:
             top = max((k for k in prof if k in KERNEL_BYTES), key=lambda k: prof[k]["ms"])
             rec = prof[top]
-            # every sample takes part in exactly iters[b] launches of each per-iteration kernel (per step)
-            total_bytes = KERNEL_BYTES[top]["own"] * n * n * sample_iters * args.steps
+            # every sample takes part in exactly iters[b] launches of each per-iteration kernel (per step); with the fused
+            # schedule the plain level-0 down-leg only runs for rebuilt residuals: once per sample and solve here
+            def part(k):
+                return float(B) if (k == "strip_pre_l0" and desc.get("fused_update")) else sample_iters
+            total_bytes = KERNEL_BYTES[top]["own"] * n * n * part(top) * args.steps
             ach = total_bytes / (rec["ms"] / 1000.0) / 1e9
             # measured DRAM traffic of that kernel (ncu --set full capture summarised under profiles/), scaled to
             # the nodes one launch of this run processes; null if the kernel was not captured
             traffic = None
             try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))["bytes_per_level0_node"]
+                tj = {}
+                for fn in ("ncu_traffic_r1.json", "ncu_traffic_r2.json"):     # later rounds override
+                    fp = os.path.join(ROOT, "profiles", fn)
+                    if os.path.exists(fp):
+                        tj.update(json.load(open(fp))["bytes_per_level0_node"])
                 if top in tj:
                     traffic = tj[top] * n * n * B
             except Exception:
@@ -399,8 +409,8 @@ def run_own(args):
                     "traffic": traffic, "algorithmic_bytes_per_launch": KERNEL_BYTES[top]["own"] * n * n * B,
                     "avg_launch_ms": rec["ms"] / rec["launches"],
                     "bytes_per_node": KERNEL_BYTES[top]["own"], "peak_source": peak_src,
-                    "achieved_survey_model": KERNEL_BYTES[top]["survey"] * n * n * sample_iters * args.steps / (rec["ms"] / 1000.0) / 1e9,
-                    "all_kernels_GBps": {k: KERNEL_BYTES[k]["own"] * n * n * sample_iters * args.steps / (prof[k]["ms"] / 1000.0) / 1e9
+                    "achieved_survey_model": KERNEL_BYTES[top]["survey"] * n * n * part(top) * args.steps / (rec["ms"] / 1000.0) / 1e9,
+                    "all_kernels_GBps": {k: KERNEL_BYTES[k]["own"] * n * n * part(k) * args.steps / (prof[k]["ms"] / 1000.0) / 1e9
                                          for k in KERNEL_BYTES if k in prof}}
 
     # ---- end to end through the C ABI with host buffers
@@ -426,6 +436,30 @@ def run_own(args):
                 "hbm_GBps": B2 * (n2 * n2 * 16.0) / (rec2["ms"] / rec2["launches"] / 1000.0) / 1e9}
         del th2
 
+    # ---- the multi-resolution chain of the evaluation scripts through the public API, RNG included:
+    # k1, k2 and the 640 x 640 theta fields come from numpy's global legacy generator, replayed bit-exactly on the device
+    also_chain = None
+    if not args.no_also and n == 640 and rank == 0 and world == 1:
+        from superresolution_for_pdes_b200 import solve_multi_resolution_batch
+        E = 64
+        np.random.seed(1)
+        solve_multi_resolution_batch(2)
+        for _ in range(2):       # warm-up: plans, jump polynomials, page-locked result buffers (recycled between calls)
+            d = solve_multi_resolution_batch(E)
+            del d
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            d = solve_multi_resolution_batch(E)
+            del d
+        torch.cuda.synchronize()
+        tc = (time.perf_counter() - t0) / reps
+        also_chain = {"workload": f"solve_multi_resolution_batch({E}): per example k1, k2, theta (640x640) drawn from np.random's MT19937 "
+                                  "stream on the device, solves at 40/80/160/320/640, host numpy results (u at 5 resolutions + theta)",
+                      "value": E / tc, "unit": "chains/s", "ms_per_call": 1e3 * tc,
+                      "reference": "about 8.6 s per chain on one host core (SURVEY.md row a9)"}
+
     # ---- CPU baseline (oracle port of the reference) on this box's host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -444,13 +478,15 @@ def run_own(args):
                                   "accuracy unchanged)" if desc.get("vcycle_f32") else "; V-cycle in fp64") +
                                  ("; q = A p recomputed in the update kernel, never stored" if desc.get("update_strip") else "") +
                                  ("; search direction stored as scaled float (x, r, q, all dots fp64)" if desc.get("p_f32") else "") +
-                                 ("; x accumulated from the stored directions at check time" if desc.get("x_defer") else ""),
+                                 ("; x accumulated from the stored directions at check time" if desc.get("x_defer") else "") +
+                                 ("; CG update fused with the level-0 down-leg of the next V-cycle (residual not re-read)"
+                                  if desc.get("fused_update") else ""),
                        "host_affinity": (f"{len(numa_cores)} cores local to the GPU" if numa_cores else "unbound"),
                        "path": "resident" if desc["resident"] else "streamed", "mean_iters": float(info.iters.mean()),
                        "max_iters": int(info.iters.max()),
                        "l2": f"inputs larger than L2 (theta = {B * n * n * 8 / 1e6:.0f} MB per GPU, workspace {desc['workspace_bytes_per_sample'] * B / 1e9:.1f} GB)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "kernels": kernels, "also": also,
+            "kernels": kernels, "also": also, "also_chain": also_chain,
         }
         emit(line)
     if world > 1:
