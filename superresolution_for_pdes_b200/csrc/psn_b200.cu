@@ -550,6 +550,7 @@ struct Context {
     int upd_band = 64;     // rows per warp task of the strip update kernel (0: twice the direction kernel's)
     int pdl = 1;           // programmatic dependent launch between the kernels of the streamed solve
     int band0 = 0;         // rows per warp task on level 0 (0 = automatic)
+    int fuse_band = 0;     // rows per warp task of the fused update + down-leg kernel (0 = automatic)
     int band_target = 8;   // largest number of bands per column the band split considers (choose_bands)
     int dir_band = 64;     // rows per warp task of the direction kernel (1 halo row per band: short bands balance better); 0: as level 0
     int host_edge_div = 2; // first / last chunk of the host pipeline = regular chunk / host_edge_div
@@ -1079,6 +1080,9 @@ void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
         }
         cfg->band[l] = best_band;
     }
+    // The fused update + down-leg kernel follows the level-0 split unless "fuse_band" says otherwise: a split from its own wave
+    // model (3 CTAs per SM) measured the same at 640^2 (797-819 us for bands of 128-320 rows) and 28 % slower at 160^2 x 8192.
+    cfg->fuse_band = g.fuse_band >= 16 ? ((g.fuse_band + 1) & ~1) : 0;
     if (g.band0 >= 16 && cfg->ls >= 1) cfg->band[0] = (g.band0 + 1) & ~1;   // experiment knob
     cfg->dir_band = g.dir_band >= 16 ? ((g.dir_band + 1) & ~1) : cfg->band[0];
     cfg->upd_band = g.upd_band >= 16 ? ((g.upd_band + 1) & ~1) : 0;
@@ -2054,6 +2058,9 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "dir_band")) {
         if (value < 0 || value > 65536) return psn_fail(PSN_ERR_INVALID, "dir_band must be 0 (automatic) or >= 16");
         g.dir_band = (int)value;
+    } else if (!strcmp(name, "fuse_band")) {
+        if (value < 0 || value > 65536) return psn_fail(PSN_ERR_INVALID, "fuse_band must be 0 (automatic) or >= 16");
+        g.fuse_band = (int)value;
     } else if (!strcmp(name, "band0")) {
         if (value < 0 || value > 65536) return psn_fail(PSN_ERR_INVALID, "band0 must be 0 (automatic) or >= 16");
         g.band0 = (int)value;

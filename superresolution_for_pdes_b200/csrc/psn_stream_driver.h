@@ -23,6 +23,7 @@ struct PsnStreamCfg {
     int upd_strip; // mode 2 only: the update kernel recomputes q = At p in strips and q is never stored
     int pf32;      // with vf32 and upd_strip: the search direction p is stored as (scaled) float as well
     int xdefer;    // with pf32: x is accumulated from the ring of stored directions when a sample is checked (PsnPend)
+    int fuse_band; // rows per warp task of the fused kernel (0: band[0]); its own wave model: 3 CTAs per SM, not 4
     int fuse;      // with xdefer: the CG update of iteration k and the level-0 down-leg of iteration k+1 are ONE strip kernel
                    // (psn_strip_upre_body): r is not re-read, 33 -> 25 bytes per node and iteration for the two
     int vf32;     // mode 2 only: V-cycle intermediates (iterates, restricted residuals, z) are STORED as float; all
@@ -177,7 +178,7 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     PsnStripArgs fa;                      // fused update + down-leg: level-0 strip task geometry
     memset(&fa, 0, sizeof(fa));
     fa.level = 0;
-    fa.band = cfg.band[0];
+    fa.band = cfg.fuse_band >= 16 ? cfg.fuse_band : cfg.band[0];
     fa.nstrips = psn_strip_count(n, psn_fused_use(plan.nu));
     fa.nbands = psn_band_count(n, fa.band);
     fa.uout = ws.q;

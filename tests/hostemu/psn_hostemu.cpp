@@ -252,6 +252,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     cfg.pf32 = cfg.vf32;
     cfg.xdefer = cfg.pf32;
     cfg.fuse = (mode == 4 && cfg.xdefer) ? 1 : 0;
+    cfg.fuse_band = (band >= 32) ? ((band / 2 + 1) & ~1) : 0;   // a different split than the other level-0 kernels
     if (mode >= 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     PsnStreamWs ws;
@@ -327,6 +328,7 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     cfg.pf32 = cfg.vf32;
     cfg.xdefer = cfg.pf32;
     cfg.fuse = 0;
+    cfg.fuse_band = 0;
     if (mode == 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
     std::vector<std::vector<double>> keep;
