@@ -220,6 +220,8 @@ KERNEL_BYTES_F32 = {
     # CG update of iteration k fused with the level-0 down-leg of iteration k+1 (describe()["fused_update"]):
     # read p (4), r (8); write r (8, second buffer), u_pre (4), coarse rhs (4/4)
     "update_pre_l0": {"own": 25.0, "survey": 114.0},
+    # the prologue fused with the first down-leg: read theta (8); write r (8), u_pre (4), coarse rhs (4/4); once per solve
+    "prologue_pre_l0": {"own": 21.0, "survey": 90.0},
 }
 KERNEL_BYTES = KERNEL_BYTES_F64
 
@@ -389,7 +391,7 @@ def run_own(args):
             # every sample takes part in exactly iters[b] launches of each per-iteration kernel (per step); with the fused
             # schedule the plain level-0 down-leg only runs for rebuilt residuals: once per sample and solve here
             def part(k):
-                return float(B) if (k == "strip_pre_l0" and desc.get("fused_update")) else sample_iters
+                return float(B) if (k == "prologue_pre_l0" or (k == "strip_pre_l0" and desc.get("fused_update"))) else sample_iters
             total_bytes = KERNEL_BYTES[top]["own"] * n * n * part(top) * args.steps
             ach = total_bytes / (rec["ms"] / 1000.0) / 1e9
             # measured DRAM traffic of that kernel (ncu --set full capture summarised under profiles/), scaled to

@@ -204,8 +204,9 @@ int psn_mt19937_jump_host(const uint32_t* key, int pos, int64_t n_words, uint32_
  * upd_strip the search direction is stored as a power-of-two-scaled float; q, <p,q>, x and r are formed in fp64 from
  * that same rounded direction, so the recurrences stay exact), "x_defer" (default 1: with p_f32 the last 12 directions
  * stay in a ring and x = sum alpha_k p_k is formed in one fp64 pass when a sample is checked or the ring is full,
- * instead of a read-modify-write of x every iteration), "fuse_upd" (default 1: with x_defer the CG update of iteration k and the
- * level-0 down-leg of iteration k+1 are one kernel; the residual is double-buffered and not re-read), "pdl" (default 1: programmatic dependent
+ * instead of a read-modify-write of x every iteration), "fuse_upd" (default 2; with x_defer, 1: the CG update of iteration k and the
+ * level-0 down-leg of iteration k+1 are one kernel, the residual is double-buffered and not re-read; 2: also the prologue and the
+ * first down-leg when the forcing comes as sine factors with theta on the solve grid; 0: separate kernels), "pdl" (default 1: programmatic dependent
  * launch between the kernels of a solve), the host-buffer pipeline of resident grids with page-locked buffers:
  * "host_slots" (default 5, 3..6: staging slots),
  * "host_prefetch" (default 3, 1..3: uploads are enqueued this many chunks ahead of the solve being enqueued),

@@ -183,7 +183,7 @@ psn_dir_strip_kernel(const __grid_constant__ PsnCgArgs a, long long ntasks) {
 #ifndef PSN_UPRE_MINB
 #define PSN_UPRE_MINB 3
 #endif
-template <int NU>
+template <int NU, int MODE>
 __global__ void __launch_bounds__(PSN_STRIP_WARPS * 32, PSN_UPRE_MINB)
 psn_upre_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constant__ PsnStripArgs a, const __grid_constant__ PsnCgArgs cg,
                       long long ntasks) {
@@ -197,10 +197,10 @@ psn_upre_strip_kernel(const __grid_constant__ PsnPlan plan, const __grid_constan
     const int rem = (int)(task - b * per);
     const int band = rem / a.nstrips, strip = rem - band * a.nstrips;
     const PsnWarp w{(int)(threadIdx.x & 31)};
-    typedef PsnTmaFeeder<NU, double, float> Feeder;
+    typedef typename PsnUpreFeederSel<NU, MODE>::type Feeder;
     Feeder fd;
     fd.attach(strip_smem + (size_t)warp * Feeder::smem_bytes());
-    psn_strip_upre_body<NU>(w, plan, a, cg, b, band, strip, fd);
+    psn_strip_upre_body<NU, MODE>(w, plan, a, cg, b, band, strip, fd);
 }
 
 __global__ void __launch_bounds__(256) psn_flush_x_kernel(const __grid_constant__ PsnCgArgs a) {
@@ -543,7 +543,8 @@ struct Context {
     int res_persist = 1;   // register-blocked resident kernel: one persistent CTA per SM loops over the samples
     int res_waves = 1;     // persistent CTAs per SM (the kernel holds 1 CTA per SM: more only queue up)
     int inv_smem = 1;      // persistent kernel: keep the coarsest-level inverse in shared memory when it fits
-    int fuse_upd = 1;      // with x_defer: CG update fused with the level-0 down-leg of the next V-cycle (PsnStreamCfg::fuse)
+    int fuse_upd = 2;      // with x_defer: 1 = CG update fused with the level-0 down-leg of the next V-cycle (PsnStreamCfg::fuse),
+                           // 2 = also the prologue with the first down-leg (sine-factor forcing + theta on the solve grid)
     int x_defer = 1;       // with p_f32: x is accumulated from the ring of stored directions when a sample is checked
     int p_f32 = 1;         // with vcycle_f32 and upd_strip: the search direction is stored as (scaled) float too
     int upd_strip = 1;     // mode 2: strip update kernel that recomputes q = At p (q is never written to HBM)
@@ -898,24 +899,31 @@ struct CudaBackend {
         }
         launch(psn_update_strip_kernel<TP, XDEFER>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, a, ntasks);
     }
-    template <int NU>
+    template <int NU, int MODE>
     void fused_launch(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
-        typedef PsnTmaFeeder<NU, double, float> Feeder;
+        typedef typename PsnUpreFeederSel<NU, MODE>::type Feeder;
         const long long ntasks = B * a.nstrips * a.nbands;
         const unsigned grid = (unsigned)((ntasks + PSN_STRIP_WARPS - 1) / PSN_STRIP_WARPS);
         const size_t smem = (size_t)PSN_STRIP_WARPS * Feeder::smem_bytes();
         static bool attr_done = false;
         if (!attr_done) {
-            cudaFuncSetAttribute(psn_upre_strip_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(psn_upre_strip_kernel<NU, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_done = true;
         }
-        launch(psn_upre_strip_kernel<NU>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, plan, a, cg, ntasks);
+        launch(psn_upre_strip_kernel<NU, MODE>, dim3(grid), dim3(PSN_STRIP_WARPS * 32), smem, plan, a, cg, ntasks);
     }
     void fused_update(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
         ProfScope p("update_pre_l0", s);
-        if (plan.nu == 1) fused_launch<1>(plan, a, cg, B);
-        else if (plan.nu == 2) fused_launch<2>(plan, a, cg, B);
-        else fused_launch<3>(plan, a, cg, B);
+        if (plan.nu == 1) fused_launch<1, 0>(plan, a, cg, B);
+        else if (plan.nu == 2) fused_launch<2, 0>(plan, a, cg, B);
+        else fused_launch<3, 0>(plan, a, cg, B);
+        chk();
+    }
+    void fused_prologue(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
+        ProfScope p("prologue_pre_l0", s);
+        if (plan.nu == 1) fused_launch<1, 1>(plan, a, cg, B);
+        else if (plan.nu == 2) fused_launch<2, 1>(plan, a, cg, B);
+        else fused_launch<3, 1>(plan, a, cg, B);
         chk();
     }
     void flush_x(const PsnCgArgs& a, long long B) {
@@ -1089,14 +1097,14 @@ void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
     cfg->upd_strip = g.upd_strip;
     cfg->pf32 = (cfg->vf32 && g.upd_strip && g.p_f32) ? 1 : 0;
     cfg->xdefer = (cfg->pf32 && g.x_defer) ? 1 : 0;
-    cfg->fuse = (cfg->xdefer && g.fuse_upd) ? 1 : 0;
+    cfg->fuse = cfg->xdefer ? g.fuse_upd : 0;
 }
 
 size_t stream_ws_bytes_per_sample(const PsnPlan& plan, const PsnStreamCfg& cfg) {
     const size_t nn = (size_t)plan.n * plan.n;
     size_t b = 5 * nn * sizeof(double);
     if (cfg.xdefer) b += (size_t)PSN_PEND_K * nn * sizeof(float) - 2 * nn * sizeof(double) + sizeof(PsnPend);
-    if (cfg.fuse) b += nn * sizeof(double);   // second residual buffer
+    if (cfg.fuse) b += nn * sizeof(double) + sizeof(double);   // second residual buffer, scale of the fused prologue
     for (int l = 1; l <= cfg.ls; ++l) {
         const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n * sizeof(double);
         b += (l < cfg.ls ? 3 : 2) * m;
@@ -1127,7 +1135,8 @@ int carve_stream_ws(Arena& ar, const PsnPlan& plan, const PsnStreamCfg& cfg, lon
     ok = ok && ws->r && ws->q && ws->z;
     if (cfg.fuse) {
         ws->r2 = arena_take<double>(ar, Bc * nn);
-        ok = ok && ws->r2;
+        ws->vs0 = arena_take<double>(ar, Bc);
+        ok = ok && ws->r2 && ws->vs0;
     }
     for (int l = 1; l <= cfg.ls && ok; ++l) {
         const size_t m = (size_t)plan.lv[l].n * plan.lv[l].n;
@@ -1196,7 +1205,7 @@ int solve_impl(const Problem& P) {
         scfg.upd_strip = g.upd_strip;
         scfg.pf32 = (scfg.vf32 && g.upd_strip && g.p_f32) ? 1 : 0;
         scfg.xdefer = (scfg.pf32 && g.x_defer) ? 1 : 0;
-        scfg.fuse = (scfg.xdefer && g.fuse_upd) ? 1 : 0;
+        scfg.fuse = scfg.xdefer ? g.fuse_upd : 0;
         if (scfg.ls < 1) return psn_fail(PSN_ERR_UNSUPPORTED, "no shared-memory coarse level for n=%d", P.n);
     }
 
@@ -2032,7 +2041,7 @@ int psn_set_option(const char* name, int64_t value) {
         if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024) return psn_fail(PSN_ERR_INVALID, "res_threads must be 0, 128, 256, 512 or 1024");
         g.res_threads = (int)value;
     } else if (!strcmp(name, "fuse_upd")) {
-        if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "fuse_upd must be 0 or 1");
+        if (value < 0 || value > 2) return psn_fail(PSN_ERR_INVALID, "fuse_upd must be 0, 1 or 2");
         g.fuse_upd = (int)value;
     } else if (!strcmp(name, "x_defer")) {
         if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "x_defer must be 0 or 1");

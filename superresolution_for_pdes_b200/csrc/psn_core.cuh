@@ -82,6 +82,8 @@ struct PsnSampleState {
     int32_t restart;   // next direction is the preconditioned residual itself (beta = 0)
     int32_t nrestart;
     int32_t pad;
+    double vs;         // power-of-two scale the float-stored V-cycle of the CURRENT outer iteration works with (psn_vscale of
+                       // the residual norm it was started from; fused schedule: of the norm one iteration earlier)
 };
 
 // Deferred solution update (PsnCgArgs::xdefer): x is only needed when a sample is checked or finished, and the
@@ -117,6 +119,15 @@ PSN_FN unsigned psn_fdiv(unsigned idx, unsigned magic) { return magic ? psn_umul
 PSN_FN int psn_stagnation_status(double rt, double bb, double rtol) {
     const double c = rtol > PSN_FLOOR_CEIL ? rtol : PSN_FLOOR_CEIL;
     return (rt <= c * c * bb) ? PSN_ST_FP64_FLOOR : PSN_ST_STAGNATED;
+}
+
+// power-of-two scale that brings a residual of squared norm rr to O(1) before it is rounded to fp32
+// (exact in fp64, makes the fp32-stored V-cycle independent of the magnitude of the data)
+PSN_HDFN double psn_vscale(double rr) {
+    if (!(rr > 0.0) || !(rr < 1e300)) return 1.0;
+    int e = 0;
+    frexp(rr, &e);
+    return ldexp(1.0, -(e / 2));
 }
 
 PSN_FN int psn_imax(int a, int b) { return a > b ? a : b; }
@@ -834,6 +845,9 @@ struct PsnCgArgs {
                              // r -> r_out double buffer, ||r||^2 partials indexed by the down-leg's tasks (fu_nparts)
     double* r_out;           // fused: [B, n, n] residual written by this iteration's update
     int fu_nparts;           // fused: partials per sample in part_u
+    int pro_fused;           // the prologue ran inside the fused kernel too (mode 1): ||bt||^2 partials are in part_u (fu_nparts of
+                             // them) and the first V-cycle was scaled with vs0[b]
+    double* vs0;             // [B] scale estimate of the fused prologue: psn_vscale(||sin_x||^2 ||sin_y||^2 h^4) (= ||bt||^2 for theta == 1)
     int chk_mode;            // 0: 2-D tile true-residual kernel; 2: strip form (sine-factor forcing + theta on the solve grid)
     double* part_u;          // [B, upd_nstrips*upd_nbands] ||r||^2 partials of the strip update / strip true-residual kernels
     double* part_b;          // [B, ntx*nty]   ||r||^2 partials
@@ -972,9 +986,11 @@ PSN_FN void psn_true_residual_body(Ctx& ctx, const PsnCgArgs& a, long long b, in
 PSN_FN void psn_state_init(const PsnCgArgs& a, long long b) {
     PsnSampleState st;
     double bb = 0.0;
-    const double* pa = a.part_a + b * (long long)(a.ntx * a.nty);
-    for (int k = 0; k < a.ntx * a.nty; ++k) bb += pa[k];
+    const int npa = a.pro_fused ? a.fu_nparts : a.ntx * a.nty;
+    const double* pa = a.pro_fused ? a.part_u + b * (long long)npa : a.part_a + b * (long long)npa;
+    for (int k = 0; k < npa; ++k) bb += pa[k];
     st.bb = bb;
+    st.vs = a.pro_fused ? a.vs0[b] : psn_vscale(bb);
     st.rz_old = 1.0;
     st.rz = 0.0;
     st.pq = 0.0;
@@ -1077,6 +1093,7 @@ PSN_FN void psn_state_after_update(const PsnCgArgs& a, long long b) {
     const int cnt = a.fused ? a.fu_nparts : (a.upd_mode ? a.upd_nstrips * a.upd_nbands : a.ntx * a.nty);
     const double* pb = (a.upd_mode || a.fused) ? a.part_u + b * (long long)cnt : a.part_b + b * (long long)cnt;
     for (int k = 0; k < cnt; ++k) rr += pb[k];
+    st.vs = psn_vscale(a.fused ? st.rr : rr);   // fused: the next down-leg has already run, scaled with the norm before this update
     st.rr_prev = st.rr;
     st.rr = rr;
     st.rz_old = st.rz;
@@ -1121,6 +1138,7 @@ PSN_FN int psn_state_after_check(const PsnCgArgs& a, long long b) {
             st.prev_true = rt;
             st.nrestart += 1;
             st.restart = 1;
+            st.vs = psn_vscale(rt);
             st.phase = PSN_PHASE_ITER;
         }
         a.state[b] = st;

@@ -24,6 +24,7 @@ struct PsnStreamCfg {
     int pf32;      // with vf32 and upd_strip: the search direction p is stored as (scaled) float as well
     int xdefer;    // with pf32: x is accumulated from the ring of stored directions when a sample is checked (PsnPend)
     int fuse_band; // rows per warp task of the fused kernel (0: band[0]); its own wave model: 3 CTAs per SM, not 4
+    //             fuse: 0 off, 1 update + down-leg, 2 (default) also prologue + first down-leg for the standard call form
     int fuse;      // with xdefer: the CG update of iteration k and the level-0 down-leg of iteration k+1 are ONE strip kernel
                    // (psn_strip_upre_body): r is not re-read, 33 -> 25 bytes per node and iteration for the two
     int vf32;     // mode 2 only: V-cycle intermediates (iterates, restricted residuals, z) are STORED as float; all
@@ -86,6 +87,7 @@ struct PsnStreamWs {
     double* r;                   // level 0: residual (= rhs of the V-cycle)
     double* r2;                  // fused schedule: second residual buffer (the update writes r[cur ^ 1])
     int rcur;                    // fused schedule: buffer that holds the current residual
+    double* vs0;                 // fused schedule: [cap] V-cycle scale the fused prologue used (read by state_init)
     double* q;                   // level 0: A p  (doubles as the pre-smoothed iterate)
     double* z;                   // level 0: preconditioned residual
     double* p[2];                // level 0: search direction, ping-pong
@@ -196,9 +198,18 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
     cg.rtol = rtol;
     cg.max_iter = max_iter;
 
+    // standard call form (sine factors + theta on the solve grid): the prologue runs inside the fused kernel as well
+    const int profuse = (fuse && cg.chk_mode == 2 && ws.vs0 && cfg.fuse >= 2) ? 1 : 0;
+    cg.pro_fused = profuse;
+    cg.vs0 = ws.vs0;
     if (start_it == 0) {
         bk.zero_counters(ws.counters, max_iter + 8);
-        bk.prologue(cg, B);
+        if (profuse) {
+            cg.r_out = rbuf[0];
+            bk.fused_prologue(plan, fa, cg, B);
+        } else {
+            bk.prologue(cg, B);
+        }
         bk.state_init(cg, B);
     }
 
@@ -215,7 +226,8 @@ int psn_stream_solve(BK& bk, const PsnPlan& plan, const PsnStreamCfg& cfg, const
         if (check_from < 0) check_from = 0;
     }
     int it = start_it;
-    bool rebuilt = true;   // fused schedule: some samples may carry a residual that no fused kernel has smoothed yet
+    // fused schedule: some samples may carry a residual that no fused kernel has smoothed yet
+    bool rebuilt = !(profuse && start_it == 0);
     for (; it < max_outer; ++it) {
         // ---- z = M^{-1} r : one V(nu,nu) cycle
         for (int l = 0; l < cfg.ls; ++l) {

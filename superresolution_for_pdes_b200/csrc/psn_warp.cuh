@@ -320,23 +320,11 @@ PSN_HDFN int psn_strip_use_post(int nu, int f32) {
     const int u = PSN_STRIP_COLS - psn_strip_hl_post(nu, f32) - 2 * nu;
     return f32 ? (u & ~3) : (u & ~1);
 }
-// power-of-two scale that brings a residual of squared norm rr to O(1) before it is rounded to fp32
-// (exact in fp64, makes the fp32-stored V-cycle independent of the magnitude of the data)
-PSN_HDFN double psn_vscale(double rr) {
-    if (!(rr > 0.0) || !(rr < 1e300)) return 1.0;
-    int e = 0;
-    frexp(rr, &e);
-    return ldexp(1.0, -(e / 2));
-}
-
-// Scale of the float-stored V-cycle of a sample's CURRENT outer iteration (a power of two near 1 / ||r||).  Unfused: from
-// the residual norm itself.  Fused schedule: the down-leg of iteration k+1 runs inside the update kernel of iteration k,
-// before ||r_{k+1}|| exists, so it scales with ||r_k|| -- which the later kernels of iteration k+1 find in rr_prev.  (The
-// scale only positions the data in the float exponent range; a residual that is 30x smaller than its scale assumes
-// loses nothing.)  Samples whose residual was rebuilt (restart) were smoothed by the plain kernel with their own norm.
-PSN_FN double psn_vcycle_scale(const PsnSampleState& st, int fused) {
-    return psn_vscale((fused && !st.restart) ? st.rr_prev : st.rr);
-}
+// Scale of the float-stored V-cycle of a sample's CURRENT outer iteration (a power of two near 1 / ||r||), kept in the sample
+// state by the state kernels.  Unfused: from the residual norm itself.  Fused schedule: the down-leg of iteration k+1 runs
+// inside the update kernel of iteration k, before ||r_{k+1}|| exists, so it scales with ||r_k||.  (The scale only positions the
+// data in the float exponent range; a residual 30x smaller than its scale assumes loses nothing.)
+PSN_FN double psn_vcycle_scale(const PsnSampleState& st, int /*fused*/) { return st.vs; }
 
 // horizontal neighbour sum of offset e (static) in a row held as v[0..3]
 #define PSN_LR(v, e, upv, dnv) \
@@ -702,7 +690,7 @@ PSN_FN void psn_strip_pre_body(const PsnWarp& w, const PsnPlan& plan, const PsnS
     const TB* bg = reinterpret_cast<const TB*>(a.b) + b * (long long)n * n;
     TV* ug = reinterpret_cast<TV*>(a.uout) + b * (long long)n * n;
     TV* cg = reinterpret_cast<TV*>(a.bc) + b * (long long)nc * nc;
-    const wd bsc = w_bcast((SCALE && a.state) ? psn_vscale(a.state[b].rr) : 1.0);
+    const wd bsc = w_bcast((SCALE && a.state) ? a.state[b].vs : 1.0);
 
     WV val[W][4], bb[W][4], acc[2];
 #pragma unroll
@@ -1193,9 +1181,13 @@ struct PsnFusedRow {     // per-task constants and running state of the update p
     wd dot;              // partial ||r_{k+1}||^2 over the owned nodes
     double* rout;        // r_{k+1} of this sample
     wb ind[2];           // column pairs inside the domain
+    // mode 1 (prologue): r_0 = bt = -(sin_y[i] sin_x[j] / theta_ij) h^2 instead of r_k - alpha q
+    wd sxv[4];           // the lane's four sin_x values
+    const double* sy;    // sin_y of this sample
+    wd h2;
 };
 
-template <int NU, bool FAST, class Feeder>
+template <int NU, int MODE, bool FAST, class Feeder>
 PSN_FN void psn_strip_upre_chunk(const PsnWarp& w, int t, int ts, int tload, int tend, int last, int n, int nc,
                                  int i0, int i1, int I0, int I1, wf (&val)[2 * NU + 2][4], wf (&bb)[2 * NU + 2][4],
                                  Feeder& fd, int par, wf (&acc)[2], const wf (&rdA)[4], const wf (&dA)[4], const wf (&mk)[4],
@@ -1223,30 +1215,48 @@ PSN_FN void psn_strip_upre_chunk(const PsnWarp& w, int t, int ts, int tload, int
         if (!FAST && tc > tend) break;
         const int P = tt & 1;
         const int k0 = tt;
-        // ---- new row: r_k(tc) and p_k(tc+1) from the feeder; q(tc), r_{k+1}(tc); first red half sweep from the zero guess
+        // ---- new row.  mode 0: r_k(tc) and p_k(tc+1) from the feeder; q(tc), r_{k+1}(tc).  mode 1: theta(tc) from the feeder,
+        //      r_0(tc) = bt(tc).  Then the first red half sweep from the zero guess.
         {
+            wd rn[4];
             typename Feeder::V0 r0[4];
             typename Feeder::V1 r1[4];
             fd.template fetch<FAST>(w, tt, tc, par, r0, r1);
-            wd pn[4];
+            if constexpr (MODE == 0) {
+                wd pn[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pn[e] = w_cvt<double>(r1[e]);
-            if (!FAST && tc + 1 > last) {
+                for (int e = 0; e < 4; ++e) pn[e] = w_cvt<double>(r1[e]);
+                if (!FAST && tc + 1 > last) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) pn[e] = zerod;          // row n of p: outside the grid (its copy was skipped)
-            }
-            const wd upv = w_up_raw(fr.pc[3]);
-            const wd dnv = w_down_raw(fr.pc[0]);
-            wd q[4], rn[4];
-            q[0] = 4.0 * fr.pc[0] - ((pn[0] + fr.pm[0]) + (upv + fr.pc[1]));
-            q[1] = 4.0 * fr.pc[1] - ((pn[1] + fr.pm[1]) + (fr.pc[0] + fr.pc[2]));
-            q[2] = 4.0 * fr.pc[2] - ((pn[2] + fr.pm[2]) + (fr.pc[1] + fr.pc[3]));
-            q[3] = 4.0 * fr.pc[3] - ((pn[3] + fr.pm[3]) + (fr.pc[2] + dnv));
+                    for (int e = 0; e < 4; ++e) pn[e] = zerod;          // row n of p: outside the grid (its copy was skipped)
+                }
+                const wd upv = w_up_raw(fr.pc[3]);
+                const wd dnv = w_down_raw(fr.pc[0]);
+                wd q[4];
+                q[0] = 4.0 * fr.pc[0] - ((pn[0] + fr.pm[0]) + (upv + fr.pc[1]));
+                q[1] = 4.0 * fr.pc[1] - ((pn[1] + fr.pm[1]) + (fr.pc[0] + fr.pc[2]));
+                q[2] = 4.0 * fr.pc[2] - ((pn[2] + fr.pm[2]) + (fr.pc[1] + fr.pc[3]));
+                q[3] = 4.0 * fr.pc[3] - ((pn[3] + fr.pm[3]) + (fr.pc[2] + dnv));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                rn[e] = w_sel(fr.ind[e >> 1], r0[e] - fr.alpha * q[e], zerod);
-                fr.pm[e] = fr.pc[e];
-                fr.pc[e] = pn[e];
+                for (int e = 0; e < 4; ++e) {
+                    rn[e] = w_sel(fr.ind[e >> 1], r0[e] - fr.alpha * q[e], zerod);
+                    fr.pm[e] = fr.pc[e];
+                    fr.pc[e] = pn[e];
+                }
+            } else {
+                if (FAST || tc <= last) {
+                    const wd syr = w_bcast(fr.sy[tc]);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        // out-of-domain lanes divide by 1 (the ring's un-copied columns are zero) and are masked
+                        const wd th = w_sel(fr.ind[e >> 1], w_cvt<double>(r0[e]), w_bcast(1.0));
+                        const wd f = (syr * fr.sxv[e]) * w_rcp(th);          // same expression as psn_rhs
+                        rn[e] = w_sel(fr.ind[e >> 1], zerod - (f * fr.h2), zerod);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rn[e] = zerod;
+                }
             }
             if (tc >= i0 && tc < i1) {
                 double* rowr = fr.rout + (long long)tc * n;
@@ -1323,12 +1333,39 @@ PSN_FN void psn_strip_upre_chunk(const PsnWarp& w, int t, int ts, int tload, int
     }
 }
 
-// Feeder: PsnTmaFeeder<NU, double /* r_k */, float /* s_k p_k, rows offset by one */>
-template <int NU, class Feeder>
+template <int NU, int MODE>
+struct PsnUpreFeederSel {
+    typedef PsnTmaFeeder<NU, double, float> type;
+};
+template <int NU>
+struct PsnUpreFeederSel<NU, 1> {
+    typedef PsnTmaFeeder<NU, double> type;
+};
+
+// sum of squares of a vector, one warp, fixed order (every task of a sample gets the identical value)
+PSN_FN double psn_warp_sum_sq(const PsnWarp& w, const double* v, int count) {
+    wd acc = w_bcast(0.0);
+    const wi lane = w_lane(w);
+    for (int k0 = 0; k0 < count; k0 += 32) {
+        const wd x = w_ld1(v + k0, lane, lane < (count - k0));
+        acc = acc + x * x;
+    }
+    return w_sum(acc);
+}
+
+// MODE 0 -- Feeder: PsnTmaFeeder<NU, double /* r_k */, float /* s_k p_k, rows offset by one */>
+// MODE 1 -- the solve's PROLOGUE fused with the first down-leg: r_0 = bt formed from theta (Feeder: PsnTmaFeeder<NU, double>)
+//           and the sine factors; the sample state does not exist yet (state_init runs afterwards and finds ||bt||^2 in
+//           part_u and the scale used here in vs0).
+template <int NU, int MODE, class Feeder>
 PSN_FN void psn_strip_upre_body(const PsnWarp& w, const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& g, long long b,
                                 int band, int strip, Feeder& fd) {
-    const PsnSampleState st = g.state[b];
-    if (st.phase != PSN_PHASE_ITER) return;
+    PsnSampleState st;
+    memset(&st, 0, sizeof(st));
+    if constexpr (MODE == 0) {
+        st = g.state[b];
+        if (st.phase != PSN_PHASE_ITER) return;
+    }
     constexpr int NS = 2 * NU, W = NS + 2;
     const int USE = psn_fused_use(NU);
     const int HL = psn_fused_hl(NU);
@@ -1341,9 +1378,18 @@ PSN_FN void psn_strip_upre_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     const int I0 = i0 >> 1, I1 = psn_imin(i1 >> 1, nc);
     const int J0 = a0 >> 1, J1 = psn_imin(a1 >> 1, nc);
 
-    const double pq = psn_warp_sum_partials(w, g.part_pq + b * (long long)g.npq, g.npq);
-    const double pscale = psn_vscale(st.rr);                       // scale of the stored direction s_k p_k
-    const double alpha = (pq > 0.0) ? st.rz / pq : 0.0;
+    double pq = 0.0, pscale = 1.0, alpha = 0.0;
+    if constexpr (MODE == 0) {
+        pq = psn_warp_sum_partials(w, g.part_pq + b * (long long)g.npq, g.npq);
+        pscale = psn_vscale(st.rr);                                // scale of the stored direction s_k p_k
+        alpha = (pq > 0.0) ? st.rz / pq : 0.0;
+    } else {
+        // ||bt||^2 does not exist yet: scale with ||sin_x||^2 ||sin_y||^2 h^4, which is ||bt||^2 for theta == 1 and within
+        // max(theta)^2 / min(theta)^2 of it otherwise -- it only positions the data in the float exponent range
+        const double sxx = psn_warp_sum_sq(w, g.rhs.sx + b * (long long)n, n);
+        const double syy = psn_warp_sum_sq(w, g.rhs.sy + b * (long long)n, n);
+        pscale = psn_vscale(sxx * syy * g.h2 * g.h2);
+    }
 
     const wi col0 = w_lane(w) * 4 + c0;
     const wi col2 = col0 + 2;
@@ -1379,10 +1425,17 @@ PSN_FN void psn_strip_upre_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     fr.rout = g.r_out + base;
     fr.ind[0] = mp[0];
     fr.ind[1] = mp[1];
-    // p rows ts-1 and ts (the feeder delivers row tc+1 at time tc)
+    fr.h2 = w_bcast(g.h2);
+    fr.sy = nullptr;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) fr.pm[e] = fr.pc[e] = zerod;
-    {
+    for (int e = 0; e < 4; ++e) fr.pm[e] = fr.pc[e] = fr.sxv[e] = zerod;
+    if constexpr (MODE == 1) {
+        fr.sy = g.rhs.sy + b * (long long)n;
+        w_ldp(g.rhs.sx + b * (long long)n, col0, mp[0], fr.sxv[0], fr.sxv[1]);
+        w_ldp(g.rhs.sx + b * (long long)n, col2, mp[1], fr.sxv[2], fr.sxv[3]);
+    }
+    // p rows ts-1 and ts (the feeder delivers row tc+1 at time tc)
+    if constexpr (MODE == 0) {
         wf t0[4], t1[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) t0[e] = t1[e] = zero;
@@ -1404,9 +1457,13 @@ PSN_FN void psn_strip_upre_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     for (int k = 0; k < W; ++k)
 #pragma unroll
         for (int e = 0; e < 4; ++e) val[k][e] = bb[k][e] = zero;
-    fd.set_base0(g.r + base);
-    fd.set_base1(pg + n);                  // array 1 runs one row ahead
-    fd.rows1_max = last - 1;               // ... and has no row n
+    if constexpr (MODE == 0) {
+        fd.set_base0(g.r + base);
+        fd.set_base1(pg + n);              // array 1 runs one row ahead
+        fd.rows1_max = last - 1;           // ... and has no row n
+    } else {
+        fd.set_base0(g.rhs.theta + base);
+    }
     fd.n = n;
     fd.tload = tload;
     psn_feeder_geom(fd, col0, mp, c0, n);
@@ -1419,21 +1476,25 @@ PSN_FN void psn_strip_upre_body(const PsnWarp& w, const PsnPlan& plan, const Psn
                           (((t - NS) >> 1) - 1 >= I0) && (((t + W - 1 - NS) >> 1) - 1 < I1);
         const int par = ((t - ts) / W) & 1;
         if (fast)
-            psn_strip_upre_chunk<NU, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv, fr,
+            psn_strip_upre_chunk<NU, MODE, true>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv, fr,
                                            ug, cgp, col0, so, cj, sc);
         else
-            psn_strip_upre_chunk<NU, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv, fr,
+            psn_strip_upre_chunk<NU, MODE, false>(w, t, ts, tload, tend, last, n, nc, i0, i1, I0, I1, val, bb, fd, par, acc, rdA, dA, mk, lv, fr,
                                             ug, cgp, col0, so, cj, sc);
     }
     const double sdot = w_sum(fr.dot);
     if (w_lane0(w)) {
         g.part_u[b * (long long)(a.nstrips * a.nbands) + (long long)band * a.nstrips + strip] = sdot;
         if (band == 0 && strip == 0) {
-            g.state[b].pq = pq;
-            PsnPend* pd = g.pend + b;       // deferred x: record the step, x receives (alpha / s_k) (s_k p_k) at the next flush
-            if (pd->lo == pd->hi) pd->lo = g.it;
-            pd->a[g.it % PSN_PEND_K] = alpha * (1.0 / pscale);
-            pd->hi = g.it + 1;
+            if constexpr (MODE == 0) {
+                g.state[b].pq = pq;
+                PsnPend* pd = g.pend + b;   // deferred x: record the step, x receives (alpha / s_k) (s_k p_k) at the next flush
+                if (pd->lo == pd->hi) pd->lo = g.it;
+                pd->a[g.it % PSN_PEND_K] = alpha * (1.0 / pscale);
+                pd->hi = g.it + 1;
+            } else {
+                g.vs0[b] = pscale;
+            }
         }
     }
 }

@@ -13,6 +13,7 @@
 
 namespace {
 
+long long g_fused_prologues = 0;
 long long g_fused_launches = 0;   // how often the fused update + down-leg backend entry ran (asserted by the tests)
 
 struct HostPlan {
@@ -140,9 +141,9 @@ struct HostBackend {
             for (int ty = 0; ty < a.nty; ++ty)
                 for (int tx = 0; tx < a.ntx; ++tx) psn_update_body(ctx, a, b, ty, tx);
     }
-    template <int NU>
+    template <int NU, int MODE>
     void fused_t(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
-        typedef PsnTmaFeeder<NU, double, float> Feeder;
+        typedef typename PsnUpreFeederSel<NU, MODE>::type Feeder;
         PsnWarp w;
         std::vector<unsigned char> ring(Feeder::smem_bytes() + 256);
         for (long long b = 0; b < B; ++b)
@@ -150,14 +151,20 @@ struct HostBackend {
                 for (int strip = 0; strip < a.nstrips; ++strip) {
                     std::fill(ring.begin(), ring.end(), (unsigned char)0xff);
                     Feeder fd; fd.attach(ring.data());
-                    psn_strip_upre_body<NU>(w, plan, a, cg, b, band, strip, fd);
+                    psn_strip_upre_body<NU, MODE>(w, plan, a, cg, b, band, strip, fd);
                 }
     }
     void fused_update(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
         ++g_fused_launches;
-        if (plan.nu == 1) fused_t<1>(plan, a, cg, B);
-        else if (plan.nu == 2) fused_t<2>(plan, a, cg, B);
-        else fused_t<3>(plan, a, cg, B);
+        if (plan.nu == 1) fused_t<1, 0>(plan, a, cg, B);
+        else if (plan.nu == 2) fused_t<2, 0>(plan, a, cg, B);
+        else fused_t<3, 0>(plan, a, cg, B);
+    }
+    void fused_prologue(const PsnPlan& plan, const PsnStripArgs& a, const PsnCgArgs& cg, long long B) {
+        ++g_fused_prologues;
+        if (plan.nu == 1) fused_t<1, 1>(plan, a, cg, B);
+        else if (plan.nu == 2) fused_t<2, 1>(plan, a, cg, B);
+        else fused_t<3, 1>(plan, a, cg, B);
     }
     void flush_x(const PsnCgArgs& a, long long B) {
         PsnHostCtx ctx;
@@ -203,6 +210,7 @@ PsnRhs make_rhs(const double* theta, const double* f, const double* sx, const do
 extern "C" {
 
 long long hostemu_fused_launches(void) { return g_fused_launches; }
+long long hostemu_fused_prologues(void) { return g_fused_prologues; }
 
 // levels / gammas of the plan, for direct comparison with the numpy prototype
 int hostemu_plan(int n, int nu, int* ns, double* gams, double* inv_out) {
@@ -243,7 +251,8 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     const PsnPlan& plan = hp.plan;
     if (ls < 1 || ls >= plan.nlev) return -1;
     PsnStreamCfg cfg;
-    // mode 3 = mode 2 (TMA-fed strips) with float storage of the V-cycle intermediates; mode 4 = mode 3 + fused update / down-leg
+    // mode 3 = mode 2 (TMA-fed strips) with float storage of the V-cycle intermediates; mode 4 = mode 3 + fused update / down-leg;
+    // mode 5 = mode 4 + fused prologue / first down-leg
     cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? (mode >= 3 ? 2 : mode) : 0;
     cfg.vf32 = (mode >= 3 && cfg.mode == 2 && psn_vf32_ok(plan, ls)) ? 1 : 0;
     cfg.dir_band = 0;
@@ -251,7 +260,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
     cfg.pf32 = cfg.vf32;
     cfg.xdefer = cfg.pf32;
-    cfg.fuse = (mode == 4 && cfg.xdefer) ? 1 : 0;
+    cfg.fuse = (mode >= 4 && cfg.xdefer) ? mode - 3 : 0;
     cfg.fuse_band = (band >= 32) ? ((band / 2 + 1) & ~1) : 0;   // a different split than the other level-0 kernels
     if (mode >= 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;
@@ -261,7 +270,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     auto alloc = [&](size_t cnt) { keep.emplace_back(cnt, std::nan("")); return keep.back().data(); };
     const size_t nn = (size_t)n * n;
     ws.cap = B;
-    if (cfg.fuse) ws.r2 = alloc(B * nn);
+    if (cfg.fuse) { ws.r2 = alloc(B * nn); ws.vs0 = alloc(B); }
     ws.r = alloc(B * nn); ws.q = alloc(B * nn); ws.z = alloc(B * nn); ws.p[0] = alloc(B * nn); ws.p[1] = alloc(B * nn);
     for (int l = 1; l <= ls; ++l) {
         size_t m = (size_t)plan.lv[l].n * plan.lv[l].n;

@@ -317,6 +317,13 @@ def test_fused_update_and_down_leg(he, n, ls, band, nu):
     assert (st4 <= 1).all() and (st3 <= 1).all()
     assert (np.abs(it4 - it3) <= 1).all() and it4.sum() <= it3.sum() + 1
     assert O.rel_l2(u4, u3) <= 1e-11
+    # mode 5: the prologue (r_0 = bt from theta and the sine factors) runs inside the fused kernel too; its V-cycle scale is an
+    # estimate (||sin_x|| ||sin_y|| h^2), a power of two like the exact one, so nothing changes in the iterates
+    he.hostemu_fused_prologues.restype = ctypes.c_longlong
+    pro = he.hostemu_fused_prologues()
+    u5, it5, rr5, st5 = run_stream(he, n, theta, None, 64, 64, ls, mode=5, band=band, nu=nu, sx=sx, sy=sy)
+    assert he.hostemu_fused_prologues() == pro + 1
+    assert (st5 <= 1).all() and (it5 == it4).all() and O.rel_l2(u5, u4) <= 1e-12
     for b in range(B):
         f = np.outer(sy[b], sx[b])
         assert O.rel_l2(u4[b], O.solve_poisson(f, theta[b], n)) <= 1e-10
@@ -343,3 +350,14 @@ def test_fused_update_restart_full_ring_and_scales(he):
         us, its, _, sts = run_stream(he, n, thb[:1], fb[:1] * scale, 64, 64, 2, mode=4, band=48)
         assert (sts <= 1).all() and its[0] <= it2[0] + 1
         assert O.rel_l2(us[0] / scale, u2[0]) <= 1e-10
+    # fused prologue with sine factors of extreme magnitude, theta far from 1 (the scale estimate ignores theta) and a zero forcing
+    rs = np.random.RandomState(3)
+    x = np.linspace(0, 1, n)
+    sx = np.stack([np.sin(2 * np.pi * 3.3 * x) * 1e-20, np.sin(2 * np.pi * 1.7 * x) * 1e18, np.zeros(n)])
+    sy = np.stack([np.sin(2 * np.pi * 5.1 * x) * 1e-15, np.sin(2 * np.pi * 2.2 * x) * 1e10, np.sin(2 * np.pi * x)])
+    th = np.stack([rs.uniform(1e-3, 2e-3, (n, n)), rs.uniform(50.0, 2000.0, (n, n)), rs.uniform(0.5, 2.0, (n, n))])
+    u5, it5, _, st5 = run_stream(he, n, th, None, 64, 64, 2, mode=5, band=48, sx=sx, sy=sy)
+    u3, it3, _, st3 = run_stream(he, n, th, None, 64, 64, 2, mode=3, band=48, sx=sx, sy=sy)
+    assert (st5 <= 1).all() and (it5 == it3).all() and (u5[2] == 0).all()
+    for b in range(2):
+        assert O.rel_l2(u5[b], u3[b]) <= 1e-11
