@@ -547,6 +547,44 @@ struct PsnBlockSolver {
         }
     }
 
+    // bt of the thread's 16 nodes.  Standard call form (sine factors, theta on the solve grid itself): row / column factors and
+    // theta come through 8 + 4 + 4 loads from per-thread base pointers -- the generic psn_rhs per node (forcing-mode branches,
+    // 64-bit index products, once in the prologue and once per true-residual check) was 20 % of the kernel's instructions.
+    // Same operations in the same order as psn_rhs, so the values are bit-identical.
+    PSN_FN void rhs16(const PsnSolveArgs& a, long long b, int t, double h2, double (&out)[16]) const {
+        const int bx = t % BX, by = t / BX;
+        const PsnRhs& s = a.rhs;
+        if (s.sx && !s.f && s.step == 1 && s.mn == N) {
+            const double* sxp = s.sx + b * (long long)N + 4 * bx;
+            const double* syp = s.sy + b * (long long)N + 4 * by;
+            double sxv[4], syv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                sxv[k] = psn_ldg(sxp + k);
+                syv[k] = psn_ldg(syp + k);
+            }
+            if (s.theta) {
+                const double* thp = s.theta + (b * (long long)N + 4 * by) * N + 4 * bx;
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        double f = syv[aa] * sxv[c];
+                        f = f * (1.0 / psn_ldg(thp + aa * N + c));
+                        out[4 * aa + c] = -(f * h2);
+                    }
+            } else {
+#pragma unroll
+                for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) out[4 * aa + c] = -((syv[aa] * sxv[c]) * h2);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) out[k] = psn_rhs(s, b, 4 * by + (k >> 2), 4 * bx + (k & 3), h2);
+        }
+    }
+
     // block-wide sum of per-thread partials (device: acc[0] of every thread; host: all entries)
     PSN_FN double tsum(const double (&acc)[PSN_BK_TS]) {
 #if defined(__CUDACC__)
@@ -578,11 +616,12 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
     PSN_BK_FOR(ctx, NT) {
         acc[PSN_BK_TI] = 0.0;
         if (t_ < NT) {
-            const int bx = t_ % BX, by = t_ / BX;
             double s = 0.0;
+            double bt16[16];
+            S.rhs16(a, b, t_, plan.h2, bt16);
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-                const double v = psn_rhs(a.rhs, b, 4 * by + (k >> 2), 4 * bx + (k & 3), plan.h2);
+                const double v = bt16[k];
                 S.r[PSN_BK_TI][k] = v;
                 S.p[PSN_BK_TI][k] = 0.0;
                 S.xs.st(k * NTPAD + t_, 0.0);
@@ -681,15 +720,16 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
                 PSN_BK_FOR(ctx, NT) {
                     acc[PSN_BK_TI] = 0.0;
                     if (t_ < NT) {
-                        const int bx = t_ % BX, by = t_ / BX;
                         double hT[4], hB[4], hL[4], hR[4];
                         S.load_halo_all(t_, hT, hB, hL, hR);
                         double s = 0.0;
+                        double bt16[16];
+                        S.rhs16(a, b, t_, plan.h2, bt16);
 #pragma unroll
                         for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
                             for (int c = 0; c < 4; ++c) {
-                                const double bt = psn_rhs(a.rhs, b, 4 * by + aa, 4 * bx + c, plan.h2);
+                                const double bt = bt16[4 * aa + c];
                                 const double rv = bt - (4.0 * S.z[PSN_BK_TI][4 * aa + c] -
                                                         PsnBlockSolver<BX, Ctx>::nbsum(S.z[PSN_BK_TI], aa, c, hT, hB, hL, hR));
                                 S.r[PSN_BK_TI][4 * aa + c] = rv;
