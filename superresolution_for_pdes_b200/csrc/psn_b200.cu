@@ -1439,7 +1439,7 @@ int solve_impl(const Problem& P) {
             {
                 ProfScope pr("smem_solve", s);
                 const unsigned grid = (unsigned)bc;
-                if (g.res_block && plan.n == 80) {
+                if (g.res_block && psn_block_ok<20>(plan)) {
                     size_t bsm = (size_t)psn_block_smem_doubles<20>(plan) * sizeof(double);
                     int invd = psn_coarse_inv_doubles(plan);
                     if (!g.inv_smem || bsm + (size_t)invd * sizeof(double) + 1024 > g.smem_optin) invd = 0;

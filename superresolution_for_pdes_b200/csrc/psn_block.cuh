@@ -10,7 +10,7 @@
 // other colour while it writes its own: one __syncthreads per half sweep, no double buffering.
 // Compared with the generic shared-memory kernel (psn_smem_solve_body) a node update drops from
 // 5 LDS + 1 STS + ~12 integer instructions to 1 LDS + 1 STS amortised and no index arithmetic.
-// Levels >= 1 (40^2 ... 5^2) reuse the shared-memory V-cycle of psn_core.cuh.
+// Levels 1 and 2 (40^2, 20^2) are register-blocked the same way (2x2 and 1 node per thread); the 10^2 level is the dense inverse.
 //
 // Dual build like the rest of the bodies: nvcc compiles one thread's view (state arrays of extent 1);
 // the host emulation (tests/hostemu) keeps the state of all threads and runs every phase as a loop
@@ -22,14 +22,24 @@
 #define PSN_BLOCK_DEEP 1
 #endif
 
+// The edge buffers are indexed by the thread's position in a thread grid with a ZERO GHOST RING, (BX + 2) x (BX + 2): the
+// neighbour in every direction exists for every thread and reads as zero outside the grid, so no halo load needs a
+// boundary predicate.  On the device the shared address of the thread's own edge cell (and of its x column) sits in one
+// register each, produced by a volatile asm so that the compiler cannot re-derive it: every halo access is then one LDS / STS
+// with an immediate offset.  (Before: S2R tid + ISETP boundary tests + FSEL and the S2UR / ULEA re-derivation of the shared
+// window base in front of the accesses were 21 % of the kernel's instructions and 16 % of its stall samples.)
 #if defined(__CUDACC__)
 #define PSN_BK_TS 1
 #define PSN_BK_FOR(ctx, NT) for (int t_ = (ctx).tid, once_ = 1; once_; once_ = 0)
 #define PSN_BK_TI 0
+#define PSN_BK_EA(S, t) ((S).ea_dev)
+#define PSN_BK_XA(S, t) ((S).xa_dev)
 #else
 #define PSN_BK_TS NTPAD
 #define PSN_BK_FOR(ctx, NT) for (int t_ = 0; t_ < (NT); ++t_)
 #define PSN_BK_TI t_
+#define PSN_BK_EA(S, t) ((S).edge.at((S).tpad(t)))
+#define PSN_BK_XA(S, t) ((S).xs.at(t))
 #endif
 
 // Shared-memory array of doubles addressed by a 32-bit shared-space address (device): every access is
@@ -67,15 +77,24 @@ struct PsnBlockGeom {
     static constexpr int N = 4 * BX;
     static constexpr int NT = BX * BX;
     static constexpr int NTPAD = (NT + 31) & ~31;
-    // shared memory (doubles): x[16][NTPAD], edges[4 sides][4 slots][NTPAD]
+    static constexpr int BP = BX + 2;                    // thread grid with a ghost ring
+    // cells per edge-buffer plane: the padded grid, then one private cell per idle thread of the last warp (their accesses
+    // need no predicate either), then slack for those threads' neighbour reads
+    static constexpr int NTP = (BP * BP + (NTPAD - NT) + BP + 1 + 7) & ~7;
+    // shared memory (doubles): x[16][NTPAD], edges[4 sides][4 slots][NTP]
     static constexpr int XS = 16 * NTPAD;
-    static constexpr int ES = 16 * NTPAD;
+    static constexpr int ES = 16 * NTP;
 };
 
 // doubles of dynamic shared memory the block kernel needs (x, edge buffers, coarse levels >= 1)
 template <int BX>
 PSN_HDFN int psn_block_smem_doubles(const PsnPlan& plan) {
-    return PsnBlockGeom<BX>::XS + PsnBlockGeom<BX>::ES + psn_pool_doubles(plan, 0);
+    return PsnBlockGeom<BX>::XS + PsnBlockGeom<BX>::ES + psn_pool_doubles(plan, 2);   // levels 1 and 2 live in registers
+}
+// the register-blocked solver needs the hierarchy n, n/2, n/4, n/8, ... with at least 4 levels
+template <int BX>
+PSN_HDFN bool psn_block_ok(const PsnPlan& plan) {
+    return plan.n == 4 * BX && plan.nlev >= 4 && plan.lv[1].n == 2 * BX && plan.lv[2].n == BX;
 }
 // doubles of the dense coarsest-level inverse, kept behind the arrays above by the persistent kernel when it fits
 PSN_HDFN int psn_coarse_inv_doubles(const PsnPlan& plan) {
@@ -86,58 +105,91 @@ PSN_HDFN int psn_coarse_inv_doubles(const PsnPlan& plan) {
 template <int BX, class Ctx>
 struct PsnBlockSolver {
     typedef PsnBlockGeom<BX> G;
-    static constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
+    static constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD, BP = G::BP, NTP = G::NTP;
     enum { TOP = 0, BOT = 1, LEFT = 2, RIGHT = 3 };
 
     Ctx& ctx;
     PsnShF64 xs;     // [16][NTPAD]
-    PsnShF64 edge;   // [4][4][NTPAD]
+    PsnShF64 edge;   // [4][4][NTP], cell index = position in the ghost-ringed thread grid (tpad)
     double z[PSN_BK_TS][16], r[PSN_BK_TS][16], p[PSN_BK_TS][16];
+#if defined(__CUDACC__)
+    PsnShF64 ea_dev, xa_dev;   // this thread's own edge cell / x column (shared addresses pinned in registers)
+    int fl_dev;                // bit 0: real thread (t < NT), bit 1: (bx + by) odd, bit 2: bx and by both odd
+#endif
 
     const double* inv_s = nullptr;   // shared-memory copy of the coarsest-level inverse (or null)
-    PSN_FN PsnBlockSolver(Ctx& c, double* smem) : ctx(c), xs(smem), edge(smem + G::XS) {}   // (explicit PsnShF64 ctors)
 
-    // element t of edge buffer (side, slot)
-    PSN_FN double EL(int side, int slot, int t) const { return edge.ld((side * 4 + slot) * NTPAD + t); }
-    PSN_FN void ES(int side, int slot, int t, double v) const { edge.st((side * 4 + slot) * NTPAD + t, v); }
-
-    // halo values of field v needed by a half sweep of colour `col` (slots of the other colour)
-    PSN_FN void load_halo(int t, int col, double (&hT)[4], double (&hB)[4], double (&hL)[4], double (&hR)[4]) {
+    // position of thread t in the ghost-ringed thread grid; the idle threads of the last warp get private cells behind it
+    PSN_FN static int tpad(int t) { return t < NT ? (t / BX + 1) * BP + (t % BX) + 1 : BP * BP + (t - NT); }
+    PSN_FN static int flags_of(int t) {
         const int bx = t % BX, by = t / BX;
+        return (t < NT ? 1 : 0) | ((((bx + by) & 1) && t < NT) ? 2 : 0) | (((bx & 1) && (by & 1) && t < NT) ? 4 : 0);
+    }
+    PSN_FN int flags(int t) const {
+#if defined(__CUDACC__)
+        return fl_dev;
+#else
+        return flags_of(t);
+#endif
+    }
+
+    PSN_FN PsnBlockSolver(Ctx& c, double* smem)
+        : ctx(c), xs(smem), edge(smem + G::XS)
+#if defined(__CUDACC__)
+          , ea_dev(smem), xa_dev(smem)
+#endif
+    {
+#if defined(__CUDACC__)
+        unsigned e = edge.base + 8u * (unsigned)tpad(c.tid), x = xs.base + 8u * (unsigned)c.tid;
+        int f = flags_of(c.tid);
+        asm volatile("mov.u32 %0, %0;" : "+r"(e));   // opaque to the compiler: kept in a register (or spilled), never re-derived
+        asm volatile("mov.u32 %0, %0;" : "+r"(x));
+        asm volatile("mov.s32 %0, %0;" : "+r"(f));
+        ea_dev.base = e;
+        xa_dev.base = x;
+        fl_dev = f;
+#endif
+    }
+
+    // edge buffer (side, slot), cell `off` relative to the thread's own cell (cursor `ea`)
+    PSN_FN static double EL(const PsnShF64& ea, int side, int slot, int off) { return ea.ld((side * 4 + slot) * NTP + off); }
+    PSN_FN static void ES(const PsnShF64& ea, int side, int slot, double v) { ea.st((side * 4 + slot) * NTP, v); }
+
+    // halo values of field v needed by a half sweep of colour `col` (slots of the other colour); ghost cells read as zero
+    PSN_FN static void load_halo(const PsnShF64& ea, int col, double (&hT)[4], double (&hB)[4], double (&hL)[4], double (&hR)[4]) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             hT[k] = hB[k] = hL[k] = hR[k] = 0.0;
             if ((k & 1) == col) {           // (0,k) and (k,0) have colour col: they need the node above / left
-                if (by > 0) hT[k] = EL(BOT, k, t - BX);
-                if (bx > 0) hL[k] = EL(RIGHT, k, t - 1);
+                hT[k] = EL(ea, BOT, k, -BP);
+                hL[k] = EL(ea, RIGHT, k, -1);
             } else {                        // (3,k) and (k,3) have colour col: they need the node below / right
-                if (by < BX - 1) hB[k] = EL(TOP, k, t + BX);
-                if (bx < BX - 1) hR[k] = EL(LEFT, k, t + 1);
+                hB[k] = EL(ea, TOP, k, BP);
+                hR[k] = EL(ea, LEFT, k, 1);
             }
         }
     }
     // all 16 halo values (both colours)
-    PSN_FN void load_halo_all(int t, double (&hT)[4], double (&hB)[4], double (&hL)[4], double (&hR)[4]) {
-        const int bx = t % BX, by = t / BX;
+    PSN_FN static void load_halo_all(const PsnShF64& ea, double (&hT)[4], double (&hB)[4], double (&hL)[4], double (&hR)[4]) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            hT[k] = (by > 0) ? EL(BOT, k, t - BX) : 0.0;
-            hB[k] = (by < BX - 1) ? EL(TOP, k, t + BX) : 0.0;
-            hL[k] = (bx > 0) ? EL(RIGHT, k, t - 1) : 0.0;
-            hR[k] = (bx < BX - 1) ? EL(LEFT, k, t + 1) : 0.0;
+            hT[k] = EL(ea, BOT, k, -BP);
+            hB[k] = EL(ea, TOP, k, BP);
+            hL[k] = EL(ea, RIGHT, k, -1);
+            hR[k] = EL(ea, LEFT, k, 1);
         }
     }
     // publish the edge values of colour `col` (col < 0: both colours) of field v
-    PSN_FN void publish(int t, const double (&v)[16], int col) {
+    PSN_FN static void publish(const PsnShF64& ea, const double (&v)[16], int col) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (col < 0 || (k & 1) == col) {        // (0,k), (k,0) have colour k&1
-                ES(TOP, k, t, v[k]);
-                ES(LEFT, k, t, v[4 * k]);
+                ES(ea, TOP, k, v[k]);
+                ES(ea, LEFT, k, v[4 * k]);
             }
             if (col < 0 || (k & 1) != col) {        // (3,k), (k,3) have colour (k+1)&1
-                ES(BOT, k, t, v[12 + k]);
-                ES(RIGHT, k, t, v[4 * k + 3]);
+                ES(ea, BOT, k, v[12 + k]);
+                ES(ea, RIGHT, k, v[4 * k + 3]);
             }
         }
     }
@@ -151,123 +203,31 @@ struct PsnBlockSolver {
         return (up + dn) + (lf + rt);
     }
 
-    // one RB-GS half sweep on z with rhs r; ends with the edges of colour `col` published and a sync
+    // one RB-GS half sweep on z with rhs r; ends with the edges of colour `col` published and a sync.  Every thread of the CTA
+    // takes part: the idle threads of the last warp work on zeros in their private cells.
     PSN_FN void half_sweep(int col, bool first) {
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                double (&zz)[16] = z[PSN_BK_TI];
-                const double (&rr)[16] = r[PSN_BK_TI];
-                double hT[4], hB[4], hL[4], hR[4];
-                if (!first) load_halo(t_, col, hT, hB, hL, hR);
-                double nv[16];
+        PSN_BK_FOR(ctx, NTPAD) {
+            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            double (&zz)[16] = z[PSN_BK_TI];
+            const double (&rr)[16] = r[PSN_BK_TI];
+            double hT[4], hB[4], hL[4], hR[4];
+            if (!first) load_halo(ea, col, hT, hB, hL, hR);
+            double nv[16];
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (((a + c) & 1) == col)
-                            nv[4 * a + c] = (rr[4 * a + c] + (first ? 0.0 : nbsum(zz, a, c, hT, hB, hL, hR))) * 0.25;
+                for (int c = 0; c < 4; ++c)
+                    if (((a + c) & 1) == col)
+                        nv[4 * a + c] = (rr[4 * a + c] + (first ? 0.0 : nbsum(zz, a, c, hT, hB, hL, hR))) * 0.25;
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if ((((k >> 2) + (k & 3)) & 1) == col) zz[k] = nv[k];
-                publish(t_, zz, col);
-            }
-        }
-        ctx.sync();
-    }
-
-    // restricted residual of level 0 -> shared rhs array of level 1 (ghost-ringed layout); needs the black edges of z
-    PSN_FN void residual_restrict(const PsnLevel& l1, double* b1) {
-        // red residuals in registers; publish the ones other blocks need as corners (row 0 / col 0, even slots)
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                const double (&zz)[16] = z[PSN_BK_TI];
-                const double (&rr)[16] = r[PSN_BK_TI];
-                double (&pp)[16] = rho[PSN_BK_TI];
-                double hT[4], hB[4], hL[4], hR[4];
-                load_halo(t_, 0, hT, hB, hL, hR);
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (((a + c) & 1) == 0) pp[4 * a + c] = rr[4 * a + c] - (4.0 * zz[4 * a + c] - nbsum(zz, a, c, hT, hB, hL, hR));
-            }
-        }
-        ctx.sync();   // everybody has read the black edges of z before the red slots are reused for rho
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                const double (&pp)[16] = rho[PSN_BK_TI];
-                ES(TOP, 0, t_, pp[0]);
-                ES(TOP, 2, t_, pp[2]);
-                ES(LEFT, 0, t_, pp[0]);
-                ES(LEFT, 2, t_, pp[8]);
-            }
-        }
-        ctx.sync();
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                const double (&pp)[16] = rho[PSN_BK_TI];
-                const int bx = t_ % BX, by = t_ / BX;
-                const bool hasR = bx < BX - 1, hasB = by < BX - 1;
-                const double r04 = hasR ? EL(LEFT, 0, t_ + 1) : 0.0, r24 = hasR ? EL(LEFT, 2, t_ + 1) : 0.0;
-                const double r40 = hasB ? EL(TOP, 0, t_ + BX) : 0.0, r42 = hasB ? EL(TOP, 2, t_ + BX) : 0.0;
-                const double r44 = (hasR && hasB) ? EL(TOP, 0, t_ + BX + 1) : 0.0;
-                const int P1 = l1.pitch;
-                double* o = b1 + (2 * by + 1) * P1 + (2 * bx + 1);
-                o[0] = pp[5] + 0.25 * ((pp[0] + pp[2]) + (pp[8] + pp[10]));
-                o[1] = pp[7] + 0.25 * ((pp[2] + r04) + (pp[10] + r24));
-                o[P1] = pp[13] + 0.25 * ((pp[8] + pp[10]) + (r40 + r42));
-                o[P1 + 1] = pp[15] + 0.25 * ((pp[10] + r24) + (r42 + r44));
-            }
-        }
-        ctx.sync();
-    }
-
-    // z += P u1 on the red nodes; ends with the red edges of z published and a sync
-    PSN_FN void prolong(const PsnLevel& l1, const double* u1) {
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                double (&zz)[16] = z[PSN_BK_TI];
-                const int bx = t_ % BX, by = t_ / BX;
-                const int P1 = l1.pitch;
-                const double* e = u1 + (2 * by + 1) * P1 + (2 * bx + 1);   // coarse (2by, 2bx)
-                const double e00 = e[0], e01 = e[1], e10 = e[P1], e11 = e[P1 + 1];
-                const double em0 = e[-P1], em1 = e[-P1 + 1], emm = e[-P1 - 1], e0m = e[-1], e1m = e[P1 - 1];
-                zz[5] += e00;
-                zz[7] += e01;
-                zz[13] += e10;
-                zz[15] += e11;
-                zz[0] += 0.25 * ((emm + em0) + (e0m + e00));
-                zz[2] += 0.25 * ((em0 + em1) + (e00 + e01));
-                zz[8] += 0.25 * ((e0m + e00) + (e1m + e10));
-                zz[10] += 0.25 * ((e00 + e01) + (e10 + e11));
-                publish(t_, zz, 0);
-            }
+            for (int k = 0; k < 16; ++k)
+                if ((((k >> 2) + (k & 3)) & 1) == col) zz[k] = nv[k];
+            publish(ea, zz, col);
         }
         ctx.sync();
     }
 
     double rho[PSN_BK_TS][16];
-
-    // z = M^{-1} r : V(nu,nu) with level 0 in registers
-    PSN_FN void vcycle(const PsnPlan& plan, double* pool) {
-        const int nu = plan.nu;
-        const PsnLevel& l1 = plan.lv[1];
-        double* b1 = pool;              // pool layout of psn_vcycle_smem: level-1 rhs, then level-1 solution
-        double* u1 = pool + l1.size;
-        half_sweep(0, true);
-        half_sweep(1, false);
-        for (int s = 1; s < nu; ++s) {
-            half_sweep(0, false);
-            half_sweep(1, false);
-        }
-        residual_restrict(l1, b1);
-        psn_vcycle_smem(ctx, plan, 1, b1, u1, pool + 2 * l1.size, inv_s);
-        prolong(l1, u1);
-        for (int s = 0; s < nu; ++s) {
-            half_sweep(1, false);
-            half_sweep(0, false);
-        }
-    }
 
     // ------------------------------------------------------------------ three register-blocked levels
     // Level 1 (2 BX)^2: each thread owns the 2x2 block under its fine block; level 2 (BX)^2: one node per
@@ -275,32 +235,31 @@ struct PsnBlockSolver {
     double z1[PSN_BK_TS][4], r1[PSN_BK_TS][4], z2[PSN_BK_TS][1], r2[PSN_BK_TS][1];
 
     template <int BS>
-    PSN_FN void load_halo_bs(int t, int col, double (&hT)[BS], double (&hB)[BS], double (&hL)[BS], double (&hR)[BS]) {
-        const int bx = t % BX, by = t / BX;
+    PSN_FN static void load_halo_bs(const PsnShF64& ea, int col, double (&hT)[BS], double (&hB)[BS], double (&hL)[BS], double (&hR)[BS]) {
 #pragma unroll
         for (int k = 0; k < BS; ++k) {
             hT[k] = hB[k] = hL[k] = hR[k] = 0.0;
             if (col < 0 || (k & 1) == col) {
-                if (by > 0) hT[k] = EL(BOT, k, t - BX);
-                if (bx > 0) hL[k] = EL(RIGHT, k, t - 1);
+                hT[k] = EL(ea, BOT, k, -BP);
+                hL[k] = EL(ea, RIGHT, k, -1);
             }
             if (col < 0 || (k & 1) != col) {
-                if (by < BX - 1) hB[k] = EL(TOP, k, t + BX);
-                if (bx < BX - 1) hR[k] = EL(LEFT, k, t + 1);
+                hB[k] = EL(ea, TOP, k, BP);
+                hR[k] = EL(ea, LEFT, k, 1);
             }
         }
     }
     template <int BS>
-    PSN_FN void publish_bs(int t, const double (&v)[BS * BS], int col) {
+    PSN_FN static void publish_bs(const PsnShF64& ea, const double (&v)[BS * BS], int col) {
 #pragma unroll
         for (int k = 0; k < BS; ++k) {
             if (col < 0 || (k & 1) == col) {
-                ES(TOP, k, t, v[k]);
-                ES(LEFT, k, t, v[BS * k]);
+                ES(ea, TOP, k, v[k]);
+                ES(ea, LEFT, k, v[BS * k]);
             }
             if (col < 0 || (k & 1) != col) {
-                ES(BOT, k, t, v[BS * (BS - 1) + k]);
-                ES(RIGHT, k, t, v[BS * k + BS - 1]);
+                ES(ea, BOT, k, v[BS * (BS - 1) + k]);
+                ES(ea, RIGHT, k, v[BS * k + BS - 1]);
             }
         }
     }
@@ -313,51 +272,54 @@ struct PsnBlockSolver {
         const double rt = (c < BS - 1) ? v[BS * a + c + 1] : hR[a];
         return (up + dn) + (lf + rt);
     }
-    // diagonal weight of local node (a, c) of a BS-blocked level (extra weight gam on the last grid row / column)
-    template <int BS>
-    PSN_FN static double diag_bs(const PsnLevel& lv, int t, int a, int c) {
+    // Diagonal weights of the thread's block on a BS-blocked level: only the threads of the last thread row / column differ
+    // from 4 (extra weight gam on the last grid row / column).  Kept as two per-thread values (last row, last column).
+    struct Diag {
+        double gr, gc;   // gam if the thread's block touches the last grid row / column, else 0
+    };
+    PSN_FN static Diag diag_of(const PsnLevel& lv, int t) {
         const int bx = t % BX, by = t / BX;
-        const bool lr = (by == BX - 1) && (a == BS - 1), lc = (bx == BX - 1) && (c == BS - 1);
-        return 4.0 + (lr ? lv.gam : 0.0) + (lc ? lv.gam : 0.0);
+        Diag d;
+        d.gr = (t < NT && by == BX - 1) ? lv.gam : 0.0;
+        d.gc = (t < NT && bx == BX - 1) ? lv.gam : 0.0;
+        return d;
     }
     template <int BS>
-    PSN_FN static double rdiag_bs(const PsnLevel& lv, int t, int a, int c) {
-        const int bx = t % BX, by = t / BX;
-        const bool lr = (by == BX - 1) && (a == BS - 1), lc = (bx == BX - 1) && (c == BS - 1);
-        return lr ? (lc ? lv.rd2 : lv.rd1) : (lc ? lv.rd1 : lv.rd0);
+    PSN_FN static double diag_bs(const Diag& d, int a, int c) {
+        return 4.0 + ((a == BS - 1) ? d.gr : 0.0) + ((c == BS - 1) ? d.gc : 0.0);
     }
-    // half sweep of a BS-blocked level held in zz / rr (thread t_); publishes the updated colour
+    // half sweep of a BS-blocked level held in zz / rr; publishes the updated colour.  rdv: reciprocal diagonals of the block
     template <int BS>
-    PSN_FN void half_sweep_bs(int t, const PsnLevel& lv, double (&zz)[BS * BS], const double (&rr)[BS * BS], int col, bool first) {
+    PSN_FN static void half_sweep_bs(const PsnShF64& ea, const double (&rdv)[BS * BS], double (&zz)[BS * BS], const double (&rr)[BS * BS],
+                                     int col, bool first) {
         double hT[BS], hB[BS], hL[BS], hR[BS];
-        if (!first) load_halo_bs<BS>(t, col, hT, hB, hL, hR);
+        if (!first) load_halo_bs<BS>(ea, col, hT, hB, hL, hR);
         double nv[BS * BS];
 #pragma unroll
         for (int a = 0; a < BS; ++a)
 #pragma unroll
             for (int c = 0; c < BS; ++c)
                 if (((a + c) & 1) == col)
-                    nv[BS * a + c] = (rr[BS * a + c] + (first ? 0.0 : nbsum_bs<BS>(zz, a, c, hT, hB, hL, hR))) * rdiag_bs<BS>(lv, t, a, c);
+                    nv[BS * a + c] = (rr[BS * a + c] + (first ? 0.0 : nbsum_bs<BS>(zz, a, c, hT, hB, hL, hR))) * rdv[BS * a + c];
 #pragma unroll
         for (int a = 0; a < BS; ++a)
 #pragma unroll
             for (int c = 0; c < BS; ++c)
                 if (((a + c) & 1) == col) zz[BS * a + c] = nv[BS * a + c];
-        publish_bs<BS>(t, zz, col);
+        publish_bs<BS>(ea, zz, col);
     }
     // level 2: one node per thread, colour (bx + by) & 1; all four sides read the single slot TOP[0]
-    PSN_FN double nb2(int t) {
-        const int bx = t % BX, by = t / BX;
-        const double up = (by > 0) ? EL(TOP, 0, t - BX) : 0.0, dn = (by < BX - 1) ? EL(TOP, 0, t + BX) : 0.0;
-        const double lf = (bx > 0) ? EL(TOP, 0, t - 1) : 0.0, rt = (bx < BX - 1) ? EL(TOP, 0, t + 1) : 0.0;
-        return (up + dn) + (lf + rt);
+    PSN_FN static double nb2(const PsnShF64& ea) {
+        return (EL(ea, TOP, 0, -BP) + EL(ea, TOP, 0, BP)) + (EL(ea, TOP, 0, -1) + EL(ea, TOP, 0, 1));
     }
-    PSN_FN void half_sweep_2(const PsnLevel& lv, int col, bool first) {
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT && (((t_ % BX) + (t_ / BX)) & 1) == col) {
-                const double v = (r2[PSN_BK_TI][0] + (first ? 0.0 : nb2(t_))) * rdiag_bs<1>(lv, t_, 0, 0);
+    PSN_FN void half_sweep_2(const double (&rd2)[PSN_BK_TS], int col, bool first) {
+        PSN_BK_FOR(ctx, NTPAD) {
+            const int fl = flags(t_);
+            if ((fl & 1) && ((fl >> 1) & 1) == col) {
+                const PsnShF64 ea = PSN_BK_EA(*this, t_);
+                const double v = (r2[PSN_BK_TI][0] + (first ? 0.0 : nb2(ea))) * rd2[PSN_BK_TI];
                 z2[PSN_BK_TI][0] = v;
-                ES(TOP, 0, t_, v);
+                ES(ea, TOP, 0, v);
             }
         }
         ctx.sync();
@@ -372,6 +334,24 @@ struct PsnBlockSolver {
         double* b3 = pool;
         double* u3 = pool + l3.size;
         double* pool4 = pool + 2 * l3.size;
+        // per-thread diagonals of levels 1 and 2 (4 is the interior value; the last thread row / column carries gam)
+        double rd1[PSN_BK_TS][4], rd2[PSN_BK_TS];
+        Diag d1[PSN_BK_TS], d2[PSN_BK_TS];
+        PSN_BK_FOR(ctx, NTPAD) {
+            d1[PSN_BK_TI] = diag_of(l1, t_);
+            d2[PSN_BK_TI] = diag_of(l2, t_);
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const bool lr = a == 1 && d1[PSN_BK_TI].gr != 0.0, lc = c == 1 && d1[PSN_BK_TI].gc != 0.0;
+                    rd1[PSN_BK_TI][2 * a + c] = lr ? (lc ? l1.rd2 : l1.rd1) : (lc ? l1.rd1 : l1.rd0);
+                }
+            {
+                const bool lr = d2[PSN_BK_TI].gr != 0.0, lc = d2[PSN_BK_TI].gc != 0.0;
+                rd2[PSN_BK_TI] = lr ? (lc ? l2.rd2 : l2.rd1) : (lc ? l2.rd1 : l2.rd0);
+            }
+        }
         // ---------------- level 0 down
         half_sweep(0, true);
         half_sweep(1, false);
@@ -379,96 +359,86 @@ struct PsnBlockSolver {
             half_sweep(0, false);
             half_sweep(1, false);
         }
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                const double (&zz)[16] = z[PSN_BK_TI];
-                const double (&rr)[16] = r[PSN_BK_TI];
-                double (&pp)[16] = rho[PSN_BK_TI];
-                double hT[4], hB[4], hL[4], hR[4];
-                load_halo(t_, 0, hT, hB, hL, hR);
+        PSN_BK_FOR(ctx, NTPAD) {
+            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            const double (&zz)[16] = z[PSN_BK_TI];
+            const double (&rr)[16] = r[PSN_BK_TI];
+            double (&pp)[16] = rho[PSN_BK_TI];
+            double hT[4], hB[4], hL[4], hR[4];
+            load_halo(ea, 0, hT, hB, hL, hR);
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if (((a + c) & 1) == 0) pp[4 * a + c] = rr[4 * a + c] - (4.0 * zz[4 * a + c] - nbsum(zz, a, c, hT, hB, hL, hR));
-                // (reads above: black slots; writes below: red slots of TOP / LEFT -> no barrier needed in between)
-                ES(TOP, 0, t_, pp[0]);
-                ES(TOP, 2, t_, pp[2]);
-                ES(LEFT, 0, t_, pp[0]);
-                ES(LEFT, 2, t_, pp[8]);
-            }
+                for (int c = 0; c < 4; ++c)
+                    if (((a + c) & 1) == 0) pp[4 * a + c] = rr[4 * a + c] - (4.0 * zz[4 * a + c] - nbsum(zz, a, c, hT, hB, hL, hR));
+            // (reads above: black slots; writes below: red slots of TOP / LEFT -> no barrier needed in between)
+            ES(ea, TOP, 0, pp[0]);
+            ES(ea, TOP, 2, pp[2]);
+            ES(ea, LEFT, 0, pp[0]);
+            ES(ea, LEFT, 2, pp[8]);
         }
         ctx.sync();
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                const double (&pp)[16] = rho[PSN_BK_TI];
-                const int bx = t_ % BX, by = t_ / BX;
-                const bool hasR = bx < BX - 1, hasB = by < BX - 1;
-                const double r04 = hasR ? EL(LEFT, 0, t_ + 1) : 0.0, r24 = hasR ? EL(LEFT, 2, t_ + 1) : 0.0;
-                const double r40 = hasB ? EL(TOP, 0, t_ + BX) : 0.0, r42 = hasB ? EL(TOP, 2, t_ + BX) : 0.0;
-                const double r44 = (hasR && hasB) ? EL(TOP, 0, t_ + BX + 1) : 0.0;
-                double (&q)[4] = r1[PSN_BK_TI];
-                q[0] = pp[5] + 0.25 * ((pp[0] + pp[2]) + (pp[8] + pp[10]));
-                q[1] = pp[7] + 0.25 * ((pp[2] + r04) + (pp[10] + r24));
-                q[2] = pp[13] + 0.25 * ((pp[8] + pp[10]) + (r40 + r42));
-                q[3] = pp[15] + 0.25 * ((pp[10] + r24) + (r42 + r44));
-            }
+        PSN_BK_FOR(ctx, NTPAD) {
+            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            const double (&pp)[16] = rho[PSN_BK_TI];
+            const double r04 = EL(ea, LEFT, 0, 1), r24 = EL(ea, LEFT, 2, 1);
+            const double r40 = EL(ea, TOP, 0, BP), r42 = EL(ea, TOP, 2, BP);
+            const double r44 = EL(ea, TOP, 0, BP + 1);
+            double (&q)[4] = r1[PSN_BK_TI];
+            q[0] = pp[5] + 0.25 * ((pp[0] + pp[2]) + (pp[8] + pp[10]));
+            q[1] = pp[7] + 0.25 * ((pp[2] + r04) + (pp[10] + r24));
+            q[2] = pp[13] + 0.25 * ((pp[8] + pp[10]) + (r40 + r42));
+            q[3] = pp[15] + 0.25 * ((pp[10] + r24) + (r42 + r44));
         }
         ctx.sync();
         // ---------------- level 1 down (2x2 per thread)
         for (int s = 0; s < nu; ++s) {
-            PSN_BK_FOR(ctx, NT) { if (t_ < NT) half_sweep_bs<2>(t_, l1, z1[PSN_BK_TI], r1[PSN_BK_TI], 0, s == 0); }
+            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, s == 0); }
             ctx.sync();
-            PSN_BK_FOR(ctx, NT) { if (t_ < NT) half_sweep_bs<2>(t_, l1, z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
+            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
             ctx.sync();
         }
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                const double (&zz)[4] = z1[PSN_BK_TI];
-                const double (&rr)[4] = r1[PSN_BK_TI];
-                double hT[2], hB[2], hL[2], hR[2];
-                load_halo_bs<2>(t_, 0, hT, hB, hL, hR);
-                const double rho00 = rr[0] - (diag_bs<2>(l1, t_, 0, 0) * zz[0] - nbsum_bs<2>(zz, 0, 0, hT, hB, hL, hR));
-                const double rho11 = rr[3] - (diag_bs<2>(l1, t_, 1, 1) * zz[3] - nbsum_bs<2>(zz, 1, 1, hT, hB, hL, hR));
-                rho[PSN_BK_TI][0] = rho00;
-                rho[PSN_BK_TI][1] = rho11;
-                ES(TOP, 0, t_, rho00);   // red slot of TOP: not read by this phase
-            }
+        PSN_BK_FOR(ctx, NTPAD) {
+            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            const double (&zz)[4] = z1[PSN_BK_TI];
+            const double (&rr)[4] = r1[PSN_BK_TI];
+            double hT[2], hB[2], hL[2], hR[2];
+            load_halo_bs<2>(ea, 0, hT, hB, hL, hR);
+            const double rho00 = rr[0] - (diag_bs<2>(d1[PSN_BK_TI], 0, 0) * zz[0] - nbsum_bs<2>(zz, 0, 0, hT, hB, hL, hR));
+            const double rho11 = rr[3] - (diag_bs<2>(d1[PSN_BK_TI], 1, 1) * zz[3] - nbsum_bs<2>(zz, 1, 1, hT, hB, hL, hR));
+            rho[PSN_BK_TI][0] = rho00;
+            rho[PSN_BK_TI][1] = rho11;
+            ES(ea, TOP, 0, rho00);   // red slot of TOP: not read by this phase
         }
         ctx.sync();
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                const int bx = t_ % BX, by = t_ / BX;
-                const bool hasR = bx < BX - 1, hasB = by < BX - 1;
-                const double c02 = hasR ? EL(TOP, 0, t_ + 1) : 0.0, c20 = hasB ? EL(TOP, 0, t_ + BX) : 0.0;
-                const double c22 = (hasR && hasB) ? EL(TOP, 0, t_ + BX + 1) : 0.0;
-                r2[PSN_BK_TI][0] = rho[PSN_BK_TI][1] + 0.25 * ((rho[PSN_BK_TI][0] + c02) + (c20 + c22));
-            }
+        PSN_BK_FOR(ctx, NTPAD) {
+            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            const double c02 = EL(ea, TOP, 0, 1), c20 = EL(ea, TOP, 0, BP);
+            const double c22 = EL(ea, TOP, 0, BP + 1);
+            r2[PSN_BK_TI][0] = rho[PSN_BK_TI][1] + 0.25 * ((rho[PSN_BK_TI][0] + c02) + (c20 + c22));
         }
         ctx.sync();
         // ---------------- level 2 down (one node per thread)
         for (int s = 0; s < nu; ++s) {
-            half_sweep_2(l2, 0, s == 0);
-            half_sweep_2(l2, 1, false);
+            half_sweep_2(rd2, 0, s == 0);
+            half_sweep_2(rd2, 1, false);
         }
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {   // residual on red nodes -> BOT[0] (TOP[0] is being read by the neighbours)
-                double rh = 0.0;
-                if ((((t_ % BX) + (t_ / BX)) & 1) == 0) rh = r2[PSN_BK_TI][0] - (diag_bs<1>(l2, t_, 0, 0) * z2[PSN_BK_TI][0] - nb2(t_));
-                rho[PSN_BK_TI][0] = rh;
-                ES(BOT, 0, t_, rh);
-            }
+        PSN_BK_FOR(ctx, NTPAD) {   // residual on red nodes -> BOT[0] (TOP[0] is being read by the neighbours)
+            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            const int fl = flags(t_);
+            double rh = 0.0;
+            if ((fl & 3) == 1) rh = r2[PSN_BK_TI][0] - (diag_bs<1>(d2[PSN_BK_TI], 0, 0) * z2[PSN_BK_TI][0] - nb2(ea));
+            rho[PSN_BK_TI][0] = rh;
+            ES(ea, BOT, 0, rh);
         }
         ctx.sync();
         PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
+            if (flags(t_) & 4) {   // bx, by both odd: centre of coarse node ((by-1)/2, (bx-1)/2) of level 3
+                const PsnShF64 ea = PSN_BK_EA(*this, t_);
                 const int bx = t_ % BX, by = t_ / BX;
-                if ((bx & 1) && (by & 1)) {   // centre of coarse node ((by-1)/2, (bx-1)/2) of level 3
-                    const bool hasR = bx < BX - 1, hasB = by < BX - 1;
-                    const double c00 = EL(BOT, 0, t_ - BX - 1), c02 = hasR ? EL(BOT, 0, t_ - BX + 1) : 0.0;
-                    const double c20 = hasB ? EL(BOT, 0, t_ + BX - 1) : 0.0, c22 = (hasR && hasB) ? EL(BOT, 0, t_ + BX + 1) : 0.0;
-                    b3[(((by - 1) >> 1) + 1) * l3.pitch + ((bx - 1) >> 1) + 1] = rho[PSN_BK_TI][0] + 0.25 * ((c00 + c02) + (c20 + c22));
-                }
+                const double c00 = EL(ea, BOT, 0, -BP - 1), c02 = EL(ea, BOT, 0, -BP + 1);
+                const double c20 = EL(ea, BOT, 0, BP - 1), c22 = EL(ea, BOT, 0, BP + 1);
+                b3[(((by - 1) >> 1) + 1) * l3.pitch + ((bx - 1) >> 1) + 1] = rho[PSN_BK_TI][0] + 0.25 * ((c00 + c02) + (c20 + c22));
             }
         }
         ctx.sync();
@@ -477,69 +447,64 @@ struct PsnBlockSolver {
         psn_vcycle_smem(ctx, plan, 3, b3, u3, pool4, inv_s);
         // ---------------- level 2 up
         PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
+            if ((flags(t_) & 3) == 1) {   // real thread, (bx + by) even
+                const PsnShF64 ea = PSN_BK_EA(*this, t_);
                 const int bx = t_ % BX, by = t_ / BX;
-                if (((bx + by) & 1) == 0) {
-                    const int P3 = l3.pitch;
-                    double add;
-                    if (by & 1) {
-                        add = u3[(((by - 1) >> 1) + 1) * P3 + ((bx - 1) >> 1) + 1];
-                    } else {
-                        const double* e = u3 + ((by >> 1) + 1) * P3 + (bx >> 1) + 1;
-                        add = 0.25 * ((e[-P3 - 1] + e[-P3]) + (e[-1] + e[0]));
-                    }
-                    z2[PSN_BK_TI][0] += add;
-                    ES(TOP, 0, t_, z2[PSN_BK_TI][0]);
+                const int P3 = l3.pitch;
+                double add;
+                if (by & 1) {
+                    add = u3[(((by - 1) >> 1) + 1) * P3 + ((bx - 1) >> 1) + 1];
+                } else {
+                    const double* e = u3 + ((by >> 1) + 1) * P3 + (bx >> 1) + 1;
+                    add = 0.25 * ((e[-P3 - 1] + e[-P3]) + (e[-1] + e[0]));
                 }
+                z2[PSN_BK_TI][0] += add;
+                ES(ea, TOP, 0, z2[PSN_BK_TI][0]);
             }
         }
         ctx.sync();
         for (int s = 0; s < nu; ++s) {
-            half_sweep_2(l2, 1, false);
-            half_sweep_2(l2, 0, false);
+            half_sweep_2(rd2, 1, false);
+            half_sweep_2(rd2, 0, false);
         }
         // ---------------- level 1 up: corrections from z2 (TOP[0] holds every thread's current z2)
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                const int bx = t_ % BX, by = t_ / BX;
-                const double e00 = z2[PSN_BK_TI][0];
-                const double em0 = (by > 0) ? EL(TOP, 0, t_ - BX) : 0.0, e0m = (bx > 0) ? EL(TOP, 0, t_ - 1) : 0.0;
-                const double emm = (by > 0 && bx > 0) ? EL(TOP, 0, t_ - BX - 1) : 0.0;
-                z1[PSN_BK_TI][3] += e00;
-                z1[PSN_BK_TI][0] += 0.25 * ((emm + em0) + (e0m + e00));
-            }
+        PSN_BK_FOR(ctx, NTPAD) {
+            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            const double e00 = z2[PSN_BK_TI][0];
+            const double em0 = EL(ea, TOP, 0, -BP), e0m = EL(ea, TOP, 0, -1);
+            const double emm = EL(ea, TOP, 0, -BP - 1);
+            z1[PSN_BK_TI][3] += e00;
+            z1[PSN_BK_TI][0] += 0.25 * ((emm + em0) + (e0m + e00));
         }
         ctx.sync();   // TOP[0] is about to be overwritten by the edges of z1
-        PSN_BK_FOR(ctx, NT) { if (t_ < NT) publish_bs<2>(t_, z1[PSN_BK_TI], 0); }
+        PSN_BK_FOR(ctx, NTPAD) { publish_bs<2>(PSN_BK_EA(*this, t_), z1[PSN_BK_TI], 0); }
         ctx.sync();
         for (int s = 0; s < nu; ++s) {
-            PSN_BK_FOR(ctx, NT) { if (t_ < NT) half_sweep_bs<2>(t_, l1, z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
+            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
             ctx.sync();
-            PSN_BK_FOR(ctx, NT) { if (t_ < NT) half_sweep_bs<2>(t_, l1, z1[PSN_BK_TI], r1[PSN_BK_TI], 0, false); }
+            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, false); }
             ctx.sync();
         }
         // ---------------- level 0 up: corrections from z1 (every edge of z1 is current in the buffers)
-        PSN_BK_FOR(ctx, NT) {
-            if (t_ < NT) {
-                double (&zz)[16] = z[PSN_BK_TI];
-                const double (&ee)[4] = z1[PSN_BK_TI];
-                const int bx = t_ % BX, by = t_ / BX;
-                const double e00 = ee[0], e01 = ee[1], e10 = ee[2], e11 = ee[3];
-                const double em0 = (by > 0) ? EL(BOT, 0, t_ - BX) : 0.0, em1 = (by > 0) ? EL(BOT, 1, t_ - BX) : 0.0;
-                const double e0m = (bx > 0) ? EL(RIGHT, 0, t_ - 1) : 0.0, e1m = (bx > 0) ? EL(RIGHT, 1, t_ - 1) : 0.0;
-                const double emm = (by > 0 && bx > 0) ? EL(BOT, 1, t_ - BX - 1) : 0.0;
-                zz[5] += e00;
-                zz[7] += e01;
-                zz[13] += e10;
-                zz[15] += e11;
-                zz[0] += 0.25 * ((emm + em0) + (e0m + e00));
-                zz[2] += 0.25 * ((em0 + em1) + (e00 + e01));
-                zz[8] += 0.25 * ((e0m + e00) + (e1m + e10));
-                zz[10] += 0.25 * ((e00 + e01) + (e10 + e11));
-            }
+        PSN_BK_FOR(ctx, NTPAD) {
+            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            double (&zz)[16] = z[PSN_BK_TI];
+            const double (&ee)[4] = z1[PSN_BK_TI];
+            const double e00 = ee[0], e01 = ee[1], e10 = ee[2], e11 = ee[3];
+            const double em0 = EL(ea, BOT, 0, -BP), em1 = EL(ea, BOT, 1, -BP);
+            const double e0m = EL(ea, RIGHT, 0, -1), e1m = EL(ea, RIGHT, 1, -1);
+            const double emm = EL(ea, BOT, 1, -BP - 1);
+            zz[5] += e00;
+            zz[7] += e01;
+            zz[13] += e10;
+            zz[15] += e11;
+            zz[0] += 0.25 * ((emm + em0) + (e0m + e00));
+            zz[2] += 0.25 * ((em0 + em1) + (e00 + e01));
+            zz[8] += 0.25 * ((e0m + e00) + (e1m + e10));
+            zz[10] += 0.25 * ((e00 + e01) + (e10 + e11));
         }
         ctx.sync();   // the z1 edges have been read; the buffers now take the red edges of z
-        PSN_BK_FOR(ctx, NT) { if (t_ < NT) publish(t_, z[PSN_BK_TI], 0); }
+        PSN_BK_FOR(ctx, NTPAD) { publish(PSN_BK_EA(*this, t_), z[PSN_BK_TI], 0); }
         ctx.sync();
         for (int s = 0; s < nu; ++s) {
             half_sweep(1, false);
@@ -605,30 +570,39 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
     constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
     PsnBlockSolver<BX, Ctx> S(ctx, smem);
     S.inv_s = inv_s;
-    double* pool = smem + G::XS + G::ES;
-    const int pool_n = psn_pool_doubles(plan, 0);
-    for (int idx = ctx.tid; idx < pool_n; idx += ctx.nthreads) pool[idx] = 0.0;   // ghost rings of the coarse levels
+    double* pool = smem + G::XS + G::ES;          // levels >= 3 (levels 1 and 2 live in registers)
+    {
+        // zero the ghost rings: of the coarse levels, and of the thread grid the edge buffers are indexed by
+        const int zn = G::ES + psn_pool_doubles(plan, 2);
+        double* z0 = smem + G::XS;
+        for (int idx = ctx.tid; idx < zn; idx += ctx.nthreads) z0[idx] = 0.0;
+    }
     double acc[PSN_BK_TS];
-    // levels 1 and 2 in registers as well when the hierarchy is n, n/2, n/4, ... with at least 4 levels
-    const bool deep = (a.sub >= -1) && plan.nlev >= 4 && plan.lv[1].n == 2 * BX && plan.lv[2].n == BX && PSN_BLOCK_DEEP;
 
     // ---- prologue: r = bt, x = 0
-    PSN_BK_FOR(ctx, NT) {
-        acc[PSN_BK_TI] = 0.0;
+    PSN_BK_FOR(ctx, NTPAD) {
+        const PsnShF64 xa = PSN_BK_XA(S, t_);
+        double bt16[16];
         if (t_ < NT) {
-            double s = 0.0;
-            double bt16[16];
             S.rhs16(a, b, t_, plan.h2, bt16);
+        } else {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const double v = bt16[k];
-                S.r[PSN_BK_TI][k] = v;
-                S.p[PSN_BK_TI][k] = 0.0;
-                S.xs.st(k * NTPAD + t_, 0.0);
-                s += v * v;
-            }
-            acc[PSN_BK_TI] = s;
+            for (int k = 0; k < 16; ++k) bt16[k] = 0.0;     // idle threads of the last warp carry zeros through every phase
         }
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const double v = bt16[k];
+            S.r[PSN_BK_TI][k] = v;
+            S.p[PSN_BK_TI][k] = 0.0;
+            S.z[PSN_BK_TI][k] = 0.0;
+            xa.st(k * NTPAD, 0.0);
+            s += v * v;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) S.z1[PSN_BK_TI][k] = S.r1[PSN_BK_TI][k] = 0.0;
+        S.z2[PSN_BK_TI][0] = S.r2[PSN_BK_TI][0] = 0.0;
+        acc[PSN_BK_TI] = s;
     }
     ctx.sync();
     const double bb = S.tsum(acc);
@@ -642,47 +616,39 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
         rr_final = 0.0;
     } else {
         for (;;) {
-            if (deep) S.vcycle3(plan, pool + plan.lv[3].off); else S.vcycle(plan, pool);
-            PSN_BK_FOR(ctx, NT) {
-                acc[PSN_BK_TI] = 0.0;
-                if (t_ < NT) {
-                    double s = 0.0;
+            S.vcycle3(plan, pool);
+            PSN_BK_FOR(ctx, NTPAD) {
+                double s = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) s += S.r[PSN_BK_TI][k] * S.z[PSN_BK_TI][k];
-                    acc[PSN_BK_TI] = s;
-                }
+                for (int k = 0; k < 16; ++k) s += S.r[PSN_BK_TI][k] * S.z[PSN_BK_TI][k];
+                acc[PSN_BK_TI] = s;
             }
             const double rz = S.tsum(acc);      // (device: block_sum syncs, so every thread is past its last edge read)
             const double beta = restart ? 0.0 : rz / rz_old;
             restart = false;
             rz_old = rz;
             // p = z + beta p, publish every edge of p
-            PSN_BK_FOR(ctx, NT) {
-                if (t_ < NT) {
+            PSN_BK_FOR(ctx, NTPAD) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) S.p[PSN_BK_TI][k] = S.z[PSN_BK_TI][k] + beta * S.p[PSN_BK_TI][k];
-                    S.publish(t_, S.p[PSN_BK_TI], -1);
-                }
+                for (int k = 0; k < 16; ++k) S.p[PSN_BK_TI][k] = S.z[PSN_BK_TI][k] + beta * S.p[PSN_BK_TI][k];
+                S.publish(PSN_BK_EA(S, t_), S.p[PSN_BK_TI], -1);
             }
             ctx.sync();
             // q = At p (kept in z), <p, q>
-            PSN_BK_FOR(ctx, NT) {
-                acc[PSN_BK_TI] = 0.0;
-                if (t_ < NT) {
-                    double hT[4], hB[4], hL[4], hR[4];
-                    S.load_halo_all(t_, hT, hB, hL, hR);
-                    double s = 0.0;
+            PSN_BK_FOR(ctx, NTPAD) {
+                double hT[4], hB[4], hL[4], hR[4];
+                S.load_halo_all(PSN_BK_EA(S, t_), hT, hB, hL, hR);
+                double s = 0.0;
 #pragma unroll
-                    for (int aa = 0; aa < 4; ++aa)
+                for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const double pc = S.p[PSN_BK_TI][4 * aa + c];
-                            const double q = 4.0 * pc - PsnBlockSolver<BX, Ctx>::nbsum(S.p[PSN_BK_TI], aa, c, hT, hB, hL, hR);
-                            S.z[PSN_BK_TI][4 * aa + c] = q;
-                            s += pc * q;
-                        }
-                    acc[PSN_BK_TI] = s;
-                }
+                    for (int c = 0; c < 4; ++c) {
+                        const double pc = S.p[PSN_BK_TI][4 * aa + c];
+                        const double q = 4.0 * pc - PsnBlockSolver<BX, Ctx>::nbsum(S.p[PSN_BK_TI], aa, c, hT, hB, hL, hR);
+                        S.z[PSN_BK_TI][4 * aa + c] = q;
+                        s += pc * q;
+                    }
+                acc[PSN_BK_TI] = s;
             }
             const double pq = S.tsum(acc);
             if (!(pq > 0.0)) {
@@ -690,53 +656,52 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
                 break;
             }
             const double alpha = rz / pq;
-            PSN_BK_FOR(ctx, NT) {
-                acc[PSN_BK_TI] = 0.0;
-                if (t_ < NT) {
-                    double s = 0.0;
+            PSN_BK_FOR(ctx, NTPAD) {
+                const PsnShF64 xa = PSN_BK_XA(S, t_);
+                double s = 0.0;
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        S.xs.add(k * NTPAD + t_, alpha * S.p[PSN_BK_TI][k]);
-                        const double rv = S.r[PSN_BK_TI][k] - alpha * S.z[PSN_BK_TI][k];
-                        S.r[PSN_BK_TI][k] = rv;
-                        s += rv * rv;
-                    }
-                    acc[PSN_BK_TI] = s;
+                for (int k = 0; k < 16; ++k) {
+                    xa.add(k * NTPAD, alpha * S.p[PSN_BK_TI][k]);
+                    const double rv = S.r[PSN_BK_TI][k] - alpha * S.z[PSN_BK_TI][k];
+                    S.r[PSN_BK_TI][k] = rv;
+                    s += rv * rv;
                 }
+                acc[PSN_BK_TI] = s;
             }
             const double rr = S.tsum(acc);
             rr_final = rr;
             ++it;
             if (rr <= tol2 || it >= a.max_iter) {
                 // true residual r = bt - At x: x block into z, publish, stencil
-                PSN_BK_FOR(ctx, NT) {
-                    if (t_ < NT) {
+                PSN_BK_FOR(ctx, NTPAD) {
+                    const PsnShF64 xa = PSN_BK_XA(S, t_);
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) S.z[PSN_BK_TI][k] = S.xs.ld(k * NTPAD + t_);
-                        S.publish(t_, S.z[PSN_BK_TI], -1);
-                    }
+                    for (int k = 0; k < 16; ++k) S.z[PSN_BK_TI][k] = xa.ld(k * NTPAD);
+                    S.publish(PSN_BK_EA(S, t_), S.z[PSN_BK_TI], -1);
                 }
                 ctx.sync();
-                PSN_BK_FOR(ctx, NT) {
-                    acc[PSN_BK_TI] = 0.0;
+                PSN_BK_FOR(ctx, NTPAD) {
+                    double hT[4], hB[4], hL[4], hR[4];
+                    S.load_halo_all(PSN_BK_EA(S, t_), hT, hB, hL, hR);
+                    double s = 0.0;
+                    double bt16[16];
                     if (t_ < NT) {
-                        double hT[4], hB[4], hL[4], hR[4];
-                        S.load_halo_all(t_, hT, hB, hL, hR);
-                        double s = 0.0;
-                        double bt16[16];
                         S.rhs16(a, b, t_, plan.h2, bt16);
+                    } else {
 #pragma unroll
-                        for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                const double bt = bt16[4 * aa + c];
-                                const double rv = bt - (4.0 * S.z[PSN_BK_TI][4 * aa + c] -
-                                                        PsnBlockSolver<BX, Ctx>::nbsum(S.z[PSN_BK_TI], aa, c, hT, hB, hL, hR));
-                                S.r[PSN_BK_TI][4 * aa + c] = rv;
-                                s += rv * rv;
-                            }
-                        acc[PSN_BK_TI] = s;
+                        for (int k = 0; k < 16; ++k) bt16[k] = 0.0;
                     }
+#pragma unroll
+                    for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const double bt = bt16[4 * aa + c];
+                            const double rv = bt - (4.0 * S.z[PSN_BK_TI][4 * aa + c] -
+                                                    PsnBlockSolver<BX, Ctx>::nbsum(S.z[PSN_BK_TI], aa, c, hT, hB, hL, hR));
+                            S.r[PSN_BK_TI][4 * aa + c] = rv;
+                            s += rv * rv;
+                        }
+                    acc[PSN_BK_TI] = s;
                 }
                 const double rt = S.tsum(acc);
                 rr_final = rt;
@@ -753,10 +718,11 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
     // ---- epilogue: u and / or the fused window + downsample outputs
     PSN_BK_FOR(ctx, NT) {
         if (t_ < NT) {
+            const PsnShF64 xa = PSN_BK_XA(S, t_);
             const int bx = t_ % BX, by = t_ / BX;
             double xv[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) xv[k] = S.xs.ld(k * NTPAD + t_);
+            for (int k = 0; k < 16; ++k) xv[k] = xa.ld(k * NTPAD);
             if (a.u) {
                 double* ug = a.u + b * (long long)(N * N);
 #pragma unroll
