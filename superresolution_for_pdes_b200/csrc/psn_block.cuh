@@ -77,10 +77,16 @@ struct PsnBlockGeom {
     static constexpr int N = 4 * BX;
     static constexpr int NT = BX * BX;
     static constexpr int NTPAD = (NT + 31) & ~31;
-    static constexpr int BP = BX + 2;                    // thread grid with a ghost ring
+    // Thread grid with a ghost ring: BX + 2 rows of pitch BP cells.  Threads are numbered tile by tile -- 16 consecutive
+    // threads (one half warp = one 64-bit shared-memory transaction) form a 4 x 4 patch of the thread grid -- and the pitch is
+    // 12 mod 16, so that the four rows of a patch fall on four disjoint groups of banks: every edge access is conflict free.
+    // (Row-major numbering with pitch BX + 2: 3 of 5 half warps straddle a row end, 1.6 wavefronts per access.)
+    static constexpr int BROWS = BX + 2;
+    static constexpr int BP = ((BX + 2 + 3) / 16) * 16 + 12;
+    static_assert(BX % 4 == 0 && BP >= BX + 2 && BP % 16 == 12, "tile numbering needs BX % 4 == 0; pitch 12 mod 16");
     // cells per edge-buffer plane: the padded grid, then one private cell per idle thread of the last warp (their accesses
     // need no predicate either), then slack for those threads' neighbour reads
-    static constexpr int NTP = (BP * BP + (NTPAD - NT) + BP + 1 + 7) & ~7;
+    static constexpr int NTP = (BROWS * BP + (NTPAD - NT) + BP + 1 + 7) & ~7;
     // shared memory (doubles): x[16][NTPAD], edges[4 sides][4 slots][NTP]
     static constexpr int XS = 16 * NTPAD;
     static constexpr int ES = 16 * NTP;
@@ -106,6 +112,10 @@ template <int BX, class Ctx>
 struct PsnBlockSolver {
     typedef PsnBlockGeom<BX> G;
     static constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD, BP = G::BP, NTP = G::NTP;
+    static constexpr int TILES = BX / 4;   // 4 x 4 patches of threads per row of the thread grid
+    // thread t -> its block (bx, by) of the thread grid: tile t / 16 (row-major over TILES x TILES), lane t % 16 inside it
+    PSN_FN static int bx_of(int t) { return 4 * ((t >> 4) % TILES) + (t & 3); }
+    PSN_FN static int by_of(int t) { return 4 * ((t >> 4) / TILES) + ((t >> 2) & 3); }
     enum { TOP = 0, BOT = 1, LEFT = 2, RIGHT = 3 };
 
     Ctx& ctx;
@@ -120,9 +130,9 @@ struct PsnBlockSolver {
     const double* inv_s = nullptr;   // shared-memory copy of the coarsest-level inverse (or null)
 
     // position of thread t in the ghost-ringed thread grid; the idle threads of the last warp get private cells behind it
-    PSN_FN static int tpad(int t) { return t < NT ? (t / BX + 1) * BP + (t % BX) + 1 : BP * BP + (t - NT); }
+    PSN_FN static int tpad(int t) { return t < NT ? (by_of(t) + 1) * BP + bx_of(t) + 1 : G::BROWS * BP + (t - NT); }
     PSN_FN static int flags_of(int t) {
-        const int bx = t % BX, by = t / BX;
+        const int bx = bx_of(t), by = by_of(t);
         return (t < NT ? 1 : 0) | ((((bx + by) & 1) && t < NT) ? 2 : 0) | (((bx & 1) && (by & 1) && t < NT) ? 4 : 0);
     }
     PSN_FN int flags(int t) const {
@@ -278,7 +288,7 @@ struct PsnBlockSolver {
         double gr, gc;   // gam if the thread's block touches the last grid row / column, else 0
     };
     PSN_FN static Diag diag_of(const PsnLevel& lv, int t) {
-        const int bx = t % BX, by = t / BX;
+        const int bx = bx_of(t), by = by_of(t);
         Diag d;
         d.gr = (t < NT && by == BX - 1) ? lv.gam : 0.0;
         d.gc = (t < NT && bx == BX - 1) ? lv.gam : 0.0;
@@ -435,7 +445,7 @@ struct PsnBlockSolver {
         PSN_BK_FOR(ctx, NT) {
             if (flags(t_) & 4) {   // bx, by both odd: centre of coarse node ((by-1)/2, (bx-1)/2) of level 3
                 const PsnShF64 ea = PSN_BK_EA(*this, t_);
-                const int bx = t_ % BX, by = t_ / BX;
+                const int bx = bx_of(t_), by = by_of(t_);
                 const double c00 = EL(ea, BOT, 0, -BP - 1), c02 = EL(ea, BOT, 0, -BP + 1);
                 const double c20 = EL(ea, BOT, 0, BP - 1), c22 = EL(ea, BOT, 0, BP + 1);
                 b3[(((by - 1) >> 1) + 1) * l3.pitch + ((bx - 1) >> 1) + 1] = rho[PSN_BK_TI][0] + 0.25 * ((c00 + c02) + (c20 + c22));
@@ -449,7 +459,7 @@ struct PsnBlockSolver {
         PSN_BK_FOR(ctx, NT) {
             if ((flags(t_) & 3) == 1) {   // real thread, (bx + by) even
                 const PsnShF64 ea = PSN_BK_EA(*this, t_);
-                const int bx = t_ % BX, by = t_ / BX;
+                const int bx = bx_of(t_), by = by_of(t_);
                 const int P3 = l3.pitch;
                 double add;
                 if (by & 1) {
@@ -517,7 +527,7 @@ struct PsnBlockSolver {
     // 64-bit index products, once in the prologue and once per true-residual check) was 20 % of the kernel's instructions.
     // Same operations in the same order as psn_rhs, so the values are bit-identical.
     PSN_FN void rhs16(const PsnSolveArgs& a, long long b, int t, double h2, double (&out)[16]) const {
-        const int bx = t % BX, by = t / BX;
+        const int bx = bx_of(t), by = by_of(t);
         const PsnRhs& s = a.rhs;
         if (s.sx && !s.f && s.step == 1 && s.mn == N) {
             const double* sxp = s.sx + b * (long long)N + 4 * bx;
@@ -719,7 +729,7 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
     PSN_BK_FOR(ctx, NT) {
         if (t_ < NT) {
             const PsnShF64 xa = PSN_BK_XA(S, t_);
-            const int bx = t_ % BX, by = t_ / BX;
+            const int bx = PsnBlockSolver<BX, Ctx>::bx_of(t_), by = PsnBlockSolver<BX, Ctx>::by_of(t_);
             double xv[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) xv[k] = xa.ld(k * NTPAD);
