@@ -541,13 +541,16 @@ struct PsnBlockSolver {
             if (s.theta) {
                 const double* thp = s.theta + (b * (long long)N + 4 * by) * N + 4 * bx;
 #pragma unroll
-                for (int aa = 0; aa < 4; ++aa)
+                for (int aa = 0; aa < 4; ++aa) {
+                    double th[4];
+                    psn_ld4(thp + aa * N, th);      // 2 x 128-bit loads (device arrays are 16-byte aligned, N % 4 == 0)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         double f = syv[aa] * sxv[c];
-                        f = f * (1.0 / psn_ldg(thp + aa * N + c));
+                        f = f * (1.0 / th[c]);
                         out[4 * aa + c] = -(f * h2);
                     }
+                }
             } else {
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa)
@@ -734,9 +737,12 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
 #pragma unroll
             for (int k = 0; k < 16; ++k) xv[k] = xa.ld(k * NTPAD);
             if (a.u) {
-                double* ug = a.u + b * (long long)(N * N);
+                double* ug = a.u + b * (long long)(N * N) + (4 * by) * N + 4 * bx;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) ug[(4 * by + (k >> 2)) * N + 4 * bx + (k & 3)] = xv[k];
+                for (int aa = 0; aa < 4; ++aa) {
+                    const double row[4] = {xv[4 * aa], xv[4 * aa + 1], xv[4 * aa + 2], xv[4 * aa + 3]};
+                    psn_st4(ug + aa * N, row);      // 2 x 128-bit stores
+                }
             }
             if (a.sub > 0) {
                 const int s = a.sub, sc = (s + 1) >> 1;
