@@ -505,6 +505,7 @@ struct Slot {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t staging_free = nullptr;   // recorded after the last copy of the chunk that used the staging arena
     cudaEvent_t h2d_done = nullptr;       // recorded on the upload stream after the chunk's last H2D copy
+    cudaEvent_t solve_done = nullptr;     // recorded on the solve stream after the chunk's last kernel (copy_streams)
 };
 
 // few streams on purpose: a process has CUDA_DEVICE_MAX_CONNECTIONS (default 8) hardware queues, streams beyond that
@@ -522,6 +523,7 @@ struct Context {
     // would alone) while the later one fills the gaps.
     cudaStream_t chunk_stream[PSN_NCHUNK_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t h2d_stream = nullptr;   // uploads of all chunks, in chunk order (host_h2d_stream)
+    cudaStream_t d2h_stream = nullptr;   // result copies of all chunks, in chunk order (copy_streams)
     bool ready = false;
     int device = -1;
     int sm_count = 0;
@@ -560,6 +562,9 @@ struct Context {
     int host_slots = 5;    // staging slots in use (3..PSN_NSLOTS): chunk c's upload waits for chunk c - host_slots to leave its slot
     int host_prefetch = 3; // uploads enqueued this many chunks ahead of the solve being enqueued (<= host_slots - 2, <= 3)
     int host_h2d_stream = 1;  // 1: uploads go through their own stream instead of the chunk's solve stream
+    int copy_streams = 1;     // streamed grids: uploads and result copies of the host pipeline each go through ONE dedicated stream
+                              // (prefetch depth unchanged).  With the copies on the four chunk streams, an upload and a result copy
+                              // of different chunks were at times serialised on one copy engine (5 ms bubbles in the 640^2 timeline).
     int vcycle_mode = 2;   // 0: shared-memory tile kernels, 1: warp strips + register prefetch, 2: warp strips + TMA ring
     // Every call shares the staging arenas, the streamed workspaces and the plan cache.  Host threads are serialised by
     // g_mu; on the device, a call on a different stream than the previous one first waits for that call's last
@@ -1276,6 +1281,7 @@ int solve_impl(const Problem& P) {
         if (Bc > cap) Bc = cap;
     }
     const int nslots = any_host ? (deep ? g.host_slots : 3) : 1;
+    const bool copy_dedicated = !resident && g.copy_streams && P.sub == 0;
     if (any_host) CU_TRY(cudaStreamSynchronize(P.stream));
     Trace trace;
     if (any_host) trace.begin(g.chunk_stream[0]);  // device inputs may still be in flight on the caller's stream
@@ -1376,7 +1382,7 @@ int solve_impl(const Problem& P) {
         const long long b0 = cx.b0, bc = cx.bc;
         const cudaStream_t solve_s = cx.s;
         // uploads either ride the chunk's own stream or a dedicated upload stream (FIFO over chunks) that the solve waits for
-        cudaStream_t s = (deep && g.host_h2d_stream) ? g.h2d_stream : solve_s;
+        cudaStream_t s = ((deep && g.host_h2d_stream) || (copy_dedicated && any_host)) ? g.h2d_stream : solve_s;
         if (c < nslots) {
             rc2 = arena_reserve(cx.slot->arena, pad256(stage_ps * Bc) + 64 * 256 + (size_t)Bc * 64);
             if (rc2) return rc2;
@@ -1511,12 +1517,18 @@ int solve_impl(const Problem& P) {
             if (any_host) CU_TRY(cudaEventRecord(g.ws_free[wk], s));
         }
         trace.mark("solve_end", c, s);
-        if ((rc2 = copy_back(s, P.u, k_u, b0 * (long long)nn, bc * nn, cx.d_u))) return rc2;
-        if ((rc2 = copy_back(s, hb_it ? hb_it : P.iters, k_it, b0, (size_t)bc, cx.d_it))) return rc2;
-        if ((rc2 = copy_back(s, hb_rr ? hb_rr : P.relres, k_rr, b0, (size_t)bc, cx.d_rr))) return rc2;
-        if ((rc2 = copy_back(s, hb_st ? hb_st : P.status, k_st, b0, (size_t)bc, cx.d_st))) return rc2;
-        trace.mark("d2h_end", c, s);
-        if (any_host) CU_TRY(cudaEventRecord(cx.slot->staging_free, s));
+        cudaStream_t cs = s;
+        if (copy_dedicated && any_host) {       // result copies on their own stream, behind this chunk's last kernel
+            CU_TRY(cudaEventRecord(cx.slot->solve_done, s));
+            CU_TRY(cudaStreamWaitEvent(g.d2h_stream, cx.slot->solve_done, 0));
+            cs = g.d2h_stream;
+        }
+        if ((rc2 = copy_back(cs, P.u, k_u, b0 * (long long)nn, bc * nn, cx.d_u))) return rc2;
+        if ((rc2 = copy_back(cs, hb_it ? hb_it : P.iters, k_it, b0, (size_t)bc, cx.d_it))) return rc2;
+        if ((rc2 = copy_back(cs, hb_rr ? hb_rr : P.relres, k_rr, b0, (size_t)bc, cx.d_rr))) return rc2;
+        if ((rc2 = copy_back(cs, hb_st ? hb_st : P.status, k_st, b0, (size_t)bc, cx.d_st))) return rc2;
+        trace.mark("d2h_end", c, cs);
+        if (any_host) CU_TRY(cudaEventRecord(cx.slot->staging_free, cs));
         return PSN_OK;
     };
 
@@ -1573,6 +1585,7 @@ int solve_impl(const Problem& P) {
     if (any_host) {
         for (int i = 0; i < PSN_NCHUNK_STREAMS; ++i) CU_TRY(cudaStreamSynchronize(g.chunk_stream[i]));
         CU_TRY(cudaStreamSynchronize(g.h2d_stream));
+        CU_TRY(cudaStreamSynchronize(g.d2h_stream));
         if (hb_it && k_it == MEM_HOST) memcpy(P.iters, hb_it, (size_t)P.B * 4);
         if (hb_rr && k_rr == MEM_HOST) memcpy(P.relres, hb_rr, (size_t)P.B * 8);
         if (hb_st && k_st == MEM_HOST) memcpy(P.status, hb_st, (size_t)P.B * 4);
@@ -1621,6 +1634,7 @@ int psn_init(int device) {
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         CU_TRY(cudaEventCreateWithFlags(&g.slots[i].staging_free, cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&g.slots[i].h2d_done, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&g.slots[i].solve_done, cudaEventDisableTiming));
         for (int k = 0; k < 4; ++k) CU_TRY(cudaEventCreateWithFlags(&g.slots[i].ev[k], cudaEventDisableTiming));
     }
     {
@@ -1632,6 +1646,7 @@ int psn_init(int device) {
             CU_TRY(cudaStreamCreateWithPriority(&g.chunk_stream[i], cudaStreamNonBlocking, pr));
         }
         CU_TRY(cudaStreamCreateWithPriority(&g.h2d_stream, cudaStreamNonBlocking, prio_hi));
+        CU_TRY(cudaStreamCreateWithPriority(&g.d2h_stream, cudaStreamNonBlocking, prio_hi));
     }
     const char* env = getenv("PSN_WS_BYTES");
     if (env) g.ws_bytes = atoll(env);
@@ -1670,6 +1685,8 @@ void psn_shutdown(void) {
     }
     if (g.h2d_stream) cudaStreamDestroy(g.h2d_stream);
     g.h2d_stream = nullptr;
+    if (g.d2h_stream) cudaStreamDestroy(g.d2h_stream);
+    g.d2h_stream = nullptr;
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         Slot& s = g.slots[i];
         if (s.arena.base) cudaFree(s.arena.base);
@@ -1680,6 +1697,7 @@ void psn_shutdown(void) {
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.staging_free) cudaEventDestroy(s.staging_free);
         if (s.h2d_done) cudaEventDestroy(s.h2d_done);
+        if (s.solve_done) cudaEventDestroy(s.solve_done);
         s = Slot();
     }
     for (auto& r : g.prof) {
@@ -2082,6 +2100,8 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "host_prefetch")) {
         if (value < 1 || value > PSN_NCHUNK_STREAMS - 1) return psn_fail(PSN_ERR_INVALID, "host_prefetch must be in 1..%d", PSN_NCHUNK_STREAMS - 1);
         g.host_prefetch = (int)value;
+    } else if (!strcmp(name, "copy_streams")) {
+        g.copy_streams = value ? 1 : 0;
     } else if (!strcmp(name, "host_h2d_stream")) {
         g.host_h2d_stream = value ? 1 : 0;
     } else if (!strcmp(name, "host_chunks")) {
