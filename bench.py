@@ -474,7 +474,7 @@ def run_own(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n, B, world), "n": n, "batch_per_gpu": B, "rtol": args.rtol,
-                       "solver": "MG-preconditioned CG, V(2,2) red-black GS, matrix-free 5-point zero-ghost stencil; CG vectors, "
+                       "solver": "MG-preconditioned CG, V(2,2) red-black GS on level 0 and V(3,3) on the coarser levels, matrix-free 5-point zero-ghost stencil; CG vectors, "
                                  "operator, inner products and stopping rule in fp64" +
                                  ("; the V-cycle preconditioner stores and smooths in fp32 (same iteration count, solution "
                                   "accuracy unchanged)" if desc.get("vcycle_f32") else "; V-cycle in fp64") +

@@ -191,7 +191,8 @@ int psn_mt19937_uniform_blocks(const uint32_t* key, int pos, int64_t n_blocks, i
  * jump-ahead polynomials the device path uses (one double = 2 words).  Used by the tests and to skip draws. */
 int psn_mt19937_jump_host(const uint32_t* key, int pos, int64_t n_words, uint32_t* key_out, int* pos_out);
 
-/* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg, default 2), "coarsest_max" (0 = automatic: 10 for grids
+/* Tuning knobs (all optional).  name: "nu" (RB-GS sweeps per leg on level 0, default 2), "nu_coarse" (sweeps per leg on the
+ * coarser levels, default 3; 0 = as on level 0), "coarsest_max" (0 = automatic: 10 for grids
  * of 32 x 32 and more, 6 below; else 2..10: largest level n x n that is solved with the precomputed dense inverse instead
  * of being smoothed), "tile" (interior
  * tile edge of the streamed kernels, default 64), "ws_bytes" (workspace budget per pipeline slot),

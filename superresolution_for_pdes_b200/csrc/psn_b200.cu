@@ -534,6 +534,7 @@ struct Context {
     size_t h_info_cap = 0;   // recorded after the last kernel that touches the shared streamed workspace
     std::map<long long, PlanEntry> plans;  // key = (n * 16 + nu) * 64 + coarsest_max
     int nu = 2;
+    int nu_coarse = 3;      // RB-GS sweeps per leg on levels >= 1 (0: as on level 0)
     int coarsest_max = 0;   // largest level solved with the dense inverse (option "coarsest_max"; 0: psn_default_coarsest(n))
     int tile = 64;
     long long ws_bytes = 24ll << 30;
@@ -645,11 +646,11 @@ int ensure_init() {
 }
 
 int get_plan(int n, PlanEntry** out) {
-    const long long key = ((long long)n * 16 + g.nu) * 64 + g.coarsest_max;
+    const long long key = (((long long)n * 16 + g.nu) * 64 + g.coarsest_max) * 8 + g.nu_coarse;
     auto it = g.plans.find(key);
     if (it == g.plans.end()) {
         PlanEntry e;
-        psn_plan_levels(&e.plan, n, g.nu, g.coarsest_max);
+        psn_plan_levels(&e.plan, n, g.nu, g.coarsest_max, g.nu_coarse);
         std::vector<double> inv = psn_coarse_inverse(e.plan);
         e.d_inv = nullptr;
         CU_TRY(cudaMalloc(&e.d_inv, inv.size() * sizeof(double)));
@@ -844,8 +845,9 @@ struct CudaBackend {
     }
     template <bool POST>
     void strip_launch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool tma, bool f32) {
-        if (plan.nu == 1) strip_launch_nu<1, POST>(plan, a, B, tma, f32);
-        else if (plan.nu == 2) strip_launch_nu<2, POST>(plan, a, B, tma, f32);
+        const int nu_l = plan.nul[a.level];
+        if (nu_l == 1) strip_launch_nu<1, POST>(plan, a, B, tma, f32);
+        else if (nu_l == 2) strip_launch_nu<2, POST>(plan, a, B, tma, f32);
         else strip_launch_nu<3, POST>(plan, a, B, tma, f32);
     }
     void leg_pre(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
@@ -855,7 +857,7 @@ struct CudaBackend {
         } else {
             const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
             ProfScope p(t.level == 0 ? "tile_pre_l0" : "tile_pre_coarse", s);
-            const size_t smem = (size_t)psn_tile_pre_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
+            const size_t smem = (size_t)psn_tile_pre_doubles(t.TH, t.TW, plan.nul[t.level]) * sizeof(double);
             launch(psn_tile_pre_kernel, dim3(dim3(t.ntx, t.nty, (unsigned)B)), dim3(PSN_TILE_THREADS), smem, plan, t);
         }
         chk();
@@ -867,7 +869,7 @@ struct CudaBackend {
         } else {
             const PsnTileArgs t = psn_leg_to_tile(plan, cfg, g);
             ProfScope p(t.level == 0 ? "tile_post_l0" : "tile_post_coarse", s);
-            const size_t smem = (size_t)psn_tile_post_doubles(t.TH, t.TW, plan.nu) * sizeof(double);
+            const size_t smem = (size_t)psn_tile_post_doubles(t.TH, t.TW, plan.nul[t.level]) * sizeof(double);
             launch(psn_tile_post_kernel, dim3(dim3(t.ntx, t.nty, (unsigned)B)), dim3(PSN_TILE_THREADS), smem, plan, t);
         }
         chk();
@@ -1072,10 +1074,10 @@ int psn_rz_max(const PsnPlan& plan, const PsnStreamCfg& cfg) {
 void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg->band[l] = 16;
     const long long slots = (long long)g.sm_count * (cfg->vf32 ? PSN_STRIP_MINB_F32 : PSN_STRIP_MINB_TMA);
-    const int halo = 4 * plan.nu;
     for (int l = 0; l < cfg->ls; ++l) {
         const int n = plan.lv[l].n;
-        const long long strips = psn_strip_count(n, psn_strip_use_pre(plan.nu, cfg->vf32));
+        const int halo = 4 * plan.nul[l];
+        const long long strips = psn_strip_count(n, psn_strip_use_pre(plan.nul[l], cfg->vf32));
         int best_band = (n + 1) & ~1;
         long long best_cost = -1;
         const int nb_max = g.band_target > 0 ? g.band_target : 1;
@@ -2033,6 +2035,9 @@ int psn_set_option(const char* name, int64_t value) {
     if (!strcmp(name, "nu")) {
         if (value < 1 || value > 3) return psn_fail(PSN_ERR_INVALID, "nu must be in 1..3");
         g.nu = (int)value;
+    } else if (!strcmp(name, "nu_coarse")) {
+        if (value < 0 || value > 3) return psn_fail(PSN_ERR_INVALID, "nu_coarse must be 0 (as level 0) or in 1..3");
+        g.nu_coarse = (int)value;
     } else if (!strcmp(name, "coarsest_max")) {
         if (value != 0 && (value < 2 || value > PSN_COARSEST_MAX)) return psn_fail(PSN_ERR_INVALID, "coarsest_max must be 0 (automatic) or in 2..%d", PSN_COARSEST_MAX);
         g.coarsest_max = (int)value;
@@ -2168,7 +2173,7 @@ int psn_describe(int n, int64_t* info) {
     g_err[0] = 0;
     if (!info || n < 2) return psn_fail(PSN_ERR_INVALID, "bad arguments");
     PsnPlan plan;
-    psn_plan_levels(&plan, n, g.nu, g.coarsest_max);
+    psn_plan_levels(&plan, n, g.nu, g.coarsest_max, g.nu_coarse);
     if (!g.ready) g.smem_optin = 232448;  // sm_100 opt-in limit; lets the CPU-only tier query the layout
     const ResidentCfg rc = resident_cfg(plan);
     memset(info, 0, 8 * sizeof(int64_t));

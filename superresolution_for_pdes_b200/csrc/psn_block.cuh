@@ -337,7 +337,7 @@ struct PsnBlockSolver {
 
     // z = M^{-1} r with levels 0, 1, 2 in registers (n = 4 BX, 2 BX, BX) and levels >= 3 in shared memory
     PSN_FN void vcycle3(const PsnPlan& plan, double* pool) {
-        const int nu = plan.nu;
+        const int nu = plan.nul[0], nu1 = plan.nul[1], nu2 = plan.nul[2];
         const PsnLevel& l1 = plan.lv[1];
         const PsnLevel& l2 = plan.lv[2];
         const PsnLevel& l3 = plan.lv[3];
@@ -402,7 +402,7 @@ struct PsnBlockSolver {
         }
         ctx.sync();
         // ---------------- level 1 down (2x2 per thread)
-        for (int s = 0; s < nu; ++s) {
+        for (int s = 0; s < nu1; ++s) {
             PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, s == 0); }
             ctx.sync();
             PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
@@ -429,7 +429,7 @@ struct PsnBlockSolver {
         }
         ctx.sync();
         // ---------------- level 2 down (one node per thread)
-        for (int s = 0; s < nu; ++s) {
+        for (int s = 0; s < nu2; ++s) {
             half_sweep_2(rd2, 0, s == 0);
             half_sweep_2(rd2, 1, false);
         }
@@ -473,7 +473,7 @@ struct PsnBlockSolver {
             }
         }
         ctx.sync();
-        for (int s = 0; s < nu; ++s) {
+        for (int s = 0; s < nu2; ++s) {
             half_sweep_2(rd2, 1, false);
             half_sweep_2(rd2, 0, false);
         }
@@ -489,7 +489,7 @@ struct PsnBlockSolver {
         ctx.sync();   // TOP[0] is about to be overwritten by the edges of z1
         PSN_BK_FOR(ctx, NTPAD) { publish_bs<2>(PSN_BK_EA(*this, t_), z1[PSN_BK_TI], 0); }
         ctx.sync();
-        for (int s = 0; s < nu; ++s) {
+        for (int s = 0; s < nu1; ++s) {
             PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
             ctx.sync();
             PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, false); }

@@ -416,11 +416,11 @@ template <class Ctx>
 PSN_FN void psn_vcycle_smem(Ctx& ctx, const PsnPlan& plan, int l0, const double* b0, double* u0, double* pool,
                             const double* inv_s = nullptr) {
     const int L = plan.nlev;
-    const int nu = plan.nu;
     const int base = psn_pool_off(plan, l0 + 1);
     for (int l = l0; l < L - 1; ++l) {
         const PsnLevel& lv = plan.lv[l];
         const PsnLevel& lc = plan.lv[l + 1];
+        const int nu = plan.nul[l];
         const int off = psn_pool_off(plan, l) - base;
         const double* bl = (l == l0) ? b0 : pool + off;
         double* ul = (l == l0) ? u0 : pool + off + lv.size;
@@ -451,6 +451,7 @@ PSN_FN void psn_vcycle_smem(Ctx& ctx, const PsnPlan& plan, int l0, const double*
     for (int l = L - 2; l >= l0; --l) {
         const PsnLevel& lv = plan.lv[l];
         const PsnLevel& lc = plan.lv[l + 1];
+        const int nu = plan.nul[l];
         const int off = psn_pool_off(plan, l) - base;
         const double* bl = (l == l0) ? b0 : pool + off;
         double* ul = (l == l0) ? u0 : pool + off + lv.size;
@@ -675,7 +676,7 @@ PSN_FN void psn_tile_pre_body(Ctx& ctx, const PsnPlan& plan, const PsnTileArgs& 
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
     const PsnLevel& lv = plan.lv[a.level];
     const PsnLevel& lc = plan.lv[a.level + 1];
-    const int n = lv.n, nc = lc.n, nu = plan.nu;
+    const int n = lv.n, nc = lc.n, nu = plan.nul[a.level];
     const int Hlo = 2 * nu, Hhi = 2 * nu + 1;
     const int i0 = ty * a.TH, j0 = tx * a.TW;
     const int PR = a.TH + Hlo + Hhi, PC = a.TW + Hlo + Hhi, pitch = PC | 1;
@@ -723,7 +724,7 @@ PSN_FN void psn_tile_post_body(Ctx& ctx, const PsnPlan& plan, const PsnTileArgs&
     if (a.state && a.state[b].phase != PSN_PHASE_ITER) return;
     const PsnLevel& lv = plan.lv[a.level];
     const PsnLevel& lc = plan.lv[a.level + 1];
-    const int n = lv.n, nc = lc.n, nu = plan.nu;
+    const int n = lv.n, nc = lc.n, nu = plan.nul[a.level];
     const int H = 2 * nu;
     const int i0 = ty * a.TH, j0 = tx * a.TW;
     const int PR = a.TH + 2 * H, PC = a.TW + 2 * H, pitch = PC | 1;

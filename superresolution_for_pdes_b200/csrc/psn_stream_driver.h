@@ -124,7 +124,8 @@ static inline PsnStripArgs psn_leg_to_strip(const PsnPlan& plan, const PsnStream
     const int n = plan.lv[g.level].n;
     a.level = g.level;
     a.band = cfg.band[g.level];
-    a.nstrips = psn_strip_count(n, post ? psn_strip_use_post(plan.nu, cfg.vf32) : psn_strip_use_pre(plan.nu, cfg.vf32));
+    const int nu_l = plan.nul[g.level];
+    a.nstrips = psn_strip_count(n, post ? psn_strip_use_post(nu_l, cfg.vf32) : psn_strip_use_pre(nu_l, cfg.vf32));
     a.nbands = psn_band_count(n, a.band);
     a.b = g.b; a.uin = g.uin; a.uout = g.uout; a.bc = g.bc; a.ec = g.ec; a.part = g.part; a.state = g.state;
     a.fused = g.fused; a.only_restart = g.only_restart;

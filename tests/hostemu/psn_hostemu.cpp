@@ -20,7 +20,8 @@ struct HostPlan {
     PsnPlan plan;
     std::vector<double> inv;
     HostPlan(int n, int nu) {
-        psn_plan_levels(&plan, n, nu);
+        // nu = 10 * nu_coarse + nu_level0 selects different sweep counts on the coarse levels (e.g. 32: 2 on level 0, 3 below)
+        psn_plan_levels(&plan, n, nu % 10, 0, nu / 10);
         inv = psn_coarse_inverse(plan);
         plan.coarse_inv = inv.data();
     }
@@ -65,8 +66,9 @@ struct HostBackend {
         }
     }
     void strip_dispatch(const PsnPlan& plan, const PsnStripArgs& a, long long B, bool post, bool tma, bool f32) {
-        if (plan.nu == 1) strip_leg<1>(plan, a, B, post, tma, f32);
-        else if (plan.nu == 2) strip_leg<2>(plan, a, B, post, tma, f32);
+        const int nu_l = plan.nul[a.level];
+        if (nu_l == 1) strip_leg<1>(plan, a, B, post, tma, f32);
+        else if (nu_l == 2) strip_leg<2>(plan, a, B, post, tma, f32);
         else strip_leg<3>(plan, a, B, post, tma, f32);
     }
     void leg_pre(const PsnPlan& plan, const PsnStreamCfg& cfg, const PsnLegArgs& g, long long B) {
@@ -77,7 +79,7 @@ struct HostBackend {
             for (int ty = 0; ty < t.nty; ++ty)
                 for (int tx = 0; tx < t.ntx; ++tx) {
                     // poison the scratch so that reads of never-written halo cells show up as NaN
-                    std::fill(smem.begin(), smem.begin() + psn_tile_pre_doubles(t.TH, t.TW, plan.nu), std::nan(""));
+                    std::fill(smem.begin(), smem.begin() + psn_tile_pre_doubles(t.TH, t.TW, plan.nul[t.level]), std::nan(""));
                     psn_tile_pre_body(ctx, plan, t, b, ty, tx, smem.data());
                 }
     }
@@ -88,7 +90,7 @@ struct HostBackend {
         for (long long b = 0; b < B; ++b)
             for (int ty = 0; ty < t.nty; ++ty)
                 for (int tx = 0; tx < t.ntx; ++tx) {
-                    std::fill(smem.begin(), smem.begin() + psn_tile_post_doubles(t.TH, t.TW, plan.nu), std::nan(""));
+                    std::fill(smem.begin(), smem.begin() + psn_tile_post_doubles(t.TH, t.TW, plan.nul[t.level]), std::nan(""));
                     psn_tile_post_body(ctx, plan, t, b, ty, tx, smem.data());
                 }
     }
@@ -282,7 +284,7 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     ws.part_a = alloc((size_t)B * gx * gy);
     ws.part_pq = alloc((size_t)B * psn_pq_max(n));
     ws.part_b = alloc((size_t)B * gx * gy);
-    ws.part_u = alloc((size_t)B * psn_pu_max(n, nu));
+    ws.part_u = alloc((size_t)B * psn_pu_max(n, plan.nu));
     std::vector<float> pring;
     std::vector<PsnPend> pend(B);
     if (cfg.xdefer) {
