@@ -27,6 +27,9 @@ for r in rows:
     elif m.group(1) == "psn_strip_kernel":
         t = [x.strip() for x in m.group(2).split(",")]
         k = ("strip_post" if t[1] == "1" else "strip_pre") + ("_l0" if t[3] == "double" else "_coarse")
+    elif m.group(1) == "psn_upre_strip_kernel":
+        t = [x.strip() for x in (m.group(2) or "2, 0").split(",")]
+        k = "prologue_pre_l0" if t[-1] == "1" else "update_pre_l0"
     elif m.group(1).startswith("psn_state") or m.group(1) in ("psn_publish_counter_kernel", "psn_finalize_kernel", "psn_zero_ints_kernel"):
         k = "state"
     else:
