@@ -38,6 +38,10 @@ PSN_FN double w_sum(wd v) {
     return v;
 }
 PSN_FN bool w_lane0(const PsnWarp& w) { return w.lane == 0; }
+// (An explicit elect.sync around the bulk-copy issue of the row feeders removes the compiler's per-instruction ELECT / PLOP3
+//  election sequences -- 138 -> 19 of them in the fused kernel, +2.6 % at 640^2 -- but the fp64-stored V(1,1) strips then
+//  converged in a varying number of iterations, i.e. raced, with or without a memory clobber or a re-sync after the issue;
+//  the cause was not found, so the lane-0 form stays.)
 // two adjacent doubles at row[col], row[col+1] (col even); masked elements read as 0.
 // vec: the row base and col are 16-byte aligned, so one 128-bit access is legal.
 PSN_FN void w_ld2(const double* row, wi col, wb m0, wb m1, bool vec, wd& a, wd& b) {
