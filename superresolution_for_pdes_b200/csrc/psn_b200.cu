@@ -1996,14 +1996,14 @@ int psn_mt19937_uniform_blocks(const uint32_t* key, int pos, int64_t n_blocks, i
     CU_TRY(cudaStreamSynchronize(s));   // h_polys and key are host temporaries
     if (first) {
         ProfScope pr("mt_jump", s);
-        psn_mt_jump_kernel<<<dim3(PSN_MT_SPLIT, 1), PSN_MT_THREADS, psn_mt_jump_smem(), s>>>(d_states, 0, 1, d_polys + (size_t)rounds * CHUNKS);
+        psn_mt_jump_kernel<<<dim3(1, PSN_MT_SPLIT), PSN_MT_THREADS, psn_mt_jump_smem(), s>>>(d_states, 0, 1, d_polys + (size_t)rounds * CHUNKS);
     }
     {
         int k = 0;
         for (long long have = 1; have < nstates - first; have *= 2, ++k) {
             const long long cnt = std::min<long long>(have, nstates - first - have);
             ProfScope pr("mt_jump", s);
-            psn_mt_jump_kernel<<<dim3(PSN_MT_SPLIT, (unsigned)cnt), PSN_MT_THREADS, psn_mt_jump_smem(), s>>>(d_states, first, first + have,
+            psn_mt_jump_kernel<<<dim3((unsigned)cnt, PSN_MT_SPLIT), PSN_MT_THREADS, psn_mt_jump_smem(), s>>>(d_states, first, first + have,
                                                                                                            d_polys + (size_t)k * CHUNKS);
         }
     }

@@ -212,7 +212,7 @@ inline void host_apply(const Poly& g, const uint32_t* s, uint32_t* out) {
 #define PSN_MT_SPLIT 16      // CTAs that share one jump (each takes 39 of the 624 polynomial chunks)
 #define PSN_MT_SEQ (psn_mt::N + 88 * 227)   // extended source sequence x[0 .. 20599] (x[19936 + 623] is the last one used)
 
-// states[dst0 + c] ^= (part of g)(F) states[src0 + c] for c = blockIdx.y; the destination states must be zero before
+// states[dst0 + c] ^= (part of g)(F) states[src0 + c] for c = blockIdx.x (part = blockIdx.y); the destination states must be zero before
 // the launch.  g(F) s = sum_i g_i F^i s and (F^i s)[j] = x[i + j]: with the source sequence extended to
 // x[0 .. 19936 + 623] in shared memory (88 barrier-separated rounds of 227 independent words) output word j is the XOR of
 // x[i + j] over the set bits i of g -- no dependent steps, so PSN_MT_SPLIT CTAs take disjoint bit ranges of g and
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(PSN_MT_THREADS) psn_mt_jump_kernel(uint32_t* s
     uint32_t* G = mt_smem + PSN_MT_SEQ;  // [CHUNKS / PSN_MT_SPLIT]
     const int t = threadIdx.x;
     constexpr int CPB = CHUNKS / PSN_MT_SPLIT;
-    const int c0 = blockIdx.x * CPB;
-    const uint32_t* src = states + (src0 + blockIdx.y) * (long long)N;
+    const int c0 = blockIdx.y * CPB;
+    const uint32_t* src = states + (src0 + blockIdx.x) * (long long)N;
     if (t < N) X[t] = src[t];
     if (t < CPB) G[t] = gchunks[c0 + t];
     __syncthreads();
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(PSN_MT_THREADS) psn_mt_jump_kernel(uint32_t* s
             for (int i = 0; i < 32; ++i)
                 if ((v >> i) & 1u) a ^= xp[i];
         }
-        if (a) atomicXor(states + (dst0 + blockIdx.y) * (long long)N + t, a);
+        if (a) atomicXor(states + (dst0 + blockIdx.x) * (long long)N + t, a);
     }
 }
 inline size_t psn_mt_jump_smem() { return (size_t)(PSN_MT_SEQ + psn_mt::CHUNKS / PSN_MT_SPLIT) * sizeof(uint32_t); }

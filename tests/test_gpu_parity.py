@@ -639,6 +639,13 @@ def test_mt19937_device_stream_from_pos_zero_and_long_draws(gpu_lib):
     got, got_sk = gpu_lib.mt19937_uniform_blocks(6, 2, 1000, 0.5, 2.0, random_state=rs)
     assert np.array_equal(got, want) and np.array_equal(got_sk, want_sk)
     assert np.array_equal(rs.random_sample(700), ref.random_sample(700))
+    # more blocks than one grid dimension's 65,535: 70,000 blocks of 2 + 5 doubles
+    rs = np.random.RandomState(5)
+    ref = np.random.RandomState(5)
+    got, got_sk = gpu_lib.mt19937_uniform_blocks(70000, 2, 5, 0.5, 2.0, random_state=rs)
+    flat = ref.random_sample(70000 * 7).reshape(70000, 7)            # same stream: 2 raw + 5 mapped doubles per block
+    assert np.array_equal(got_sk, flat[:, :2]) and np.array_equal(got, 0.5 + 1.5 * flat[:, 2:])
+    assert rs.uniform() == ref.uniform()
     # one long draw, cut into 32,768-double blocks + remainder, on the GLOBAL generator
     np.random.seed(99)
     a = gpu_lib.mt19937_uniform((37, 80, 80), 0.5, 2.0)
