@@ -162,10 +162,19 @@ struct PsnDevCtx {
         flip ^= 1;
         if ((tid & 31) == 0) buf[tid >> 5] = v;
         __syncthreads();
+        // fixed order, four interleaved chains: the dependent-add depth is nw / 4 + 2 instead of nw (every thread adds the same
+        // values in the same order, so the result is identical across the CTA and from run to run)
         const int nw = (nthreads + 31) >> 5;
-        double s = buf[0];
-        for (int w = 1; w < nw; ++w) s += buf[w];
-        return s;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int w = 0;
+        for (; w + 3 < nw; w += 4) {
+            s0 += buf[w];
+            s1 += buf[w + 1];
+            s2 += buf[w + 2];
+            s3 += buf[w + 3];
+        }
+        for (; w < nw; ++w) s0 += buf[w];
+        return (s0 + s1) + (s2 + s3);
     }
 };
 #endif

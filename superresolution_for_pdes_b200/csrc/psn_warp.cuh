@@ -1185,6 +1185,8 @@ struct PsnFusedRow {     // per-task constants and running state of the update p
     wd dot;              // partial ||r_{k+1}||^2 over the owned nodes
     double* rout;        // r_{k+1} of this sample
     wb ind[2];           // column pairs inside the domain
+    bool edge;           // the strip window leaves the domain on a side (warp-uniform): only then are the selects on `ind` needed
+    wd mo[2];            // 1.0 for the column pairs this task owns, else 0.0 (dot-product mask)
     // mode 1 (prologue): r_0 = bt = -(sin_y[i] sin_x[j] / theta_ij) h^2 instead of r_k - alpha q
     wd sxv[4];           // the lane's four sin_x values
     const double* sy;    // sin_y of this sample
@@ -1243,9 +1245,13 @@ PSN_FN void psn_strip_upre_chunk(const PsnWarp& w, int t, int ts, int tload, int
                 q[3] = 4.0 * fr.pc[3] - ((pn[3] + fr.pm[3]) + (fr.pc[2] + dnv));
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    rn[e] = w_sel(fr.ind[e >> 1], r0[e] - fr.alpha * q[e], zerod);
+                    rn[e] = r0[e] - fr.alpha * q[e];
                     fr.pm[e] = fr.pc[e];
                     fr.pc[e] = pn[e];
+                }
+                if (fr.edge) {   // out-of-domain columns next to the domain would carry -alpha q != 0
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rn[e] = w_sel(fr.ind[e >> 1], rn[e], zerod);
                 }
             } else {
                 if (FAST || tc <= last) {
@@ -1266,7 +1272,7 @@ PSN_FN void psn_strip_upre_chunk(const PsnWarp& w, int t, int ts, int tload, int
                 double* rowr = fr.rout + (long long)tc * n;
                 w_stp(rowr, col0, so[0], rn[0], rn[1]);
                 w_stp(rowr, col0 + 2, so[1], rn[2], rn[3]);
-                fr.dot = fr.dot + w_sel(so[0], rn[0] * rn[0] + rn[1] * rn[1], zerod) + w_sel(so[1], rn[2] * rn[2] + rn[3] * rn[3], zerod);
+                fr.dot = fr.dot + fr.mo[0] * (rn[0] * rn[0] + rn[1] * rn[1]) + fr.mo[1] * (rn[2] * rn[2] + rn[3] * rn[3]);
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) bb[k0][e] = w_cvt<float>(rn[e] * fr.bsc);
@@ -1429,6 +1435,9 @@ PSN_FN void psn_strip_upre_body(const PsnWarp& w, const PsnPlan& plan, const Psn
     fr.rout = g.r_out + base;
     fr.ind[0] = mp[0];
     fr.ind[1] = mp[1];
+    fr.edge = (c0 < 0) || (c0 + PSN_STRIP_COLS > n);
+    fr.mo[0] = w_sel(so[0], w_bcast(1.0), zerod);
+    fr.mo[1] = w_sel(so[1], w_bcast(1.0), zerod);
     fr.h2 = w_bcast(g.h2);
     fr.sy = nullptr;
 #pragma unroll
