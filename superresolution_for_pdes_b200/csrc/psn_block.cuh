@@ -1,8 +1,9 @@
 // psn_block.cuh -- register-blocked resident solver for n = 4*BX (the 80x80 "super-fine" grid: BX = 20).
 //
 // One CTA solves one sample.  Thread (bx, by) owns the 4x4 block of finest-level nodes
-// rows 4by..4by+3, cols 4bx..4bx+3 and keeps r (residual = V-cycle rhs), z (V-cycle iterate) and
-// p (search direction) of that block in REGISTERS; x sits in shared memory in a [16][thread] layout.
+// rows 4by..4by+3, cols 4bx..4bx+3 and keeps r (residual), p (search direction), q = A p (fp64) and the
+// V-cycle's rhs and iterate (float, see PSN_BLOCK_VF32) of that block in REGISTERS; x sits in shared memory
+// in a [16][thread] layout.
 // A red-black half sweep updates 8 nodes per thread with neighbours taken from registers, except the
 // 8 block-edge neighbours, which come from four shared-memory edge buffers ([slot][thread] layout:
 // lanes are contiguous, so every access is bank-conflict free) that the owning thread re-publishes
@@ -32,13 +33,11 @@
 #define PSN_BK_TS 1
 #define PSN_BK_FOR(ctx, NT) for (int t_ = (ctx).tid, once_ = 1; once_; once_ = 0)
 #define PSN_BK_TI 0
-#define PSN_BK_EA(S, t) ((S).ea_dev)
 #define PSN_BK_XA(S, t) ((S).xa_dev)
 #else
 #define PSN_BK_TS NTPAD
 #define PSN_BK_FOR(ctx, NT) for (int t_ = 0; t_ < (NT); ++t_)
 #define PSN_BK_TI t_
-#define PSN_BK_EA(S, t) ((S).edge.at((S).tpad(t)))
 #define PSN_BK_XA(S, t) ((S).xs.at(t))
 #endif
 
@@ -72,6 +71,37 @@ struct PsnShF64 {
 };
 #endif
 
+#if defined(__CUDACC__)
+struct PsnShF32 {
+    unsigned base;
+    __device__ __forceinline__ explicit PsnShF32(double* p) : base((unsigned)__cvta_generic_to_shared(p)) {}
+    __device__ __forceinline__ PsnShF32 at(int off) const { PsnShF32 r(*this); r.base = base + 4u * (unsigned)off; return r; }
+    __device__ __forceinline__ float ld(int i) const {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * (unsigned)i) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void st(int i, float v) const {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4u * (unsigned)i), "f"(v) : "memory");
+    }
+};
+#else
+struct PsnShF32 {
+    float* base;
+    explicit PsnShF32(double* p) : base(reinterpret_cast<float*>(p)) {}
+    PsnShF32 at(int off) const { PsnShF32 r(*this); r.base = base + off; return r; }
+    float ld(int i) const { return base[i]; }
+    void st(int i, float v) const { base[i] = v; }
+};
+#endif
+
+// V-cycle inside the register-blocked solver in fp32 (1, default) or fp64 (0): like the float-stored preconditioner of the
+// streamed path, everything between "r in" and "z out" -- iterates, restricted residuals, edge exchange -- is float, scaled by
+// a power of two near 1 / ||r||; r, p, q, x, every inner product and the stopping rule stay fp64.
+#ifndef PSN_BLOCK_VF32
+#define PSN_BLOCK_VF32 1
+#endif
+
 template <int BX>
 struct PsnBlockGeom {
     static constexpr int N = 4 * BX;
@@ -87,6 +117,11 @@ struct PsnBlockGeom {
     // cells per edge-buffer plane: the padded grid, then one private cell per idle thread of the last warp (their accesses
     // need no predicate either), then slack for those threads' neighbour reads
     static constexpr int NTP = (BROWS * BP + (NTPAD - NT) + BP + 1 + 7) & ~7;
+    // float planes of the V-cycle exchange (they alias the fp64 planes): a warp is two tiles = 4 rows x 8 cells per 32-bit
+    // transaction, so the pitch is 8 mod 32
+    static constexpr int BPF = ((BX + 2 - 8 + 31) / 32) * 32 + 8;
+    static constexpr int NTPF = (BROWS * BPF + (NTPAD - NT) + BPF + 1 + 7) & ~7;
+    static_assert(BPF >= BX + 2 && BPF % 32 == 8 && 16 * NTPF * 4 <= 16 * NTP * 8, "float planes must fit into the fp64 planes");
     // shared memory (doubles): x[16][NTPAD], edges[4 sides][4 slots][NTP]
     static constexpr int XS = 16 * NTPAD;
     static constexpr int ES = 16 * NTP;
@@ -111,26 +146,51 @@ PSN_HDFN int psn_coarse_inv_doubles(const PsnPlan& plan) {
 template <int BX, class Ctx>
 struct PsnBlockSolver {
     typedef PsnBlockGeom<BX> G;
-    static constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD, BP = G::BP, NTP = G::NTP;
+    static constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
     static constexpr int TILES = BX / 4;   // 4 x 4 patches of threads per row of the thread grid
     // thread t -> its block (bx, by) of the thread grid: tile t / 16 (row-major over TILES x TILES), lane t % 16 inside it
     PSN_FN static int bx_of(int t) { return 4 * ((t >> 4) % TILES) + (t & 3); }
     PSN_FN static int by_of(int t) { return 4 * ((t >> 4) / TILES) + ((t >> 2) & 3); }
     enum { TOP = 0, BOT = 1, LEFT = 2, RIGHT = 3 };
 
+#if PSN_BLOCK_VF32
+    typedef float VT;                      // element type inside the V-cycle
+    typedef PsnShF32 ShV;
+    static constexpr int BPV = G::BPF, NTPV = G::NTPF;
+#else
+    typedef double VT;
+    typedef PsnShF64 ShV;
+    static constexpr int BPV = G::BP, NTPV = G::NTP;
+#endif
+    // cursor = shared address of the thread's own edge cell, with the geometry of its planes
+    struct CurD {                          // fp64 planes: CG exchange of p and x
+        PsnShF64 a;
+        typedef double T;
+        static constexpr int P = G::BP, PL = G::NTP;
+    };
+    struct CurV {                          // V-cycle planes
+        ShV a;
+        typedef VT T;
+        static constexpr int P = BPV, PL = NTPV;
+    };
+
     Ctx& ctx;
     PsnShF64 xs;     // [16][NTPAD]
-    PsnShF64 edge;   // [4][4][NTP], cell index = position in the ghost-ringed thread grid (tpad)
-    double z[PSN_BK_TS][16], r[PSN_BK_TS][16], p[PSN_BK_TS][16];
+    PsnShF64 edge;   // [4][4][NTP] doubles / [4][4][NTPV] VT, cell index = position in the ghost-ringed thread grid
+    ShV edgev;
+    double r[PSN_BK_TS][16], p[PSN_BK_TS][16];   // CG residual and search direction
+    double q[PSN_BK_TS][16];                     // A p; block of x during the true-residual check
+    VT z[PSN_BK_TS][16], bv[PSN_BK_TS][16];      // V-cycle: iterate and (scaled) right-hand side on level 0
 #if defined(__CUDACC__)
     PsnShF64 ea_dev, xa_dev;   // this thread's own edge cell / x column (shared addresses pinned in registers)
+    ShV ev_dev;
     int fl_dev;                // bit 0: real thread (t < NT), bit 1: (bx + by) odd, bit 2: bx and by both odd
 #endif
 
     const double* inv_s = nullptr;   // shared-memory copy of the coarsest-level inverse (or null)
 
-    // position of thread t in the ghost-ringed thread grid; the idle threads of the last warp get private cells behind it
-    PSN_FN static int tpad(int t) { return t < NT ? (by_of(t) + 1) * BP + bx_of(t) + 1 : G::BROWS * BP + (t - NT); }
+    // position of thread t in the ghost-ringed thread grid of pitch P; the idle threads of the last warp get private cells behind it
+    PSN_FN static int tpad(int t, int P) { return t < NT ? (by_of(t) + 1) * P + bx_of(t) + 1 : G::BROWS * P + (t - NT); }
     PSN_FN static int flags_of(int t) {
         const int bx = bx_of(t), by = by_of(t);
         return (t < NT ? 1 : 0) | ((((bx + by) & 1) && t < NT) ? 2 : 0) | (((bx & 1) && (by & 1) && t < NT) ? 4 : 0);
@@ -142,200 +202,236 @@ struct PsnBlockSolver {
         return flags_of(t);
 #endif
     }
+    PSN_FN CurD curd(int t) const {
+#if defined(__CUDACC__)
+        return CurD{ea_dev};
+#else
+        return CurD{edge.at(tpad(t, G::BP))};
+#endif
+    }
+    PSN_FN CurV curv(int t) const {
+#if defined(__CUDACC__)
+        return CurV{ev_dev};
+#else
+        return CurV{edgev.at(tpad(t, BPV))};
+#endif
+    }
 
     PSN_FN PsnBlockSolver(Ctx& c, double* smem)
-        : ctx(c), xs(smem), edge(smem + G::XS)
+        : ctx(c), xs(smem), edge(smem + G::XS), edgev(smem + G::XS)
 #if defined(__CUDACC__)
-          , ea_dev(smem), xa_dev(smem)
+          , ea_dev(smem), xa_dev(smem), ev_dev(smem)
 #endif
     {
 #if defined(__CUDACC__)
-        unsigned e = edge.base + 8u * (unsigned)tpad(c.tid), x = xs.base + 8u * (unsigned)c.tid;
+        unsigned e = edge.base + 8u * (unsigned)tpad(c.tid, G::BP), x = xs.base + 8u * (unsigned)c.tid;
+        unsigned v = edgev.base + (unsigned)sizeof(VT) * (unsigned)tpad(c.tid, BPV);
         int f = flags_of(c.tid);
         asm volatile("mov.u32 %0, %0;" : "+r"(e));   // opaque to the compiler: kept in a register (or spilled), never re-derived
         asm volatile("mov.u32 %0, %0;" : "+r"(x));
+        asm volatile("mov.u32 %0, %0;" : "+r"(v));
         asm volatile("mov.s32 %0, %0;" : "+r"(f));
         ea_dev.base = e;
         xa_dev.base = x;
+        ev_dev.base = v;
         fl_dev = f;
 #endif
     }
 
-    // edge buffer (side, slot), cell `off` relative to the thread's own cell (cursor `ea`)
-    PSN_FN static double EL(const PsnShF64& ea, int side, int slot, int off) { return ea.ld((side * 4 + slot) * NTP + off); }
-    PSN_FN static void ES(const PsnShF64& ea, int side, int slot, double v) { ea.st((side * 4 + slot) * NTP, v); }
+    // edge buffer (side, slot), cell (dy, dx) relative to the thread's own cell
+    template <class C>
+    PSN_FN static typename C::T EL(const C& c, int side, int slot, int dy, int dx) { return c.a.ld((side * 4 + slot) * C::PL + dy * C::P + dx); }
+    template <class C>
+    PSN_FN static void ES(const C& c, int side, int slot, typename C::T v) { c.a.st((side * 4 + slot) * C::PL, v); }
 
     // halo values of field v needed by a half sweep of colour `col` (slots of the other colour); ghost cells read as zero
-    PSN_FN static void load_halo(const PsnShF64& ea, int col, double (&hT)[4], double (&hB)[4], double (&hL)[4], double (&hR)[4]) {
+    template <class C, class T>
+    PSN_FN static void load_halo(const C& c, int col, T (&hT)[4], T (&hB)[4], T (&hL)[4], T (&hR)[4]) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            hT[k] = hB[k] = hL[k] = hR[k] = 0.0;
+            hT[k] = hB[k] = hL[k] = hR[k] = (T)0;
             if ((k & 1) == col) {           // (0,k) and (k,0) have colour col: they need the node above / left
-                hT[k] = EL(ea, BOT, k, -BP);
-                hL[k] = EL(ea, RIGHT, k, -1);
+                hT[k] = EL(c, BOT, k, -1, 0);
+                hL[k] = EL(c, RIGHT, k, 0, -1);
             } else {                        // (3,k) and (k,3) have colour col: they need the node below / right
-                hB[k] = EL(ea, TOP, k, BP);
-                hR[k] = EL(ea, LEFT, k, 1);
+                hB[k] = EL(c, TOP, k, 1, 0);
+                hR[k] = EL(c, LEFT, k, 0, 1);
             }
         }
     }
     // all 16 halo values (both colours)
-    PSN_FN static void load_halo_all(const PsnShF64& ea, double (&hT)[4], double (&hB)[4], double (&hL)[4], double (&hR)[4]) {
+    template <class C, class T>
+    PSN_FN static void load_halo_all(const C& c, T (&hT)[4], T (&hB)[4], T (&hL)[4], T (&hR)[4]) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            hT[k] = EL(ea, BOT, k, -BP);
-            hB[k] = EL(ea, TOP, k, BP);
-            hL[k] = EL(ea, RIGHT, k, -1);
-            hR[k] = EL(ea, LEFT, k, 1);
+            hT[k] = EL(c, BOT, k, -1, 0);
+            hB[k] = EL(c, TOP, k, 1, 0);
+            hL[k] = EL(c, RIGHT, k, 0, -1);
+            hR[k] = EL(c, LEFT, k, 0, 1);
         }
     }
     // publish the edge values of colour `col` (col < 0: both colours) of field v
-    PSN_FN static void publish(const PsnShF64& ea, const double (&v)[16], int col) {
+    template <class C, class T>
+    PSN_FN static void publish(const C& c, const T (&v)[16], int col) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (col < 0 || (k & 1) == col) {        // (0,k), (k,0) have colour k&1
-                ES(ea, TOP, k, v[k]);
-                ES(ea, LEFT, k, v[4 * k]);
+                ES(c, TOP, k, v[k]);
+                ES(c, LEFT, k, v[4 * k]);
             }
             if (col < 0 || (k & 1) != col) {        // (3,k), (k,3) have colour (k+1)&1
-                ES(ea, BOT, k, v[12 + k]);
-                ES(ea, RIGHT, k, v[4 * k + 3]);
+                ES(c, BOT, k, v[12 + k]);
+                ES(c, RIGHT, k, v[4 * k + 3]);
             }
         }
     }
+    // The float planes of the V-cycle alias the fp64 planes of the CG exchange, so each side overwrites the other's ghost ring:
+    // thread t re-zeroes its share of the ring cells of all 16 planes of layout C (called once per PCG iteration and layout,
+    // in a phase where nobody reads the planes; the next barrier orders it before the first halo load).
+    static constexpr int RING = 2 * (BX + 2) + 2 * BX;
+    template <class C, class Sh>
+    PSN_FN static void zero_ghosts(const Sh& planes, int t) {
+        for (int g = t; g < 16 * RING; g += NTPAD) {
+            const int pl = g / RING, c = g - pl * RING;
+            int cell;
+            if (c < BX + 2) cell = c;
+            else if (c < 2 * (BX + 2)) cell = (BX + 1) * C::P + (c - (BX + 2));
+            else cell = (1 + ((c - 2 * (BX + 2)) >> 1)) * C::P + (((c - 2 * (BX + 2)) & 1) ? BX + 1 : 0);
+            planes.st(pl * C::PL + cell, (typename C::T)0);
+        }
+    }
     // sum of the four neighbours of local node (a, c)
-    PSN_FN static double nbsum(const double (&v)[16], int a, int c, const double (&hT)[4], const double (&hB)[4],
-                               const double (&hL)[4], const double (&hR)[4]) {
-        const double up = (a > 0) ? v[4 * (a - 1) + c] : hT[c];
-        const double dn = (a < 3) ? v[4 * (a + 1) + c] : hB[c];
-        const double lf = (c > 0) ? v[4 * a + c - 1] : hL[a];
-        const double rt = (c < 3) ? v[4 * a + c + 1] : hR[a];
+    template <class T>
+    PSN_FN static T nbsum(const T (&v)[16], int a, int c, const T (&hT)[4], const T (&hB)[4], const T (&hL)[4], const T (&hR)[4]) {
+        const T up = (a > 0) ? v[4 * (a - 1) + c] : hT[c];
+        const T dn = (a < 3) ? v[4 * (a + 1) + c] : hB[c];
+        const T lf = (c > 0) ? v[4 * a + c - 1] : hL[a];
+        const T rt = (c < 3) ? v[4 * a + c + 1] : hR[a];
         return (up + dn) + (lf + rt);
     }
 
-    // one RB-GS half sweep on z with rhs r; ends with the edges of colour `col` published and a sync.  Every thread of the CTA
+    // one RB-GS half sweep on z with rhs bv; ends with the edges of colour `col` published and a sync.  Every thread of the CTA
     // takes part: the idle threads of the last warp work on zeros in their private cells.
     PSN_FN void half_sweep(int col, bool first) {
         PSN_BK_FOR(ctx, NTPAD) {
-            const PsnShF64 ea = PSN_BK_EA(*this, t_);
-            double (&zz)[16] = z[PSN_BK_TI];
-            const double (&rr)[16] = r[PSN_BK_TI];
-            double hT[4], hB[4], hL[4], hR[4];
-            if (!first) load_halo(ea, col, hT, hB, hL, hR);
-            double nv[16];
+            const CurV c = curv(t_);
+            VT (&zz)[16] = z[PSN_BK_TI];
+            const VT (&rr)[16] = bv[PSN_BK_TI];
+            VT hT[4], hB[4], hL[4], hR[4];
+            if (!first) load_halo(c, col, hT, hB, hL, hR);
+            VT nv[16];
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (((a + c) & 1) == col)
-                        nv[4 * a + c] = (rr[4 * a + c] + (first ? 0.0 : nbsum(zz, a, c, hT, hB, hL, hR))) * 0.25;
+                for (int cc = 0; cc < 4; ++cc)
+                    if (((a + cc) & 1) == col)
+                        nv[4 * a + cc] = (rr[4 * a + cc] + (first ? (VT)0 : nbsum(zz, a, cc, hT, hB, hL, hR))) * (VT)0.25;
 #pragma unroll
             for (int k = 0; k < 16; ++k)
                 if ((((k >> 2) + (k & 3)) & 1) == col) zz[k] = nv[k];
-            publish(ea, zz, col);
+            publish(c, zz, col);
         }
         ctx.sync();
     }
 
-    double rho[PSN_BK_TS][16];
+    VT rho[PSN_BK_TS][16];
 
     // ------------------------------------------------------------------ three register-blocked levels
     // Level 1 (2 BX)^2: each thread owns the 2x2 block under its fine block; level 2 (BX)^2: one node per
     // thread.  Same edge-buffer exchange (slots k < block size); levels >= 3 stay in the shared-memory code.
-    double z1[PSN_BK_TS][4], r1[PSN_BK_TS][4], z2[PSN_BK_TS][1], r2[PSN_BK_TS][1];
+    VT z1[PSN_BK_TS][4], r1[PSN_BK_TS][4], z2[PSN_BK_TS][1], r2[PSN_BK_TS][1];
 
     template <int BS>
-    PSN_FN static void load_halo_bs(const PsnShF64& ea, int col, double (&hT)[BS], double (&hB)[BS], double (&hL)[BS], double (&hR)[BS]) {
+    PSN_FN static void load_halo_bs(const CurV& c, int col, VT (&hT)[BS], VT (&hB)[BS], VT (&hL)[BS], VT (&hR)[BS]) {
 #pragma unroll
         for (int k = 0; k < BS; ++k) {
-            hT[k] = hB[k] = hL[k] = hR[k] = 0.0;
+            hT[k] = hB[k] = hL[k] = hR[k] = (VT)0;
             if (col < 0 || (k & 1) == col) {
-                hT[k] = EL(ea, BOT, k, -BP);
-                hL[k] = EL(ea, RIGHT, k, -1);
+                hT[k] = EL(c, BOT, k, -1, 0);
+                hL[k] = EL(c, RIGHT, k, 0, -1);
             }
             if (col < 0 || (k & 1) != col) {
-                hB[k] = EL(ea, TOP, k, BP);
-                hR[k] = EL(ea, LEFT, k, 1);
+                hB[k] = EL(c, TOP, k, 1, 0);
+                hR[k] = EL(c, LEFT, k, 0, 1);
             }
         }
     }
     template <int BS>
-    PSN_FN static void publish_bs(const PsnShF64& ea, const double (&v)[BS * BS], int col) {
+    PSN_FN static void publish_bs(const CurV& c, const VT (&v)[BS * BS], int col) {
 #pragma unroll
         for (int k = 0; k < BS; ++k) {
             if (col < 0 || (k & 1) == col) {
-                ES(ea, TOP, k, v[k]);
-                ES(ea, LEFT, k, v[BS * k]);
+                ES(c, TOP, k, v[k]);
+                ES(c, LEFT, k, v[BS * k]);
             }
             if (col < 0 || (k & 1) != col) {
-                ES(ea, BOT, k, v[BS * (BS - 1) + k]);
-                ES(ea, RIGHT, k, v[BS * k + BS - 1]);
+                ES(c, BOT, k, v[BS * (BS - 1) + k]);
+                ES(c, RIGHT, k, v[BS * k + BS - 1]);
             }
         }
     }
     template <int BS>
-    PSN_FN static double nbsum_bs(const double (&v)[BS * BS], int a, int c, const double (&hT)[BS], const double (&hB)[BS],
-                                  const double (&hL)[BS], const double (&hR)[BS]) {
-        const double up = (a > 0) ? v[BS * (a - 1) + c] : hT[c];
-        const double dn = (a < BS - 1) ? v[BS * (a + 1) + c] : hB[c];
-        const double lf = (c > 0) ? v[BS * a + c - 1] : hL[a];
-        const double rt = (c < BS - 1) ? v[BS * a + c + 1] : hR[a];
+    PSN_FN static VT nbsum_bs(const VT (&v)[BS * BS], int a, int c, const VT (&hT)[BS], const VT (&hB)[BS],
+                              const VT (&hL)[BS], const VT (&hR)[BS]) {
+        const VT up = (a > 0) ? v[BS * (a - 1) + c] : hT[c];
+        const VT dn = (a < BS - 1) ? v[BS * (a + 1) + c] : hB[c];
+        const VT lf = (c > 0) ? v[BS * a + c - 1] : hL[a];
+        const VT rt = (c < BS - 1) ? v[BS * a + c + 1] : hR[a];
         return (up + dn) + (lf + rt);
     }
     // Diagonal weights of the thread's block on a BS-blocked level: only the threads of the last thread row / column differ
     // from 4 (extra weight gam on the last grid row / column).  Kept as two per-thread values (last row, last column).
     struct Diag {
-        double gr, gc;   // gam if the thread's block touches the last grid row / column, else 0
+        VT gr, gc;   // gam if the thread's block touches the last grid row / column, else 0
     };
     PSN_FN static Diag diag_of(const PsnLevel& lv, int t) {
         const int bx = bx_of(t), by = by_of(t);
         Diag d;
-        d.gr = (t < NT && by == BX - 1) ? lv.gam : 0.0;
-        d.gc = (t < NT && bx == BX - 1) ? lv.gam : 0.0;
+        d.gr = (t < NT && by == BX - 1) ? (VT)lv.gam : (VT)0;
+        d.gc = (t < NT && bx == BX - 1) ? (VT)lv.gam : (VT)0;
         return d;
     }
     template <int BS>
-    PSN_FN static double diag_bs(const Diag& d, int a, int c) {
-        return 4.0 + ((a == BS - 1) ? d.gr : 0.0) + ((c == BS - 1) ? d.gc : 0.0);
+    PSN_FN static VT diag_bs(const Diag& d, int a, int c) {
+        return (VT)4 + ((a == BS - 1) ? d.gr : (VT)0) + ((c == BS - 1) ? d.gc : (VT)0);
     }
     // half sweep of a BS-blocked level held in zz / rr; publishes the updated colour.  rdv: reciprocal diagonals of the block
     template <int BS>
-    PSN_FN static void half_sweep_bs(const PsnShF64& ea, const double (&rdv)[BS * BS], double (&zz)[BS * BS], const double (&rr)[BS * BS],
-                                     int col, bool first) {
-        double hT[BS], hB[BS], hL[BS], hR[BS];
-        if (!first) load_halo_bs<BS>(ea, col, hT, hB, hL, hR);
-        double nv[BS * BS];
+    PSN_FN static void half_sweep_bs(const CurV& c, const VT (&rdv)[BS * BS], VT (&zz)[BS * BS], const VT (&rr)[BS * BS], int col, bool first) {
+        VT hT[BS], hB[BS], hL[BS], hR[BS];
+        if (!first) load_halo_bs<BS>(c, col, hT, hB, hL, hR);
+        VT nv[BS * BS];
 #pragma unroll
         for (int a = 0; a < BS; ++a)
 #pragma unroll
-            for (int c = 0; c < BS; ++c)
-                if (((a + c) & 1) == col)
-                    nv[BS * a + c] = (rr[BS * a + c] + (first ? 0.0 : nbsum_bs<BS>(zz, a, c, hT, hB, hL, hR))) * rdv[BS * a + c];
+            for (int cc = 0; cc < BS; ++cc)
+                if (((a + cc) & 1) == col)
+                    nv[BS * a + cc] = (rr[BS * a + cc] + (first ? (VT)0 : nbsum_bs<BS>(zz, a, cc, hT, hB, hL, hR))) * rdv[BS * a + cc];
 #pragma unroll
         for (int a = 0; a < BS; ++a)
 #pragma unroll
-            for (int c = 0; c < BS; ++c)
-                if (((a + c) & 1) == col) zz[BS * a + c] = nv[BS * a + c];
-        publish_bs<BS>(ea, zz, col);
+            for (int cc = 0; cc < BS; ++cc)
+                if (((a + cc) & 1) == col) zz[BS * a + cc] = nv[BS * a + cc];
+        publish_bs<BS>(c, zz, col);
     }
     // level 2: one node per thread, colour (bx + by) & 1; all four sides read the single slot TOP[0]
-    PSN_FN static double nb2(const PsnShF64& ea) {
-        return (EL(ea, TOP, 0, -BP) + EL(ea, TOP, 0, BP)) + (EL(ea, TOP, 0, -1) + EL(ea, TOP, 0, 1));
+    PSN_FN static VT nb2(const CurV& c) {
+        return (EL(c, TOP, 0, -1, 0) + EL(c, TOP, 0, 1, 0)) + (EL(c, TOP, 0, 0, -1) + EL(c, TOP, 0, 0, 1));
     }
-    PSN_FN void half_sweep_2(const double (&rd2)[PSN_BK_TS], int col, bool first) {
+    PSN_FN void half_sweep_2(const VT (&rd2)[PSN_BK_TS], int col, bool first) {
         PSN_BK_FOR(ctx, NTPAD) {
             const int fl = flags(t_);
             if ((fl & 1) && ((fl >> 1) & 1) == col) {
-                const PsnShF64 ea = PSN_BK_EA(*this, t_);
-                const double v = (r2[PSN_BK_TI][0] + (first ? 0.0 : nb2(ea))) * rd2[PSN_BK_TI];
+                const CurV c = curv(t_);
+                const VT v = (r2[PSN_BK_TI][0] + (first ? (VT)0 : nb2(c))) * rd2[PSN_BK_TI];
                 z2[PSN_BK_TI][0] = v;
-                ES(ea, TOP, 0, v);
+                ES(c, TOP, 0, v);
             }
         }
         ctx.sync();
     }
 
-    // z = M^{-1} r with levels 0, 1, 2 in registers (n = 4 BX, 2 BX, BX) and levels >= 3 in shared memory
+    // z = M^{-1} bv with levels 0, 1, 2 in registers (n = 4 BX, 2 BX, BX) and levels >= 3 in shared memory (fp64)
     PSN_FN void vcycle3(const PsnPlan& plan, double* pool) {
         const int nu = plan.nul[0], nu1 = plan.nul[1], nu2 = plan.nul[2];
         const PsnLevel& l1 = plan.lv[1];
@@ -345,7 +441,7 @@ struct PsnBlockSolver {
         double* u3 = pool + l3.size;
         double* pool4 = pool + 2 * l3.size;
         // per-thread diagonals of levels 1 and 2 (4 is the interior value; the last thread row / column carries gam)
-        double rd1[PSN_BK_TS][4], rd2[PSN_BK_TS];
+        VT rd1[PSN_BK_TS][4], rd2[PSN_BK_TS];
         Diag d1[PSN_BK_TS], d2[PSN_BK_TS];
         PSN_BK_FOR(ctx, NTPAD) {
             d1[PSN_BK_TI] = diag_of(l1, t_);
@@ -354,12 +450,12 @@ struct PsnBlockSolver {
             for (int a = 0; a < 2; ++a)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    const bool lr = a == 1 && d1[PSN_BK_TI].gr != 0.0, lc = c == 1 && d1[PSN_BK_TI].gc != 0.0;
-                    rd1[PSN_BK_TI][2 * a + c] = lr ? (lc ? l1.rd2 : l1.rd1) : (lc ? l1.rd1 : l1.rd0);
+                    const bool lr = a == 1 && d1[PSN_BK_TI].gr != (VT)0, lc = c == 1 && d1[PSN_BK_TI].gc != (VT)0;
+                    rd1[PSN_BK_TI][2 * a + c] = (VT)(lr ? (lc ? l1.rd2 : l1.rd1) : (lc ? l1.rd1 : l1.rd0));
                 }
             {
-                const bool lr = d2[PSN_BK_TI].gr != 0.0, lc = d2[PSN_BK_TI].gc != 0.0;
-                rd2[PSN_BK_TI] = lr ? (lc ? l2.rd2 : l2.rd1) : (lc ? l2.rd1 : l2.rd0);
+                const bool lr = d2[PSN_BK_TI].gr != (VT)0, lc = d2[PSN_BK_TI].gc != (VT)0;
+                rd2[PSN_BK_TI] = (VT)(lr ? (lc ? l2.rd2 : l2.rd1) : (lc ? l2.rd1 : l2.rd0));
             }
         }
         // ---------------- level 0 down
@@ -370,62 +466,62 @@ struct PsnBlockSolver {
             half_sweep(1, false);
         }
         PSN_BK_FOR(ctx, NTPAD) {
-            const PsnShF64 ea = PSN_BK_EA(*this, t_);
-            const double (&zz)[16] = z[PSN_BK_TI];
-            const double (&rr)[16] = r[PSN_BK_TI];
-            double (&pp)[16] = rho[PSN_BK_TI];
-            double hT[4], hB[4], hL[4], hR[4];
-            load_halo(ea, 0, hT, hB, hL, hR);
+            const CurV c = curv(t_);
+            const VT (&zz)[16] = z[PSN_BK_TI];
+            const VT (&rr)[16] = bv[PSN_BK_TI];
+            VT (&pp)[16] = rho[PSN_BK_TI];
+            VT hT[4], hB[4], hL[4], hR[4];
+            load_halo(c, 0, hT, hB, hL, hR);
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if (((a + c) & 1) == 0) pp[4 * a + c] = rr[4 * a + c] - (4.0 * zz[4 * a + c] - nbsum(zz, a, c, hT, hB, hL, hR));
+                for (int cc = 0; cc < 4; ++cc)
+                    if (((a + cc) & 1) == 0) pp[4 * a + cc] = rr[4 * a + cc] - ((VT)4 * zz[4 * a + cc] - nbsum(zz, a, cc, hT, hB, hL, hR));
             // (reads above: black slots; writes below: red slots of TOP / LEFT -> no barrier needed in between)
-            ES(ea, TOP, 0, pp[0]);
-            ES(ea, TOP, 2, pp[2]);
-            ES(ea, LEFT, 0, pp[0]);
-            ES(ea, LEFT, 2, pp[8]);
+            ES(c, TOP, 0, pp[0]);
+            ES(c, TOP, 2, pp[2]);
+            ES(c, LEFT, 0, pp[0]);
+            ES(c, LEFT, 2, pp[8]);
         }
         ctx.sync();
         PSN_BK_FOR(ctx, NTPAD) {
-            const PsnShF64 ea = PSN_BK_EA(*this, t_);
-            const double (&pp)[16] = rho[PSN_BK_TI];
-            const double r04 = EL(ea, LEFT, 0, 1), r24 = EL(ea, LEFT, 2, 1);
-            const double r40 = EL(ea, TOP, 0, BP), r42 = EL(ea, TOP, 2, BP);
-            const double r44 = EL(ea, TOP, 0, BP + 1);
-            double (&q)[4] = r1[PSN_BK_TI];
-            q[0] = pp[5] + 0.25 * ((pp[0] + pp[2]) + (pp[8] + pp[10]));
-            q[1] = pp[7] + 0.25 * ((pp[2] + r04) + (pp[10] + r24));
-            q[2] = pp[13] + 0.25 * ((pp[8] + pp[10]) + (r40 + r42));
-            q[3] = pp[15] + 0.25 * ((pp[10] + r24) + (r42 + r44));
+            const CurV c = curv(t_);
+            const VT (&pp)[16] = rho[PSN_BK_TI];
+            const VT r04 = EL(c, LEFT, 0, 0, 1), r24 = EL(c, LEFT, 2, 0, 1);
+            const VT r40 = EL(c, TOP, 0, 1, 0), r42 = EL(c, TOP, 2, 1, 0);
+            const VT r44 = EL(c, TOP, 0, 1, 1);
+            VT (&qq)[4] = r1[PSN_BK_TI];
+            qq[0] = pp[5] + (VT)0.25 * ((pp[0] + pp[2]) + (pp[8] + pp[10]));
+            qq[1] = pp[7] + (VT)0.25 * ((pp[2] + r04) + (pp[10] + r24));
+            qq[2] = pp[13] + (VT)0.25 * ((pp[8] + pp[10]) + (r40 + r42));
+            qq[3] = pp[15] + (VT)0.25 * ((pp[10] + r24) + (r42 + r44));
         }
         ctx.sync();
         // ---------------- level 1 down (2x2 per thread)
         for (int s = 0; s < nu1; ++s) {
-            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, s == 0); }
+            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(curv(t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, s == 0); }
             ctx.sync();
-            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
+            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(curv(t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
             ctx.sync();
         }
         PSN_BK_FOR(ctx, NTPAD) {
-            const PsnShF64 ea = PSN_BK_EA(*this, t_);
-            const double (&zz)[4] = z1[PSN_BK_TI];
-            const double (&rr)[4] = r1[PSN_BK_TI];
-            double hT[2], hB[2], hL[2], hR[2];
-            load_halo_bs<2>(ea, 0, hT, hB, hL, hR);
-            const double rho00 = rr[0] - (diag_bs<2>(d1[PSN_BK_TI], 0, 0) * zz[0] - nbsum_bs<2>(zz, 0, 0, hT, hB, hL, hR));
-            const double rho11 = rr[3] - (diag_bs<2>(d1[PSN_BK_TI], 1, 1) * zz[3] - nbsum_bs<2>(zz, 1, 1, hT, hB, hL, hR));
+            const CurV c = curv(t_);
+            const VT (&zz)[4] = z1[PSN_BK_TI];
+            const VT (&rr)[4] = r1[PSN_BK_TI];
+            VT hT[2], hB[2], hL[2], hR[2];
+            load_halo_bs<2>(c, 0, hT, hB, hL, hR);
+            const VT rho00 = rr[0] - (diag_bs<2>(d1[PSN_BK_TI], 0, 0) * zz[0] - nbsum_bs<2>(zz, 0, 0, hT, hB, hL, hR));
+            const VT rho11 = rr[3] - (diag_bs<2>(d1[PSN_BK_TI], 1, 1) * zz[3] - nbsum_bs<2>(zz, 1, 1, hT, hB, hL, hR));
             rho[PSN_BK_TI][0] = rho00;
             rho[PSN_BK_TI][1] = rho11;
-            ES(ea, TOP, 0, rho00);   // red slot of TOP: not read by this phase
+            ES(c, TOP, 0, rho00);   // red slot of TOP: not read by this phase
         }
         ctx.sync();
         PSN_BK_FOR(ctx, NTPAD) {
-            const PsnShF64 ea = PSN_BK_EA(*this, t_);
-            const double c02 = EL(ea, TOP, 0, 1), c20 = EL(ea, TOP, 0, BP);
-            const double c22 = EL(ea, TOP, 0, BP + 1);
-            r2[PSN_BK_TI][0] = rho[PSN_BK_TI][1] + 0.25 * ((rho[PSN_BK_TI][0] + c02) + (c20 + c22));
+            const CurV c = curv(t_);
+            const VT c02 = EL(c, TOP, 0, 0, 1), c20 = EL(c, TOP, 0, 1, 0);
+            const VT c22 = EL(c, TOP, 0, 1, 1);
+            r2[PSN_BK_TI][0] = rho[PSN_BK_TI][1] + (VT)0.25 * ((rho[PSN_BK_TI][0] + c02) + (c20 + c22));
         }
         ctx.sync();
         // ---------------- level 2 down (one node per thread)
@@ -434,31 +530,31 @@ struct PsnBlockSolver {
             half_sweep_2(rd2, 1, false);
         }
         PSN_BK_FOR(ctx, NTPAD) {   // residual on red nodes -> BOT[0] (TOP[0] is being read by the neighbours)
-            const PsnShF64 ea = PSN_BK_EA(*this, t_);
+            const CurV c = curv(t_);
             const int fl = flags(t_);
-            double rh = 0.0;
-            if ((fl & 3) == 1) rh = r2[PSN_BK_TI][0] - (diag_bs<1>(d2[PSN_BK_TI], 0, 0) * z2[PSN_BK_TI][0] - nb2(ea));
+            VT rh = (VT)0;
+            if ((fl & 3) == 1) rh = r2[PSN_BK_TI][0] - (diag_bs<1>(d2[PSN_BK_TI], 0, 0) * z2[PSN_BK_TI][0] - nb2(c));
             rho[PSN_BK_TI][0] = rh;
-            ES(ea, BOT, 0, rh);
+            ES(c, BOT, 0, rh);
         }
         ctx.sync();
         PSN_BK_FOR(ctx, NT) {
             if (flags(t_) & 4) {   // bx, by both odd: centre of coarse node ((by-1)/2, (bx-1)/2) of level 3
-                const PsnShF64 ea = PSN_BK_EA(*this, t_);
+                const CurV c = curv(t_);
                 const int bx = bx_of(t_), by = by_of(t_);
-                const double c00 = EL(ea, BOT, 0, -BP - 1), c02 = EL(ea, BOT, 0, -BP + 1);
-                const double c20 = EL(ea, BOT, 0, BP - 1), c22 = EL(ea, BOT, 0, BP + 1);
-                b3[(((by - 1) >> 1) + 1) * l3.pitch + ((bx - 1) >> 1) + 1] = rho[PSN_BK_TI][0] + 0.25 * ((c00 + c02) + (c20 + c22));
+                const VT c00 = EL(c, BOT, 0, -1, -1), c02 = EL(c, BOT, 0, -1, 1);
+                const VT c20 = EL(c, BOT, 0, 1, -1), c22 = EL(c, BOT, 0, 1, 1);
+                b3[(((by - 1) >> 1) + 1) * l3.pitch + ((bx - 1) >> 1) + 1] = (double)(rho[PSN_BK_TI][0] + (VT)0.25 * ((c00 + c02) + (c20 + c22)));
             }
         }
         ctx.sync();
-        // ---------------- levels >= 3 in shared memory (all warps; running them on a single warp with
+        // ---------------- levels >= 3 in shared memory, fp64 (all warps; running them on a single warp with
         // __syncwarp instead of CTA barriers was measured 7 % slower)
         psn_vcycle_smem(ctx, plan, 3, b3, u3, pool4, inv_s);
         // ---------------- level 2 up
         PSN_BK_FOR(ctx, NT) {
             if ((flags(t_) & 3) == 1) {   // real thread, (bx + by) even
-                const PsnShF64 ea = PSN_BK_EA(*this, t_);
+                const CurV c = curv(t_);
                 const int bx = bx_of(t_), by = by_of(t_);
                 const int P3 = l3.pitch;
                 double add;
@@ -468,8 +564,8 @@ struct PsnBlockSolver {
                     const double* e = u3 + ((by >> 1) + 1) * P3 + (bx >> 1) + 1;
                     add = 0.25 * ((e[-P3 - 1] + e[-P3]) + (e[-1] + e[0]));
                 }
-                z2[PSN_BK_TI][0] += add;
-                ES(ea, TOP, 0, z2[PSN_BK_TI][0]);
+                z2[PSN_BK_TI][0] += (VT)add;
+                ES(c, TOP, 0, z2[PSN_BK_TI][0]);
             }
         }
         ctx.sync();
@@ -479,42 +575,42 @@ struct PsnBlockSolver {
         }
         // ---------------- level 1 up: corrections from z2 (TOP[0] holds every thread's current z2)
         PSN_BK_FOR(ctx, NTPAD) {
-            const PsnShF64 ea = PSN_BK_EA(*this, t_);
-            const double e00 = z2[PSN_BK_TI][0];
-            const double em0 = EL(ea, TOP, 0, -BP), e0m = EL(ea, TOP, 0, -1);
-            const double emm = EL(ea, TOP, 0, -BP - 1);
+            const CurV c = curv(t_);
+            const VT e00 = z2[PSN_BK_TI][0];
+            const VT em0 = EL(c, TOP, 0, -1, 0), e0m = EL(c, TOP, 0, 0, -1);
+            const VT emm = EL(c, TOP, 0, -1, -1);
             z1[PSN_BK_TI][3] += e00;
-            z1[PSN_BK_TI][0] += 0.25 * ((emm + em0) + (e0m + e00));
+            z1[PSN_BK_TI][0] += (VT)0.25 * ((emm + em0) + (e0m + e00));
         }
         ctx.sync();   // TOP[0] is about to be overwritten by the edges of z1
-        PSN_BK_FOR(ctx, NTPAD) { publish_bs<2>(PSN_BK_EA(*this, t_), z1[PSN_BK_TI], 0); }
+        PSN_BK_FOR(ctx, NTPAD) { publish_bs<2>(curv(t_), z1[PSN_BK_TI], 0); }
         ctx.sync();
         for (int s = 0; s < nu1; ++s) {
-            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
+            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(curv(t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
             ctx.sync();
-            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(PSN_BK_EA(*this, t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, false); }
+            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(curv(t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, false); }
             ctx.sync();
         }
         // ---------------- level 0 up: corrections from z1 (every edge of z1 is current in the buffers)
         PSN_BK_FOR(ctx, NTPAD) {
-            const PsnShF64 ea = PSN_BK_EA(*this, t_);
-            double (&zz)[16] = z[PSN_BK_TI];
-            const double (&ee)[4] = z1[PSN_BK_TI];
-            const double e00 = ee[0], e01 = ee[1], e10 = ee[2], e11 = ee[3];
-            const double em0 = EL(ea, BOT, 0, -BP), em1 = EL(ea, BOT, 1, -BP);
-            const double e0m = EL(ea, RIGHT, 0, -1), e1m = EL(ea, RIGHT, 1, -1);
-            const double emm = EL(ea, BOT, 1, -BP - 1);
+            const CurV c = curv(t_);
+            VT (&zz)[16] = z[PSN_BK_TI];
+            const VT (&ee)[4] = z1[PSN_BK_TI];
+            const VT e00 = ee[0], e01 = ee[1], e10 = ee[2], e11 = ee[3];
+            const VT em0 = EL(c, BOT, 0, -1, 0), em1 = EL(c, BOT, 1, -1, 0);
+            const VT e0m = EL(c, RIGHT, 0, 0, -1), e1m = EL(c, RIGHT, 1, 0, -1);
+            const VT emm = EL(c, BOT, 1, -1, -1);
             zz[5] += e00;
             zz[7] += e01;
             zz[13] += e10;
             zz[15] += e11;
-            zz[0] += 0.25 * ((emm + em0) + (e0m + e00));
-            zz[2] += 0.25 * ((em0 + em1) + (e00 + e01));
-            zz[8] += 0.25 * ((e0m + e00) + (e1m + e10));
-            zz[10] += 0.25 * ((e00 + e01) + (e10 + e11));
+            zz[0] += (VT)0.25 * ((emm + em0) + (e0m + e00));
+            zz[2] += (VT)0.25 * ((em0 + em1) + (e00 + e01));
+            zz[8] += (VT)0.25 * ((e0m + e00) + (e1m + e10));
+            zz[10] += (VT)0.25 * ((e00 + e01) + (e10 + e11));
         }
         ctx.sync();   // the z1 edges have been read; the buffers now take the red edges of z
-        PSN_BK_FOR(ctx, NTPAD) { publish(PSN_BK_EA(*this, t_), z[PSN_BK_TI], 0); }
+        PSN_BK_FOR(ctx, NTPAD) { publish(curv(t_), z[PSN_BK_TI], 0); }
         ctx.sync();
         for (int s = 0; s < nu; ++s) {
             half_sweep(1, false);
@@ -580,8 +676,10 @@ template <int BX, class Ctx>
 PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveArgs& a, long long b, double* smem,
                                  const double* inv_s = nullptr) {
     typedef PsnBlockGeom<BX> G;
+    typedef PsnBlockSolver<BX, Ctx> SV;
+    typedef typename SV::VT VT;
     constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
-    PsnBlockSolver<BX, Ctx> S(ctx, smem);
+    SV S(ctx, smem);
     S.inv_s = inv_s;
     double* pool = smem + G::XS + G::ES;          // levels >= 3 (levels 1 and 2 live in registers)
     {
@@ -591,10 +689,16 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
         for (int idx = ctx.tid; idx < zn; idx += ctx.nthreads) z0[idx] = 0.0;
     }
     double acc[PSN_BK_TS];
+#if defined(__CUDACC__)
+    const PsnShF64 xa_ = S.xa_dev;
+#define PSN_BK_XA2(t) xa_
+#else
+#define PSN_BK_XA2(t) S.xs.at(t)
+#endif
 
     // ---- prologue: r = bt, x = 0
     PSN_BK_FOR(ctx, NTPAD) {
-        const PsnShF64 xa = PSN_BK_XA(S, t_);
+        const PsnShF64 xa = PSN_BK_XA2(t_);
         double bt16[16];
         if (t_ < NT) {
             S.rhs16(a, b, t_, plan.h2, bt16);
@@ -608,13 +712,15 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
             const double v = bt16[k];
             S.r[PSN_BK_TI][k] = v;
             S.p[PSN_BK_TI][k] = 0.0;
-            S.z[PSN_BK_TI][k] = 0.0;
+            S.q[PSN_BK_TI][k] = 0.0;
+            S.z[PSN_BK_TI][k] = (VT)0;
+            S.bv[PSN_BK_TI][k] = (VT)0;
             xa.st(k * NTPAD, 0.0);
             s += v * v;
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) S.z1[PSN_BK_TI][k] = S.r1[PSN_BK_TI][k] = 0.0;
-        S.z2[PSN_BK_TI][0] = S.r2[PSN_BK_TI][0] = 0.0;
+        for (int k = 0; k < 4; ++k) S.z1[PSN_BK_TI][k] = S.r1[PSN_BK_TI][k] = (VT)0;
+        S.z2[PSN_BK_TI][0] = S.r2[PSN_BK_TI][0] = (VT)0;
         acc[PSN_BK_TI] = s;
     }
     ctx.sync();
@@ -629,39 +735,49 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
         rr_final = 0.0;
     } else {
         for (;;) {
+            // right-hand side of the V-cycle: the residual, scaled by a power of two near 1 / ||r|| when the cycle runs in float
+            // (exact in fp64; undone in <r,z> and in the direction update), so that the preconditioner does not depend on the
+            // magnitude of the data
+            const double vs = (sizeof(VT) == 4) ? psn_vscale(rr_final) : 1.0;
+            const double vinv = 1.0 / vs;
+            PSN_BK_FOR(ctx, NTPAD) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) S.bv[PSN_BK_TI][k] = (VT)(S.r[PSN_BK_TI][k] * vs);
+            }
             S.vcycle3(plan, pool);
             PSN_BK_FOR(ctx, NTPAD) {
                 double s = 0.0;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) s += S.r[PSN_BK_TI][k] * S.z[PSN_BK_TI][k];
-                acc[PSN_BK_TI] = s;
+                for (int k = 0; k < 16; ++k) s += S.r[PSN_BK_TI][k] * (double)S.z[PSN_BK_TI][k];
+                acc[PSN_BK_TI] = (S.flags(t_) & 1) ? s : 0.0;   // (float cycle: the idle lanes may hold garbage from aliased cells)
+                if (PSN_BLOCK_VF32) SV::template zero_ghosts<typename SV::CurD>(S.edge, t_);   // the V-cycle is past its last access
             }
-            const double rz = S.tsum(acc);      // (device: block_sum syncs, so every thread is past its last edge read)
+            const double rz = S.tsum(acc) * vinv;   // (device: block_sum syncs, so every thread is past its last edge read)
             const double beta = restart ? 0.0 : rz / rz_old;
             restart = false;
             rz_old = rz;
             // p = z + beta p, publish every edge of p
             PSN_BK_FOR(ctx, NTPAD) {
 #pragma unroll
-                for (int k = 0; k < 16; ++k) S.p[PSN_BK_TI][k] = S.z[PSN_BK_TI][k] + beta * S.p[PSN_BK_TI][k];
-                S.publish(PSN_BK_EA(S, t_), S.p[PSN_BK_TI], -1);
+                for (int k = 0; k < 16; ++k) S.p[PSN_BK_TI][k] = (double)S.z[PSN_BK_TI][k] * vinv + beta * S.p[PSN_BK_TI][k];
+                SV::publish(S.curd(t_), S.p[PSN_BK_TI], -1);
             }
             ctx.sync();
-            // q = At p (kept in z), <p, q>
+            // q = At p, <p, q>
             PSN_BK_FOR(ctx, NTPAD) {
                 double hT[4], hB[4], hL[4], hR[4];
-                S.load_halo_all(PSN_BK_EA(S, t_), hT, hB, hL, hR);
+                SV::load_halo_all(S.curd(t_), hT, hB, hL, hR);
                 double s = 0.0;
 #pragma unroll
                 for (int aa = 0; aa < 4; ++aa)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const double pc = S.p[PSN_BK_TI][4 * aa + c];
-                        const double q = 4.0 * pc - PsnBlockSolver<BX, Ctx>::nbsum(S.p[PSN_BK_TI], aa, c, hT, hB, hL, hR);
-                        S.z[PSN_BK_TI][4 * aa + c] = q;
-                        s += pc * q;
+                        const double qv = 4.0 * pc - SV::nbsum(S.p[PSN_BK_TI], aa, c, hT, hB, hL, hR);
+                        S.q[PSN_BK_TI][4 * aa + c] = qv;
+                        s += pc * qv;
                     }
-                acc[PSN_BK_TI] = s;
+                acc[PSN_BK_TI] = (S.flags(t_) & 1) ? s : 0.0;
             }
             const double pq = S.tsum(acc);
             if (!(pq > 0.0)) {
@@ -670,32 +786,33 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
             }
             const double alpha = rz / pq;
             PSN_BK_FOR(ctx, NTPAD) {
-                const PsnShF64 xa = PSN_BK_XA(S, t_);
+                const PsnShF64 xa = PSN_BK_XA2(t_);
                 double s = 0.0;
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     xa.add(k * NTPAD, alpha * S.p[PSN_BK_TI][k]);
-                    const double rv = S.r[PSN_BK_TI][k] - alpha * S.z[PSN_BK_TI][k];
+                    const double rv = S.r[PSN_BK_TI][k] - alpha * S.q[PSN_BK_TI][k];
                     S.r[PSN_BK_TI][k] = rv;
                     s += rv * rv;
                 }
-                acc[PSN_BK_TI] = s;
+                acc[PSN_BK_TI] = (S.flags(t_) & 1) ? s : 0.0;
+                if (PSN_BLOCK_VF32) SV::template zero_ghosts<typename SV::CurV>(S.edgev, t_);   // every halo of p has been read
             }
             const double rr = S.tsum(acc);
             rr_final = rr;
             ++it;
             if (rr <= tol2 || it >= a.max_iter) {
-                // true residual r = bt - At x: x block into z, publish, stencil
+                // true residual r = bt - At x: x block into q, publish, stencil
                 PSN_BK_FOR(ctx, NTPAD) {
-                    const PsnShF64 xa = PSN_BK_XA(S, t_);
+                    const PsnShF64 xa = PSN_BK_XA2(t_);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) S.z[PSN_BK_TI][k] = xa.ld(k * NTPAD);
-                    S.publish(PSN_BK_EA(S, t_), S.z[PSN_BK_TI], -1);
+                    for (int k = 0; k < 16; ++k) S.q[PSN_BK_TI][k] = xa.ld(k * NTPAD);
+                    SV::publish(S.curd(t_), S.q[PSN_BK_TI], -1);
                 }
                 ctx.sync();
                 PSN_BK_FOR(ctx, NTPAD) {
                     double hT[4], hB[4], hL[4], hR[4];
-                    S.load_halo_all(PSN_BK_EA(S, t_), hT, hB, hL, hR);
+                    SV::load_halo_all(S.curd(t_), hT, hB, hL, hR);
                     double s = 0.0;
                     double bt16[16];
                     if (t_ < NT) {
@@ -709,12 +826,11 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const double bt = bt16[4 * aa + c];
-                            const double rv = bt - (4.0 * S.z[PSN_BK_TI][4 * aa + c] -
-                                                    PsnBlockSolver<BX, Ctx>::nbsum(S.z[PSN_BK_TI], aa, c, hT, hB, hL, hR));
+                            const double rv = bt - (4.0 * S.q[PSN_BK_TI][4 * aa + c] - SV::nbsum(S.q[PSN_BK_TI], aa, c, hT, hB, hL, hR));
                             S.r[PSN_BK_TI][4 * aa + c] = rv;
                             s += rv * rv;
                         }
-                    acc[PSN_BK_TI] = s;
+                    acc[PSN_BK_TI] = (S.flags(t_) & 1) ? s : 0.0;
                 }
                 const double rt = S.tsum(acc);
                 rr_final = rt;
@@ -724,6 +840,11 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
                 prev_true = rt;
                 ++nrestart;
                 restart = true;
+                // the fp64 planes have just carried x: the float ghost ring must read as zero again (tsum above was the barrier
+                // behind the last halo load of x; the first half sweep of the V-cycle has one before its first float load)
+                if (PSN_BLOCK_VF32) {
+                    PSN_BK_FOR(ctx, NTPAD) { SV::template zero_ghosts<typename SV::CurV>(S.edgev, t_); }
+                }
             }
         }
     }
@@ -731,8 +852,8 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
     // ---- epilogue: u and / or the fused window + downsample outputs
     PSN_BK_FOR(ctx, NT) {
         if (t_ < NT) {
-            const PsnShF64 xa = PSN_BK_XA(S, t_);
-            const int bx = PsnBlockSolver<BX, Ctx>::bx_of(t_), by = PsnBlockSolver<BX, Ctx>::by_of(t_);
+            const PsnShF64 xa = PSN_BK_XA2(t_);
+            const int bx = SV::bx_of(t_), by = SV::by_of(t_);
             double xv[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) xv[k] = xa.ld(k * NTPAD);
@@ -770,6 +891,7 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
             }
         }
     }
+#undef PSN_BK_XA2
     if (ctx.tid == 0) {
         if (a.iters) a.iters[b] = it;
         if (a.relres) a.relres[b] = (bb > 0.0) ? sqrt(rr_final / bb) : 0.0;
