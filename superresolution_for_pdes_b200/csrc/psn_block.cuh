@@ -35,8 +35,15 @@
 #define PSN_BK_TI 0
 #define PSN_BK_XA(S, t) ((S).xa_dev)
 #else
+// Host emulation: a phase is a loop over the virtual threads.  psn_bk_reverse_order() = 1 walks them backwards: a phase in which
+// one thread reads what another writes (a missing barrier) then gives different bits, which tests/test_hostemu_kernels.py checks.
+inline int& psn_bk_reverse_order() {
+    static int rev = 0;
+    return rev;
+}
 #define PSN_BK_TS NTPAD
-#define PSN_BK_FOR(ctx, NT) for (int t_ = 0; t_ < (NT); ++t_)
+#define PSN_BK_FOR(ctx, NT) \
+    for (int i_ = 0, t_ = psn_bk_reverse_order() ? (NT) - 1 : 0; i_ < (NT); ++i_, t_ += psn_bk_reverse_order() ? -1 : 1)
 #define PSN_BK_TI t_
 #define PSN_BK_XA(S, t) ((S).xs.at(t))
 #endif
@@ -238,11 +245,27 @@ struct PsnBlockSolver {
 #endif
     }
 
-    // edge buffer (side, slot), cell (dy, dx) relative to the thread's own cell
-    template <class C>
-    PSN_FN static typename C::T EL(const C& c, int side, int slot, int dy, int dx) { return c.a.ld((side * 4 + slot) * C::PL + dy * C::P + dx); }
-    template <class C>
-    PSN_FN static void ES(const C& c, int side, int slot, typename C::T v) { c.a.st((side * 4 + slot) * C::PL, v); }
+    // Planes.  Level 0 (and the fp64 exchange of the CG part) uses plane 4 side + slot.  With the float V-cycle there is room
+    // for 22 float planes in the space of the 16 fp64 ones, and levels 1 and 2 get planes that the neighbouring level does not
+    // touch at the moment of a transfer, so that "read the other level's edges" and "publish my own" share one barrier interval:
+    //   level 1 (slots 0, 1): TOP -> 16 + slot, LEFT -> 18 + slot, BOT / RIGHT -> slots 0 and 2 of the level-0 side.  Going down,
+    //     the restriction reads the level-0 planes TOP / LEFT 0, 2 while the first level-1 half sweep writes 16, 18, BOT 2, RIGHT 2;
+    //     going up, the level-0 correction reads BOT / RIGHT 0, 2 while the red edges of z go to TOP / LEFT 0, 2 and BOT / RIGHT 1, 3.
+    //   level 2: iterate -> 20, residual -> 21.
+    static constexpr bool SPLIT = PSN_BLOCK_VF32 != 0;
+    static constexpr int NPLV = SPLIT ? 22 : 16;
+    static_assert((long long)NPLV * NTPV * (long long)sizeof(VT) <= 16ll * G::NTP * 8, "V-cycle planes must fit into the fp64 planes");
+    template <int LV>
+    PSN_FN static constexpr int plane(int side, int slot) {
+        return (!SPLIT || LV == 0) ? side * 4 + slot
+               : (LV == 1)         ? (side == TOP ? 16 + slot : side == LEFT ? 18 + slot : side * 4 + 2 * slot)
+                                   : (side == TOP ? 20 : 21);
+    }
+    // edge buffer (side, slot) of level LV, cell (dy, dx) relative to the thread's own cell
+    template <int LV = 0, class C>
+    PSN_FN static typename C::T EL(const C& c, int side, int slot, int dy, int dx) { return c.a.ld(plane<LV>(side, slot) * C::PL + dy * C::P + dx); }
+    template <int LV = 0, class C>
+    PSN_FN static void ES(const C& c, int side, int slot, typename C::T v) { c.a.st(plane<LV>(side, slot) * C::PL, v); }
 
     // halo values of field v needed by a half sweep of colour `col` (slots of the other colour); ghost cells read as zero
     template <class C, class T>
@@ -286,12 +309,12 @@ struct PsnBlockSolver {
         }
     }
     // The float planes of the V-cycle alias the fp64 planes of the CG exchange, so each side overwrites the other's ghost ring:
-    // thread t re-zeroes its share of the ring cells of all 16 planes of layout C (called once per PCG iteration and layout,
+    // thread t re-zeroes its share of the ring cells of all planes of layout C (called once per PCG iteration and layout,
     // in a phase where nobody reads the planes; the next barrier orders it before the first halo load).
     static constexpr int RING = 2 * (BX + 2) + 2 * BX;
     template <class C, class Sh>
-    PSN_FN static void zero_ghosts(const Sh& planes, int t) {
-        for (int g = t; g < 16 * RING; g += NTPAD) {
+    PSN_FN static void zero_ghosts(const Sh& planes, int t, int nplanes) {
+        for (int g = t; g < nplanes * RING; g += NTPAD) {
             const int pl = g / RING, c = g - pl * RING;
             int cell;
             if (c < BX + 2) cell = c;
@@ -312,7 +335,8 @@ struct PsnBlockSolver {
 
     // one RB-GS half sweep on z with rhs bv; ends with the edges of colour `col` published and a sync.  Every thread of the CTA
     // takes part: the idle threads of the last warp work on zeros in their private cells.
-    PSN_FN void half_sweep(int col, bool first) {
+    // (last: the final half sweep of the V-cycle -- nobody reads z's edges after it, and the next phase has a barrier of its own)
+    PSN_FN void half_sweep(int col, bool first, bool last = false) {
         PSN_BK_FOR(ctx, NTPAD) {
             const CurV c = curv(t_);
             VT (&zz)[16] = z[PSN_BK_TI];
@@ -329,9 +353,9 @@ struct PsnBlockSolver {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
                 if ((((k >> 2) + (k & 3)) & 1) == col) zz[k] = nv[k];
-            publish(c, zz, col);
+            if (!last) publish(c, zz, col);
         }
-        ctx.sync();
+        if (!last) ctx.sync();
     }
 
     VT rho[PSN_BK_TS][16];
@@ -341,18 +365,19 @@ struct PsnBlockSolver {
     // thread.  Same edge-buffer exchange (slots k < block size); levels >= 3 stay in the shared-memory code.
     VT z1[PSN_BK_TS][4], r1[PSN_BK_TS][4], z2[PSN_BK_TS][1], r2[PSN_BK_TS][1];
 
+    // (the BS-blocked helpers serve level 1: BS = 2)
     template <int BS>
     PSN_FN static void load_halo_bs(const CurV& c, int col, VT (&hT)[BS], VT (&hB)[BS], VT (&hL)[BS], VT (&hR)[BS]) {
 #pragma unroll
         for (int k = 0; k < BS; ++k) {
             hT[k] = hB[k] = hL[k] = hR[k] = (VT)0;
             if (col < 0 || (k & 1) == col) {
-                hT[k] = EL(c, BOT, k, -1, 0);
-                hL[k] = EL(c, RIGHT, k, 0, -1);
+                hT[k] = EL<1>(c, BOT, k, -1, 0);
+                hL[k] = EL<1>(c, RIGHT, k, 0, -1);
             }
             if (col < 0 || (k & 1) != col) {
-                hB[k] = EL(c, TOP, k, 1, 0);
-                hR[k] = EL(c, LEFT, k, 0, 1);
+                hB[k] = EL<1>(c, TOP, k, 1, 0);
+                hR[k] = EL<1>(c, LEFT, k, 0, 1);
             }
         }
     }
@@ -361,12 +386,12 @@ struct PsnBlockSolver {
 #pragma unroll
         for (int k = 0; k < BS; ++k) {
             if (col < 0 || (k & 1) == col) {
-                ES(c, TOP, k, v[k]);
-                ES(c, LEFT, k, v[BS * k]);
+                ES<1>(c, TOP, k, v[k]);
+                ES<1>(c, LEFT, k, v[BS * k]);
             }
             if (col < 0 || (k & 1) != col) {
-                ES(c, BOT, k, v[BS * (BS - 1) + k]);
-                ES(c, RIGHT, k, v[BS * k + BS - 1]);
+                ES<1>(c, BOT, k, v[BS * (BS - 1) + k]);
+                ES<1>(c, RIGHT, k, v[BS * k + BS - 1]);
             }
         }
     }
@@ -416,18 +441,17 @@ struct PsnBlockSolver {
     }
     // level 2: one node per thread, colour (bx + by) & 1; all four sides read the single slot TOP[0]
     PSN_FN static VT nb2(const CurV& c) {
-        return (EL(c, TOP, 0, -1, 0) + EL(c, TOP, 0, 1, 0)) + (EL(c, TOP, 0, 0, -1) + EL(c, TOP, 0, 0, 1));
+        return (EL<2>(c, TOP, 0, -1, 0) + EL<2>(c, TOP, 0, 1, 0)) + (EL<2>(c, TOP, 0, 0, -1) + EL<2>(c, TOP, 0, 0, 1));
+    }
+    PSN_FN static void half_sweep_2_body(const CurV& c, int fl, VT rd, VT& zz, VT rr, int col, bool first) {
+        if ((fl & 1) && ((fl >> 1) & 1) == col) {
+            const VT v = (rr + (first ? (VT)0 : nb2(c))) * rd;
+            zz = v;
+            ES<2>(c, TOP, 0, v);
+        }
     }
     PSN_FN void half_sweep_2(const VT (&rd2)[PSN_BK_TS], int col, bool first) {
-        PSN_BK_FOR(ctx, NTPAD) {
-            const int fl = flags(t_);
-            if ((fl & 1) && ((fl >> 1) & 1) == col) {
-                const CurV c = curv(t_);
-                const VT v = (r2[PSN_BK_TI][0] + (first ? (VT)0 : nb2(c))) * rd2[PSN_BK_TI];
-                z2[PSN_BK_TI][0] = v;
-                ES(c, TOP, 0, v);
-            }
-        }
+        PSN_BK_FOR(ctx, NTPAD) { half_sweep_2_body(curv(t_), flags(t_), rd2[PSN_BK_TI], z2[PSN_BK_TI][0], r2[PSN_BK_TI][0], col, first); }
         ctx.sync();
     }
 
@@ -495,12 +519,16 @@ struct PsnBlockSolver {
             qq[1] = pp[7] + (VT)0.25 * ((pp[2] + r04) + (pp[10] + r24));
             qq[2] = pp[13] + (VT)0.25 * ((pp[8] + pp[10]) + (r40 + r42));
             qq[3] = pp[15] + (VT)0.25 * ((pp[10] + r24) + (r42 + r44));
+            // own planes: the first half sweep of level 1 (no halo reads) writes none of the planes read above
+            if (SPLIT) half_sweep_bs<2>(c, rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, true);
         }
         ctx.sync();
         // ---------------- level 1 down (2x2 per thread)
         for (int s = 0; s < nu1; ++s) {
-            PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(curv(t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, s == 0); }
-            ctx.sync();
+            if (!(SPLIT && s == 0)) {
+                PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(curv(t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 0, s == 0); }
+                ctx.sync();
+            }
             PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(curv(t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
             ctx.sync();
         }
@@ -514,36 +542,37 @@ struct PsnBlockSolver {
             const VT rho11 = rr[3] - (diag_bs<2>(d1[PSN_BK_TI], 1, 1) * zz[3] - nbsum_bs<2>(zz, 1, 1, hT, hB, hL, hR));
             rho[PSN_BK_TI][0] = rho00;
             rho[PSN_BK_TI][1] = rho11;
-            ES(c, TOP, 0, rho00);   // red slot of TOP: not read by this phase
+            ES<1>(c, TOP, 0, rho00);   // red slot of TOP: not read by this phase
         }
         ctx.sync();
         PSN_BK_FOR(ctx, NTPAD) {
             const CurV c = curv(t_);
-            const VT c02 = EL(c, TOP, 0, 0, 1), c20 = EL(c, TOP, 0, 1, 0);
-            const VT c22 = EL(c, TOP, 0, 1, 1);
+            const VT c02 = EL<1>(c, TOP, 0, 0, 1), c20 = EL<1>(c, TOP, 0, 1, 0);
+            const VT c22 = EL<1>(c, TOP, 0, 1, 1);
             r2[PSN_BK_TI][0] = rho[PSN_BK_TI][1] + (VT)0.25 * ((rho[PSN_BK_TI][0] + c02) + (c20 + c22));
+            if (SPLIT) half_sweep_2_body(c, flags(t_), rd2[PSN_BK_TI], z2[PSN_BK_TI][0], r2[PSN_BK_TI][0], 0, true);
         }
         ctx.sync();
         // ---------------- level 2 down (one node per thread)
         for (int s = 0; s < nu2; ++s) {
-            half_sweep_2(rd2, 0, s == 0);
+            if (!(SPLIT && s == 0)) half_sweep_2(rd2, 0, s == 0);
             half_sweep_2(rd2, 1, false);
         }
-        PSN_BK_FOR(ctx, NTPAD) {   // residual on red nodes -> BOT[0] (TOP[0] is being read by the neighbours)
+        PSN_BK_FOR(ctx, NTPAD) {   // residual on red nodes -> second plane of level 2 (the first is being read by the neighbours)
             const CurV c = curv(t_);
             const int fl = flags(t_);
             VT rh = (VT)0;
             if ((fl & 3) == 1) rh = r2[PSN_BK_TI][0] - (diag_bs<1>(d2[PSN_BK_TI], 0, 0) * z2[PSN_BK_TI][0] - nb2(c));
             rho[PSN_BK_TI][0] = rh;
-            ES(c, BOT, 0, rh);
+            ES<2>(c, BOT, 0, rh);
         }
         ctx.sync();
         PSN_BK_FOR(ctx, NT) {
             if (flags(t_) & 4) {   // bx, by both odd: centre of coarse node ((by-1)/2, (bx-1)/2) of level 3
                 const CurV c = curv(t_);
                 const int bx = bx_of(t_), by = by_of(t_);
-                const VT c00 = EL(c, BOT, 0, -1, -1), c02 = EL(c, BOT, 0, -1, 1);
-                const VT c20 = EL(c, BOT, 0, 1, -1), c22 = EL(c, BOT, 0, 1, 1);
+                const VT c00 = EL<2>(c, BOT, 0, -1, -1), c02 = EL<2>(c, BOT, 0, -1, 1);
+                const VT c20 = EL<2>(c, BOT, 0, 1, -1), c22 = EL<2>(c, BOT, 0, 1, 1);
                 b3[(((by - 1) >> 1) + 1) * l3.pitch + ((bx - 1) >> 1) + 1] = (double)(rho[PSN_BK_TI][0] + (VT)0.25 * ((c00 + c02) + (c20 + c22)));
             }
         }
@@ -565,7 +594,7 @@ struct PsnBlockSolver {
                     add = 0.25 * ((e[-P3 - 1] + e[-P3]) + (e[-1] + e[0]));
                 }
                 z2[PSN_BK_TI][0] += (VT)add;
-                ES(c, TOP, 0, z2[PSN_BK_TI][0]);
+                ES<2>(c, TOP, 0, z2[PSN_BK_TI][0]);
             }
         }
         ctx.sync();
@@ -573,18 +602,21 @@ struct PsnBlockSolver {
             half_sweep_2(rd2, 1, false);
             half_sweep_2(rd2, 0, false);
         }
-        // ---------------- level 1 up: corrections from z2 (TOP[0] holds every thread's current z2)
+        // ---------------- level 1 up: corrections from z2 (its plane holds every thread's current z2)
         PSN_BK_FOR(ctx, NTPAD) {
             const CurV c = curv(t_);
             const VT e00 = z2[PSN_BK_TI][0];
-            const VT em0 = EL(c, TOP, 0, -1, 0), e0m = EL(c, TOP, 0, 0, -1);
-            const VT emm = EL(c, TOP, 0, -1, -1);
+            const VT em0 = EL<2>(c, TOP, 0, -1, 0), e0m = EL<2>(c, TOP, 0, 0, -1);
+            const VT emm = EL<2>(c, TOP, 0, -1, -1);
             z1[PSN_BK_TI][3] += e00;
             z1[PSN_BK_TI][0] += (VT)0.25 * ((emm + em0) + (e0m + e00));
+            if (SPLIT) publish_bs<2>(c, z1[PSN_BK_TI], 0);
         }
-        ctx.sync();   // TOP[0] is about to be overwritten by the edges of z1
-        PSN_BK_FOR(ctx, NTPAD) { publish_bs<2>(curv(t_), z1[PSN_BK_TI], 0); }
         ctx.sync();
+        if (!SPLIT) {   // shared planes: the plane just read takes the edges of z1 only now
+            PSN_BK_FOR(ctx, NTPAD) { publish_bs<2>(curv(t_), z1[PSN_BK_TI], 0); }
+            ctx.sync();
+        }
         for (int s = 0; s < nu1; ++s) {
             PSN_BK_FOR(ctx, NTPAD) { half_sweep_bs<2>(curv(t_), rd1[PSN_BK_TI], z1[PSN_BK_TI], r1[PSN_BK_TI], 1, false); }
             ctx.sync();
@@ -597,9 +629,9 @@ struct PsnBlockSolver {
             VT (&zz)[16] = z[PSN_BK_TI];
             const VT (&ee)[4] = z1[PSN_BK_TI];
             const VT e00 = ee[0], e01 = ee[1], e10 = ee[2], e11 = ee[3];
-            const VT em0 = EL(c, BOT, 0, -1, 0), em1 = EL(c, BOT, 1, -1, 0);
-            const VT e0m = EL(c, RIGHT, 0, 0, -1), e1m = EL(c, RIGHT, 1, 0, -1);
-            const VT emm = EL(c, BOT, 1, -1, -1);
+            const VT em0 = EL<1>(c, BOT, 0, -1, 0), em1 = EL<1>(c, BOT, 1, -1, 0);
+            const VT e0m = EL<1>(c, RIGHT, 0, 0, -1), e1m = EL<1>(c, RIGHT, 1, 0, -1);
+            const VT emm = EL<1>(c, BOT, 1, -1, -1);
             zz[5] += e00;
             zz[7] += e01;
             zz[13] += e10;
@@ -608,13 +640,16 @@ struct PsnBlockSolver {
             zz[2] += (VT)0.25 * ((em0 + em1) + (e00 + e01));
             zz[8] += (VT)0.25 * ((e0m + e00) + (e1m + e10));
             zz[10] += (VT)0.25 * ((e00 + e01) + (e10 + e11));
+            if (SPLIT) publish(c, zz, 0);
         }
-        ctx.sync();   // the z1 edges have been read; the buffers now take the red edges of z
-        PSN_BK_FOR(ctx, NTPAD) { publish(curv(t_), z[PSN_BK_TI], 0); }
         ctx.sync();
+        if (!SPLIT) {   // shared planes: the z1 edges have been read; the buffers now take the red edges of z
+            PSN_BK_FOR(ctx, NTPAD) { publish(curv(t_), z[PSN_BK_TI], 0); }
+            ctx.sync();
+        }
         for (int s = 0; s < nu; ++s) {
             half_sweep(1, false);
-            half_sweep(0, false);
+            half_sweep(0, false, s == nu - 1);
         }
     }
 
@@ -750,9 +785,8 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
 #pragma unroll
                 for (int k = 0; k < 16; ++k) s += S.r[PSN_BK_TI][k] * (double)S.z[PSN_BK_TI][k];
                 acc[PSN_BK_TI] = (S.flags(t_) & 1) ? s : 0.0;   // (float cycle: the idle lanes may hold garbage from aliased cells)
-                if (PSN_BLOCK_VF32) SV::template zero_ghosts<typename SV::CurD>(S.edge, t_);   // the V-cycle is past its last access
             }
-            const double rz = S.tsum(acc) * vinv;   // (device: block_sum syncs, so every thread is past its last edge read)
+            const double rz = S.tsum(acc) * vinv;   // (device: block_sum syncs, so every thread is past the V-cycle's last edge read)
             const double beta = restart ? 0.0 : rz / rz_old;
             restart = false;
             rz_old = rz;
@@ -761,6 +795,7 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
 #pragma unroll
                 for (int k = 0; k < 16; ++k) S.p[PSN_BK_TI][k] = (double)S.z[PSN_BK_TI][k] * vinv + beta * S.p[PSN_BK_TI][k];
                 SV::publish(S.curd(t_), S.p[PSN_BK_TI], -1);
+                if (PSN_BLOCK_VF32) SV::template zero_ghosts<typename SV::CurD>(S.edge, t_, 16);   // the V-cycle's float planes overwrote them
             }
             ctx.sync();
             // q = At p, <p, q>
@@ -796,7 +831,7 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
                     s += rv * rv;
                 }
                 acc[PSN_BK_TI] = (S.flags(t_) & 1) ? s : 0.0;
-                if (PSN_BLOCK_VF32) SV::template zero_ghosts<typename SV::CurV>(S.edgev, t_);   // every halo of p has been read
+                if (PSN_BLOCK_VF32) SV::template zero_ghosts<typename SV::CurV>(S.edgev, t_, SV::NPLV);   // every halo of p has been read
             }
             const double rr = S.tsum(acc);
             rr_final = rr;
@@ -843,7 +878,7 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
                 // the fp64 planes have just carried x: the float ghost ring must read as zero again (tsum above was the barrier
                 // behind the last halo load of x; the first half sweep of the V-cycle has one before its first float load)
                 if (PSN_BLOCK_VF32) {
-                    PSN_BK_FOR(ctx, NTPAD) { SV::template zero_ghosts<typename SV::CurV>(S.edgev, t_); }
+                    PSN_BK_FOR(ctx, NTPAD) { SV::template zero_ghosts<typename SV::CurV>(S.edgev, t_, SV::NPLV); }
                 }
             }
         }

@@ -372,6 +372,9 @@ int hostemu_stream_vcycle(int n, int nu, int TH, int TW, int ls, int mode, int b
     return 0;
 }
 
+// order in which the emulated threads of the register-blocked solver run inside a phase (0 forward, 1 backward)
+void hostemu_block_thread_order(int reverse) { psn_bk_reverse_order() = reverse; }
+
 // register-blocked resident solver (n = 80), all threads of the CTA emulated phase by phase
 int hostemu_solve_block(int n, long long B, const double* theta, const double* f, const double* sx, const double* sy,
                         int mn, int step, double rtol, int max_iter, int nu,

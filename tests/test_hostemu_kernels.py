@@ -222,6 +222,33 @@ def test_register_blocked_resident_solver_matches_generic(he, nu):
         assert np.array_equal(uc[b], u[b][win][::2, ::2]) and np.array_equal(fc[b], f[b][win][::2, ::2])
 
 
+@pytest.mark.parametrize("nu", [1, 2])
+def test_register_blocked_solver_phases_are_race_free(he, nu):
+    """Every phase between two barriers of psn_block.cuh must not depend on the order of its threads: levels 1 and 2 exchange
+    through planes of their own so that 'read the other level's edges' and 'publish mine' share a barrier interval, the float
+    planes alias the fp64 ones, and the ghost rings are re-zeroed in passing.  The emulation runs the threads of a phase one
+    after the other; forwards and backwards must give the same bits."""
+    n = 80
+    f, theta = batch_inputs(n, 1)
+    B = f.shape[0]
+    x0 = np.array([0, 39, 17], dtype=np.int32)
+    y0 = np.array([39, 0, 5], dtype=np.int32)
+    res = []
+    for rev in (0, 1):
+        he.hostemu_block_thread_order(ctypes.c_int(rev))
+        u = np.full((B, n, n), np.nan)
+        it, rr, st = np.zeros(B, np.int32), np.zeros(B), np.zeros(B, np.int32)
+        try:
+            rc = he.hostemu_solve_block(ctypes.c_int(n), ctypes.c_longlong(B), P(theta), P(f), None, None, ctypes.c_int(n), ctypes.c_int(1),
+                                        ctypes.c_double(1e-12), ctypes.c_int(100), ctypes.c_int(nu), P(u), PI(it), P(rr), PI(st),
+                                        ctypes.c_int(0), PI(x0), PI(y0), None, None, None, None)
+        finally:
+            he.hostemu_block_thread_order(ctypes.c_int(0))
+        assert rc == 0 and (st == 0).all()
+        res.append((u, it, rr))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
 @pytest.mark.parametrize("n,ls,band,nu", [(96, 1, 96, 2), (160, 2, 48, 2), (160, 1, 64, 1), (160, 2, 32, 3), (320, 3, 64, 2), (200, 1, 200, 2)])
 def test_float_storage_vcycle_is_as_good_a_preconditioner(he, n, ls, band, nu):
     """Mode 3 = TMA-fed strips with the V-cycle intermediates STORED as float (arithmetic, CG vectors and dot
