@@ -141,7 +141,7 @@ def test_host_logic_generate_dataset(oracle_backend, tmp_path):
             assert np.array_equal(ds[k], gold[k]), k
     # two batched calls instead of 2*N factorisations
     # batched calls (a few chunks per grid so that host sine evaluation overlaps the GPU) instead of 2*N factorisations
-    assert [c[1] for c in oracle_backend.calls] == [40] * 4 + [20] * 4 and sum(c[2] for c in oracle_backend.calls) == 12
+    assert [c[1] for c in oracle_backend.calls] == [40] * 2 + [20] * 2 and sum(c[2] for c in oracle_backend.calls) == 12
     # RNG stream left exactly where the reference leaves it
     nxt = np.random.uniform()
     np.random.seed(0)
