@@ -131,6 +131,9 @@ int psn_subdomain_batch(int n_super, int n_fine, int64_t batch,
  *   resolutions [n_res] int32 (each must divide n_finest);  theta_finest [batch, n_finest, n_finest]
  *   or NULL;  sin_x, sin_y [batch, n_finest];  u_out[k] -> [batch, r_k, r_k];
  *   iters / relres / status: [n_res, batch] (may be NULL)
+ * Host master fields are uploaded once per chunk of examples.  Host outputs: every resolution is solved into device
+ * buffers, largest grid first, and copied back on the result-copy stream while the next one is solved (option
+ * "multires_pipeline", default 1; 0 = one blocking host-output solve per resolution; same bits either way).
  */
 int psn_multires(int n_finest, const int32_t* resolutions, int n_res, int64_t batch,
                  const double* theta_finest, const double* sin_x, const double* sin_y,

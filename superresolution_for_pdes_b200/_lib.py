@@ -510,6 +510,33 @@ def to_host(a) -> np.ndarray:
     return h
 
 
+_COPY_STREAM = None
+
+
+def to_host_async(a):
+    """Like to_host, but the copy runs on a side stream: returns (host array, wait) -- the array is valid once ``wait()`` has
+    returned (it returns the array).  Used by the multi-resolution chain driver, whose master theta (produced on the device)
+    goes back to the host while the solves are running."""
+    global _COPY_STREAM
+    if isinstance(a, np.ndarray):
+        return a, (lambda: a)
+    import torch
+    h = host_empty(tuple(a.shape), {"torch.float64": np.float64, "torch.float32": np.float32, "torch.int32": np.int32}[str(a.dtype)])
+    if _COPY_STREAM is None:
+        _COPY_STREAM = torch.cuda.Stream()
+    _COPY_STREAM.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(_COPY_STREAM):
+        torch.from_numpy(h).copy_(a, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(_COPY_STREAM)
+
+    def wait(_keep=a):   # (_keep: the device tensor must outlive the copy)
+        ev.synchronize()
+        return h
+
+    return h, wait
+
+
 def device_empty_f64(shape):
     """float64 CUDA tensor on the library's device (torch is the allocator here, nothing more)."""
     import torch

@@ -573,6 +573,9 @@ struct Context {
     Arena mt_arena;                        // psn_mt19937_uniform_blocks: jumped states, polynomials, staging
     Arena master[2];                       // psn_multires: device copies of host master fields (theta, sine factors)
     cudaEvent_t master_done[2] = {nullptr, nullptr};
+    Arena multi_out;                       // psn_multires with host outputs: device results of every resolution of a chunk
+    cudaEvent_t multi_solved = nullptr;    // recorded behind each resolution's solve; the result-copy stream waits for it
+    int multires_pipeline = 1;             // option: 0 = one blocking host-output solve per resolution (the round-1 behaviour)
     cudaEvent_t last_call = nullptr;
     cudaStream_t last_stream = nullptr;
     bool have_last = false;
@@ -1632,6 +1635,7 @@ int psn_init(int device) {
     for (int k = 0; k < 2; ++k) CU_TRY(cudaEventCreateWithFlags(&g.ws_free[k], cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&g.last_call, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) CU_TRY(cudaEventCreateWithFlags(&g.master_done[k], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&g.multi_solved, cudaEventDisableTiming));
     g.have_last = false;
     for (int i = 0; i < PSN_NSLOTS; ++i) {
         CU_TRY(cudaEventCreateWithFlags(&g.slots[i].staging_free, cudaEventDisableTiming));
@@ -1677,6 +1681,10 @@ void psn_shutdown(void) {
         if (g.master[k].base) cudaFree(g.master[k].base);
         g.master[k] = Arena();
     }
+    if (g.multi_solved) cudaEventDestroy(g.multi_solved);
+    g.multi_solved = nullptr;
+    if (g.multi_out.base) cudaFree(g.multi_out.base);
+    g.multi_out = Arena();
     g.have_last = false;
     if (g.h_info) cudaFreeHost(g.h_info);
     g.h_info = nullptr;
@@ -1759,7 +1767,57 @@ int psn_multires(int n_finest, const int32_t* resolutions, int n_res, int64_t ba
     if (rc) return rc;
     if (batch < 0) return psn_fail(PSN_ERR_INVALID, "batch must be >= 0");
     if (batch == 0) return PSN_OK;
+    // Host outputs: every resolution is solved into device buffers on the caller's stream, largest grid first, and copied
+    // back on the result-copy stream while the next resolution is being solved (before: solve, copy, synchronise per
+    // resolution -- for 64 examples x 40..640 the copies were half of the call).
+    bool pipelined = g.multires_pipeline != 0;
+    for (int k = 0; k < n_res; ++k) pipelined = pipelined && classify(u_out[k]) == MEM_HOST;
+    if (iters && classify(iters) != MEM_HOST) pipelined = false;
+    if (relres && classify(relres) != MEM_HOST) pipelined = false;
+    if (status && classify(status) != MEM_HOST) pipelined = false;
+    std::vector<int> order(n_res);
+    for (int k = 0; k < n_res; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return resolutions[a] > resolutions[b]; });
+    size_t out_per = 0;   // bytes of device results per example
+    for (int k = 0; k < n_res; ++k) out_per += pad256((size_t)resolutions[k] * resolutions[k] * 8) + 16;
+    auto solve_range_pipelined = [&](const double* th, const double* sx, const double* sy, long long b0, long long bc) -> int {
+        const cudaStream_t s = (cudaStream_t)stream;
+        int rc2 = arena_reserve(g.multi_out, out_per * (size_t)bc + (size_t)n_res * 4 * 256);
+        if (rc2) return rc2;
+        std::vector<double*> d_u(n_res);
+        std::vector<int32_t*> d_it(n_res), d_st(n_res);
+        std::vector<double*> d_rr(n_res);
+        for (int k = 0; k < n_res; ++k) {
+            d_u[k] = arena_take<double>(g.multi_out, (size_t)bc * resolutions[k] * resolutions[k]);
+            d_it[k] = arena_take<int32_t>(g.multi_out, (size_t)bc);
+            d_rr[k] = arena_take<double>(g.multi_out, (size_t)bc);
+            d_st[k] = arena_take<int32_t>(g.multi_out, (size_t)bc);
+            if (!d_u[k] || !d_it[k] || !d_rr[k] || !d_st[k]) return psn_fail(PSN_ERR_CUDA, "multires result arena too small");
+        }
+        for (int o = 0; o < n_res; ++o) {
+            const int k = order[o];
+            Problem P;
+            memset(&P, 0, sizeof(P));
+            const size_t rr = (size_t)resolutions[k] * resolutions[k];
+            P.n = resolutions[k]; P.B = bc; P.theta = th; P.sx = sx; P.sy = sy;
+            P.mn = n_finest; P.step = n_finest / resolutions[k]; P.rtol = rtol; P.max_iter = max_iter;
+            P.u = d_u[k]; P.iters = d_it[k]; P.relres = d_rr[k]; P.status = d_st[k];
+            P.stream = s;
+            if ((rc2 = solve_internal(P))) return rc2;
+            CU_TRY(cudaEventRecord(g.multi_solved, s));
+            CU_TRY(cudaStreamWaitEvent(g.d2h_stream, g.multi_solved, 0));
+            CU_TRY(cudaMemcpyAsync(u_out[k] + (size_t)b0 * rr, d_u[k], (size_t)bc * rr * 8, cudaMemcpyDeviceToHost, g.d2h_stream));
+        }
+        CU_TRY(cudaStreamSynchronize(g.d2h_stream));   // (behind the last solve: the caller's stream is complete as well)
+        for (int k = 0; k < n_res; ++k) {              // small, and the callers' arrays are usually pageable
+            if (iters) CU_TRY(cudaMemcpy(iters + (size_t)k * batch + b0, d_it[k], (size_t)bc * 4, cudaMemcpyDeviceToHost));
+            if (relres) CU_TRY(cudaMemcpy(relres + (size_t)k * batch + b0, d_rr[k], (size_t)bc * 8, cudaMemcpyDeviceToHost));
+            if (status) CU_TRY(cudaMemcpy(status + (size_t)k * batch + b0, d_st[k], (size_t)bc * 4, cudaMemcpyDeviceToHost));
+        }
+        return PSN_OK;
+    };
     auto solve_range = [&](const double* th, const double* sx, const double* sy, long long b0, long long bc) -> int {
+        if (pipelined) return solve_range_pipelined(th, sx, sy, b0, bc);
         for (int k = 0; k < n_res; ++k) {
             Problem P;
             memset(&P, 0, sizeof(P));
@@ -1777,14 +1835,25 @@ int psn_multires(int n_finest, const int32_t* resolutions, int n_res, int64_t ba
         return PSN_OK;
     };
     const MemKind k_th = classify(theta_finest), k_sx = classify(sin_x), k_sy = classify(sin_y);
-    if (k_th != MEM_HOST && k_sx != MEM_HOST && k_sy != MEM_HOST) return solve_range(theta_finest, sin_x, sin_y, 0, batch);
+    if (k_th != MEM_HOST && k_sx != MEM_HOST && k_sy != MEM_HOST) {
+        if (!pipelined) return solve_range(theta_finest, sin_x, sin_y, 0, batch);
+        long long Bo = (long long)((4ull << 30) / out_per);   // examples per result arena
+        if (Bo < 1) Bo = 1;
+        for (long long b0 = 0; b0 < batch; b0 += Bo) {
+            const long long bc = std::min<long long>(Bo, batch - b0);
+            if ((rc = solve_range(theta_finest + (size_t)b0 * n_finest * n_finest, sin_x + (size_t)b0 * n_finest,
+                                  sin_y + (size_t)b0 * n_finest, b0, bc)))
+                return rc;
+        }
+        return PSN_OK;
+    }
 
     // Host master fields: every resolution reads the SAME theta / sine factors through a stride gather, so they are
     // uploaded once per chunk of examples (two alternating device buffers: the upload of chunk c+1 runs on the upload
     // stream while the resolutions of chunk c are solved) instead of once per resolution.
     const size_t mm = (size_t)n_finest * n_finest;
     const size_t per = (k_th == MEM_HOST ? mm * 8 : 0) + 2 * pad256((size_t)n_finest * 8) + 64;
-    long long Bm = (long long)((4ull << 30) / per);
+    long long Bm = (long long)((4ull << 30) / (per + (pipelined ? out_per : 0)));
     if (Bm < 1) Bm = 1;
     if (Bm > batch) Bm = batch;
     const long long nchunks = (batch + Bm - 1) / Bm;
@@ -2105,6 +2174,9 @@ int psn_set_option(const char* name, int64_t value) {
     } else if (!strcmp(name, "host_prefetch")) {
         if (value < 1 || value > PSN_NCHUNK_STREAMS - 1) return psn_fail(PSN_ERR_INVALID, "host_prefetch must be in 1..%d", PSN_NCHUNK_STREAMS - 1);
         g.host_prefetch = (int)value;
+    } else if (!strcmp(name, "multires_pipeline")) {
+        if (value < 0 || value > 1) return psn_fail(PSN_ERR_INVALID, "multires_pipeline must be 0 or 1");
+        g.multires_pipeline = (int)value;
     } else if (!strcmp(name, "copy_streams")) {
         g.copy_streams = value ? 1 : 0;
     } else if (!strcmp(name, "host_h2d_stream")) {

@@ -21,13 +21,16 @@ def _sines_kfirst(k1: np.ndarray, k2: np.ndarray, x: np.ndarray):
     return np.sin((k1 * 2 * np.pi) * x[None, :]), np.sin((k2 * 2 * np.pi) * x[None, :])
 
 
-def draw_examples(n_examples: int, n_finest: int, k_range: Tuple[float, float], *, device_rng: bool = True, theta_on_host: bool = True):
+def draw_examples(n_examples: int, n_finest: int, k_range: Tuple[float, float], *, device_rng: bool = True, theta_on_host: bool = True,
+                  defer_host: bool = False):
     """The RNG part of ``n_examples`` consecutive chains: per example k1, k2 ~ U(*k_range) and the master field
     theta ~ U(0.5, 2.0) on the finest grid, from numpy's GLOBAL legacy generator in the reference's order
     (src/resolution_comparison.py:27-28,42; src/subdomain_upscaling.py:19-20,31).  With ``device_rng`` the
     Mersenne-Twister stream is replayed on the GPU (``psn_mt19937_uniform_blocks``: bit-identical values, global state
     advanced as numpy would) and theta stays a CUDA tensor for the solve -- the 2 ms per 640 x 640 field of host RNG and
-    its PCIe upload disappear.  Returns (k1 [E], k2 [E], theta for the solver, theta as a host array or None)."""
+    its PCIe upload disappear.  Returns (k1 [E], k2 [E], theta for the solver, theta as a host array or None); with
+    ``defer_host`` the last item is a zero-argument callable that waits for the (asynchronous) device-to-host copy and
+    returns the array, so that the copy can run behind the caller's solves."""
     lo, hi = float(k_range[0]), float(k_range[1])
     nn = n_finest * n_finest
     if device_rng:
@@ -36,6 +39,8 @@ def draw_examples(n_examples: int, n_finest: int, k_range: Tuple[float, float], 
         k1 = lo + (hi - lo) * raw[:, 0]        # numpy's random_uniform: lower + range * d (separate multiply and add)
         k2 = lo + (hi - lo) * raw[:, 1]
         theta_dev = _lib.reshaped(theta_dev, (n_examples, n_finest, n_finest))
+        if theta_on_host and defer_host:
+            return k1, k2, theta_dev, _lib.to_host_async(theta_dev)[1]
         theta_host = _lib.to_host(theta_dev) if theta_on_host else None
         return k1, k2, theta_dev, theta_host
     k1 = np.empty(n_examples)
@@ -45,7 +50,7 @@ def draw_examples(n_examples: int, n_finest: int, k_range: Tuple[float, float], 
         k1[e] = np.random.uniform(lo, hi)
         k2[e] = np.random.uniform(lo, hi)
         theta[e] = np.random.uniform(0.5, 2.0, size=(n_finest, n_finest))
-    return k1, k2, theta, theta
+    return k1, k2, theta, ((lambda: theta) if (theta_on_host and defer_host) else theta)
 
 
 def solve_multi_resolution(n_coarse: int = 40, resolutions: List[int] = [80, 160, 320, 640], *, device_rng: bool = True,
@@ -103,11 +108,13 @@ def solve_multi_resolution_batch(n_examples: int, n_coarse: int = 40, resolution
     ``theta_on_host=False`` leaves the master fields on the device (``theta_finest`` is then a CUDA tensor)."""
     resolutions = list(resolutions)
     n_finest = max(resolutions)
-    k1, k2, theta_solver, theta_host = draw_examples(n_examples, n_finest, k_range, device_rng=device_rng, theta_on_host=theta_on_host)
+    k1, k2, theta_solver, theta_wait = draw_examples(n_examples, n_finest, k_range, device_rng=device_rng, theta_on_host=theta_on_host,
+                                                     defer_host=True)
     x = np.linspace(0, 1, n_finest)
     sx, sy = _sines_kfirst(k1, k2, x)
     all_res = [n_coarse] + resolutions
     us, info = _lib.multires(n_finest, all_res, n_examples, theta_solver, sx, sy, rtol=rtol, max_iter=max_iter)
+    theta_host = theta_wait() if theta_on_host else None   # device RNG: the copy of theta ran behind the solves
     info.raise_if_failed("solve_multi_resolution_batch")
     return {'k1': k1, 'k2': k2, 'theta_finest': theta_host if theta_host is not None else theta_solver, 'sin_x': sx, 'sin_y': sy,
             'u': us, 'info': info}

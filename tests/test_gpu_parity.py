@@ -586,6 +586,18 @@ def test_multires_uploads_the_master_field_once(gpu_lib):
         for b in (0, B - 1):
             ref = O.solve_poisson(np.outer(sy[b], sx[b])[::st, ::st], theta[b, ::st, ::st], r)
             assert O.rel_l2(us[r][b], ref) <= TOL
+    # host outputs are copied back while the next resolution is solved (largest grid first): same bits as the blocking
+    # per-resolution schedule, for host and for device-resident master fields
+    gpu_lib.set_option("multires_pipeline", 0)
+    try:
+        us0, info0 = gpu_lib.multires(N, res, B, theta, sx, sy)
+    finally:
+        gpu_lib.set_option("multires_pipeline", 1)
+    usd, infod = gpu_lib.multires(N, res, B, torch.from_numpy(theta).cuda(), sx, sy)
+    for r in res:
+        assert np.array_equal(us[r], us0[r]) and np.array_equal(us[r], usd[r]), r
+    for i_ in (info0, infod):
+        assert np.array_equal(info.iters, i_.iters) and np.array_equal(info.status, i_.status) and np.array_equal(info.relres, i_.relres)
     # theta == 1 (NULL master field) with host sines
     us1, info1 = gpu_lib.multires(N, res[:2], B, None, sx, sy)
     for r in res[:2]:
