@@ -125,7 +125,9 @@ struct PsnBlockGeom {
     // need no predicate either), then slack for those threads' neighbour reads
     static constexpr int NTP = (BROWS * BP + (NTPAD - NT) + BP + 1 + 7) & ~7;
     // float planes of the V-cycle exchange (they alias the fp64 planes): a warp is two tiles = 4 rows x 8 cells per 32-bit
-    // transaction, so the pitch is 8 mod 32
+    // transaction, so the pitch is 8 mod 32.  (Two tiles are disjoint in banks iff their tile columns differ by an odd number;
+    // the 2 of 13 warps that hold the last tile of a tile row and the first of the next conflict 2-way: with 25 tiles no pitch
+    // pairs them all.)
     static constexpr int BPF = ((BX + 2 - 8 + 31) / 32) * 32 + 8;
     static constexpr int NTPF = (BROWS * BPF + (NTPAD - NT) + BPF + 1 + 7) & ~7;
     static_assert(BPF >= BX + 2 && BPF % 32 == 8 && 16 * NTPF * 4 <= 16 * NTP * 8, "float planes must fit into the fp64 planes");
