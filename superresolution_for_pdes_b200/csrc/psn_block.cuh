@@ -118,9 +118,12 @@ struct PsnBlockGeom {
     // threads (one half warp = one 64-bit shared-memory transaction) form a 4 x 4 patch of the thread grid -- and the pitch is
     // 12 mod 16, so that the four rows of a patch fall on four disjoint groups of banks: every edge access is conflict free.
     // (Row-major numbering with pitch BX + 2: 3 of 5 half warps straddle a row end, 1.6 wavefronts per access.)
+    // BX not a multiple of 4 (BX = 10, the 40 x 40 grid): threads are numbered row by row and the pitch is BX + 2 -- 32
+    // consecutive threads then spread over 32 + 2 * 3 positions, i.e. at most 6 of them share a bank with another one.
+    static constexpr bool TILED = BX % 4 == 0;
     static constexpr int BROWS = BX + 2;
-    static constexpr int BP = ((BX + 2 + 3) / 16) * 16 + 12;
-    static_assert(BX % 4 == 0 && BP >= BX + 2 && BP % 16 == 12, "tile numbering needs BX % 4 == 0; pitch 12 mod 16");
+    static constexpr int BP = TILED ? ((BX + 2 + 3) / 16) * 16 + 12 : BX + 2;
+    static_assert(BP >= BX + 2 && (!TILED || BP % 16 == 12), "tile numbering: pitch 12 mod 16");
     // cells per edge-buffer plane: the padded grid, then one private cell per idle thread of the last warp (their accesses
     // need no predicate either), then slack for those threads' neighbour reads
     static constexpr int NTP = (BROWS * BP + (NTPAD - NT) + BP + 1 + 7) & ~7;
@@ -128,9 +131,9 @@ struct PsnBlockGeom {
     // transaction, so the pitch is 8 mod 32.  (Two tiles are disjoint in banks iff their tile columns differ by an odd number;
     // the 2 of 13 warps that hold the last tile of a tile row and the first of the next conflict 2-way: with 25 tiles no pitch
     // pairs them all.)
-    static constexpr int BPF = ((BX + 2 - 8 + 31) / 32) * 32 + 8;
+    static constexpr int BPF = TILED ? ((BX + 2 - 8 + 31) / 32) * 32 + 8 : BX + 2;
     static constexpr int NTPF = (BROWS * BPF + (NTPAD - NT) + BPF + 1 + 7) & ~7;
-    static_assert(BPF >= BX + 2 && BPF % 32 == 8 && 16 * NTPF * 4 <= 16 * NTP * 8, "float planes must fit into the fp64 planes");
+    static_assert(BPF >= BX + 2 && (!TILED || BPF % 32 == 8) && 16 * NTPF * 4 <= 16 * NTP * 8, "float planes must fit into the fp64 planes");
     // shared memory (doubles): x[16][NTPAD], edges[4 sides][4 slots][NTP]
     static constexpr int XS = 16 * NTPAD;
     static constexpr int ES = 16 * NTP;
@@ -156,10 +159,11 @@ template <int BX, class Ctx>
 struct PsnBlockSolver {
     typedef PsnBlockGeom<BX> G;
     static constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
-    static constexpr int TILES = BX / 4;   // 4 x 4 patches of threads per row of the thread grid
-    // thread t -> its block (bx, by) of the thread grid: tile t / 16 (row-major over TILES x TILES), lane t % 16 inside it
-    PSN_FN static int bx_of(int t) { return 4 * ((t >> 4) % TILES) + (t & 3); }
-    PSN_FN static int by_of(int t) { return 4 * ((t >> 4) / TILES) + ((t >> 2) & 3); }
+    static constexpr int TILES = G::TILED ? BX / 4 : 1;   // 4 x 4 patches of threads per row of the thread grid
+    // thread t -> its block (bx, by) of the thread grid: tile t / 16 (row-major over TILES x TILES), lane t % 16 inside it;
+    // row by row when BX is not a multiple of 4
+    PSN_FN static int bx_of(int t) { return G::TILED ? 4 * ((t >> 4) % TILES) + (t & 3) : t % BX; }
+    PSN_FN static int by_of(int t) { return G::TILED ? 4 * ((t >> 4) / TILES) + ((t >> 2) & 3) : t / BX; }
     enum { TOP = 0, BOT = 1, LEFT = 2, RIGHT = 3 };
 
 #if PSN_BLOCK_VF32

@@ -64,7 +64,8 @@ static inline int psn_level_size(int n) {
 
 // Fill every field except coarse_inv.
 #define PSN_COARSEST_SMALL 6
-static inline int psn_default_coarsest(int n) { return n >= 32 ? PSN_COARSEST_MAX : PSN_COARSEST_SMALL; }
+// (n = 40 runs in the register-blocked kernel, which keeps three levels in registers above the dense one: 40, 20, 10 | 5)
+static inline int psn_default_coarsest(int n) { return n == 40 ? 5 : n >= 32 ? PSN_COARSEST_MAX : PSN_COARSEST_SMALL; }
 
 // coarsest_max <= 0: the default for this n; nu_coarse <= 0: the same number of sweeps on every level
 static inline void psn_plan_levels(PsnPlan* p, int n, int nu, int coarsest_max = 0, int nu_coarse = 0) {

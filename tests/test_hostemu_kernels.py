@@ -194,41 +194,40 @@ def test_fp64_floor_status(he):
     assert O.rel_l2(u[0], O.solve_poisson(f, theta, n)) <= 1e-10
 
 
-@pytest.mark.parametrize("nu", [1, 2, 3])
-def test_register_blocked_resident_solver_matches_generic(he, nu):
-    """psn_block.cuh (80x80: 4x4 / 2x2 / 1 node(s) per thread on levels 0 / 1 / 2 in registers, edge buffers in
-    shared memory), emulated with the state of all 400 threads, against the generic shared-memory solver
+@pytest.mark.parametrize("n,nu", [(80, 1), (80, 2), (80, 3), (40, 1), (40, 2), (40, 3)])
+def test_register_blocked_resident_solver_matches_generic(he, n, nu):
+    """psn_block.cuh (80x80 and 40x40: 4x4 / 2x2 / 1 node(s) per thread on levels 0 / 1 / 2 in registers, edge buffers in
+    shared memory), emulated with the state of all 400 / 100 threads, against the generic shared-memory solver
     and the oracle."""
-    n = 80
     f, theta = batch_inputs(n, 1)
     B = f.shape[0]
     u = np.full((B, n, n), np.nan)
     it, rr, st = np.zeros(B, np.int32), np.zeros(B), np.zeros(B, np.int32)
-    x0 = np.array([0, 39, 17], dtype=np.int32)
-    y0 = np.array([39, 0, 5], dtype=np.int32)
-    uf, ff = np.full((B, 40, 40), np.nan), np.full((B, 40, 40), np.nan)
-    uc, fc = np.full((B, 20, 20), np.nan), np.full((B, 20, 20), np.nan)
+    w = n // 2
+    x0 = np.array([0, w - 1, 17], dtype=np.int32)
+    y0 = np.array([w - 1, 0, 5], dtype=np.int32)
+    uf, ff = np.full((B, w, w), np.nan), np.full((B, w, w), np.nan)
+    uc, fc = np.full((B, w // 2, w // 2), np.nan), np.full((B, w // 2, w // 2), np.nan)
     rc = he.hostemu_solve_block(ctypes.c_int(n), ctypes.c_longlong(B), P(theta), P(f), None, None, ctypes.c_int(n), ctypes.c_int(1),
                                 ctypes.c_double(1e-12), ctypes.c_int(100), ctypes.c_int(nu), P(u), PI(it), P(rr), PI(st),
-                                ctypes.c_int(40), PI(x0), PI(y0), P(uf), P(ff), P(uc), P(fc))
+                                ctypes.c_int(w), PI(x0), PI(y0), P(uf), P(ff), P(uc), P(fc))
     assert rc == 0
     ug, itg, _, _, _ = run_smem(he, n, theta, f=f, nu=nu)
     assert (it == itg).all() and (st == 0).all()
     assert O.rel_l2(u, ug) <= 1e-14
     for b in range(B):
         assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= 1e-10
-        win = (slice(y0[b], y0[b] + 40), slice(x0[b], x0[b] + 40))
+        win = (slice(y0[b], y0[b] + w), slice(x0[b], x0[b] + w))
         assert np.array_equal(uf[b], u[b][win]) and np.array_equal(ff[b], f[b][win])
         assert np.array_equal(uc[b], u[b][win][::2, ::2]) and np.array_equal(fc[b], f[b][win][::2, ::2])
 
 
-@pytest.mark.parametrize("nu", [1, 2])
-def test_register_blocked_solver_phases_are_race_free(he, nu):
+@pytest.mark.parametrize("n,nu", [(80, 1), (80, 2), (40, 2)])
+def test_register_blocked_solver_phases_are_race_free(he, n, nu):
     """Every phase between two barriers of psn_block.cuh must not depend on the order of its threads: levels 1 and 2 exchange
     through planes of their own so that 'read the other level's edges' and 'publish mine' share a barrier interval, the float
     planes alias the fp64 ones, and the ghost rings are re-zeroed in passing.  The emulation runs the threads of a phase one
     after the other; forwards and backwards must give the same bits."""
-    n = 80
     f, theta = batch_inputs(n, 1)
     B = f.shape[0]
     x0 = np.array([0, 39, 17], dtype=np.int32)
