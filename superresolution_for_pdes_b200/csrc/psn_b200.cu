@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(T) psn_smem_solve_kernel(const __grid_constant
 //  __maxnreg__(152) compiles but cannot be launched)
 // BX = 10 (40 x 40): 128 threads and ~46 KB per sample, four samples per SM (three with 168 registers and no spills: 6.2M
 // instead of 6.6M solves/s).
-#define PSN_BLOCK_CTAS(BX) ((BX) >= 20 ? 1 : 4)
+// BX = 5 (20 x 20): one warp and ~18 KB per sample, eleven samples per SM.
+#define PSN_BLOCK_CTAS(BX) ((BX) >= 20 ? 1 : (BX) >= 10 ? 4 : 11)
 template <int BX>
 __global__ void __launch_bounds__(PsnBlockGeom<BX>::NTPAD, PSN_BLOCK_CTAS(BX)) psn_block_solve_kernel(const __grid_constant__ PsnPlan plan,
                                                                                      const __grid_constant__ PsnSolveArgs a,
@@ -709,6 +710,7 @@ int set_kernel_attrs() {
 #define PSN_RES_ATTR(T_, X_) CU_TRY(cudaFuncSetAttribute(psn_smem_solve_kernel<T_, X_>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
     CU_TRY(cudaFuncSetAttribute(psn_block_solve_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CU_TRY(cudaFuncSetAttribute(psn_block_solve_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_block_solve_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     PSN_RES_ATTR(128, 4); PSN_RES_ATTR(256, 4); PSN_RES_ATTR(256, 8); PSN_RES_ATTR(512, 4);
     PSN_RES_ATTR(512, 8); PSN_RES_ATTR(1024, 4); PSN_RES_ATTR(512, 16); PSN_RES_ATTR(1024, 8);
 #undef PSN_RES_ATTR
@@ -1454,19 +1456,23 @@ int solve_impl(const Problem& P) {
             {
                 ProfScope pr("smem_solve", s);
                 const unsigned grid = (unsigned)bc;
-                if (g.res_block && (psn_block_ok<20>(plan) || psn_block_ok<10>(plan))) {
-                    const bool big = psn_block_ok<20>(plan);
-                    size_t bsm = (size_t)(big ? psn_block_smem_doubles<20>(plan) : psn_block_smem_doubles<10>(plan)) * sizeof(double);
+                const int bxk = !g.res_block ? 0 : psn_block_ok<20>(plan) ? 20 : psn_block_ok<10>(plan) ? 10 : psn_block_ok<5>(plan) ? 5 : 0;
+                if (bxk) {
+                    size_t bsm = (size_t)(bxk == 20 ? psn_block_smem_doubles<20>(plan)
+                                                    : bxk == 10 ? psn_block_smem_doubles<10>(plan) : psn_block_smem_doubles<5>(plan)) * sizeof(double);
                     int invd = psn_coarse_inv_doubles(plan);
                     if (!g.inv_smem || bsm + (size_t)invd * sizeof(double) + 1024 > g.smem_optin) invd = 0;
                     bsm += (size_t)invd * sizeof(double);
-                    const int per_sm = big ? PSN_BLOCK_CTAS(20) : PSN_BLOCK_CTAS(10);
+                    const int per_sm = bxk == 20 ? PSN_BLOCK_CTAS(20) : bxk == 10 ? PSN_BLOCK_CTAS(10) : PSN_BLOCK_CTAS(5);
                     const unsigned pgrid =
                         (unsigned)std::min<long long>(bc, (long long)g.sm_count * per_sm * (g.res_waves > 0 ? g.res_waves : 1));
-                    if (big)
-                        psn_block_solve_kernel<20><<<g.res_persist ? pgrid : grid, PsnBlockGeom<20>::NTPAD, bsm, s>>>(plan, a, bc, invd);
+                    const unsigned gr = g.res_persist ? pgrid : grid;
+                    if (bxk == 20)
+                        psn_block_solve_kernel<20><<<gr, PsnBlockGeom<20>::NTPAD, bsm, s>>>(plan, a, bc, invd);
+                    else if (bxk == 10)
+                        psn_block_solve_kernel<10><<<gr, PsnBlockGeom<10>::NTPAD, bsm, s>>>(plan, a, bc, invd);
                     else
-                        psn_block_solve_kernel<10><<<g.res_persist ? pgrid : grid, PsnBlockGeom<10>::NTPAD, bsm, s>>>(plan, a, bc, invd);
+                        psn_block_solve_kernel<5><<<gr, PsnBlockGeom<5>::NTPAD, bsm, s>>>(plan, a, bc, invd);
                 } else {
 #define PSN_RES_LAUNCH(T_, X_) \
     if (rcfg.T == T_ && rcfg.XPT == X_) psn_smem_solve_kernel<T_, X_><<<grid, T_, rcfg.smem, s>>>(plan, a)

@@ -140,14 +140,17 @@ struct PsnBlockGeom {
 };
 
 // doubles of dynamic shared memory the block kernel needs (x, edge buffers, coarse levels >= 1)
+// Levels 0 and 1 always live in registers; level 2 too when there is a level below it (n, n/2, n/4 | n/8 ...), otherwise
+// level 2 is the dense one (n = 20: 20, 10 | 5) and its right-hand side / solution pass through shared memory.
+PSN_HDFN int psn_block_pool_doubles(const PsnPlan& plan) { return psn_pool_doubles(plan, plan.nlev >= 4 ? 2 : 1); }
 template <int BX>
 PSN_HDFN int psn_block_smem_doubles(const PsnPlan& plan) {
-    return PsnBlockGeom<BX>::XS + PsnBlockGeom<BX>::ES + psn_pool_doubles(plan, 2);   // levels 1 and 2 live in registers
+    return PsnBlockGeom<BX>::XS + PsnBlockGeom<BX>::ES + psn_block_pool_doubles(plan);
 }
-// the register-blocked solver needs the hierarchy n, n/2, n/4, n/8, ... with at least 4 levels
+// the register-blocked solver needs the hierarchy n, n/2, n/4, ... with at least 3 levels
 template <int BX>
 PSN_HDFN bool psn_block_ok(const PsnPlan& plan) {
-    return plan.n == 4 * BX && plan.nlev >= 4 && plan.lv[1].n == 2 * BX && plan.lv[2].n == BX;
+    return plan.n == 4 * BX && plan.nlev >= 3 && plan.lv[1].n == 2 * BX && plan.lv[2].n == BX;
 }
 // doubles of the dense coarsest-level inverse, kept behind the arrays above by the persistent kernel when it fits
 PSN_HDFN int psn_coarse_inv_doubles(const PsnPlan& plan) {
@@ -466,7 +469,8 @@ struct PsnBlockSolver {
         const int nu = plan.nul[0], nu1 = plan.nul[1], nu2 = plan.nul[2];
         const PsnLevel& l1 = plan.lv[1];
         const PsnLevel& l2 = plan.lv[2];
-        const PsnLevel& l3 = plan.lv[3];
+        const bool dense2 = plan.nlev == 3;              // level 2 is the dense level (n = 20); CTA-uniform
+        const PsnLevel& l3 = plan.lv[dense2 ? 2 : 3];    // first level kept in shared memory
         double* b3 = pool;
         double* u3 = pool + l3.size;
         double* pool4 = pool + 2 * l3.size;
@@ -556,9 +560,25 @@ struct PsnBlockSolver {
             const VT c02 = EL<1>(c, TOP, 0, 0, 1), c20 = EL<1>(c, TOP, 0, 1, 0);
             const VT c22 = EL<1>(c, TOP, 0, 1, 1);
             r2[PSN_BK_TI][0] = rho[PSN_BK_TI][1] + (VT)0.25 * ((rho[PSN_BK_TI][0] + c02) + (c20 + c22));
-            if (SPLIT) half_sweep_2_body(c, flags(t_), rd2[PSN_BK_TI], z2[PSN_BK_TI][0], r2[PSN_BK_TI][0], 0, true);
+            if (dense2) {
+                if (flags(t_) & 1) b3[(by_of(t_) + 1) * l3.pitch + bx_of(t_) + 1] = (double)r2[PSN_BK_TI][0];
+            } else if (SPLIT) {
+                half_sweep_2_body(c, flags(t_), rd2[PSN_BK_TI], z2[PSN_BK_TI][0], r2[PSN_BK_TI][0], 0, true);
+            }
         }
         ctx.sync();
+        if (dense2) {
+            // ---------------- level 2 is the dense level: solve it, every thread fetches its node and publishes it
+            psn_vcycle_smem(ctx, plan, 2, b3, u3, pool4, inv_s);
+            PSN_BK_FOR(ctx, NTPAD) {
+                if (flags(t_) & 1) {
+                    const VT v = (VT)u3[(by_of(t_) + 1) * l3.pitch + bx_of(t_) + 1];
+                    z2[PSN_BK_TI][0] = v;
+                    ES<2>(curv(t_), TOP, 0, v);
+                }
+            }
+            ctx.sync();
+        } else {
         // ---------------- level 2 down (one node per thread)
         for (int s = 0; s < nu2; ++s) {
             if (!(SPLIT && s == 0)) half_sweep_2(rd2, 0, s == 0);
@@ -608,6 +628,7 @@ struct PsnBlockSolver {
             half_sweep_2(rd2, 1, false);
             half_sweep_2(rd2, 0, false);
         }
+        }   // !dense2
         // ---------------- level 1 up: corrections from z2 (its plane holds every thread's current z2)
         PSN_BK_FOR(ctx, NTPAD) {
             const CurV c = curv(t_);
@@ -725,7 +746,7 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
     double* pool = smem + G::XS + G::ES;          // levels >= 3 (levels 1 and 2 live in registers)
     {
         // zero the ghost rings: of the coarse levels, and of the thread grid the edge buffers are indexed by
-        const int zn = G::ES + psn_pool_doubles(plan, 2);
+        const int zn = G::ES + psn_block_pool_doubles(plan);
         double* z0 = smem + G::XS;
         for (int idx = ctx.tid; idx < zn; idx += ctx.nthreads) z0[idx] = 0.0;
     }

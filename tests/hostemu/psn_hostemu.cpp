@@ -381,20 +381,23 @@ int hostemu_solve_block(int n, long long B, const double* theta, const double* f
                         double* u, int32_t* iters, double* relres, int32_t* status,
                         int sub, const int32_t* start_x, const int32_t* start_y,
                         double* u_fine, double* f_fine, double* u_coarse, double* f_coarse) {
-    if (n != 80 && n != 40) return -1;
+    if (n != 80 && n != 40 && n != 20) return -1;
     HostPlan hp(n, nu);
-    if (n == 40 ? !psn_block_ok<10>(hp.plan) : !psn_block_ok<20>(hp.plan)) return -2;
+    if (n == 20 ? !psn_block_ok<5>(hp.plan) : n == 40 ? !psn_block_ok<10>(hp.plan) : !psn_block_ok<20>(hp.plan)) return -2;
     PsnSolveArgs a;
     a.rhs = make_rhs(theta, f, sx, sy, nullptr, nullptr, mn, step);
     a.rtol = rtol; a.max_iter = max_iter; a.u = u; a.iters = iters; a.relres = relres; a.status = status;
     a.sub = sub; a.start_x = start_x; a.start_y = start_y;
     a.u_fine = u_fine; a.f_fine = f_fine; a.u_coarse = u_coarse; a.f_coarse = f_coarse;
     a.th_fine = nullptr; a.th_coarse = nullptr;
-    std::vector<double> smem((n == 40 ? psn_block_smem_doubles<10>(hp.plan) : psn_block_smem_doubles<20>(hp.plan)) + 64);
+    std::vector<double> smem((n == 20 ? psn_block_smem_doubles<5>(hp.plan)
+                                      : n == 40 ? psn_block_smem_doubles<10>(hp.plan) : psn_block_smem_doubles<20>(hp.plan)) + 64);
     PsnHostCtx ctx;
     for (long long b = 0; b < B; ++b) {
         std::fill(smem.begin(), smem.end(), std::nan(""));
-        if (n == 40)
+        if (n == 20)
+            psn_block_solve_body<5>(ctx, hp.plan, a, b, smem.data());
+        else if (n == 40)
             psn_block_solve_body<10>(ctx, hp.plan, a, b, smem.data());
         else
             psn_block_solve_body<20>(ctx, hp.plan, a, b, smem.data());

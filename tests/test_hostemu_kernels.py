@@ -194,7 +194,7 @@ def test_fp64_floor_status(he):
     assert O.rel_l2(u[0], O.solve_poisson(f, theta, n)) <= 1e-10
 
 
-@pytest.mark.parametrize("n,nu", [(80, 1), (80, 2), (80, 3), (40, 1), (40, 2), (40, 3)])
+@pytest.mark.parametrize("n,nu", [(80, 1), (80, 2), (80, 3), (40, 1), (40, 2), (40, 3), (20, 1), (20, 2), (20, 3)])
 def test_register_blocked_resident_solver_matches_generic(he, n, nu):
     """psn_block.cuh (80x80 and 40x40: 4x4 / 2x2 / 1 node(s) per thread on levels 0 / 1 / 2 in registers, edge buffers in
     shared memory), emulated with the state of all 400 / 100 threads, against the generic shared-memory solver
@@ -204,7 +204,7 @@ def test_register_blocked_resident_solver_matches_generic(he, n, nu):
     u = np.full((B, n, n), np.nan)
     it, rr, st = np.zeros(B, np.int32), np.zeros(B), np.zeros(B, np.int32)
     w = n // 2
-    x0 = np.array([0, w - 1, 17], dtype=np.int32)
+    x0 = np.array([0, w - 1, min(17, w - 3)], dtype=np.int32)
     y0 = np.array([w - 1, 0, 5], dtype=np.int32)
     uf, ff = np.full((B, w, w), np.nan), np.full((B, w, w), np.nan)
     uc, fc = np.full((B, w // 2, w // 2), np.nan), np.full((B, w // 2, w // 2), np.nan)
@@ -222,7 +222,7 @@ def test_register_blocked_resident_solver_matches_generic(he, n, nu):
         assert np.array_equal(uc[b], u[b][win][::2, ::2]) and np.array_equal(fc[b], f[b][win][::2, ::2])
 
 
-@pytest.mark.parametrize("n,nu", [(80, 1), (80, 2), (40, 2)])
+@pytest.mark.parametrize("n,nu", [(80, 1), (80, 2), (40, 2), (20, 2)])
 def test_register_blocked_solver_phases_are_race_free(he, n, nu):
     """Every phase between two barriers of psn_block.cuh must not depend on the order of its threads: levels 1 and 2 exchange
     through planes of their own so that 'read the other level's edges' and 'publish mine' share a barrier interval, the float
