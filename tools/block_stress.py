@@ -1,4 +1,4 @@
-"""Dev tool (GPU box): the register-blocked 80x80 kernel on awkward data -- forcing scales from 1e-30 to 1e30, theta contrasts
+"""Dev tool (GPU box): the register-blocked kernels (80x80 by default; `block_stress.py SEED 40` / `20` for the others) on awkward data -- forcing scales from 1e-30 to 1e30, theta contrasts
 up to 1e6, high wave numbers, a zero right-hand side -- against the oracle (SciPy spsolve restatement of the reference).
 The V-cycle of that kernel runs in float on a power-of-two-scaled residual; this checks that the scaling makes it
 insensitive to the magnitude of the data.  Exits 1 on any failure."""
@@ -10,7 +10,7 @@ from oracle import poisson_oracle as O
 
 _lib.init(0)
 rs = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
-n = 80
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 80
 x = np.linspace(0, 1, n)
 bad = 0
 iters_seen = []
@@ -18,7 +18,7 @@ for scale in [1e-30, 1e-12, 1.0, 1e9, 1e30]:
     for lo, hi in [(0.5, 2.0), (1e-3, 1e3), (1.0, 1.0)]:
         for B in [1, 7, 300]:
             theta = np.exp(rs.uniform(np.log(lo), np.log(hi), size=(B, n, n)))
-            k = rs.uniform(0.5, 30.0, size=(B, 2))
+            k = rs.uniform(0.5, 0.375 * n, size=(B, 2))
             sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
             if B == 7:
                 sx[3] = 0.0   # zero right-hand side: u = 0, status converged, no NaN from the 1 / ||r|| scaling

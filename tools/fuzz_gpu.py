@@ -9,7 +9,7 @@ from oracle import poisson_oracle as O
 _lib.init(0)
 rs = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 ncases = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-sizes = [40, 64, 80, 80, 88, 90, 96, 100, 104, 112, 120, 128, 131, 144, 160, 168, 176, 192, 200, 208, 224, 240, 256, 272, 288, 300, 320, 352, 384, 416, 448]
+sizes = [20, 20, 40, 40, 64, 80, 80, 88, 90, 96, 100, 104, 112, 120, 128, 131, 144, 160, 168, 176, 192, 200, 208, 224, 240, 256, 272, 288, 300, 320, 352, 384, 416, 448]
 bad = 0
 t0 = time.time()
 for case in range(ncases):
