@@ -215,6 +215,7 @@ int psn_mt19937_jump_host(const uint32_t* key, int pos, int64_t n_words, uint32_
  * "host_slots" (default 5, 3..6: staging slots),
  * "host_prefetch" (default 3, 1..3: uploads are enqueued this many chunks ahead of the solve being enqueued),
  * "host_h2d_stream" (default 1: uploads of all chunks go through one dedicated stream, in chunk order),
+ * "coarse_block" (default 1: an 80 x 80 level of a streamed hierarchy and everything below it run in the register-blocked V-cycle kernel),
  * "coarse_max_n", "host_chunks", "host_edge_div", "dir_band", "upd_band",
  * "band_target", "res_block", "serialize_solves" (pipeline / decomposition tuning, see psn_b200.cu). */
 int psn_set_option(const char* name, int64_t value);

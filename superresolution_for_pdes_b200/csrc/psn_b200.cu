@@ -95,6 +95,29 @@ __global__ void __launch_bounds__(PsnBlockGeom<BX>::NTPAD, PSN_BLOCK_CTAS(BX)) p
     }
 }
 
+// Coarse tail of the streamed solver when it has an 80 x 80 level: the register-blocked V-cycle of psn_block.cuh on that level
+// and everything below it, one persistent CTA per SM; the dense inverse and the zeroed edge planes are set up before the
+// programmatic-dependent-launch wait, i.e. under the tail of the kernel in front.
+template <int BX, class TV>
+__global__ void __launch_bounds__(PsnBlockGeom<BX>::NTPAD, PSN_BLOCK_CTAS(BX)) psn_block_vcycle_kernel(const __grid_constant__ PsnPlan plan, int L0,
+                                                                                                      const TV* bg, TV* ug,
+                                                                                                      const PsnSampleState* state, long long B,
+                                                                                                      int inv_doubles) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double red[64];
+    PsnDevCtx ctx{(int)threadIdx.x, PsnBlockGeom<BX>::NTPAD, red, 0};
+    const int own = psn_block_vcycle_smem_doubles<BX>(plan, L0);
+    double* inv_s = nullptr;
+    if (inv_doubles > 0) {
+        inv_s = smem + own;
+        for (int i = threadIdx.x; i < inv_doubles; i += PsnBlockGeom<BX>::NTPAD) inv_s[i] = __ldg(plan.coarse_inv + i);
+    }
+    for (int i = threadIdx.x; i < own; i += PsnBlockGeom<BX>::NTPAD) smem[i] = 0.0;
+    __syncthreads();
+    psn_pdl_enter();
+    for (long long b = blockIdx.x; b < B; b += gridDim.x) psn_block_vcycle_body<BX>(ctx, plan, L0, bg, ug, state, b, smem, inv_s, true);
+}
+
 #define PSN_TILE_THREADS 256
 #define PSN_COARSE_THREADS 512
 #define PSN_CG_THREADS 256
@@ -544,6 +567,7 @@ struct Context {
     long long ws_bytes = 24ll << 30;
     int smem_max_n = 0;
     int coarse_max_n = 40; // largest level handed to the shared-memory coarse V-cycle kernel (0: as large as fits)
+    int coarse_block = 1;  // hierarchies with an 80 x 80 level: that level and below go to the register-blocked V-cycle kernel
     int serialize_solves = 0;
     int res_block = 1;     // use the register-blocked resident kernel where one is compiled (n = 80)
     int res_threads = 0;   // 0: smallest variant that fits; else force this CTA size for the resident kernel
@@ -696,6 +720,9 @@ ResidentCfg resident_cfg(const PsnPlan& plan) {
 
 // first level that the shared-memory coarse kernel can take
 int stream_ls(const PsnPlan& plan) {
+    if (g.coarse_block)   // an 80 x 80 level: the register-blocked V-cycle kernel takes it and everything below
+        for (int l = 1; l < plan.nlev; ++l)
+            if (psn_block_ok_at<20>(plan, l)) return l;
     for (int l = 1; l < plan.nlev; ++l) {
         size_t bytes = ((size_t)2 * plan.lv[l].size + psn_pool_doubles(plan, l)) * sizeof(double);
         if (g.coarse_max_n > 0 && plan.lv[l].n > g.coarse_max_n && l + 1 < plan.nlev) continue;
@@ -718,6 +745,8 @@ int set_kernel_attrs() {
     CU_TRY(cudaFuncSetAttribute(psn_tile_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CU_TRY(cudaFuncSetAttribute(psn_coarse_vcycle_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CU_TRY(cudaFuncSetAttribute(psn_coarse_vcycle_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_block_vcycle_kernel<20, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CU_TRY(cudaFuncSetAttribute(psn_block_vcycle_kernel<20, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     g.attrs_set = true;
     return PSN_OK;
 }
@@ -886,6 +915,20 @@ struct CudaBackend {
     void coarse_vcycle(const PsnPlan& plan, const PsnStreamCfg& cfg, const double* bg, double* ug, const PsnSampleState* st, long long B) {
         ProfScope p("coarse_vcycle", s);
         const int l0 = cfg.ls;
+        if (cfg.coarse_block && psn_block_ok_at<20>(plan, l0)) {
+            size_t bsm = (size_t)psn_block_vcycle_smem_doubles<20>(plan, l0) * sizeof(double);
+            int invd = psn_coarse_inv_doubles(plan);
+            if (!g.inv_smem || bsm + (size_t)invd * sizeof(double) + 1024 > g.smem_optin) invd = 0;
+            bsm += (size_t)invd * sizeof(double);
+            const unsigned grid = (unsigned)std::min<long long>(B, (long long)g.sm_count);
+            if (cfg.mode == 2 && cfg.vf32)
+                launch(psn_block_vcycle_kernel<20, float>, dim3(grid), dim3(PsnBlockGeom<20>::NTPAD), bsm, plan, l0,
+                       reinterpret_cast<const float*>(bg), reinterpret_cast<float*>(ug), st, B, invd);
+            else
+                launch(psn_block_vcycle_kernel<20, double>, dim3(grid), dim3(PsnBlockGeom<20>::NTPAD), bsm, plan, l0, bg, ug, st, B, invd);
+            chk();
+            return;
+        }
         const size_t smem = ((size_t)2 * plan.lv[l0].size + psn_pool_doubles(plan, l0)) * sizeof(double);
         if (cfg.mode == 2 && cfg.vf32)
             launch(psn_coarse_vcycle_kernel<float>, dim3((unsigned)B), dim3(PSN_COARSE_THREADS), smem, plan, l0, reinterpret_cast<const float*>(bg),
@@ -1216,6 +1259,7 @@ int solve_impl(const Problem& P) {
     scfg.mode = g.vcycle_mode;
     if (!resident) {
         scfg.ls = stream_ls(plan);
+        scfg.coarse_block = (g.coarse_block && scfg.ls >= 1 && psn_block_ok_at<20>(plan, scfg.ls)) ? 1 : 0;
         if (scfg.ls >= 1 && !psn_strip_ok(plan, scfg.ls)) scfg.mode = 0;   // odd level sizes: shared-memory tile kernels
         scfg.vf32 = (scfg.mode == 2 && g.vcycle_f32 && scfg.ls >= 1 && psn_vf32_ok(plan, scfg.ls)) ? 1 : 0;
         scfg.upd_strip = g.upd_strip;
@@ -2134,6 +2178,8 @@ int psn_set_option(const char* name, int64_t value) {
         g.ws_bytes = value;
     } else if (!strcmp(name, "smem_max_n")) {
         g.smem_max_n = (int)value;
+    } else if (!strcmp(name, "coarse_block")) {
+        g.coarse_block = value ? 1 : 0;
     } else if (!strcmp(name, "coarse_max_n")) {
         if (value < 0) return psn_fail(PSN_ERR_INVALID, "coarse_max_n must be >= 0");
         g.coarse_max_n = (int)value;
@@ -2277,6 +2323,7 @@ int psn_describe(int n, int64_t* info) {
         PsnStreamCfg sc;
         memset(&sc, 0, sizeof(sc));
         sc.ls = stream_ls(plan); sc.TH = sc.TW = g.tile; sc.mode = g.vcycle_mode;
+        sc.coarse_block = (g.coarse_block && sc.ls >= 1 && psn_block_ok_at<20>(plan, sc.ls)) ? 1 : 0;
         if (sc.ls >= 1 && !psn_strip_ok(plan, sc.ls)) sc.mode = 0;
         sc.vf32 = (sc.mode == 2 && g.vcycle_f32 && sc.ls >= 1 && psn_vf32_ok(plan, sc.ls)) ? 1 : 0;
         info[7] = sc.vf32 | ((sc.mode == 2 && g.upd_strip && (plan.n & 1) == 0) ? 2 : 0);

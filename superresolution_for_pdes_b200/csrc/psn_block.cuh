@@ -142,15 +142,28 @@ struct PsnBlockGeom {
 // doubles of dynamic shared memory the block kernel needs (x, edge buffers, coarse levels >= 1)
 // Levels 0 and 1 always live in registers; level 2 too when there is a level below it (n, n/2, n/4 | n/8 ...), otherwise
 // level 2 is the dense one (n = 20: 20, 10 | 5) and its right-hand side / solution pass through shared memory.
-PSN_HDFN int psn_block_pool_doubles(const PsnPlan& plan) { return psn_pool_doubles(plan, plan.nlev >= 4 ? 2 : 1); }
+// (L0: the level of the plan that the block code treats as its level 0 -- 0 for the stand-alone solver, the first coarse
+// level handed over by the streamed solver for the V-cycle-only kernel)
+PSN_HDFN int psn_block_pool_doubles(const PsnPlan& plan, int L0 = 0) {
+    return psn_pool_doubles(plan, L0 + (plan.nlev >= L0 + 4 ? 2 : 1));
+}
 template <int BX>
 PSN_HDFN int psn_block_smem_doubles(const PsnPlan& plan) {
     return PsnBlockGeom<BX>::XS + PsnBlockGeom<BX>::ES + psn_block_pool_doubles(plan);
 }
-// the register-blocked solver needs the hierarchy n, n/2, n/4, ... with at least 3 levels
+// the register-blocked code needs the hierarchy n, n/2, n/4, ... with at least 3 levels from level L0 on
+template <int BX>
+PSN_HDFN bool psn_block_ok_at(const PsnPlan& plan, int L0) {
+    return L0 >= 0 && plan.nlev >= L0 + 3 && plan.lv[L0].n == 4 * BX && plan.lv[L0 + 1].n == 2 * BX && plan.lv[L0 + 2].n == BX;
+}
 template <int BX>
 PSN_HDFN bool psn_block_ok(const PsnPlan& plan) {
-    return plan.n == 4 * BX && plan.nlev >= 3 && plan.lv[1].n == 2 * BX && plan.lv[2].n == BX;
+    return plan.n == 4 * BX && psn_block_ok_at<BX>(plan, 0);
+}
+// shared memory of the V-cycle-only kernel: edge planes and the levels below the register levels (no x)
+template <int BX>
+PSN_HDFN int psn_block_vcycle_smem_doubles(const PsnPlan& plan, int L0) {
+    return PsnBlockGeom<BX>::ES + psn_block_pool_doubles(plan, L0);
 }
 // doubles of the dense coarsest-level inverse, kept behind the arrays above by the persistent kernel when it fits
 PSN_HDFN int psn_coarse_inv_doubles(const PsnPlan& plan) {
@@ -200,16 +213,34 @@ struct PsnBlockSolver {
 #if defined(__CUDACC__)
     PsnShF64 ea_dev, xa_dev;   // this thread's own edge cell / x column (shared addresses pinned in registers)
     ShV ev_dev;
-    int fl_dev;                // bit 0: real thread (t < NT), bit 1: (bx + by) odd, bit 2: bx and by both odd
+    int fl_dev;                // bit 0: real thread (t < NT), bit 1: (bx + by) odd, bit 2: bx and by both odd,
+                               // bits 3 / 4: last thread row / column
 #endif
 
     const double* inv_s = nullptr;   // shared-memory copy of the coarsest-level inverse (or null)
+    int L0 = 0;                      // level of the plan that is this solver's level 0
+    // GAM0 (V-cycle-only kernel: level 0 is a coarse level of a larger hierarchy, whose last row / column carry the extra
+    // diagonal weight gam): reciprocal diagonals 1/4, 1/(4 + gam), 1/(4 + 2 gam) and gam itself
+    VT R0[3] = {(VT)0.25, (VT)0.25, (VT)0.25};
+    VT gam0 = (VT)0;
+    template <bool GAM0>
+    PSN_FN VT rdiag0(int a, int cc, int fl) const {
+        if (!GAM0 || (a < 3 && cc < 3)) return (VT)0.25;
+        const bool lr = a == 3 && (fl & 8), lc = cc == 3 && (fl & 16);
+        return lr ? (lc ? R0[2] : R0[1]) : (lc ? R0[1] : R0[0]);
+    }
+    template <bool GAM0>
+    PSN_FN VT diag0(int a, int cc, int fl) const {
+        if (!GAM0 || (a < 3 && cc < 3)) return (VT)4;
+        return (VT)4 + ((a == 3 && (fl & 8)) ? gam0 : (VT)0) + ((cc == 3 && (fl & 16)) ? gam0 : (VT)0);
+    }
 
     // position of thread t in the ghost-ringed thread grid of pitch P; the idle threads of the last warp get private cells behind it
     PSN_FN static int tpad(int t, int P) { return t < NT ? (by_of(t) + 1) * P + bx_of(t) + 1 : G::BROWS * P + (t - NT); }
     PSN_FN static int flags_of(int t) {
         const int bx = bx_of(t), by = by_of(t);
-        return (t < NT ? 1 : 0) | ((((bx + by) & 1) && t < NT) ? 2 : 0) | (((bx & 1) && (by & 1) && t < NT) ? 4 : 0);
+        return (t < NT ? 1 : 0) | ((((bx + by) & 1) && t < NT) ? 2 : 0) | (((bx & 1) && (by & 1) && t < NT) ? 4 : 0) |
+               ((by == BX - 1 && t < NT) ? 8 : 0) | ((bx == BX - 1 && t < NT) ? 16 : 0);
     }
     PSN_FN int flags(int t) const {
 #if defined(__CUDACC__)
@@ -345,9 +376,11 @@ struct PsnBlockSolver {
     // one RB-GS half sweep on z with rhs bv; ends with the edges of colour `col` published and a sync.  Every thread of the CTA
     // takes part: the idle threads of the last warp work on zeros in their private cells.
     // (last: the final half sweep of the V-cycle -- nobody reads z's edges after it, and the next phase has a barrier of its own)
+    template <bool GAM0 = false>
     PSN_FN void half_sweep(int col, bool first, bool last = false) {
         PSN_BK_FOR(ctx, NTPAD) {
             const CurV c = curv(t_);
+            const int fl = GAM0 ? flags(t_) : 0;
             VT (&zz)[16] = z[PSN_BK_TI];
             const VT (&rr)[16] = bv[PSN_BK_TI];
             VT hT[4], hB[4], hL[4], hR[4];
@@ -358,7 +391,7 @@ struct PsnBlockSolver {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc)
                     if (((a + cc) & 1) == col)
-                        nv[4 * a + cc] = (rr[4 * a + cc] + (first ? (VT)0 : nbsum(zz, a, cc, hT, hB, hL, hR))) * (VT)0.25;
+                        nv[4 * a + cc] = (rr[4 * a + cc] + (first ? (VT)0 : nbsum(zz, a, cc, hT, hB, hL, hR))) * rdiag0<GAM0>(a, cc, fl);
 #pragma unroll
             for (int k = 0; k < 16; ++k)
                 if ((((k >> 2) + (k & 3)) & 1) == col) zz[k] = nv[k];
@@ -465,12 +498,13 @@ struct PsnBlockSolver {
     }
 
     // z = M^{-1} bv with levels 0, 1, 2 in registers (n = 4 BX, 2 BX, BX) and levels >= 3 in shared memory (fp64)
+    template <bool GAM0>
     PSN_FN void vcycle3(const PsnPlan& plan, double* pool) {
-        const int nu = plan.nul[0], nu1 = plan.nul[1], nu2 = plan.nul[2];
-        const PsnLevel& l1 = plan.lv[1];
-        const PsnLevel& l2 = plan.lv[2];
-        const bool dense2 = plan.nlev == 3;              // level 2 is the dense level (n = 20); CTA-uniform
-        const PsnLevel& l3 = plan.lv[dense2 ? 2 : 3];    // first level kept in shared memory
+        const int nu = plan.nul[L0], nu1 = plan.nul[L0 + 1], nu2 = plan.nul[L0 + 2];
+        const PsnLevel& l1 = plan.lv[L0 + 1];
+        const PsnLevel& l2 = plan.lv[L0 + 2];
+        const bool dense2 = plan.nlev == L0 + 3;              // level 2 is the dense level (n = 20); CTA-uniform
+        const PsnLevel& l3 = plan.lv[L0 + (dense2 ? 2 : 3)];  // first level kept in shared memory
         double* b3 = pool;
         double* u3 = pool + l3.size;
         double* pool4 = pool + 2 * l3.size;
@@ -493,11 +527,11 @@ struct PsnBlockSolver {
             }
         }
         // ---------------- level 0 down
-        half_sweep(0, true);
-        half_sweep(1, false);
+        half_sweep<GAM0>(0, true);
+        half_sweep<GAM0>(1, false);
         for (int s = 1; s < nu; ++s) {
-            half_sweep(0, false);
-            half_sweep(1, false);
+            half_sweep<GAM0>(0, false);
+            half_sweep<GAM0>(1, false);
         }
         PSN_BK_FOR(ctx, NTPAD) {
             const CurV c = curv(t_);
@@ -510,7 +544,8 @@ struct PsnBlockSolver {
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc)
-                    if (((a + cc) & 1) == 0) pp[4 * a + cc] = rr[4 * a + cc] - ((VT)4 * zz[4 * a + cc] - nbsum(zz, a, cc, hT, hB, hL, hR));
+                    if (((a + cc) & 1) == 0)
+                        pp[4 * a + cc] = rr[4 * a + cc] - (diag0<GAM0>(a, cc, GAM0 ? flags(t_) : 0) * zz[4 * a + cc] - nbsum(zz, a, cc, hT, hB, hL, hR));
             // (reads above: black slots; writes below: red slots of TOP / LEFT -> no barrier needed in between)
             ES(c, TOP, 0, pp[0]);
             ES(c, TOP, 2, pp[2]);
@@ -569,7 +604,7 @@ struct PsnBlockSolver {
         ctx.sync();
         if (dense2) {
             // ---------------- level 2 is the dense level: solve it, every thread fetches its node and publishes it
-            psn_vcycle_smem(ctx, plan, 2, b3, u3, pool4, inv_s);
+            psn_vcycle_smem(ctx, plan, L0 + 2, b3, u3, pool4, inv_s);
             PSN_BK_FOR(ctx, NTPAD) {
                 if (flags(t_) & 1) {
                     const VT v = (VT)u3[(by_of(t_) + 1) * l3.pitch + bx_of(t_) + 1];
@@ -605,7 +640,7 @@ struct PsnBlockSolver {
         ctx.sync();
         // ---------------- levels >= 3 in shared memory, fp64 (all warps; running them on a single warp with
         // __syncwarp instead of CTA barriers was measured 7 % slower)
-        psn_vcycle_smem(ctx, plan, 3, b3, u3, pool4, inv_s);
+        psn_vcycle_smem(ctx, plan, L0 + 3, b3, u3, pool4, inv_s);
         // ---------------- level 2 up
         PSN_BK_FOR(ctx, NT) {
             if ((flags(t_) & 3) == 1) {   // real thread, (bx + by) even
@@ -675,8 +710,8 @@ struct PsnBlockSolver {
             ctx.sync();
         }
         for (int s = 0; s < nu; ++s) {
-            half_sweep(1, false);
-            half_sweep(0, false, s == nu - 1);
+            half_sweep<GAM0>(1, false);
+            half_sweep<GAM0>(0, false, s == nu - 1);
         }
     }
 
@@ -806,7 +841,7 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
 #pragma unroll
                 for (int k = 0; k < 16; ++k) S.bv[PSN_BK_TI][k] = (VT)(S.r[PSN_BK_TI][k] * vs);
             }
-            S.vcycle3(plan, pool);
+            S.template vcycle3<false>(plan, pool);
             PSN_BK_FOR(ctx, NTPAD) {
                 double s = 0.0;
 #pragma unroll
@@ -959,4 +994,60 @@ PSN_FN void psn_block_solve_body(Ctx& ctx, const PsnPlan& plan, const PsnSolveAr
         if (a.relres) a.relres[b] = (bb > 0.0) ? sqrt(rr_final / bb) : 0.0;
         if (a.status) a.status[b] = status;
     }
+}
+
+// ----------------------------------------------------------------------------- V-cycle only (coarse tail of the streamed solver)
+// u = M^{-1} b on level L0 of the plan (n_L0 = 4 BX) and everything below it, for sample b of [B, n, n] arrays of TV (the float
+// storage of the streamed V-cycle, or double): the register-blocked V-cycle above with level L0 as its level 0 -- which, being a
+// coarse level, carries the boundary weight gam in its diagonal (GAM0).  Replaces the last strip levels and the shared-memory
+// coarse kernel of the streamed path when an 80 x 80 level exists (n = 160, 320, 640).  `zeroed`: the caller has zeroed the
+// edge planes and the pool once for this CTA -- the V-cycle never writes a ghost cell, so that holds for every sample.
+template <int BX, class TV, class Ctx>
+PSN_FN void psn_block_vcycle_body(Ctx& ctx, const PsnPlan& plan, int L0, const TV* bglob, TV* uglob, const PsnSampleState* state,
+                                  long long b, double* smem, const double* inv_s, bool zeroed) {
+    if (state && state[b].phase != PSN_PHASE_ITER) return;   // (uniform over the CTA)
+    typedef PsnBlockGeom<BX> G;
+    typedef PsnBlockSolver<BX, Ctx> SV;
+    typedef typename SV::VT VT;
+    constexpr int N = G::N, NT = G::NT, NTPAD = G::NTPAD;
+    (void)NTPAD;   // (only the host emulation's phase loops use it)
+    // the solver addresses "x, then the planes": hand it a base such that the planes start at smem (x is never touched here)
+    SV S(ctx, smem - G::XS);
+    S.inv_s = inv_s;
+    S.L0 = L0;
+    const PsnLevel& lv = plan.lv[L0];
+    S.R0[0] = (VT)lv.rd0; S.R0[1] = (VT)lv.rd1; S.R0[2] = (VT)lv.rd2;
+    S.gam0 = (VT)lv.gam;
+    double* pool = smem + G::ES;
+    if (!zeroed) {
+        const int zn = G::ES + psn_block_pool_doubles(plan, L0);
+        for (int idx = ctx.tid; idx < zn; idx += ctx.nthreads) smem[idx] = 0.0;
+        ctx.sync();
+    }
+    const TV* bg = bglob + b * (long long)(N * N);
+    TV* ug = uglob + b * (long long)(N * N);
+    PSN_BK_FOR(ctx, NTPAD) {
+        const int bx = SV::bx_of(t_), by = SV::by_of(t_);
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                S.bv[PSN_BK_TI][4 * a + c] = (t_ < NT) ? (VT)bg[(4 * by + a) * N + 4 * bx + c] : (VT)0;
+                S.z[PSN_BK_TI][4 * a + c] = (VT)0;
+            }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) S.z1[PSN_BK_TI][k] = S.r1[PSN_BK_TI][k] = (VT)0;
+        S.z2[PSN_BK_TI][0] = S.r2[PSN_BK_TI][0] = (VT)0;
+    }
+    S.template vcycle3<true>(plan, pool);
+    PSN_BK_FOR(ctx, NT) {
+        if (t_ < NT) {
+            const int bx = SV::bx_of(t_), by = SV::by_of(t_);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) ug[(4 * by + a) * N + 4 * bx + c] = (TV)S.z[PSN_BK_TI][4 * a + c];
+        }
+    }
+    ctx.sync();   // the next sample's first half sweep publishes into planes that the last up-sweep of this one still reads
 }

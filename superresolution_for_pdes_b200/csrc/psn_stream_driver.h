@@ -14,6 +14,7 @@
 
 struct PsnStreamCfg {
     int ls;       // first level handled by the shared-memory coarse kernel (levels 0..ls-1 are streamed)
+    int coarse_block = 0;   // level ls is 80 x 80 and goes to the register-blocked V-cycle kernel (psn_block_vcycle_body)
     int TH, TW;   // interior tile of the shared-memory tile kernels (mode 0)
     int mode;     // V-cycle legs: 0 = shared-memory tiles, 1 = warp strips fed by register prefetch,
                   //               2 = warp strips fed by TMA bulk copies through a shared-memory ring

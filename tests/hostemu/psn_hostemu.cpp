@@ -96,6 +96,19 @@ struct HostBackend {
     }
     void coarse_vcycle(const PsnPlan& plan, const PsnStreamCfg& cfg, const double* bg, double* ug, const PsnSampleState* st, long long B) {
         PsnHostCtx ctx;
+        if (cfg.coarse_block && psn_block_ok_at<20>(plan, cfg.ls)) {   // register-blocked V-cycle on the 80 x 80 level and below
+            std::vector<double> sm(psn_block_vcycle_smem_doubles<20>(plan, cfg.ls) + PsnBlockGeom<20>::XS + 64);
+            for (long long b = 0; b < B; ++b) {
+                std::fill(sm.begin(), sm.end(), std::nan(""));
+                double* base = sm.data() + PsnBlockGeom<20>::XS;   // (the body hands the solver "base - XS")
+                if (cfg.mode == 2 && cfg.vf32)
+                    psn_block_vcycle_body<20>(ctx, plan, cfg.ls, reinterpret_cast<const float*>(bg), reinterpret_cast<float*>(ug), st, b, base,
+                                              (const double*)nullptr, false);
+                else
+                    psn_block_vcycle_body<20>(ctx, plan, cfg.ls, bg, ug, st, b, base, (const double*)nullptr, false);
+            }
+            return;
+        }
         for (long long b = 0; b < B; ++b) {
             if (cfg.mode == 2 && cfg.vf32)
                 psn_coarse_vcycle_body(ctx, plan, cfg.ls, reinterpret_cast<const float*>(bg), reinterpret_cast<float*>(ug), st, b, smem.data());
@@ -255,14 +268,16 @@ int hostemu_solve_stream(int n, long long B, const double* theta, const double* 
     PsnStreamCfg cfg;
     // mode 3 = mode 2 (TMA-fed strips) with float storage of the V-cycle intermediates; mode 4 = mode 3 + fused update / down-leg;
     // mode 5 = mode 4 + fused prologue / first down-leg
+    // mode 6 = mode 5 with the 80 x 80 level (ls) and everything below in the register-blocked V-cycle kernel
     cfg.ls = ls; cfg.TH = TH; cfg.TW = TW; cfg.mode = (mode >= 1 && psn_strip_ok(plan, ls)) ? (mode >= 3 ? 2 : mode) : 0;
+    cfg.coarse_block = (mode >= 6 && psn_block_ok_at<20>(plan, ls)) ? 1 : 0;
     cfg.vf32 = (mode >= 3 && cfg.mode == 2 && psn_vf32_ok(plan, ls)) ? 1 : 0;
     cfg.dir_band = 0;
     cfg.upd_band = 0;
     cfg.upd_strip = (cfg.mode == 2) ? 1 : 0;
     cfg.pf32 = cfg.vf32;
     cfg.xdefer = cfg.pf32;
-    cfg.fuse = (mode >= 4 && cfg.xdefer) ? mode - 3 : 0;
+    cfg.fuse = (mode >= 4 && cfg.xdefer) ? (mode >= 5 ? 2 : 1) : 0;
     cfg.fuse_band = (band >= 32) ? ((band / 2 + 1) & ~1) : 0;   // a different split than the other level-0 kernels
     if (mode >= 3 && !cfg.vf32) return -2;
     for (int l = 0; l < PSN_MAX_LEVELS; ++l) cfg.band[l] = band;

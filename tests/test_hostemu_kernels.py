@@ -356,6 +356,28 @@ def test_fused_update_and_down_leg(he, n, ls, band, nu):
         assert O.residual_rel(u4[b], f, theta[b]) <= 1e-11
 
 
+@pytest.mark.parametrize("n,ls,band,nu", [(160, 1, 64, 2), (320, 2, 64, 2), (160, 1, 48, 1)])
+def test_coarse_tail_in_the_register_blocked_vcycle(he, n, ls, band, nu):
+    """Mode 6 = mode 5 with the 80 x 80 level and everything below it in the register-blocked V-cycle of psn_block.cuh (float,
+    level 0 of the block code carrying the boundary weight of a coarse level) instead of strips down to 40 x 40 plus the
+    shared-memory coarse kernel: same iteration counts to within one, 1e-10 against the reference operator."""
+    rs = np.random.RandomState(n + nu + 7)
+    B = 2
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    k = rs.uniform(0.5, 12.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    u6, it6, rr6, st6 = run_stream(he, n, theta, None, 64, 64, ls, mode=6, band=band, nu=nu, sx=sx, sy=sy)
+    u5, it5, rr5, st5 = run_stream(he, n, theta, None, 64, 64, ls + 1, mode=5, band=band, nu=nu, sx=sx, sy=sy)
+    assert (st6 == 0).all() and (st5 == 0).all()
+    assert (np.abs(it6 - it5) <= 1).all()
+    assert O.rel_l2(u6, u5) <= 1e-11
+    for b in range(B):
+        f = np.outer(sy[b], sx[b])
+        assert O.rel_l2(u6[b], O.solve_poisson(f, theta[b], n)) <= 1e-10
+        assert O.residual_rel(u6[b], f, theta[b]) <= 1e-11
+
+
 def test_fused_update_restart_full_ring_and_scales(he):
     """Fused schedule through its rare paths: (a) a failed check restarts from the recomputed residual (the plain
     down-leg then runs for that sample only); (b) more outer iterations than ring slots; (c) data of extreme magnitude
