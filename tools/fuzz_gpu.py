@@ -9,7 +9,7 @@ from oracle import poisson_oracle as O
 _lib.init(0)
 rs = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 ncases = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-sizes = [20, 20, 40, 40, 64, 80, 80, 88, 90, 96, 100, 104, 112, 120, 128, 131, 144, 160, 168, 176, 192, 200, 208, 224, 240, 256, 272, 288, 300, 320, 352, 384, 416, 448]
+sizes = [20, 20, 40, 40, 64, 80, 80, 160, 160, 320, 320, 640, 88, 90, 96, 100, 104, 112, 120, 128, 131, 144, 160, 168, 176, 192, 200, 208, 224, 240, 256, 272, 288, 300, 320, 352, 384, 416, 448]
 bad = 0
 t0 = time.time()
 for case in range(ncases):
@@ -18,7 +18,8 @@ for case in range(ncases):
     opts = {"vcycle_f32": int(rs.rand() < 0.8), "upd_strip": int(rs.rand() < 0.8), "p_f32": int(rs.rand() < 0.8),
             "x_defer": int(rs.rand() < 0.8), "nu": int(rs.choice([1, 2, 2, 2, 3])), "pdl": int(rs.rand() < 0.7),
             "vcycle_mode": int(rs.choice([2, 2, 2, 1, 0])), "fuse_upd": int(rs.choice([2, 2, 1, 0])),
-            "copy_streams": int(rs.rand() < 0.7), "coarsest_max": int(rs.choice([0, 0, 6, 10]))}
+            "copy_streams": int(rs.rand() < 0.7), "coarsest_max": int(rs.choice([0, 0, 6, 10])),
+            "coarse_block": int(rs.rand() < 0.75), "res_block": int(rs.rand() < 0.85)}
     host = rs.rand() < 0.5
     theta = rs.uniform(0.5, 2.0, size=(B, n, n))
     k = rs.uniform(0.5, 12.0, size=(B, 2))
@@ -48,7 +49,7 @@ for case in range(ncases):
     bad += 0 if ok else 1
     print(f"{'ok  ' if ok else 'FAIL'} n={n:4d} B={B:3d} host={int(host)} scale={scale:g} opts={opts} iters={None if info is None else int(np.max(info.iters))} err={errs}")
 for kname, v in {"vcycle_f32": 1, "upd_strip": 1, "p_f32": 1, "x_defer": 1, "nu": 2, "pdl": 1, "vcycle_mode": 2, "fuse_upd": 2,
-                 "copy_streams": 1, "coarsest_max": 0}.items():
+                 "copy_streams": 1, "coarsest_max": 0, "coarse_block": 1, "res_block": 1}.items():
     _lib.set_option(kname, v)
 print(f"{ncases - bad}/{ncases} cases ok in {time.time() - t0:.0f} s")
 sys.exit(1 if bad else 0)
