@@ -7,7 +7,7 @@ rows = list(csv.reader(open(sys.argv[1])))
 hdr = None
 agg, cnt = collections.Counter(), collections.Counter()
 ALIAS = {"psn_upre_strip_kernel": "update_pre_l0", "psn_dir_strip_kernel": "dir_apply_dot", "psn_flush_x_kernel": "flush_x",
-         "psn_prologue_kernel": "prologue", "psn_true_residual_strip_kernel": "true_residual", "psn_coarse_vcycle_kernel": "coarse_vcycle",
+         "psn_prologue_kernel": "prologue", "psn_true_residual_strip_kernel": "true_residual", "psn_coarse_vcycle_kernel": "coarse_vcycle", "psn_block_vcycle_kernel": "coarse_vcycle",
          "psn_update_strip_kernel": "update_norm", "psn_block_solve_kernel": "smem_solve", "psn_smem_solve_kernel": "smem_solve"}
 for r in rows:
     if "Kernel Name" in r:
