@@ -121,6 +121,62 @@ def test_float_stored_vcycle_is_scale_invariant(gpu_lib):
         assert O.rel_l2(us / scale, u) <= 1e-10
 
 
+@pytest.mark.parametrize("n,B", [(20, 700), (40, 650), (80, 310)])
+def test_register_blocked_kernels_against_the_generic_one(gpu_lib, n, B):
+    """20 x 20, 40 x 40 and 80 x 80 run in the register-blocked kernels (float V-cycle, levels n, n/2, n/4 in registers);
+    `res_block = 0` sends them through the generic shared-memory kernel (fp64 V-cycle).  Same iteration counts to within one,
+    same solutions to round-off, 1e-10 against the reference operator -- in every forcing form the kernel has a path for
+    (sine factors, f array, wave numbers; theta or none) and with the fused window / downsample outputs."""
+    rs = np.random.RandomState(3 * n)
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    k = rs.uniform(0.5, n / 4.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    f = sy[:, :, None] * sx[:, None, :]
+    forms = [dict(theta=theta, sin_x=sx, sin_y=sy), dict(theta=theta, f=f), dict(theta=None, sin_x=sx, sin_y=sy),
+             dict(theta=theta, k1=k[:, 0].copy(), k2=k[:, 1].copy())]
+    assert gpu_lib.describe(n)["resident"]
+    for kw in forms:
+        u, info = gpu_lib.solve_batch(n, B, **kw)
+        gpu_lib.set_option("res_block", 0)
+        try:
+            ug, infog = gpu_lib.solve_batch(n, B, **kw)
+        finally:
+            gpu_lib.set_option("res_block", 1)
+        assert (info.status == 0).all() and (infog.status == 0).all()
+        assert (np.abs(info.iters - infog.iters) <= 1).all()
+        assert O.rel_l2(u, ug) <= 1e-11
+    u, info = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    for b in (0, B // 2, B - 1):
+        assert O.rel_l2(u[b], O.solve_poisson(f[b], theta[b], n)) <= TOL
+
+
+@pytest.mark.parametrize("n,B", [(160, 150), (320, 7), (640, 3)])
+def test_coarse_tail_in_the_register_blocked_vcycle_kernel(gpu_lib, n, B):
+    """Hierarchies with an 80 x 80 level hand it (and everything below) to the register-blocked V-cycle kernel; with
+    `coarse_block = 0` the strips go down to 40 x 40 and the shared-memory coarse kernel takes over.  Same iteration counts to
+    within one, solutions equal to round-off, 1e-10 against the reference operator; the layout query reports the level."""
+    rs = np.random.RandomState(n + 5)
+    theta = rs.uniform(0.5, 2.0, size=(B, n, n))
+    k = rs.uniform(0.5, 12.0, size=(B, 2))
+    x = np.linspace(0, 1, n)
+    sx, sy = np.sin(2 * np.pi * k[:, :1] * x), np.sin(2 * np.pi * k[:, 1:] * x)
+    lvl = gpu_lib.describe(n)["first_smem_level"]
+    u, info = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    gpu_lib.set_option("coarse_block", 0)
+    try:
+        lvl0 = gpu_lib.describe(n)["first_smem_level"]
+        u0, info0 = gpu_lib.solve_batch(n, B, theta=theta, sin_x=sx, sin_y=sy)
+    finally:
+        gpu_lib.set_option("coarse_block", 1)
+    assert lvl0 == lvl + 1 and n >> lvl == 80
+    assert info.accepted().all() and info0.accepted().all()
+    assert (np.abs(info.iters - info0.iters) <= 1).all()
+    assert O.rel_l2(u, u0) <= 1e-11
+    for b in (0, B - 1):
+        assert O.rel_l2(u[b], O.solve_poisson(np.outer(sy[b], sx[b]), theta[b], n)) <= TOL
+
+
 @pytest.mark.parametrize("nu", [1, 3])
 @pytest.mark.parametrize("n,B", [(160, 300), (320, 5)])
 def test_other_sweep_counts_on_the_streamed_path(gpu_lib, nu, n, B):
