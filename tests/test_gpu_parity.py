@@ -126,7 +126,8 @@ def test_register_blocked_kernels_against_the_generic_one(gpu_lib, n, B):
     """20 x 20, 40 x 40 and 80 x 80 run in the register-blocked kernels (float V-cycle, levels n, n/2, n/4 in registers);
     `res_block = 0` sends them through the generic shared-memory kernel (fp64 V-cycle).  Same iteration counts to within one,
     same solutions to round-off, 1e-10 against the reference operator -- in every forcing form the kernel has a path for
-    (sine factors, f array, wave numbers; theta or none) and with the fused window / downsample outputs."""
+    (sine factors, f array, wave numbers; theta or none).  (The fused window / downsample outputs of the 80 x 80 kernel are
+    covered by the subdomain-dataset fixtures.)"""
     rs = np.random.RandomState(3 * n)
     theta = rs.uniform(0.5, 2.0, size=(B, n, n))
     k = rs.uniform(0.5, n / 4.0, size=(B, 2))
