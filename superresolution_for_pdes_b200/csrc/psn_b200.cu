@@ -74,8 +74,14 @@ __global__ void __launch_bounds__(T) psn_smem_solve_kernel(const __grid_constant
 //  __maxnreg__(152) compiles but cannot be launched)
 // BX = 10 (40 x 40): 128 threads and ~46 KB per sample, four samples per SM (three with 168 registers and no spills: 6.2M
 // instead of 6.6M solves/s).
-// BX = 5 (20 x 20): one warp and ~18 KB per sample, eleven samples per SM.
-#define PSN_BLOCK_CTAS(BX) ((BX) >= 20 ? 1 : (BX) >= 10 ? 4 : 11)
+// BX = 5 (20 x 20): one warp and ~18 KB per sample.  Eight samples per SM: 206 registers and no spills.  Shared memory would
+// allow eleven, but then the register cap is 168, the kernel spills 128 B per thread, and with 220 KB of the SM's 256 KB
+// carved out as shared memory the spill traffic no longer fits the remaining L1: 3.7M - 17M solves/s from run to run
+// instead of a steady 25M (10 per SM: 25.3M with 120 B of spills; 9: 23.5M).
+#ifndef PSN_BLOCK_CTAS5
+#define PSN_BLOCK_CTAS5 8
+#endif
+#define PSN_BLOCK_CTAS(BX) ((BX) >= 20 ? 1 : (BX) >= 10 ? 4 : PSN_BLOCK_CTAS5)
 template <int BX>
 __global__ void __launch_bounds__(PsnBlockGeom<BX>::NTPAD, PSN_BLOCK_CTAS(BX)) psn_block_solve_kernel(const __grid_constant__ PsnPlan plan,
                                                                                      const __grid_constant__ PsnSolveArgs a,

@@ -118,22 +118,27 @@ struct PsnBlockGeom {
     // threads (one half warp = one 64-bit shared-memory transaction) form a 4 x 4 patch of the thread grid -- and the pitch is
     // 12 mod 16, so that the four rows of a patch fall on four disjoint groups of banks: every edge access is conflict free.
     // (Row-major numbering with pitch BX + 2: 3 of 5 half warps straddle a row end, 1.6 wavefronts per access.)
-    // BX not a multiple of 4 (BX = 10, the 40 x 40 grid): threads are numbered row by row and the pitch is BX + 2 -- 32
-    // consecutive threads then spread over 32 + 2 * 3 positions, i.e. at most 6 of them share a bank with another one.
+    // BX not a multiple of 4 (BX = 10 / 5, the 40 x 40 / 20 x 20 grids): threads are numbered row by row.  With ghost COLUMNS
+    // (pitch BX + 2) 32 consecutive threads spread over 32 + 3 * 2 positions and every edge access takes two wavefronts --
+    // the 40 x 40 kernel ran at 76 % of the shared-memory pipe, 41 % of it conflict wavefronts.  So these grids have ghost rows
+    // only, pitch BX: thread t sits at cell t + BX, consecutive threads on consecutive cells, no conflict at any alignment; the
+    // left / right neighbour of a thread in the first / last column is masked with the thread's flags instead (EL below), and
+    // the idle threads of the last warp sit 32 cells behind their row-major position (same banks, behind the bottom ghost row).
     static constexpr bool TILED = BX % 4 == 0;
+    static constexpr bool GHOSTCOLS = TILED;
     static constexpr int BROWS = BX + 2;
-    static constexpr int BP = TILED ? ((BX + 2 + 3) / 16) * 16 + 12 : BX + 2;
-    static_assert(BP >= BX + 2 && (!TILED || BP % 16 == 12), "tile numbering: pitch 12 mod 16");
+    static constexpr int BP = TILED ? ((BX + 2 + 3) / 16) * 16 + 12 : BX;
+    static_assert(!TILED || (BP >= BX + 2 && BP % 16 == 12), "tile numbering: pitch 12 mod 16");
     // cells per edge-buffer plane: the padded grid, then one private cell per idle thread of the last warp (their accesses
     // need no predicate either), then slack for those threads' neighbour reads
-    static constexpr int NTP = (BROWS * BP + (NTPAD - NT) + BP + 1 + 7) & ~7;
+    static constexpr int NTP = (BROWS * BP + (TILED ? 0 : 32) + (NTPAD - NT) + BP + 1 + 7) & ~7;
     // float planes of the V-cycle exchange (they alias the fp64 planes): a warp is two tiles = 4 rows x 8 cells per 32-bit
     // transaction, so the pitch is 8 mod 32.  (Two tiles are disjoint in banks iff their tile columns differ by an odd number;
     // the 2 of 13 warps that hold the last tile of a tile row and the first of the next conflict 2-way: with 25 tiles no pitch
     // pairs them all.)
-    static constexpr int BPF = TILED ? ((BX + 2 - 8 + 31) / 32) * 32 + 8 : BX + 2;
-    static constexpr int NTPF = (BROWS * BPF + (NTPAD - NT) + BPF + 1 + 7) & ~7;
-    static_assert(BPF >= BX + 2 && (!TILED || BPF % 32 == 8) && 16 * NTPF * 4 <= 16 * NTP * 8, "float planes must fit into the fp64 planes");
+    static constexpr int BPF = TILED ? ((BX + 2 - 8 + 31) / 32) * 32 + 8 : BX;
+    static constexpr int NTPF = (BROWS * BPF + (TILED ? 0 : 32) + (NTPAD - NT) + BPF + 1 + 7) & ~7;
+    static_assert((!TILED || (BPF >= BX + 2 && BPF % 32 == 8)) && 16 * NTPF * 4 <= 16 * NTP * 8, "float planes must fit into the fp64 planes");
     // shared memory (doubles): x[16][NTPAD], edges[4 sides][4 slots][NTP]
     static constexpr int XS = 16 * NTPAD;
     static constexpr int ES = 16 * NTP;
@@ -194,11 +199,13 @@ struct PsnBlockSolver {
     // cursor = shared address of the thread's own edge cell, with the geometry of its planes
     struct CurD {                          // fp64 planes: CG exchange of p and x
         PsnShF64 a;
+        int fl;                            // the thread's flags (first / last column masks of the layouts without ghost columns)
         typedef double T;
         static constexpr int P = G::BP, PL = G::NTP;
     };
     struct CurV {                          // V-cycle planes
         ShV a;
+        int fl;
         typedef VT T;
         static constexpr int P = BPV, PL = NTPV;
     };
@@ -214,7 +221,7 @@ struct PsnBlockSolver {
     PsnShF64 ea_dev, xa_dev;   // this thread's own edge cell / x column (shared addresses pinned in registers)
     ShV ev_dev;
     int fl_dev;                // bit 0: real thread (t < NT), bit 1: (bx + by) odd, bit 2: bx and by both odd,
-                               // bits 3 / 4: last thread row / column
+                               // bits 3 / 4: last thread row / column, bit 5: first thread column
 #endif
 
     const double* inv_s = nullptr;   // shared-memory copy of the coarsest-level inverse (or null)
@@ -236,11 +243,14 @@ struct PsnBlockSolver {
     }
 
     // position of thread t in the ghost-ringed thread grid of pitch P; the idle threads of the last warp get private cells behind it
-    PSN_FN static int tpad(int t, int P) { return t < NT ? (by_of(t) + 1) * P + bx_of(t) + 1 : G::BROWS * P + (t - NT); }
+    PSN_FN static int tpad(int t, int P) {
+        if (!G::GHOSTCOLS) return t < NT ? t + BX : t + BX + 32;   // (P == BX: cell (by + 1) * BX + bx)
+        return t < NT ? (by_of(t) + 1) * P + bx_of(t) + 1 : G::BROWS * P + (t - NT);
+    }
     PSN_FN static int flags_of(int t) {
         const int bx = bx_of(t), by = by_of(t);
         return (t < NT ? 1 : 0) | ((((bx + by) & 1) && t < NT) ? 2 : 0) | (((bx & 1) && (by & 1) && t < NT) ? 4 : 0) |
-               ((by == BX - 1 && t < NT) ? 8 : 0) | ((bx == BX - 1 && t < NT) ? 16 : 0);
+               ((by == BX - 1 && t < NT) ? 8 : 0) | ((bx == BX - 1 && t < NT) ? 16 : 0) | ((bx == 0 && t < NT) ? 32 : 0);
     }
     PSN_FN int flags(int t) const {
 #if defined(__CUDACC__)
@@ -251,16 +261,16 @@ struct PsnBlockSolver {
     }
     PSN_FN CurD curd(int t) const {
 #if defined(__CUDACC__)
-        return CurD{ea_dev};
+        return CurD{ea_dev, fl_dev};
 #else
-        return CurD{edge.at(tpad(t, G::BP))};
+        return CurD{edge.at(tpad(t, G::BP)), flags_of(t)};
 #endif
     }
     PSN_FN CurV curv(int t) const {
 #if defined(__CUDACC__)
-        return CurV{ev_dev};
+        return CurV{ev_dev, fl_dev};
 #else
-        return CurV{edgev.at(tpad(t, BPV))};
+        return CurV{edgev.at(tpad(t, BPV)), flags_of(t)};
 #endif
     }
 
@@ -303,7 +313,14 @@ struct PsnBlockSolver {
     }
     // edge buffer (side, slot) of level LV, cell (dy, dx) relative to the thread's own cell
     template <int LV = 0, class C>
-    PSN_FN static typename C::T EL(const C& c, int side, int slot, int dy, int dx) { return c.a.ld(plane<LV>(side, slot) * C::PL + dy * C::P + dx); }
+    PSN_FN static typename C::T EL(const C& c, int side, int slot, int dy, int dx) {
+        typename C::T v = c.a.ld(plane<LV>(side, slot) * C::PL + dy * C::P + dx);
+        if (!G::GHOSTCOLS) {   // no ghost columns: the cell left of the first / right of the last column belongs to another row
+            if (dx < 0 && (c.fl & 32)) v = (typename C::T)0;
+            if (dx > 0 && (c.fl & 16)) v = (typename C::T)0;
+        }
+        return v;
+    }
     template <int LV = 0, class C>
     PSN_FN static void ES(const C& c, int side, int slot, typename C::T v) { c.a.st(plane<LV>(side, slot) * C::PL, v); }
 
@@ -351,15 +368,16 @@ struct PsnBlockSolver {
     // The float planes of the V-cycle alias the fp64 planes of the CG exchange, so each side overwrites the other's ghost ring:
     // thread t re-zeroes its share of the ring cells of all planes of layout C (called once per PCG iteration and layout,
     // in a phase where nobody reads the planes; the next barrier orders it before the first halo load).
-    static constexpr int RING = 2 * (BX + 2) + 2 * BX;
-    // Two schedules.  One warp per sample (BX = 5: 24 ring cells, 32 threads): thread t owns ring cell t in every plane, so the
+    static constexpr int RING = G::GHOSTCOLS ? 2 * (BX + 2) + 2 * BX : 2 * BX;   // (ghost rows only: top and bottom row)
+    // Two schedules.  One warp per sample (BX = 5: 10 ring cells -- the two ghost rows -- for 32 threads): thread t owns ring cell t in every plane, so the
     // cell's offset is worked out once per call and the stores need no index arithmetic -- with a division and a branch per
     // cell the re-zeroing was 15 % of that kernel's instructions (23.0M -> 25.5M solves/s).  Larger CTAs: the cells of all
     // planes are dealt round-robin to all threads (3 - 4 each); the per-cell-owner form leaves most warps idle while a few
     // store, and measured 1 % (40 x 40) and 5 % (80 x 80) slower.
-    static constexpr bool ZOWNER = NTPAD < 2 * RING;
+    static constexpr bool ZOWNER = NTPAD <= 32;
     static_assert(NTPAD >= RING, "every ring cell needs a thread");
     PSN_FN static int ring_cell(int c, int P) {
+        if (!G::GHOSTCOLS) return c < BX ? c : (BX + 1) * P + (c - BX);
         if (c < BX + 2) return c;
         if (c < 2 * (BX + 2)) return (BX + 1) * P + (c - (BX + 2));
         return (1 + ((c - 2 * (BX + 2)) >> 1)) * P + (((c - 2 * (BX + 2)) & 1) ? BX + 1 : 0);
