@@ -118,13 +118,19 @@ struct PsnBlockGeom {
     // threads (one half warp = one 64-bit shared-memory transaction) form a 4 x 4 patch of the thread grid -- and the pitch is
     // 12 mod 16, so that the four rows of a patch fall on four disjoint groups of banks: every edge access is conflict free.
     // (Row-major numbering with pitch BX + 2: 3 of 5 half warps straddle a row end, 1.6 wavefronts per access.)
-    // BX not a multiple of 4 (BX = 10 / 5, the 40 x 40 / 20 x 20 grids): threads are numbered row by row.  With ghost COLUMNS
+    // Threads are numbered row by row (always for BX = 10 / 5, which the 4 x 4 tiles do not divide).  With ghost COLUMNS
     // (pitch BX + 2) 32 consecutive threads spread over 32 + 3 * 2 positions and every edge access takes two wavefronts --
     // the 40 x 40 kernel ran at 76 % of the shared-memory pipe, 41 % of it conflict wavefronts.  So these grids have ghost rows
     // only, pitch BX: thread t sits at cell t + BX, consecutive threads on consecutive cells, no conflict at any alignment; the
     // left / right neighbour of a thread in the first / last column is masked with the thread's flags instead (EL below), and
     // the idle threads of the last warp sit 32 cells behind their row-major position (same banks, behind the bottom ghost row).
-    static constexpr bool TILED = BX % 4 == 0;
+// (PSN_BLOCK_TILED = 1: the layout of the first half of round 2 -- ghost columns, threads numbered in 4 x 4 tiles, pitch 12 mod
+// 16 -- which left 13 % conflict wavefronts on the float planes, in the warps whose two tiles straddle a tile row.  The
+// ghost-row-only layout below is conflict free for every warp: 80 x 80 1.553M -> 1.620M solves/s.)
+#ifndef PSN_BLOCK_TILED
+#define PSN_BLOCK_TILED 0
+#endif
+    static constexpr bool TILED = BX % 4 == 0 && PSN_BLOCK_TILED;
     static constexpr bool GHOSTCOLS = TILED;
     static constexpr int BROWS = BX + 2;
     static constexpr int BP = TILED ? ((BX + 2 + 3) / 16) * 16 + 12 : BX;
