@@ -374,8 +374,15 @@ def solve_from_wavenumbers(n: int, k1, k2, *, theta=None, out=None, chunks: Opti
         # call pays the copy pipeline's fill and drain again: 80x80 x 18,944 measured 29.5 / 29.1 / 29.9 / 30.7 / 32.6 ms for
         # 1 / 2 / 3 / 4 / 8 chunks); large grids: sines are negligible and one call keeps the library's own pipeline intact
         chunks = 2 if n <= 100 else 1
+        uneven = True
+    else:
+        uneven = False
     chunks = max(1, min(int(chunks), B)) if B else 1
     bounds = [(B * c) // chunks for c in range(chunks + 1)]
+    if uneven and chunks == 2 and B >= 4096:
+        # a short first chunk: the GPU starts after 1/8 of the sines, and the sines of the long second chunk are evaluated
+        # while the first one is in the C call
+        bounds = [0, B // 8, B]
 
     def sines_range(lo, hi):
         w1 = (k1[lo:hi] * 2 * np.pi) if kfirst else (2 * np.pi * k1[lo:hi])
@@ -386,7 +393,9 @@ def solve_from_wavenumbers(n: int, k1, k2, *, theta=None, out=None, chunks: Opti
     def sines(c):
         lo, hi = bounds[c], bounds[c + 1]
         work = (hi - lo) * n
-        nt = 1 if work < (1 << 16) else min(8, os.cpu_count() or 1, max(1, (hi - lo) // 8))
+        # up to 16 threads, but only this rank's share of the host cores (torchrun: one rank per GPU on the same host)
+        cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)))
+        nt = 1 if work < (1 << 16) else min(16, cores, max(1, (hi - lo) // 8))
         if nt <= 1:
             sines_range(lo, hi)
             return
