@@ -192,6 +192,14 @@ def test_host_logic_multires(oracle_backend):
     r0 = O.solve_multi_resolution(40, [80])
     r1 = O.solve_multi_resolution(40, [80])
     assert O.rel_l2(b["u"][80][0], r0["u"][80]) <= 1e-13 and O.rel_l2(b["u"][40][1], r1["u"][40]) <= 1e-13
+    # the master theta of the batched chain is handed back as a host array in every mode (its device-to-host copy is started
+    # before the solves and waited for afterwards); draw_examples(defer_host=True) returns the waiter
+    assert isinstance(b["theta_finest"], np.ndarray) and np.array_equal(b["theta_finest"][0], r0["theta"][80])
+    np.random.seed(5)
+    k1, k2, th_solver, th_wait = pkg.resolution_comparison.draw_examples(2, 80, (10.0, 11.0), defer_host=True)
+    assert callable(th_wait) and np.array_equal(th_wait(), b["theta_finest"]) and np.array_equal(k1, b["k1"])
+    a, wait = _lib.to_host_async(b["theta_finest"])
+    assert a is b["theta_finest"] and wait() is a          # numpy arrays pass through
 
 
 def test_host_logic_evaluation_script_callers(oracle_backend, tmp_path, monkeypatch):
