@@ -1157,7 +1157,14 @@ void choose_bands(const PsnPlan& plan, PsnStreamCfg* cfg, long long Bc) {
     // model (3 CTAs per SM) measured the same at 640^2 (797-819 us for bands of 128-320 rows) and 28 % slower at 160^2 x 8192.
     cfg->fuse_band = g.fuse_band >= 16 ? ((g.fuse_band + 1) & ~1) : 0;
     if (g.band0 >= 16 && cfg->ls >= 1) cfg->band[0] = (g.band0 + 1) & ~1;   // experiment knob
-    cfg->dir_band = g.dir_band >= 16 ? ((g.dir_band + 1) & ~1) : cfg->band[0];
+    // direction kernel: bands of about "dir_band" rows, equalised over the column (160 rows as 64 + 64 + 32 left the last band of
+    // every strip half empty: 499 us per launch at 160^2 x 8192 against 444 us for 80 + 80; 320 and 640 divide evenly anyway)
+    if (g.dir_band >= 16) {
+        const int nb = std::max(1, plan.n / g.dir_band);
+        cfg->dir_band = ((plan.n + nb - 1) / nb + 1) & ~1;
+    } else {
+        cfg->dir_band = cfg->band[0];
+    }
     cfg->upd_band = g.upd_band >= 16 ? ((g.upd_band + 1) & ~1) : 0;
     cfg->upd_strip = g.upd_strip;
     cfg->pf32 = (cfg->vf32 && g.upd_strip && g.p_f32) ? 1 : 0;
